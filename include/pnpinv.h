@@ -1,0 +1,145 @@
+/* pnpinv.h -- C ABI of libpnpinv.so: the B200-native (sm_100a) hot path of cure-lab/PnPInversion.
+ *
+ * The reference has no FFI: its "plugin API" is three duck-typed Python seams.  This header
+ * is what a replacement for seam B (the `model` handle the loops call) and seam C (the attention controller) binds
+ * to.  Every entry point cites the reference interface it replaces.  Conventions:
+ *   - all functions return 0 on success, <0 on error; the message is available from pnp_last_error();
+ *   - nothing throws across the boundary; a handle is not thread-safe; one handle per GPU/process;
+ *   - every launch goes to the caller-supplied cudaStream_t (passed as void*; 0 = legacy default stream);
+ *   - pointers named *_dev are device pointers borrowed for the duration of the call (until the stream reaches it),
+ *     pointers named *_host are host pointers read before the call returns;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef PNPINV_H_
+#define PNPINV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNP_MAX_BATCH 32   /* UNet batch rows (CFG pair included) */
+#define PNP_MAX_SLOTS 8    /* edited (target) rows with their own 77-entry tables */
+#define PNP_TOKENS 77      /* MAX_NUM_WORDS, models/p2p/attention_control.py:8 */
+#define PNP_LATENT_ELEMS 16384 /* 4 x 64 x 64 */
+
+typedef struct pnp_engine pnp_engine;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------------- */
+/* replaces StableDiffusionPipeline.from_pretrained(...).to(device) for the UNet part, models/p2p_editor.py:23-24 */
+int pnp_create(int device_ordinal, int max_batch, pnp_engine** out);
+void pnp_destroy(pnp_engine* h);
+const char* pnp_last_error(void);
+const char* pnp_version(void);
+
+/* ---- parameters: the 686 tensors of the SD-1.x UNet state_dict, names verbatim --------- */
+int pnp_unet_param_count(void);
+/* name_out: >=128 bytes; shape_out: 4 ints (unused dims = 0) */
+int pnp_unet_param_spec(int index, char* name_out, int* ndim_out, int* shape_out);
+/* data_host: fp16 values in PyTorch layout (conv OIHW, linear (out,in)); copied before returning */
+int pnp_load_param(pnp_engine* h, const char* name, const uint16_t* data_host, int64_t numel);
+/* repacks everything once into the kernel layouts (conv -> (Cout, 9*Cin [+Cin_shortcut]) K-major, fused QKV, GEGLU
+ * tile interleave) and uploads; all 686 tensors must have been loaded */
+int pnp_finalize_params(pnp_engine* h);
+
+/* ---- per-schedule / per-prompt precomputation --------------------------------------------------------------- */
+/* replaces Timesteps + TimestepEmbedding + every ResnetBlock2D.time_emb_proj evaluated per UNet call
+ * (my_diffusers/models/embeddings.py:21-80, resnet.py:348-350): computed once for the n distinct timestep values */
+int pnp_set_timesteps(pnp_engine* h, const int64_t* timesteps_host, int n, void* stream);
+/* replaces attn2.to_k / attn2.to_v on encoder_hidden_states in all 16 cross-attention layers
+ * (my_diffusers/models/attention.py:255-257): context is step-invariant, so K/V are computed once.
+ * ctx_dev: [batch, 77, 768] fp32 */
+int pnp_set_context(pnp_engine* h, const float* ctx_dev, int batch, void* stream);
+
+/* ---- seam C: the attention controller lowered to a descriptor ------------------------------------------------ */
+/* replaces controller(attn, is_cross, place_in_unet) (models/p2p/attention_control.py:43-45,178-190,269-282) and
+ * editor(q,k,v,sim,attn,...) (models/masactrl/masactrl_utils.py:119-121).  Rows are UNet batch rows. */
+typedef struct pnp_attn_ctrl {
+  /* self-attention: in transformer blocks [self_layer_lo, self_layer_hi) with <= self_max_tokens tokens, batch row r
+   * takes Q from row self_q_row[r], K from self_k_row[r], V from self_v_row[r] (identity = r). */
+  int32_t self_layer_lo, self_layer_hi, self_max_tokens;
+  int32_t self_q_row[PNP_MAX_BATCH];
+  int32_t self_k_row[PNP_MAX_BATCH];
+  int32_t self_v_row[PNP_MAX_BATCH];
+  /* cross-attention: row r with cross_base_row[r] >= 0 is a target row whose probabilities become
+   *   ((P_src[:, mapper] * alphas + P_r * (1 - alphas)) * equalizer) * cross_alpha + (1 - cross_alpha) * P_r
+   * with the tables of slot cross_slot[r]  (AttentionRefine / AttentionReweight / time gate). */
+  int32_t cross_base_row[PNP_MAX_BATCH];
+  int32_t cross_slot[PNP_MAX_BATCH];
+  int32_t mapper[PNP_MAX_SLOTS][PNP_TOKENS];
+  float alphas[PNP_MAX_SLOTS][PNP_TOKENS];
+  float equalizer[PNP_MAX_SLOTS][PNP_TOKENS];
+  float cross_alpha[PNP_MAX_SLOTS][PNP_TOKENS];
+  /* AttentionStore for LocalBlend: rows with store_slot[r] >= 0 accumulate their (post-injection) 16x16 cross maps of
+   * the five layers down_cross[2:4] + up_cross[:3] into slot store_slot[r]. */
+  int32_t store_slot[PNP_MAX_BATCH];
+} pnp_attn_ctrl;
+void pnp_attn_ctrl_init(pnp_attn_ctrl* c); /* identity / disabled everywhere */
+
+/* ---- seam B: model.unet(latents, t, encoder_hidden_states=ctx)["sample"] ------------------------------------- */
+/* replaces UNet2DConditionModel.forward (my_diffusers/models/unet_2d_condition.py:189-273; called at
+ * models/p2p/inversion.py:273, p2p_guidance_forward.py:109).  x_dev/eps_out_dev: [batch,4,64,64] fp32 NCHW;
+ * t_index: index into the list given to pnp_set_timesteps; context from pnp_set_context (same batch);
+ * ctrl_host may be NULL (= no controller). */
+int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, const pnp_attn_ctrl* ctrl_host,
+                     float* eps_out_dev, void* stream);
+
+/* ---- the fused step epilogue: CFG + DDIM (inverse) step + the "3 lines" -------------------------------------- */
+/* replaces next_step / prev_step / DDIMSchedulerDev.step, the CFG combine, `loss = latent_prev - rec` and
+ * `latents[:1] + noise_loss[:1]` (models/p2p/inversion.py:247-270,383-389; scheduler_dev.py:40-51,91-94;
+ * p2p_guidance_forward.py:111-114).  All coefficient scalars are computed by the caller from the alphas_cumprod
+ * table exactly as the reference does (integer timestep arithmetic stays on the host, bit-exact). */
+typedef struct pnp_step_args {
+  const float* x_dev;      /* [n,16384] current latents */
+  const float* eps_u_dev;  /* [n,16384] unconditional prediction, or NULL (no guidance: eps = eps_c) */
+  const float* eps_c_dev;  /* [n,16384] */
+  float* x_out_dev;        /* [n,16384] (may alias x_dev) */
+  int32_t n;
+  float guidance;
+  float sqrt_a_from, sqrt_1m_a_from, sqrt_a_to, sqrt_1m_a_to;
+  const float* target_dev; /* offset mode: [target_rows,16384], or NULL */
+  int32_t target_rows;
+  float* loss_out_dev;     /* offset mode: [n,16384] */
+  const float* noise_loss_dev; /* rectification: [n,16384], or NULL */
+  uint32_t add_mask;       /* bit r: add noise_loss row r */
+} pnp_step_args;
+int pnp_step_epilogue(pnp_engine* h, const pnp_step_args* a, void* stream);
+
+/* replaces LocalBlend.__call__ (models/p2p/attention_control.py:97-121) on the latents [2,4,64,64] (row 0 source,
+ * row 1 target) using the maps accumulated through pnp_attn_ctrl.store_slot {0,1}. words/alpha: the non-zero
+ * entries of alpha_layers per prompt (<= 8 each). mask_out_dev: optional [2,4096] floats. */
+int pnp_local_blend(pnp_engine* h, float* x_dev, const int32_t* nwords2_host, const int32_t* words2x8_host,
+                    const float* alpha2x8_host, float threshold, float* mask_out_dev, void* stream);
+int pnp_store_reset(pnp_engine* h, void* stream);          /* AttentionStore.reset() */
+/* debug/inspection: copy the accumulated maps [5][2*PNP_MAX_SLOTS... see DESIGN.md] */
+int pnp_store_read(pnp_engine* h, float* out_dev, int64_t max_floats, void* stream);
+
+/* ---- instrumentation ----------------------------------------------------------------------------------------- */
+int pnp_kernel_launches(pnp_engine* h, int64_t* out); /* kernels launched by this handle so far (graph nodes count) */
+int pnp_set_use_graph(pnp_engine* h, int enable);     /* capture each UNet forward into a CUDA graph (default on) */
+
+/* ---- stand-alone kernel entry points (used by tests/ and bench.py to measure single kernels) ------------------ */
+/* D[M,N] = A[M,K].W[N,K]^T (+bias)(+residual) ; mode 0 plain, 1 GEGLU (N = 2*out columns, weights pre-interleaved by
+ * pnp_test_pack_geglu) ; conv3x3: A is NHWC [B,H,W,C], W packed (N, 9*C) tap-major */
+int pnp_test_gemm(const uint16_t* a_dev, int M, int K, int lda, const uint16_t* w_dev, int N, const float* bias_dev,
+                  const uint16_t* residual_dev, uint16_t* out_dev, int ldc, int geglu, int bn, void* stream);
+int pnp_test_conv3x3(const uint16_t* x_dev, int B, int H, int W, int C, const uint16_t* w_dev, int N,
+                     const uint16_t* sc0_dev, int sc0_C, const uint16_t* sc1_dev, int sc1_C, const float* bias_dev,
+                     const uint16_t* residual_dev, uint16_t* out_dev, int bn, void* stream);
+int pnp_test_groupnorm(const uint16_t* x0_dev, int C0, const uint16_t* x1_dev, int C1, int B, int HW,
+                       const float* gamma_dev, const float* beta_dev, float eps, int silu, uint16_t* out_dev,
+                       void* stream);
+int pnp_test_layernorm(const uint16_t* x_dev, int rows, int C, const float* gamma_dev, const float* beta_dev,
+                       float eps, uint16_t* out_dev, void* stream);
+int pnp_test_self_attention(const uint16_t* qkv_dev, int B, int H, int N, int d, const int32_t* q_row_dev,
+                            const int32_t* k_row_dev, const int32_t* v_row_dev, uint16_t* out_dev, void* stream);
+int pnp_test_cross_attention(const uint16_t* q_dev, const uint16_t* kv_dev, int B, int H, int N, int d, int nk,
+                             const pnp_attn_ctrl* ctrl_host, float* store_dev, uint16_t* out_dev, void* stream);
+int pnp_test_upsample2x(const uint16_t* x_dev, int B, int H, int W, int C, uint16_t* out_dev, void* stream);
+int pnp_test_im2col_s2(const uint16_t* x_dev, int B, int H, int W, int C, uint16_t* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNPINV_H_ */

@@ -1,0 +1,138 @@
+"""ctypes binding of libpnpinv.so (C ABI declared in include/pnpinv.h).
+
+There is deliberately no fallback: if the shared library is missing or a CUDA device is absent, every compute call
+raises.  torch tensors are only containers here (`tensor.data_ptr()`, `torch.cuda.current_stream().cuda_stream`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+PNP_MAX_BATCH = 32
+PNP_MAX_SLOTS = 8
+PNP_TOKENS = 77
+LATENT_ELEMS = 4 * 64 * 64
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpnpinv.so")
+
+
+class PnpError(RuntimeError):
+    pass
+
+
+class AttnCtrl(C.Structure):
+    """Mirror of `pnp_attn_ctrl` (include/pnpinv.h)."""
+
+    _fields_ = [
+        ("self_layer_lo", C.c_int32),
+        ("self_layer_hi", C.c_int32),
+        ("self_max_tokens", C.c_int32),
+        ("self_q_row", C.c_int32 * PNP_MAX_BATCH),
+        ("self_k_row", C.c_int32 * PNP_MAX_BATCH),
+        ("self_v_row", C.c_int32 * PNP_MAX_BATCH),
+        ("cross_base_row", C.c_int32 * PNP_MAX_BATCH),
+        ("cross_slot", C.c_int32 * PNP_MAX_BATCH),
+        ("mapper", (C.c_int32 * PNP_TOKENS) * PNP_MAX_SLOTS),
+        ("alphas", (C.c_float * PNP_TOKENS) * PNP_MAX_SLOTS),
+        ("equalizer", (C.c_float * PNP_TOKENS) * PNP_MAX_SLOTS),
+        ("cross_alpha", (C.c_float * PNP_TOKENS) * PNP_MAX_SLOTS),
+        ("store_slot", C.c_int32 * PNP_MAX_BATCH),
+    ]
+
+
+class StepArgs(C.Structure):
+    """Mirror of `pnp_step_args`."""
+
+    _fields_ = [
+        ("x_dev", C.c_void_p),
+        ("eps_u_dev", C.c_void_p),
+        ("eps_c_dev", C.c_void_p),
+        ("x_out_dev", C.c_void_p),
+        ("n", C.c_int32),
+        ("guidance", C.c_float),
+        ("sqrt_a_from", C.c_float),
+        ("sqrt_1m_a_from", C.c_float),
+        ("sqrt_a_to", C.c_float),
+        ("sqrt_1m_a_to", C.c_float),
+        ("target_dev", C.c_void_p),
+        ("target_rows", C.c_int32),
+        ("loss_out_dev", C.c_void_p),
+        ("noise_loss_dev", C.c_void_p),
+        ("add_mask", C.c_uint32),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+# name -> (restype, argtypes); also the list tests/test_capi_cpu.py checks against include/pnpinv.h
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+SIGNATURES = {
+    "pnp_create": (_i, [_i, _i, C.POINTER(_vp)]),
+    "pnp_destroy": (None, [_vp]),
+    "pnp_last_error": (C.c_char_p, []),
+    "pnp_version": (C.c_char_p, []),
+    "pnp_unet_param_count": (_i, []),
+    "pnp_unet_param_spec": (_i, [_i, C.c_char_p, C.POINTER(_i), C.POINTER(_i)]),
+    "pnp_load_param": (_i, [_vp, C.c_char_p, _vp, _i64]),
+    "pnp_finalize_params": (_i, [_vp]),
+    "pnp_set_timesteps": (_i, [_vp, C.POINTER(_i64), _i, _vp]),
+    "pnp_set_context": (_i, [_vp, _vp, _i, _vp]),
+    "pnp_attn_ctrl_init": (None, [C.POINTER(AttnCtrl)]),
+    "pnp_unet_forward": (_i, [_vp, _vp, _i, _i, C.POINTER(AttnCtrl), _vp, _vp]),
+    "pnp_step_epilogue": (_i, [_vp, C.POINTER(StepArgs), _vp]),
+    "pnp_local_blend": (_i, [_vp, _vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_f), _f, _vp, _vp]),
+    "pnp_store_reset": (_i, [_vp, _vp]),
+    "pnp_store_read": (_i, [_vp, _vp, _i64, _vp]),
+    "pnp_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
+    "pnp_set_use_graph": (_i, [_vp, _i]),
+    "pnp_test_gemm": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "pnp_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "pnp_test_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp]),
+    "pnp_test_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
+    "pnp_test_self_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pnp_test_cross_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(AttnCtrl), _vp, _vp, _vp]),
+    "pnp_test_upsample2x": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "pnp_test_im2col_s2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+}
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Loads libpnpinv.so (built in-tree by `make` / `__graft_entry__.build()`); raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise PnpError(
+            f"{_LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "pnpinversion_b200 has no CPU/PyTorch fallback."
+        )
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().pnp_last_error()
+        raise PnpError(f"libpnpinv error {rc}: {msg.decode() if msg else '?'}")
+
+
+def current_stream_ptr() -> int:
+    import torch
+
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def new_ctrl() -> AttnCtrl:
+    c = AttnCtrl()
+    load().pnp_attn_ctrl_init(C.byref(c))
+    return c

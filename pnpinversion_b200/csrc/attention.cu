@@ -1,0 +1,485 @@
+// Attention kernels with the Prompt-to-Prompt / MasaCtrl controller algebra compiled in as kernel modes.
+//
+// The reference materialises sim/attn as (B*8, HW, K) fp32 tensors and hands them to a Python callback between
+// softmax and P.V (models/p2p/attention_control.py:34-45; MasaCtrl models/masactrl/masactrl_utils.py:84-123).
+// Here nothing is materialised:
+//   * self-attention  = flash kernel (online softmax), 64 queries x 64 keys per step, fp16 mma.sync m16n8k16 with
+//     fp32 accumulation.  The controllers reduce to per-batch-row *indirection*:
+//        P2P self-replace  (attention_control.py:258-263,279): target row uses the source row's Q and K, its own V
+//        MasaCtrl mutual self-attention (masactrl.py:41-72):    both rows use the source row's K and V
+//   * cross-attention = 77 keys, whole probability row lives in registers; P2P injection
+//     (attention_control.py:269-282,319-323,340-345) needs the *source* row's probabilities for the same query, so an
+//     edited row computes both softmaxes in the same CTA, gathers by `mapper`, blends with `alphas`, scales with the
+//     equalizer, gates with cross_replace_alpha[step], and multiplies V without renormalising -- exactly the
+//     reference algebra.  The five 16x16 maps LocalBlend reads (attention_control.py:112) are accumulated
+//     post-injection (the aliasing the survey documents).
+//
+// (tcgen05 version of the self-attention inner loops is the next optimisation step; mma.sync is the correct-first
+// implementation.)
+#include <algorithm>
+
+#include "pnp_attn.h"
+#include "pnp_internal.h"
+
+namespace pnp {
+namespace {
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int D>
+struct Geo {
+  static constexpr int DP = (D % 16 == 0) ? D : D + 8;  // K-dim of QK^T padded to a multiple of 16 (40 -> 48)
+  static constexpr int PITCH = DP * 2 + 16;             // bytes; +16 makes ldmatrix conflict-free for 48/80/160
+  static constexpr int CHUNKS = D / 8;                  // 16-byte chunks of real data per row
+  static constexpr int KS = DP / 16;
+  static constexpr int NT = D / 8;  // output n-tiles
+};
+
+// copy `rows` rows of D halves (global, row stride ld halves) into a padded smem tile; rows >= valid_rows are zeroed
+template <int D>
+__device__ __forceinline__ void load_tile_async(uint8_t* dst, const __half* src, int ld, int rows, int valid_rows) {
+  using G = Geo<D>;
+  for (int idx = threadIdx.x; idx < rows * G::CHUNKS; idx += blockDim.x) {
+    const int r = idx / G::CHUNKS, ch = idx - r * G::CHUNKS;
+    uint8_t* d = dst + r * G::PITCH + ch * 16;
+    if (r < valid_rows) {
+      cp_async16(s_u32(d), src + static_cast<size_t>(r) * ld + ch * 8);
+    } else {
+      *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+template <int D>
+__device__ __forceinline__ void zero_pad_cols(uint8_t* dst, int rows) {
+  using G = Geo<D>;
+  if (G::DP != D) {
+    for (int r = threadIdx.x; r < rows; r += blockDim.x)
+      *reinterpret_cast<uint4*>(dst + r * G::PITCH + D * 2) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// S[16 x 8*NTILES] = Q(16 x DP) . K^T for this warp; K rows = keys in smem
+template <int D, int NTILES>
+__device__ __forceinline__ void qk_tile(float (&s)[NTILES][4], const uint32_t (&qf)[Geo<D>::KS][4], const uint8_t* sK,
+                                        int lane) {
+  using G = Geo<D>;
+#pragma unroll
+  for (int i = 0; i < NTILES; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+  const uint32_t base = s_u32(sK) + ((lane & 7) + (lane >> 4) * 8) * G::PITCH + (((lane >> 3) & 1) * 8) * 2;
+#pragma unroll
+  for (int ks = 0; ks < G::KS; ++ks) {
+#pragma unroll
+    for (int np = 0; np < NTILES / 2; ++np) {
+      uint32_t kb[4];
+      ldsm_x4(kb, base + np * 16 * G::PITCH + ks * 32);
+      mma16816(s[2 * np], qf[ks], kb[0], kb[1]);
+      mma16816(s[2 * np + 1], qf[ks], kb[2], kb[3]);
+    }
+  }
+}
+
+// O[16 x D] += P(16 x 16*KT) . V ; P given as fp32 C-fragments of the QK tile
+template <int D, int NTILES>
+__device__ __forceinline__ void pv_tile(float (&o)[Geo<D>::NT][4], const float (&s)[NTILES][4], const uint8_t* sV,
+                                        int lane) {
+  using G = Geo<D>;
+  const uint32_t base = s_u32(sV) + ((lane & 7) + ((lane >> 3) & 1) * 8) * G::PITCH + ((lane >> 4) * 8) * 2;
+#pragma unroll
+  for (int kt = 0; kt < NTILES / 2; ++kt) {
+    uint32_t pa[4];
+    pa[0] = pack2(s[2 * kt][0], s[2 * kt][1]);
+    pa[1] = pack2(s[2 * kt][2], s[2 * kt][3]);
+    pa[2] = pack2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+    pa[3] = pack2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < G::NT / 2; ++dp) {
+      uint32_t vb[4];
+      ldsm_x4_t(vb, base + kt * 16 * G::PITCH + dp * 32);
+      mma16816(o[2 * dp], pa, vb[0], vb[1]);
+      mma16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+    }
+    if (G::NT & 1) {
+      uint32_t vb[2];
+      ldsm_x2_t(vb, base + kt * 16 * G::PITCH + (G::NT - 1) * 16);
+      mma16816(o[G::NT - 1], pa, vb[0], vb[1]);
+    }
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void load_q_frags(uint32_t (&qf)[Geo<D>::KS][4], const uint8_t* sQ, int warp, int lane) {
+  using G = Geo<D>;
+  const uint32_t base =
+      s_u32(sQ) + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * G::PITCH + ((lane >> 4) * 8) * 2;
+#pragma unroll
+  for (int ks = 0; ks < G::KS; ++ks) ldsm_x4(qf[ks], base + ks * 32);
+}
+
+template <int D>
+__device__ __forceinline__ void store_o(const float (&o)[Geo<D>::NT][4], float inv0, float inv1, __half* og, int ldo,
+                                        int row0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  __half* r0 = og + static_cast<size_t>(row0 + g) * ldo + 2 * t;
+  __half* r1 = og + static_cast<size_t>(row0 + g + 8) * ldo + 2 * t;
+#pragma unroll
+  for (int nt = 0; nt < Geo<D>::NT; ++nt) {
+    *reinterpret_cast<__half2*>(r0 + nt * 8) = __floats2half2_rn(o[nt][0] * inv0, o[nt][1] * inv0);
+    *reinterpret_cast<__half2*>(r1 + nt * 8) = __floats2half2_rn(o[nt][2] * inv1, o[nt][3] * inv1);
+  }
+}
+
+// ------------------------------------------------------------------ self-attention (flash)
+template <int D>
+__global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnParams p) {
+  using G = Geo<D>;
+  constexpr int TILE = 64 * G::PITCH;
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint8_t* sQ = sm;
+  uint8_t* sK = sm + TILE;      // 2 stages
+  uint8_t* sV = sm + 3 * TILE;  // 2 stages
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bq = p.q_row ? p.q_row[b] : b;
+  const int bk = p.k_row ? p.k_row[b] : b;
+  const int bv = p.v_row ? p.v_row[b] : b;
+  const __half* qg = p.q + (static_cast<size_t>(bq) * p.N + qt * 64) * p.ld + h * D;
+  const __half* kg = p.k + static_cast<size_t>(bk) * p.N * p.ld + h * D;
+  const __half* vg = p.v + static_cast<size_t>(bv) * p.N * p.ld + h * D;
+
+  zero_pad_cols<D>(sQ, 64);
+  zero_pad_cols<D>(sK, 128);
+  load_tile_async<D>(sQ, qg, p.ld, 64, 64);
+  load_tile_async<D>(sK, kg, p.ld, 64, 64);
+  load_tile_async<D>(sV, vg, p.ld, 64, 64);
+  cp_async_commit();
+
+  const float sl2 = p.scale * 1.4426950408889634f;
+  float o[G::NT][4];
+#pragma unroll
+  for (int i = 0; i < G::NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  uint32_t qf[G::KS][4];
+
+  const int ntiles = p.N / 64;
+  for (int j = 0; j < ntiles; ++j) {
+    cp_async_wait<0>();
+    __syncthreads();
+    if (j == 0) load_q_frags<D>(qf, sQ, warp, lane);
+    if (j + 1 < ntiles) {
+      const int st = (j + 1) & 1;
+      load_tile_async<D>(sK + st * TILE, kg + static_cast<size_t>(j + 1) * 64 * p.ld, p.ld, 64, 64);
+      load_tile_async<D>(sV + st * TILE, vg + static_cast<size_t>(j + 1) * 64 * p.ld, p.ld, 64, 64);
+      cp_async_commit();
+    }
+    const uint8_t* cK = sK + (j & 1) * TILE;
+    const uint8_t* cV = sV + (j & 1) * TILE;
+    float s[8][4];
+    qk_tile<D, 8>(s, qf, cK, lane);
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float a0 = exp2f((m0 - mn0) * sl2), a1 = exp2f((m1 - mn1) * sl2);
+    m0 = mn0;
+    m1 = mn1;
+    const float off0 = mn0 * sl2, off1 = mn1 * sl2;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] * sl2 - off0);
+      s[nt][1] = exp2f(s[nt][1] * sl2 - off0);
+      s[nt][2] = exp2f(s[nt][2] * sl2 - off1);
+      s[nt][3] = exp2f(s[nt][3] * sl2 - off1);
+      rs0 += s[nt][0] + s[nt][1];
+      rs1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * a0 + rs0;
+    l1 = l1 * a1 + rs1;
+#pragma unroll
+    for (int nt = 0; nt < G::NT; ++nt) {
+      o[nt][0] *= a0; o[nt][1] *= a0;
+      o[nt][2] *= a1; o[nt][3] *= a1;
+    }
+    pv_tile<D, 8>(o, s, cV, lane);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  __half* og = p.o + static_cast<size_t>(b) * p.N * p.ldo + h * D;
+  store_o<D>(o, 1.f / l0, 1.f / l1, og, p.ldo, qt * 64 + warp * 16, lane);
+}
+
+// ------------------------------------------------------------------ cross-attention (77 keys) with P2P injection
+constexpr int XK = 80;  // keys padded to 5 x 16
+constexpr int XNT = 10;
+
+// softmax over the 77 real keys of one 16x80 score tile held in C-fragments; returns normalised probabilities
+__device__ __forceinline__ void softmax77(float (&s)[XNT][4], float sl2, int nk, int lane) {
+  const int t = lane & 3;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < XNT; ++nt) {
+    const int c = nt * 8 + 2 * t;
+    if (c >= nk) s[nt][0] = s[nt][2] = -INFINITY;
+    if (c + 1 >= nk) s[nt][1] = s[nt][3] = -INFINITY;
+    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float off0 = mx0 * sl2, off1 = mx1 * sl2;
+  float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < XNT; ++nt) {
+    s[nt][0] = exp2f(s[nt][0] * sl2 - off0);
+    s[nt][1] = exp2f(s[nt][1] * sl2 - off0);
+    s[nt][2] = exp2f(s[nt][2] * sl2 - off1);
+    s[nt][3] = exp2f(s[nt][3] * sl2 - off1);
+    rs0 += s[nt][0] + s[nt][1];
+    rs1 += s[nt][2] + s[nt][3];
+  }
+  rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
+  rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+  rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
+  rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+  const float i0 = 1.f / rs0, i1 = 1.f / rs1;
+#pragma unroll
+  for (int nt = 0; nt < XNT; ++nt) {
+    s[nt][0] *= i0; s[nt][1] *= i0;
+    s[nt][2] *= i1; s[nt][3] *= i1;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnParams p) {
+  using G = Geo<D>;
+  constexpr int QT = 64 * G::PITCH;
+  constexpr int KT = XK * G::PITCH;
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint8_t* sQ = sm;
+  uint8_t* sK = sQ + QT;
+  uint8_t* sV = sK + KT;
+  uint8_t* sQs = sV + KT;   // source-row Q (edited rows only)
+  uint8_t* sKs = sQs + QT;  // source-row K
+  float* sP = reinterpret_cast<float*>(sKs + KT);  // [4 warps][16][XK]
+  float* sTab = sP + 4 * 16 * XK;                  // alphas[80], eq[80], ca[80], then int mapper[80]
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int C = p.H * D;
+  const int base = p.base_row ? p.base_row[b] : -1;
+  const int slot = p.edit_slot ? p.edit_slot[b] : -1;
+  const bool edit = base >= 0 && slot >= 0;
+  const int rows_valid = min(64, p.N - qt * 64);
+
+  const __half* qg = p.q + (static_cast<size_t>(b) * p.N + qt * 64) * p.ldq + h * D;
+  const __half* kg = p.kv + static_cast<size_t>(b) * p.nk * p.ldkv + h * D;
+  const __half* vg = kg + C;
+  zero_pad_cols<D>(sQ, 64);
+  zero_pad_cols<D>(sK, XK);
+  load_tile_async<D>(sQ, qg, p.ldq, 64, rows_valid);
+  load_tile_async<D>(sK, kg, p.ldkv, XK, p.nk);
+  load_tile_async<D>(sV, vg, p.ldkv, XK, p.nk);
+  if (edit) {
+    const __half* qsg = p.q + (static_cast<size_t>(base) * p.N + qt * 64) * p.ldq + h * D;
+    const __half* ksg = p.kv + static_cast<size_t>(base) * p.nk * p.ldkv + h * D;
+    zero_pad_cols<D>(sQs, 64);
+    zero_pad_cols<D>(sKs, XK);
+    load_tile_async<D>(sQs, qsg, p.ldq, 64, rows_valid);
+    load_tile_async<D>(sKs, ksg, p.ldkv, XK, p.nk);
+    for (int i = threadIdx.x; i < XK; i += blockDim.x) {
+      const bool ok = i < p.nk;
+      sTab[i] = ok ? p.alphas[slot * 77 + i] : 0.f;
+      sTab[XK + i] = ok ? p.equalizer[slot * 77 + i] : 0.f;
+      sTab[2 * XK + i] = ok ? p.cross_alpha[slot * 77 + i] : 0.f;
+      reinterpret_cast<int*>(sTab + 3 * XK)[i] = ok ? p.mapper[slot * 77 + i] : 0;
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const float sl2 = p.scale * 1.4426950408889634f;
+  uint32_t qf[G::KS][4];
+  float s[XNT][4];
+  if (edit) {
+    // source probabilities for the same queries -> smem
+    load_q_frags<D>(qf, sQs, warp, lane);
+    qk_tile<D, XNT>(s, qf, sKs, lane);
+    softmax77(s, sl2, p.nk, lane);
+    float* myP = sP + warp * 16 * XK;
+#pragma unroll
+    for (int nt = 0; nt < XNT; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      myP[g * XK + c] = s[nt][0];
+      myP[g * XK + c + 1] = s[nt][1];
+      myP[(g + 8) * XK + c] = s[nt][2];
+      myP[(g + 8) * XK + c + 1] = s[nt][3];
+    }
+    __syncwarp();
+  }
+  load_q_frags<D>(qf, sQ, warp, lane);
+  qk_tile<D, XNT>(s, qf, sK, lane);
+  softmax77(s, sl2, p.nk, lane);
+  if (edit) {
+    // attention_control.py:319-323 (Refine gather+blend), :340-345 (Reweight), :276-277 (time gate)
+    const float* myP = sP + warp * 16 * XK;
+    const float* al = sTab;
+    const float* eq = sTab + XK;
+    const float* ca = sTab + 2 * XK;
+    const int* mp = reinterpret_cast<const int*>(sTab + 3 * XK);
+#pragma unroll
+    for (int nt = 0; nt < XNT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = nt * 8 + 2 * t + (e & 1);
+        const int r = g + (e >> 1) * 8;
+        if (c < p.nk) {
+          const float pt = s[nt][e];
+          int mc = mp[c];
+          if (mc < 0) mc += p.nk;  // torch negative index: -1 -> last column (seq_aligner.py:96,116)
+          const float ps = myP[r * XK + mc];
+          float nw = ps * al[c] + pt * (1.f - al[c]);
+          nw = nw * eq[c];
+          s[nt][e] = nw * ca[c] + (1.f - ca[c]) * pt;
+        }
+      }
+    }
+  }
+  if (p.store != nullptr) {
+    const int ss = p.store_slot ? p.store_slot[b] : -1;
+    if (ss >= 0) {
+      float* st = p.store + ((static_cast<size_t>(ss) * p.H + h) * p.N + qt * 64 + warp * 16) * 77;
+#pragma unroll
+      for (int nt = 0; nt < XNT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = nt * 8 + 2 * t + (e & 1);
+          const int r = g + (e >> 1) * 8;
+          if (c < p.nk && warp * 16 + r < rows_valid) st[r * 77 + c] += s[nt][e];
+        }
+      }
+    }
+  }
+  float o[G::NT][4];
+#pragma unroll
+  for (int i = 0; i < G::NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  pv_tile<D, XNT>(o, s, sV, lane);
+  __half* og = p.o + static_cast<size_t>(b) * p.N * p.ldo + h * D;
+  if (rows_valid == 64) {
+    store_o<D>(o, 1.f, 1.f, og, p.ldo, qt * 64 + warp * 16, lane);
+  } else {
+    const int r0 = warp * 16 + g;
+#pragma unroll
+    for (int nt = 0; nt < G::NT; ++nt) {
+      if (r0 < rows_valid)
+        *reinterpret_cast<__half2*>(og + static_cast<size_t>(qt * 64 + r0) * p.ldo + nt * 8 + 2 * t) =
+            __floats2half2_rn(o[nt][0], o[nt][1]);
+      if (r0 + 8 < rows_valid)
+        *reinterpret_cast<__half2*>(og + static_cast<size_t>(qt * 64 + r0 + 8) * p.ldo + nt * 8 + 2 * t) =
+            __floats2half2_rn(o[nt][2], o[nt][3]);
+    }
+  }
+}
+
+template <int D>
+size_t self_smem() { return 5 * 64 * Geo<D>::PITCH; }
+template <int D>
+size_t cross_smem() {
+  return 2 * 64 * Geo<D>::PITCH + 3 * XK * Geo<D>::PITCH + 4 * 16 * XK * sizeof(float) + 4 * XK * sizeof(float);
+}
+
+template <int D>
+int launch_self(const SelfAttnParams& p, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    PNP_CUDA(cudaFuncSetAttribute(self_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(self_smem<D>())));
+    attr = true;
+  }
+  self_attn_kernel<D><<<dim3(p.N / 64, p.H, p.B), 128, self_smem<D>(), s>>>(p);
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int D>
+int launch_cross(const CrossAttnParams& p, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    PNP_CUDA(cudaFuncSetAttribute(cross_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(cross_smem<D>())));
+    attr = true;
+  }
+  cross_attn_kernel<D><<<dim3((p.N + 63) / 64, p.H, p.B), 128, cross_smem<D>(), s>>>(p);
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int self_attention_launch(const SelfAttnParams& p, cudaStream_t s) {
+  PNP_CHECK(p.N % 64 == 0, "self-attention: token count must be a multiple of 64");
+  PNP_CHECK(p.ld % 8 == 0 && p.ldo % 2 == 0, "self-attention: alignment");
+  switch (p.d) {
+    case 40: return launch_self<40>(p, s);
+    case 80: return launch_self<80>(p, s);
+    case 160: return launch_self<160>(p, s);
+  }
+  set_last_error("self-attention: head dim must be 40, 80 or 160");
+  return -2;
+}
+
+int cross_attention_launch(const CrossAttnParams& p, cudaStream_t s) {
+  PNP_CHECK(p.nk >= 1 && p.nk <= 77, "cross-attention: at most 77 keys");
+  PNP_CHECK(p.ldq % 8 == 0 && p.ldkv % 8 == 0 && p.ldo % 2 == 0, "cross-attention: alignment");
+  switch (p.d) {
+    case 40: return launch_cross<40>(p, s);
+    case 80: return launch_cross<80>(p, s);
+    case 160: return launch_cross<160>(p, s);
+  }
+  set_last_error("cross-attention: head dim must be 40, 80 or 160");
+  return -2;
+}
+
+}  // namespace pnp

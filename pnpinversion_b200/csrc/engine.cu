@@ -1,0 +1,1243 @@
+// The UNet engine: owns the repacked SD-1.x UNet parameters, a static activation arena per batch size, the
+// precomputed time-embedding table and context K/V, and a static list of kernel launches ("plan") for one
+// UNet2DConditionModel.forward, captured into a CUDA graph.  Arithmetic spec = the reference's vendored diffusers 0.3.0
+// (models/edict/my_diffusers/models/unet_2d_condition.py:189-273, unet_blocks.py, resnet.py:331-365,
+// attention.py:140-151,186-200,250-288,329-333, embeddings.py:21-80); see DESIGN.md for the kernel map.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pnpinv.h"
+#include "pnp_attn.h"
+#include "pnp_internal.h"
+
+namespace pnp {
+
+// ------------------------------------------------------------------ error + debug plumbing
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+
+static unsigned int* g_dbg_host = nullptr;
+static unsigned int* g_dbg_dev = nullptr;
+volatile unsigned int* debug_words_device() {
+  if (g_dbg_host == nullptr) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&g_dbg_host), 64, cudaHostAllocMapped) == cudaSuccess) {
+      memset(g_dbg_host, 0, 64);
+      if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_dbg_dev), g_dbg_host, 0) != cudaSuccess)
+        g_dbg_dev = nullptr;
+    }
+  }
+  return g_dbg_dev;
+}
+const unsigned int* debug_words_host() { return g_dbg_host; }
+
+// ------------------------------------------------------------------ architecture table (mirrors pnpinversion_b200/arch.py)
+static const int kBlockOut[4] = {320, 640, 1280, 1280};
+static const int kTimeDim = 1280;
+static const int kCrossDim = 768;
+static const int kHeads = 8;
+
+struct ParamSpec {
+  std::string name;
+  int ndim;
+  int shape[4];
+  int64_t numel() const {
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= shape[i];
+    return n;
+  }
+};
+
+static void add_spec(std::vector<ParamSpec>& v, const std::string& n, std::initializer_list<int> shp) {
+  ParamSpec s;
+  s.name = n;
+  s.ndim = static_cast<int>(shp.size());
+  int i = 0;
+  for (int d : shp) s.shape[i++] = d;
+  for (; i < 4; ++i) s.shape[i] = 0;
+  v.push_back(s);
+}
+static void spec_resnet(std::vector<ParamSpec>& v, const std::string& p, int cin, int cout) {
+  add_spec(v, p + ".norm1.weight", {cin});
+  add_spec(v, p + ".norm1.bias", {cin});
+  add_spec(v, p + ".conv1.weight", {cout, cin, 3, 3});
+  add_spec(v, p + ".conv1.bias", {cout});
+  add_spec(v, p + ".time_emb_proj.weight", {cout, kTimeDim});
+  add_spec(v, p + ".time_emb_proj.bias", {cout});
+  add_spec(v, p + ".norm2.weight", {cout});
+  add_spec(v, p + ".norm2.bias", {cout});
+  add_spec(v, p + ".conv2.weight", {cout, cout, 3, 3});
+  add_spec(v, p + ".conv2.bias", {cout});
+  if (cin != cout) {
+    add_spec(v, p + ".conv_shortcut.weight", {cout, cin, 1, 1});
+    add_spec(v, p + ".conv_shortcut.bias", {cout});
+  }
+}
+static void spec_transformer(std::vector<ParamSpec>& v, const std::string& p, int c) {
+  const std::string t = p + ".transformer_blocks.0";
+  add_spec(v, p + ".norm.weight", {c});
+  add_spec(v, p + ".norm.bias", {c});
+  add_spec(v, p + ".proj_in.weight", {c, c, 1, 1});
+  add_spec(v, p + ".proj_in.bias", {c});
+  add_spec(v, t + ".attn1.to_q.weight", {c, c});
+  add_spec(v, t + ".attn1.to_k.weight", {c, c});
+  add_spec(v, t + ".attn1.to_v.weight", {c, c});
+  add_spec(v, t + ".attn1.to_out.0.weight", {c, c});
+  add_spec(v, t + ".attn1.to_out.0.bias", {c});
+  add_spec(v, t + ".ff.net.0.proj.weight", {8 * c, c});
+  add_spec(v, t + ".ff.net.0.proj.bias", {8 * c});
+  add_spec(v, t + ".ff.net.2.weight", {c, 4 * c});
+  add_spec(v, t + ".ff.net.2.bias", {c});
+  add_spec(v, t + ".attn2.to_q.weight", {c, c});
+  add_spec(v, t + ".attn2.to_k.weight", {c, kCrossDim});
+  add_spec(v, t + ".attn2.to_v.weight", {c, kCrossDim});
+  add_spec(v, t + ".attn2.to_out.0.weight", {c, c});
+  add_spec(v, t + ".attn2.to_out.0.bias", {c});
+  for (int i = 1; i <= 3; ++i) {
+    add_spec(v, t + ".norm" + std::to_string(i) + ".weight", {c});
+    add_spec(v, t + ".norm" + std::to_string(i) + ".bias", {c});
+  }
+  add_spec(v, p + ".proj_out.weight", {c, c, 1, 1});
+  add_spec(v, p + ".proj_out.bias", {c});
+}
+
+const std::vector<ParamSpec>& param_specs() {
+  static std::vector<ParamSpec> v;
+  if (!v.empty()) return v;
+  add_spec(v, "conv_in.weight", {320, 4, 3, 3});
+  add_spec(v, "conv_in.bias", {320});
+  add_spec(v, "time_embedding.linear_1.weight", {kTimeDim, 320});
+  add_spec(v, "time_embedding.linear_1.bias", {kTimeDim});
+  add_spec(v, "time_embedding.linear_2.weight", {kTimeDim, kTimeDim});
+  add_spec(v, "time_embedding.linear_2.bias", {kTimeDim});
+  int cin = 320;
+  for (int i = 0; i < 4; ++i) {
+    const int cout = kBlockOut[i];
+    const std::string b = "down_blocks." + std::to_string(i);
+    for (int j = 0; j < 2; ++j) {
+      spec_resnet(v, b + ".resnets." + std::to_string(j), j == 0 ? cin : cout, cout);
+      if (i < 3) spec_transformer(v, b + ".attentions." + std::to_string(j), cout);
+    }
+    if (i < 3) {
+      add_spec(v, b + ".downsamplers.0.conv.weight", {cout, cout, 3, 3});
+      add_spec(v, b + ".downsamplers.0.conv.bias", {cout});
+    }
+    cin = cout;
+  }
+  spec_resnet(v, "mid_block.resnets.0", 1280, 1280);
+  spec_transformer(v, "mid_block.attentions.0", 1280);
+  spec_resnet(v, "mid_block.resnets.1", 1280, 1280);
+  const int rev[4] = {1280, 1280, 640, 320};
+  int prev = 1280;
+  for (int i = 0; i < 4; ++i) {
+    const int cout = rev[i];
+    const int cin_blk = rev[std::min(i + 1, 3)];
+    const std::string b = "up_blocks." + std::to_string(i);
+    for (int j = 0; j < 3; ++j) {
+      const int skip = (j == 2) ? cin_blk : cout;
+      const int rin = (j == 0) ? prev : cout;
+      spec_resnet(v, b + ".resnets." + std::to_string(j), rin + skip, cout);
+      if (i > 0) spec_transformer(v, b + ".attentions." + std::to_string(j), cout);
+    }
+    if (i < 3) {
+      add_spec(v, b + ".upsamplers.0.conv.weight", {cout, cout, 3, 3});
+      add_spec(v, b + ".upsamplers.0.conv.bias", {cout});
+    }
+    prev = cout;
+  }
+  add_spec(v, "conv_norm_out.weight", {320});
+  add_spec(v, "conv_norm_out.bias", {320});
+  add_spec(v, "conv_out.weight", {4, 320, 3, 3});
+  add_spec(v, "conv_out.bias", {4});
+  return v;
+}
+
+// ------------------------------------------------------------------ small kernels private to the engine
+namespace {
+
+// out[t][n] = act_out( bias[n] + sum_k act_in(in[t][k]) * W[n][k] ), one warp per (t, n)
+__global__ void linear_rows_kernel(const float* __restrict__ in, int ldin, int K, const __half* __restrict__ W, int N,
+                                   const float* __restrict__ bias, float* __restrict__ out, int ldout, int T,
+                                   int silu_in, int silu_out) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= T * N) return;
+  const int t = gw / N, n = gw - t * N;
+  const float* x = in + static_cast<size_t>(t) * ldin;
+  const __half* w = W + static_cast<size_t>(n) * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float v = x[k];
+    if (silu_in) v = v / (1.f + expf(-v));
+    acc += v * __half2float(w[k]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    float r = acc + bias[n];
+    if (silu_out) r = r / (1.f + expf(-r));
+    out[static_cast<size_t>(t) * ldout + n] = r;
+  }
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = __float2half_rn(in[i]);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ engine
+struct ResnetW {
+  std::string name;
+  int cin, cout;
+  bool shortcut;
+  float *g1, *b1, *g2, *b2;  // norm params
+  __half* w1;                // [cout, 9*cin]
+  float* bias1;
+  __half* w2;  // [cout, 9*cout (+cin)]
+  float* bias2;
+  int temb_off;
+};
+struct XfmrW {
+  std::string name;
+  int c;
+  float *gn_g, *gn_b;
+  __half* proj_in;
+  float* proj_in_b;
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+  __half* qkv;  // [3c, c]
+  __half* o1;
+  float* o1_b;
+  __half* q2;   // [c, c]
+  __half* kv2;  // [2c, 768]
+  __half* o2;
+  float* o2_b;
+  __half* geglu;  // [8c, c] tile-interleaved (BN=256)
+  float* geglu_b;
+  __half* ff2;  // [c, 4c]
+  float* ff2_b;
+  __half* proj_out;
+  float* proj_out_b;
+};
+struct SampW {
+  __half* w;
+  float* b;
+  int c;
+};
+
+struct DevCtrl {  // device-resident controller state for one forward
+  int self_q[16][PNP_MAX_BATCH];
+  int self_k[16][PNP_MAX_BATCH];
+  int self_v[16][PNP_MAX_BATCH];
+  int cross_base[PNP_MAX_BATCH];
+  int cross_slot[PNP_MAX_BATCH];
+  int store_slot[PNP_MAX_BATCH];
+  int mapper[PNP_MAX_SLOTS][PNP_TOKENS];
+  float alphas[PNP_MAX_SLOTS][PNP_TOKENS];
+  float equalizer[PNP_MAX_SLOTS][PNP_TOKENS];
+  float cross_alpha[PNP_MAX_SLOTS][PNP_TOKENS];
+  int t_index;
+};
+
+struct Plan {
+  int B = 0;
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<std::unique_ptr<GemmPlan>> gemms;
+  std::vector<void*> bufs;
+  float* x_in = nullptr;    // [B,4,64,64]
+  float* eps_out = nullptr;  // [B,4,64,64]
+  cudaGraphExec_t graph = nullptr;
+  std::vector<std::function<int(cudaStream_t)>> ctx_ops;  // context K/V projection for this batch
+  __half* ctx16 = nullptr;
+  __half* ctxkv[16] = {nullptr};
+};
+
+constexpr int kStoreLayers = 5;
+constexpr size_t kStoreFloats = static_cast<size_t>(kStoreLayers) * 2 * PNP_MAX_SLOTS * 8 * 256 * 77;
+
+}  // namespace pnp
+
+using namespace pnp;
+
+struct pnp_engine {
+  int device = 0, num_sms = 148, max_batch = 4;
+  bool finalized = false;
+  bool use_graph = true;
+  int64_t launches = 0;
+  std::unordered_map<std::string, std::vector<__half>> host;
+  std::vector<void*> allocs;
+  std::vector<ResnetW> resnets;  // execution order
+  std::vector<XfmrW> xf;         // execution order (16)
+  SampW down[3], up[3];
+  float *conv_in_w = nullptr, *conv_in_b = nullptr, *conv_out_w = nullptr, *conv_out_b = nullptr;
+  float *norm_out_g = nullptr, *norm_out_b = nullptr;
+  __half *te1 = nullptr, *te2 = nullptr, *temb_proj = nullptr;  // temb_proj: [sum cout, 1280]
+  float *te1_b = nullptr, *te2_b = nullptr, *temb_proj_b = nullptr;
+  int temb_total = 0;
+  float* temb_table = nullptr;  // [n_t][temb_total]
+  int n_t = 0;
+  DevCtrl* d_ctrl = nullptr;
+  DevCtrl* h_ctrl_ring = nullptr;  // pinned
+  int ring_pos = 0;
+  float* store = nullptr;
+  float* gn_partials = nullptr;
+  int ctx_batch = 0;
+  std::map<int, std::unique_ptr<Plan>> plans;
+
+  template <typename T>
+  T* dalloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+    allocs.push_back(p);
+    return static_cast<T*>(p);
+  }
+};
+
+namespace pnp {
+
+static constexpr int kRing = 64;
+static constexpr int kMaxTimesteps = 1000;
+
+static const std::vector<__half>* find_param(pnp_engine* e, const std::string& n) {
+  auto it = e->host.find(n);
+  return it == e->host.end() ? nullptr : &it->second;
+}
+
+static float* upload_f32(pnp_engine* e, const std::vector<float>& v) {
+  float* d = e->dalloc<float>(v.size());
+  if (d == nullptr) return nullptr;
+  if (cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  return d;
+}
+static __half* upload_f16(pnp_engine* e, const std::vector<__half>& v) {
+  __half* d = e->dalloc<__half>(v.size());
+  if (d == nullptr) return nullptr;
+  if (cudaMemcpy(d, v.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  return d;
+}
+static std::vector<float> to_f32(const std::vector<__half>& v) {
+  std::vector<float> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __half2float(v[i]);
+  return o;
+}
+static float* up_vec(pnp_engine* e, const std::string& n) { return upload_f32(e, to_f32(*find_param(e, n))); }
+static __half* up_mat(pnp_engine* e, const std::string& n) { return upload_f16(e, *find_param(e, n)); }
+
+// OIHW 3x3 -> [co][(ky*3+kx)*cin + ci], optionally followed by extra 1x1 columns
+static std::vector<__half> pack_conv3(const std::vector<__half>& w, int cout, int cin, const std::vector<__half>* sc,
+                                      int sc_cin) {
+  const size_t K = static_cast<size_t>(9) * cin + (sc ? sc_cin : 0);
+  std::vector<__half> p(static_cast<size_t>(cout) * K);
+  for (int co = 0; co < cout; ++co) {
+    __half* row = p.data() + static_cast<size_t>(co) * K;
+    const __half* src = w.data() + static_cast<size_t>(co) * cin * 9;
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tap = 0; tap < 9; ++tap) row[static_cast<size_t>(tap) * cin + ci] = src[ci * 9 + tap];
+    if (sc) memcpy(row + static_cast<size_t>(9) * cin, sc->data() + static_cast<size_t>(co) * sc_cin, sc_cin * sizeof(__half));
+  }
+  return p;
+}
+
+static int finalize(pnp_engine* e) {
+  for (const auto& s : param_specs()) {
+    const auto* p = find_param(e, s.name);
+    PNP_CHECK(p != nullptr && static_cast<int64_t>(p->size()) == s.numel(),
+              ("parameter missing or wrong size: " + s.name).c_str());
+  }
+  // --- resnets in execution order, with their time-embedding slice
+  std::vector<std::pair<std::string, std::pair<int, int>>> rn;
+  {
+    int cin = 320;
+    for (int i = 0; i < 4; ++i) {
+      for (int j = 0; j < 2; ++j)
+        rn.push_back({"down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j),
+                      {j == 0 ? cin : kBlockOut[i], kBlockOut[i]}});
+      cin = kBlockOut[i];
+    }
+    rn.push_back({"mid_block.resnets.0", {1280, 1280}});
+    rn.push_back({"mid_block.resnets.1", {1280, 1280}});
+    const int rev[4] = {1280, 1280, 640, 320};
+    int prev = 1280;
+    for (int i = 0; i < 4; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        const int skip = (j == 2) ? rev[std::min(i + 1, 3)] : rev[i];
+        rn.push_back({"up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j),
+                      {(j == 0 ? prev : rev[i]) + skip, rev[i]}});
+      }
+      prev = rev[i];
+    }
+  }
+  int toff = 0;
+  std::vector<__half> tproj;
+  std::vector<float> tproj_b;
+  for (auto& r : rn) {
+    ResnetW w;
+    w.name = r.first;
+    w.cin = r.second.first;
+    w.cout = r.second.second;
+    w.shortcut = w.cin != w.cout;
+    w.g1 = up_vec(e, w.name + ".norm1.weight");
+    w.b1 = up_vec(e, w.name + ".norm1.bias");
+    w.g2 = up_vec(e, w.name + ".norm2.weight");
+    w.b2 = up_vec(e, w.name + ".norm2.bias");
+    w.w1 = upload_f16(e, pack_conv3(*find_param(e, w.name + ".conv1.weight"), w.cout, w.cin, nullptr, 0));
+    w.bias1 = up_vec(e, w.name + ".conv1.bias");
+    std::vector<float> b2 = to_f32(*find_param(e, w.name + ".conv2.bias"));
+    if (w.shortcut) {
+      w.w2 = upload_f16(e, pack_conv3(*find_param(e, w.name + ".conv2.weight"), w.cout, w.cout,
+                                      find_param(e, w.name + ".conv_shortcut.weight"), w.cin));
+      std::vector<float> bs = to_f32(*find_param(e, w.name + ".conv_shortcut.bias"));
+      for (int i = 0; i < w.cout; ++i) b2[i] += bs[i];
+    } else {
+      w.w2 = upload_f16(e, pack_conv3(*find_param(e, w.name + ".conv2.weight"), w.cout, w.cout, nullptr, 0));
+    }
+    w.bias2 = upload_f32(e, b2);
+    w.temb_off = toff;
+    toff += w.cout;
+    const auto& tp = *find_param(e, w.name + ".time_emb_proj.weight");
+    tproj.insert(tproj.end(), tp.begin(), tp.end());
+    std::vector<float> tb = to_f32(*find_param(e, w.name + ".time_emb_proj.bias"));
+    tproj_b.insert(tproj_b.end(), tb.begin(), tb.end());
+    PNP_CHECK(w.g1 && w.b1 && w.g2 && w.b2 && w.w1 && w.w2 && w.bias1 && w.bias2, "resnet upload failed (out of memory?)");
+    e->resnets.push_back(w);
+  }
+  e->temb_total = toff;
+  e->temb_proj = upload_f16(e, tproj);
+  e->temb_proj_b = upload_f32(e, tproj_b);
+  e->te1 = up_mat(e, "time_embedding.linear_1.weight");
+  e->te1_b = up_vec(e, "time_embedding.linear_1.bias");
+  e->te2 = up_mat(e, "time_embedding.linear_2.weight");
+  e->te2_b = up_vec(e, "time_embedding.linear_2.bias");
+  // --- transformers in execution order
+  std::vector<std::pair<std::string, int>> tn;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 2; ++j)
+      tn.push_back({"down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), kBlockOut[i]});
+  tn.push_back({"mid_block.attentions.0", 1280});
+  {
+    const int rev[4] = {1280, 1280, 640, 320};
+    for (int i = 1; i < 4; ++i)
+      for (int j = 0; j < 3; ++j)
+        tn.push_back({"up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), rev[i]});
+  }
+  for (auto& t : tn) {
+    XfmrW w;
+    w.name = t.first;
+    w.c = t.second;
+    const int c = w.c;
+    const std::string tb = w.name + ".transformer_blocks.0";
+    w.gn_g = up_vec(e, w.name + ".norm.weight");
+    w.gn_b = up_vec(e, w.name + ".norm.bias");
+    w.proj_in = up_mat(e, w.name + ".proj_in.weight");
+    w.proj_in_b = up_vec(e, w.name + ".proj_in.bias");
+    w.ln1_g = up_vec(e, tb + ".norm1.weight");
+    w.ln1_b = up_vec(e, tb + ".norm1.bias");
+    w.ln2_g = up_vec(e, tb + ".norm2.weight");
+    w.ln2_b = up_vec(e, tb + ".norm2.bias");
+    w.ln3_g = up_vec(e, tb + ".norm3.weight");
+    w.ln3_b = up_vec(e, tb + ".norm3.bias");
+    std::vector<__half> qkv = *find_param(e, tb + ".attn1.to_q.weight");
+    const auto& k1 = *find_param(e, tb + ".attn1.to_k.weight");
+    const auto& v1 = *find_param(e, tb + ".attn1.to_v.weight");
+    qkv.insert(qkv.end(), k1.begin(), k1.end());
+    qkv.insert(qkv.end(), v1.begin(), v1.end());
+    w.qkv = upload_f16(e, qkv);
+    w.o1 = up_mat(e, tb + ".attn1.to_out.0.weight");
+    w.o1_b = up_vec(e, tb + ".attn1.to_out.0.bias");
+    w.q2 = up_mat(e, tb + ".attn2.to_q.weight");
+    std::vector<__half> kv = *find_param(e, tb + ".attn2.to_k.weight");
+    const auto& v2 = *find_param(e, tb + ".attn2.to_v.weight");
+    kv.insert(kv.end(), v2.begin(), v2.end());
+    w.kv2 = upload_f16(e, kv);
+    w.o2 = up_mat(e, tb + ".attn2.to_out.0.weight");
+    w.o2_b = up_vec(e, tb + ".attn2.to_out.0.bias");
+    {
+      // GEGLU tile interleave for BN = 256: packed rows [t*256, t*256+128) = value rows [t*128, ...),
+      // packed rows [t*256+128, (t+1)*256) = gate rows 4c + [t*128, ...)
+      const auto& gw = *find_param(e, tb + ".ff.net.0.proj.weight");
+      const std::vector<float> gb = to_f32(*find_param(e, tb + ".ff.net.0.proj.bias"));
+      std::vector<__half> pw(gw.size());
+      std::vector<float> pb(gb.size());
+      const int half_n = 4 * c;
+      for (int t2 = 0; t2 < 8 * c / 256; ++t2)
+        for (int j = 0; j < 256; ++j) {
+          const int src = (j < 128) ? (t2 * 128 + j) : (half_n + t2 * 128 + (j - 128));
+          const int dst = t2 * 256 + j;
+          memcpy(pw.data() + static_cast<size_t>(dst) * c, gw.data() + static_cast<size_t>(src) * c, c * sizeof(__half));
+          pb[dst] = gb[src];
+        }
+      w.geglu = upload_f16(e, pw);
+      w.geglu_b = upload_f32(e, pb);
+    }
+    w.ff2 = up_mat(e, tb + ".ff.net.2.weight");
+    w.ff2_b = up_vec(e, tb + ".ff.net.2.bias");
+    w.proj_out = up_mat(e, w.name + ".proj_out.weight");
+    w.proj_out_b = up_vec(e, w.name + ".proj_out.bias");
+    PNP_CHECK(w.proj_out_b && w.geglu && w.kv2 && w.qkv, "transformer upload failed (out of memory?)");
+    e->xf.push_back(w);
+  }
+  for (int i = 0; i < 3; ++i) {
+    const std::string d = "down_blocks." + std::to_string(i) + ".downsamplers.0.conv";
+    e->down[i].c = kBlockOut[i];
+    e->down[i].w = upload_f16(e, pack_conv3(*find_param(e, d + ".weight"), kBlockOut[i], kBlockOut[i], nullptr, 0));
+    e->down[i].b = up_vec(e, d + ".bias");
+    const int rev[3] = {1280, 1280, 640};
+    const std::string u = "up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
+    e->up[i].c = rev[i];
+    e->up[i].w = upload_f16(e, pack_conv3(*find_param(e, u + ".weight"), rev[i], rev[i], nullptr, 0));
+    e->up[i].b = up_vec(e, u + ".bias");
+  }
+  e->conv_in_w = up_vec(e, "conv_in.weight");
+  e->conv_in_b = up_vec(e, "conv_in.bias");
+  e->conv_out_w = up_vec(e, "conv_out.weight");
+  e->conv_out_b = up_vec(e, "conv_out.bias");
+  e->norm_out_g = up_vec(e, "conv_norm_out.weight");
+  e->norm_out_b = up_vec(e, "conv_norm_out.bias");
+  PNP_CHECK(e->norm_out_b != nullptr, "upload failed");
+  e->host.clear();
+  e->d_ctrl = e->dalloc<DevCtrl>(1);
+  PNP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ctrl_ring), sizeof(DevCtrl) * kRing, cudaHostAllocDefault));
+  e->store = e->dalloc<float>(kStoreFloats);
+  PNP_CHECK(e->d_ctrl && e->store, "alloc failed");
+  PNP_CUDA(cudaMemset(e->store, 0, kStoreFloats * sizeof(float)));
+  e->gn_partials = e->dalloc<float>(static_cast<size_t>(PNP_MAX_BATCH) * 64 * 32 * 2 * 4);
+  PNP_CHECK(e->gn_partials != nullptr, "alloc failed");
+  e->temb_table = e->dalloc<float>(static_cast<size_t>(kMaxTimesteps) * e->temb_total);
+  PNP_CHECK(e->temb_table != nullptr, "alloc failed");
+  e->finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------ plan construction
+struct PlanBuilder {
+  pnp_engine* e;
+  Plan* pl;
+  int B;
+  int rc = 0;
+
+  __half* buf(size_t elems) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, elems * sizeof(__half)) != cudaSuccess) {
+      rc = -1;
+      set_last_error("plan: cudaMalloc failed");
+      return nullptr;
+    }
+    pl->bufs.push_back(p);
+    return static_cast<__half*>(p);
+  }
+  void op(std::function<int(cudaStream_t)> f) { pl->ops.push_back(std::move(f)); }
+
+  void gemm(std::vector<std::function<int(cudaStream_t)>>& ops, const ASource* srcs, int nsrc, int taps, bool linear,
+            int b, int h, int w, const __half* wt, int n, int ktot, const GemmEpilogue& ep) {
+    if (rc) return;
+    auto gp = std::make_unique<GemmPlan>();
+    rc = gemm_plan_create(gp.get(), srcs, nsrc, taps, linear, b, h, w, wt, n, ktot, ep, 0, e->num_sms);
+    if (rc) return;
+    GemmPlan* raw = gp.get();
+    pl->gemms.push_back(std::move(gp));
+    ops.push_back([raw](cudaStream_t s) { return gemm_launch(*raw, s); });
+  }
+  void linear(const __half* a, int M, int K, int lda, const __half* wt, int N, const GemmEpilogue& ep) {
+    ASource s{a, K, lda};
+    gemm(pl->ops, &s, 1, 1, true, 1, 1, M, wt, N, K, ep);
+  }
+  void groupnorm(const __half* x0, int c0, const __half* x1, int c1, int hw, const float* g, const float* b, float eps,
+                 bool silu, __half* out) {
+    pnp_engine* en = e;
+    const int Bn = B;
+    op([=](cudaStream_t s) { return groupnorm_launch(x0, c0, x1, c1, Bn, hw, g, b, eps, silu, out, en->gn_partials, s); });
+  }
+  void layernorm(const __half* x, int rows, int c, const float* g, const float* b, __half* out) {
+    op([=](cudaStream_t s) { return layernorm_launch(x, rows, c, g, b, 1e-5f, out, s); });
+  }
+};
+
+static int build_plan(pnp_engine* e, int B, Plan* pl) {
+  PlanBuilder pb{e, pl, B};
+  pl->B = B;
+  const int* d_tidx = &e->d_ctrl->t_index;
+  const size_t rows64 = static_cast<size_t>(B) * 4096;
+  PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl->x_in), static_cast<size_t>(B) * PNP_LATENT_ELEMS * sizeof(float)));
+  pl->bufs.push_back(pl->x_in);
+  PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl->eps_out), static_cast<size_t>(B) * PNP_LATENT_ELEMS * sizeof(float)));
+  pl->bufs.push_back(pl->eps_out);
+
+  // scratch buffers sized for the largest user
+  __half* NRM = pb.buf(rows64 * 960);   // normalised activations (largest: 960 ch @ 64x64)
+  __half* H1 = pb.buf(rows64 * 320);    // conv1 output (largest rows*cout: 320 @ 64x64 == 640 @ 32x32 ...)
+  __half* HA = pb.buf(rows64 * 640);    // hidden ping (largest: upsampled 640 @ 64x64)
+  __half* HB = pb.buf(rows64 * 640);    // hidden pong
+  __half* UPS = pb.buf(rows64 * 640);   // nearest-upsampled tensor
+  __half* IM2 = pb.buf(rows64 / 4 * 9 * 320);  // stride-2 im2col (largest: 320 ch from 64x64)
+  __half* T_H = pb.buf(rows64 * 320);
+  __half* T_LN = pb.buf(rows64 * 320);
+  __half* T_QKV = pb.buf(rows64 * 960);
+  __half* T_ATT = pb.buf(rows64 * 320);
+  __half* T_Q = pb.buf(rows64 * 320);
+  __half* T_FF = pb.buf(rows64 * 1280);
+  // the 12 skip tensors
+  const int skip_c[12] = {320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280};
+  const int skip_hw[12] = {64, 64, 64, 32, 32, 32, 16, 16, 16, 8, 8, 8};
+  __half* SK[12];
+  for (int i = 0; i < 12; ++i) SK[i] = pb.buf(static_cast<size_t>(B) * skip_hw[i] * skip_hw[i] * skip_c[i]);
+  if (pb.rc) return pb.rc;
+
+  // context K/V buffers and their projection plans
+  pl->ctx16 = pb.buf(static_cast<size_t>(B) * 77 * kCrossDim);
+  for (int l = 0; l < 16; ++l) {
+    const int c = e->xf[l].c;
+    pl->ctxkv[l] = pb.buf(static_cast<size_t>(B) * 77 * 2 * c);
+    if (pb.rc) return pb.rc;
+    GemmEpilogue ep;
+    ep.out = pl->ctxkv[l];
+    ep.ldc = 2 * c;
+    ASource s{pl->ctx16, kCrossDim, kCrossDim};
+    pb.gemm(pl->ctx_ops, &s, 1, 1, true, 1, 1, B * 77, e->xf[l].kv2, 2 * c, kCrossDim, ep);
+  }
+  if (pb.rc) return pb.rc;
+
+  int res_idx = 0, xf_idx = 0;
+  auto resnet = [&](const __half* x0, int c0, const __half* x1, int c1, int hw, __half* out) {
+    const ResnetW& w = e->resnets[res_idx++];
+    const int cin = c0 + c1;
+    if (cin != w.cin) { pb.rc = -2; set_last_error("plan: resnet channel mismatch " + w.name); return; }
+    // h = conv1(silu(gn(x))) + temb
+    pb.groupnorm(x0, c0, x1, c1, hw * hw, w.g1, w.b1, 1e-5f, true, NRM);
+    {
+      GemmEpilogue ep;
+      ep.bias = w.bias1;
+      ep.temb_table = e->temb_table + w.temb_off;  // row t_index of the per-timestep table, this resnet's columns
+      ep.t_index = d_tidx;
+      ep.temb_stride = e->temb_total;
+      ep.out = H1;
+      ep.ldc = w.cout;
+      ASource s{NRM, cin, cin};
+      pb.gemm(pl->ops, &s, 1, 9, false, B, hw, hw, w.w1, w.cout, 9 * cin, ep);
+      if (pb.rc) return;
+    }
+    // out = conv2(silu(gn(h))) + shortcut(x)
+    pb.groupnorm(H1, w.cout, nullptr, 0, hw * hw, w.g2, w.b2, 1e-5f, true, NRM);
+    {
+      GemmEpilogue ep;
+      ep.bias = w.bias2;
+      ep.out = out;
+      ep.ldc = w.cout;
+      ASource s[3];
+      int ns = 1;
+      s[0] = ASource{NRM, w.cout, w.cout};
+      int ktot = 9 * w.cout;
+      if (w.shortcut) {
+        s[ns++] = ASource{x0, c0, c0};
+        if (x1 != nullptr) s[ns++] = ASource{x1, c1, c1};
+        ktot += cin;
+      } else {
+        ep.residual = x0;
+        ep.ldr = c0;
+      }
+      pb.gemm(pl->ops, s, ns, 9, false, B, hw, hw, w.w2, w.cout, ktot, ep);
+    }
+  };
+
+  auto transformer = [&](const __half* x, int c, int hw, __half* out) {
+    const int layer = xf_idx;
+    const XfmrW& w = e->xf[xf_idx++];
+    if (c != w.c) { pb.rc = -2; set_last_error("plan: transformer channel mismatch " + w.name); return; }
+    const int N = hw * hw;
+    const int M = B * N;
+    const int d = c / kHeads;
+    pb.groupnorm(x, c, nullptr, 0, N, w.gn_g, w.gn_b, 1e-6f, false, NRM);
+    { GemmEpilogue ep; ep.bias = w.proj_in_b; ep.out = T_H; ep.ldc = c; pb.linear(NRM, M, c, c, w.proj_in, c, ep); }
+    // attn1 (self)
+    pb.layernorm(T_H, M, c, w.ln1_g, w.ln1_b, T_LN);
+    { GemmEpilogue ep; ep.out = T_QKV; ep.ldc = 3 * c; pb.linear(T_LN, M, c, c, w.qkv, 3 * c, ep); }
+    {
+      SelfAttnParams sp;
+      sp.q = T_QKV; sp.k = T_QKV + c; sp.v = T_QKV + 2 * c; sp.ld = 3 * c;
+      sp.o = T_ATT; sp.ldo = c; sp.B = B; sp.H = kHeads; sp.N = N; sp.d = d;
+      sp.scale = 1.0f / sqrtf(static_cast<float>(d));
+      sp.q_row = e->d_ctrl->self_q[layer]; sp.k_row = e->d_ctrl->self_k[layer]; sp.v_row = e->d_ctrl->self_v[layer];
+      pb.op([sp](cudaStream_t s) { return self_attention_launch(sp, s); });
+    }
+    { GemmEpilogue ep; ep.bias = w.o1_b; ep.residual = T_H; ep.ldr = c; ep.out = T_H; ep.ldc = c;
+      pb.linear(T_ATT, M, c, c, w.o1, c, ep); }
+    // attn2 (cross)
+    pb.layernorm(T_H, M, c, w.ln2_g, w.ln2_b, T_LN);
+    { GemmEpilogue ep; ep.out = T_Q; ep.ldc = c; pb.linear(T_LN, M, c, c, w.q2, c, ep); }
+    {
+      CrossAttnParams cp;
+      cp.q = T_Q; cp.ldq = c; cp.kv = pl->ctxkv[layer]; cp.ldkv = 2 * c; cp.o = T_ATT; cp.ldo = c;
+      cp.B = B; cp.H = kHeads; cp.N = N; cp.d = d; cp.nk = 77;
+      cp.scale = 1.0f / sqrtf(static_cast<float>(d));
+      cp.base_row = e->d_ctrl->cross_base; cp.edit_slot = e->d_ctrl->cross_slot;
+      cp.mapper = &e->d_ctrl->mapper[0][0]; cp.alphas = &e->d_ctrl->alphas[0][0];
+      cp.equalizer = &e->d_ctrl->equalizer[0][0]; cp.cross_alpha = &e->d_ctrl->cross_alpha[0][0];
+      // the five 16x16 cross layers LocalBlend reads: down_cross[2:4] + up_cross[:3] = transformer blocks 4,5,7,8,9
+      int store_layer = -1;
+      if (layer == 4) store_layer = 0; else if (layer == 5) store_layer = 1;
+      else if (layer == 7) store_layer = 2; else if (layer == 8) store_layer = 3; else if (layer == 9) store_layer = 4;
+      cp.store = store_layer >= 0 ? e->store + static_cast<size_t>(store_layer) * 2 * PNP_MAX_SLOTS * 8 * 256 * 77 : nullptr;
+      cp.store_slot = e->d_ctrl->store_slot;
+      pb.op([cp](cudaStream_t s) { return cross_attention_launch(cp, s); });
+    }
+    { GemmEpilogue ep; ep.bias = w.o2_b; ep.residual = T_H; ep.ldr = c; ep.out = T_H; ep.ldc = c;
+      pb.linear(T_ATT, M, c, c, w.o2, c, ep); }
+    // feed-forward
+    pb.layernorm(T_H, M, c, w.ln3_g, w.ln3_b, T_LN);
+    { GemmEpilogue ep; ep.bias = w.geglu_b; ep.geglu = true; ep.out = T_FF; ep.ldc = 4 * c;
+      ASource s{T_LN, c, c};
+      if (!pb.rc) {
+        auto gp = std::make_unique<GemmPlan>();
+        pb.rc = gemm_plan_create(gp.get(), &s, 1, 1, true, 1, 1, M, w.geglu, 8 * c, c, ep, 256, e->num_sms);
+        if (!pb.rc) { GemmPlan* raw = gp.get(); pl->gemms.push_back(std::move(gp));
+          pl->ops.push_back([raw](cudaStream_t st) { return gemm_launch(*raw, st); }); }
+      } }
+    { GemmEpilogue ep; ep.bias = w.ff2_b; ep.residual = T_H; ep.ldr = c; ep.out = T_H; ep.ldc = c;
+      pb.linear(T_FF, M, 4 * c, 4 * c, w.ff2, c, ep); }
+    { GemmEpilogue ep; ep.bias = w.proj_out_b; ep.residual = x; ep.ldr = c; ep.out = out; ep.ldc = c;
+      pb.linear(T_H, M, c, c, w.proj_out, c, ep); }
+  };
+
+  // ---- conv_in
+  {
+    float* xin = pl->x_in;
+    const float* wi = e->conv_in_w; const float* bi = e->conv_in_b; __half* o = SK[0];
+    pb.op([=](cudaStream_t s) { return conv_in_launch(xin, B, 64, 64, wi, bi, o, s); });
+  }
+  // ---- down blocks
+  const __half* h = SK[0];
+  int hc = 320, hw = 64, sk = 1;
+  for (int i = 0; i < 4; ++i) {
+    const int cout = kBlockOut[i];
+    for (int j = 0; j < 2; ++j) {
+      if (i < 3) {
+        resnet(h, hc, nullptr, 0, hw, HA);
+        transformer(HA, cout, hw, SK[sk]);
+      } else {
+        resnet(h, hc, nullptr, 0, hw, SK[sk]);
+      }
+      h = SK[sk++];
+      hc = cout;
+      if (pb.rc) return pb.rc;
+    }
+    if (i < 3) {
+      const __half* src = h; const int c = cout, hh = hw;
+      pb.op([=](cudaStream_t s) { return im2col_s2_launch(src, B, hh, hh, c, IM2, s); });
+      GemmEpilogue ep; ep.bias = e->down[i].b; ep.out = SK[sk]; ep.ldc = cout;
+      pb.linear(IM2, B * (hw / 2) * (hw / 2), 9 * cout, 9 * cout, e->down[i].w, cout, ep);
+      h = SK[sk++];
+      hw /= 2;
+    }
+  }
+  // ---- mid
+  resnet(h, 1280, nullptr, 0, 8, HA);
+  transformer(HA, 1280, 8, HB);
+  resnet(HB, 1280, nullptr, 0, 8, HA);
+  h = HA;
+  hc = 1280;
+  hw = 8;
+  if (pb.rc) return pb.rc;
+  // ---- up blocks
+  const int rev[4] = {1280, 1280, 640, 320};
+  int top = 11;
+  for (int i = 0; i < 4; ++i) {
+    const int cout = rev[i];
+    for (int j = 0; j < 3; ++j) {
+      const __half* skp = SK[top];
+      const int skc = skip_c[top];
+      --top;
+      __half* r_out = (h == HA) ? HB : HA;
+      resnet(h, hc, skp, skc, hw, r_out);
+      if (i > 0) {
+        __half* t_out = (r_out == HA) ? HB : HA;
+        transformer(r_out, cout, hw, t_out);
+        h = t_out;
+      } else {
+        h = r_out;
+      }
+      hc = cout;
+      if (pb.rc) return pb.rc;
+    }
+    if (i < 3) {
+      const __half* src = h; const int c = cout, hh = hw;
+      pb.op([=](cudaStream_t s) { return upsample2x_launch(src, B, hh, hh, c, UPS, s); });
+      hw *= 2;
+      __half* o = (h == HA) ? HB : HA;
+      GemmEpilogue ep; ep.bias = e->up[i].b; ep.out = o; ep.ldc = cout;
+      ASource s{UPS, cout, cout};
+      pb.gemm(pl->ops, &s, 1, 9, false, B, hw, hw, e->up[i].w, cout, 9 * cout, ep);
+      h = o;
+    }
+  }
+  if (pb.rc) return pb.rc;
+  // ---- out
+  pb.groupnorm(h, 320, nullptr, 0, 4096, e->norm_out_g, e->norm_out_b, 1e-5f, true, NRM);
+  {
+    const float* wo = e->conv_out_w; const float* bo = e->conv_out_b; float* o = pl->eps_out;
+    pb.op([=](cudaStream_t s) { return conv_out_launch(NRM, B, 64, 64, 320, wo, bo, o, s); });
+  }
+  (void)H1;
+  return pb.rc;
+}
+
+static int get_plan(pnp_engine* e, int B, Plan** out) {
+  PNP_CHECK(e->finalized, "parameters not finalized");
+  PNP_CHECK(B >= 1 && B <= e->max_batch && B <= PNP_MAX_BATCH, "batch out of range");
+  auto it = e->plans.find(B);
+  if (it == e->plans.end()) {
+    auto pl = std::make_unique<Plan>();
+    int rc = build_plan(e, B, pl.get());
+    if (rc) return rc;
+    it = e->plans.emplace(B, std::move(pl)).first;
+  }
+  *out = it->second.get();
+  return 0;
+}
+
+}  // namespace pnp
+
+// ====================================================================================================================
+// C ABI (include/pnpinv.h)
+// ====================================================================================================================
+using namespace pnp;
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* pnp_last_error(void) { return get_last_error(); }
+const char* pnp_version(void) { return "pnpinv-b200 0.1 (sm_100a, tcgen05 GEMM/conv, mma.sync attention)"; }
+
+int pnp_create(int device_ordinal, int max_batch, pnp_engine** out) {
+  PNP_CHECK(out != nullptr, "pnp_create: out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev == 0) {
+    set_last_error(std::string("pnp_create: no CUDA device available (") + cudaGetErrorString(e0) +
+                   "); this library has no CPU fallback");
+    return -1;
+  }
+  PNP_CHECK(device_ordinal >= 0 && device_ordinal < ndev, "pnp_create: bad device ordinal");
+  PNP_CHECK(max_batch >= 1 && max_batch <= PNP_MAX_BATCH, "pnp_create: max_batch out of range");
+  PNP_CUDA(cudaSetDevice(device_ordinal));
+  cudaDeviceProp prop;
+  PNP_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major != 10) {
+    set_last_error("pnp_create: this library is built for sm_100a (B200) only; found compute capability " +
+                   std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    return -1;
+  }
+  auto* e = new pnp_engine();
+  e->device = device_ordinal;
+  e->num_sms = prop.multiProcessorCount;
+  e->max_batch = max_batch;
+  debug_words_device();
+  *out = e;
+  return 0;
+}
+
+void pnp_destroy(pnp_engine* h) {
+  if (h == nullptr) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->plans) {
+    if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+    for (void* p : kv.second->bufs) cudaFree(p);
+  }
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_ctrl_ring) cudaFreeHost(h->h_ctrl_ring);
+  delete h;
+}
+
+int pnp_unet_param_count(void) { return static_cast<int>(param_specs().size()); }
+
+int pnp_unet_param_spec(int index, char* name_out, int* ndim_out, int* shape_out) {
+  const auto& v = param_specs();
+  PNP_CHECK(index >= 0 && index < static_cast<int>(v.size()), "param index out of range");
+  PNP_CHECK(name_out && ndim_out && shape_out, "null output");
+  snprintf(name_out, 128, "%s", v[index].name.c_str());
+  *ndim_out = v[index].ndim;
+  for (int i = 0; i < 4; ++i) shape_out[i] = v[index].shape[i];
+  return 0;
+}
+
+int pnp_load_param(pnp_engine* h, const char* name, const uint16_t* data_host, int64_t numel) {
+  PNP_CHECK(h && name && data_host, "pnp_load_param: null argument");
+  PNP_CHECK(!h->finalized, "pnp_load_param: parameters already finalized");
+  const ParamSpec* spec = nullptr;
+  for (const auto& s : param_specs())
+    if (s.name == name) { spec = &s; break; }
+  PNP_CHECK(spec != nullptr, (std::string("pnp_load_param: unknown parameter name ") + name).c_str());
+  PNP_CHECK(spec->numel() == numel, (std::string("pnp_load_param: wrong element count for ") + name).c_str());
+  std::vector<__half> v(static_cast<size_t>(numel));
+  memcpy(v.data(), data_host, static_cast<size_t>(numel) * sizeof(uint16_t));
+  h->host[name] = std::move(v);
+  return 0;
+}
+
+int pnp_finalize_params(pnp_engine* h) {
+  PNP_CHECK(h != nullptr, "null handle");
+  PNP_CHECK(!h->finalized, "already finalized");
+  PNP_CUDA(cudaSetDevice(h->device));
+  return finalize(h);
+}
+
+int pnp_set_timesteps(pnp_engine* h, const int64_t* ts, int n, void* stream) {
+  PNP_CHECK(h && h->finalized, "pnp_set_timesteps: engine not ready");
+  PNP_CHECK(ts != nullptr && n >= 1 && n <= kMaxTimesteps, "pnp_set_timesteps: 1..1000 timesteps");
+  cudaStream_t s = as_stream(stream);
+  // sinusoidal embedding on the host in double, [cos | sin] order (flip_sin_to_cos=True, freq_shift=0):
+  // my_diffusers/models/embeddings.py:40-55
+  std::vector<float> sinus(static_cast<size_t>(n) * 320);
+  for (int t = 0; t < n; ++t)
+    for (int i = 0; i < 160; ++i) {
+      const double f = std::exp(-std::log(10000.0) * i / 160.0);
+      const double a = static_cast<double>(ts[t]) * f;
+      sinus[static_cast<size_t>(t) * 320 + i] = static_cast<float>(std::cos(a));
+      sinus[static_cast<size_t>(t) * 320 + 160 + i] = static_cast<float>(std::sin(a));
+    }
+  float *d_sin = nullptr, *d_h1 = nullptr, *d_emb = nullptr;
+  PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_sin), sinus.size() * sizeof(float)));
+  PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_h1), static_cast<size_t>(n) * kTimeDim * sizeof(float)));
+  PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_emb), static_cast<size_t>(n) * kTimeDim * sizeof(float)));
+  PNP_CUDA(cudaMemcpyAsync(d_sin, sinus.data(), sinus.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  auto blocks = [](long warps) { return static_cast<int>((warps * 32 + 255) / 256); };
+  // linear_1 -> SiLU -> linear_2 (embeddings.py:63-80); every resnet then applies Linear(SiLU(emb)) (resnet.py:348-350)
+  linear_rows_kernel<<<blocks(static_cast<long>(n) * kTimeDim), 256, 0, s>>>(d_sin, 320, 320, h->te1, kTimeDim, h->te1_b,
+                                                                            d_h1, kTimeDim, n, 0, 1);
+  linear_rows_kernel<<<blocks(static_cast<long>(n) * kTimeDim), 256, 0, s>>>(d_h1, kTimeDim, kTimeDim, h->te2, kTimeDim,
+                                                                            h->te2_b, d_emb, kTimeDim, n, 0, 0);
+  linear_rows_kernel<<<blocks(static_cast<long>(n) * h->temb_total), 256, 0, s>>>(
+      d_emb, kTimeDim, kTimeDim, h->temb_proj, h->temb_total, h->temb_proj_b, h->temb_table, h->temb_total, n, 1, 0);
+  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_sin);
+  cudaFree(d_h1);
+  cudaFree(d_emb);
+  h->n_t = n;
+  h->launches += 3;
+  return 0;
+}
+
+int pnp_set_context(pnp_engine* h, const float* ctx_dev, int batch, void* stream) {
+  PNP_CHECK(h && h->finalized, "pnp_set_context: engine not ready");
+  PNP_CHECK(ctx_dev != nullptr, "pnp_set_context: null context");
+  Plan* pl = nullptr;
+  int rc = get_plan(h, batch, &pl);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  const size_t n = static_cast<size_t>(batch) * 77 * kCrossDim;
+  f32_to_f16_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 2048)), 256, 0, s>>>(ctx_dev, pl->ctx16, n);
+  PNP_CUDA(cudaGetLastError());
+  for (auto& f : pl->ctx_ops) {
+    rc = f(s);
+    if (rc) return rc;
+  }
+  h->launches += 1 + static_cast<int64_t>(pl->ctx_ops.size());
+  h->ctx_batch = batch;
+  return 0;
+}
+
+void pnp_attn_ctrl_init(pnp_attn_ctrl* c) {
+  if (c == nullptr) return;
+  memset(c, 0, sizeof *c);
+  c->self_layer_lo = 0;
+  c->self_layer_hi = 0;
+  c->self_max_tokens = 0;
+  for (int r = 0; r < PNP_MAX_BATCH; ++r) {
+    c->self_q_row[r] = c->self_k_row[r] = c->self_v_row[r] = r;
+    c->cross_base_row[r] = -1;
+    c->cross_slot[r] = -1;
+    c->store_slot[r] = -1;
+  }
+  for (int s = 0; s < PNP_MAX_SLOTS; ++s)
+    for (int i = 0; i < PNP_TOKENS; ++i) {
+      c->mapper[s][i] = i;
+      c->alphas[s][i] = 1.f;
+      c->equalizer[s][i] = 1.f;
+      c->cross_alpha[s][i] = 0.f;
+    }
+}
+
+static const int kXfTokens[16] = {4096, 4096, 1024, 1024, 256, 256, 64, 256, 256, 256, 1024, 1024, 1024, 4096, 4096, 4096};
+
+static int push_ctrl(pnp_engine* h, int batch, int t_index, const pnp_attn_ctrl* c, cudaStream_t s) {
+  DevCtrl* hc = &h->h_ctrl_ring[h->ring_pos];
+  h->ring_pos = (h->ring_pos + 1) % kRing;
+  if (h->ring_pos == 0) PNP_CUDA(cudaStreamSynchronize(s));  // ring wrap: make sure old slots were consumed
+  pnp_attn_ctrl ident;
+  if (c == nullptr) {
+    pnp_attn_ctrl_init(&ident);
+    c = &ident;
+  }
+  for (int r = 0; r < batch; ++r) {
+    PNP_CHECK(c->self_q_row[r] >= 0 && c->self_q_row[r] < batch && c->self_k_row[r] >= 0 && c->self_k_row[r] < batch &&
+                  c->self_v_row[r] >= 0 && c->self_v_row[r] < batch,
+              "controller: self-attention row index out of range");
+    PNP_CHECK(c->cross_base_row[r] < batch && c->cross_slot[r] < PNP_MAX_SLOTS && c->store_slot[r] < 2 * PNP_MAX_SLOTS,
+              "controller: cross-attention row/slot out of range");
+  }
+  for (int l = 0; l < 16; ++l) {
+    const bool on = l >= c->self_layer_lo && l < c->self_layer_hi && kXfTokens[l] <= c->self_max_tokens;
+    for (int r = 0; r < PNP_MAX_BATCH; ++r) {
+      hc->self_q[l][r] = on ? c->self_q_row[r] : r;
+      hc->self_k[l][r] = on ? c->self_k_row[r] : r;
+      hc->self_v[l][r] = on ? c->self_v_row[r] : r;
+    }
+  }
+  memcpy(hc->cross_base, c->cross_base_row, sizeof hc->cross_base);
+  memcpy(hc->cross_slot, c->cross_slot, sizeof hc->cross_slot);
+  memcpy(hc->store_slot, c->store_slot, sizeof hc->store_slot);
+  memcpy(hc->mapper, c->mapper, sizeof hc->mapper);
+  memcpy(hc->alphas, c->alphas, sizeof hc->alphas);
+  memcpy(hc->equalizer, c->equalizer, sizeof hc->equalizer);
+  memcpy(hc->cross_alpha, c->cross_alpha, sizeof hc->cross_alpha);
+  hc->t_index = t_index;
+  PNP_CUDA(cudaMemcpyAsync(h->d_ctrl, hc, sizeof(DevCtrl), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, const pnp_attn_ctrl* ctrl_host,
+                     float* eps_out_dev, void* stream) {
+  PNP_CHECK(h && h->finalized, "pnp_unet_forward: engine not ready");
+  PNP_CHECK(x_dev && eps_out_dev, "pnp_unet_forward: null tensor");
+  PNP_CHECK(t_index >= 0 && t_index < h->n_t, "pnp_unet_forward: t_index outside the list given to pnp_set_timesteps");
+  PNP_CHECK(h->ctx_batch == batch, "pnp_unet_forward: pnp_set_context was not called for this batch size");
+  Plan* pl = nullptr;
+  int rc = get_plan(h, batch, &pl);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  rc = push_ctrl(h, batch, t_index, ctrl_host, s);
+  if (rc) return rc;
+  const size_t bytes = static_cast<size_t>(batch) * PNP_LATENT_ELEMS * sizeof(float);
+  PNP_CUDA(cudaMemcpyAsync(pl->x_in, x_dev, bytes, cudaMemcpyDeviceToDevice, s));
+  if (h->use_graph) {
+    if (pl->graph == nullptr) {
+      // warm-up run outside capture (sets function attributes, catches launch errors with a readable message)
+      for (auto& f : pl->ops) {
+        rc = f(s);
+        if (rc) return rc;
+      }
+      PNP_CUDA(cudaStreamSynchronize(s));
+      cudaGraph_t g = nullptr;
+      PNP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      for (auto& f : pl->ops) {
+        rc = f(s);
+        if (rc) {
+          cudaStreamEndCapture(s, &g);
+          if (g) cudaGraphDestroy(g);
+          return rc;
+        }
+      }
+      PNP_CUDA(cudaStreamEndCapture(s, &g));
+      PNP_CUDA(cudaGraphInstantiate(&pl->graph, g, 0));
+      cudaGraphDestroy(g);
+    }
+    PNP_CUDA(cudaGraphLaunch(pl->graph, s));
+  } else {
+    for (auto& f : pl->ops) {
+      rc = f(s);
+      if (rc) return rc;
+    }
+  }
+  // groupnorm = 2 kernels per op; count them
+  h->launches += static_cast<int64_t>(pl->ops.size());
+  PNP_CUDA(cudaMemcpyAsync(eps_out_dev, pl->eps_out, bytes, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int pnp_step_epilogue(pnp_engine* h, const pnp_step_args* a, void* stream) {
+  PNP_CHECK(h && a, "pnp_step_epilogue: null argument");
+  PNP_CHECK(a->x_dev && a->eps_c_dev && a->x_out_dev, "pnp_step_epilogue: null tensor");
+  StepParams p;
+  p.x = a->x_dev; p.eps_u = a->eps_u_dev; p.eps_c = a->eps_c_dev; p.x_out = a->x_out_dev; p.n = a->n;
+  p.guidance = a->guidance;
+  p.sqrt_a_from = a->sqrt_a_from; p.sqrt_1m_a_from = a->sqrt_1m_a_from;
+  p.sqrt_a_to = a->sqrt_a_to; p.sqrt_1m_a_to = a->sqrt_1m_a_to;
+  p.target = a->target_dev; p.target_rows = a->target_rows; p.loss_out = a->loss_out_dev;
+  p.noise_loss = a->noise_loss_dev; p.add_mask = a->add_mask;
+  h->launches += 1;
+  return step_epilogue_launch(p, as_stream(stream));
+}
+
+int pnp_local_blend(pnp_engine* h, float* x_dev, const int32_t* nwords2, const int32_t* words2x8,
+                    const float* alpha2x8, float threshold, float* mask_out_dev, void* stream) {
+  PNP_CHECK(h && h->finalized && x_dev && nwords2 && words2x8 && alpha2x8, "pnp_local_blend: null argument");
+  LocalBlendParams p;
+  // slots 0 (source prompt) and 1 (target prompt) of each of the five layers
+  p.store = h->store;
+  for (int i = 0; i < 2; ++i) {
+    p.nwords[i] = nwords2[i];
+    PNP_CHECK(nwords2[i] >= 0 && nwords2[i] <= 8, "pnp_local_blend: at most 8 blend words per prompt");
+    for (int j = 0; j < 8; ++j) {
+      p.words[i][j] = words2x8[i * 8 + j];
+      p.alpha[i][j] = alpha2x8[i * 8 + j];
+      PNP_CHECK(j >= nwords2[i] || (p.words[i][j] >= 0 && p.words[i][j] < PNP_TOKENS), "pnp_local_blend: word index");
+    }
+  }
+  p.threshold = threshold;
+  p.x = x_dev;
+  p.mask_out = mask_out_dev;
+  h->launches += 1;
+  return local_blend_launch(p, as_stream(stream));
+}
+
+int pnp_store_reset(pnp_engine* h, void* stream) {
+  PNP_CHECK(h && h->finalized, "pnp_store_reset: engine not ready");
+  PNP_CUDA(cudaMemsetAsync(h->store, 0, kStoreFloats * sizeof(float), as_stream(stream)));
+  return 0;
+}
+
+int pnp_store_read(pnp_engine* h, float* out_dev, int64_t max_floats, void* stream) {
+  PNP_CHECK(h && h->finalized && out_dev, "pnp_store_read: bad argument");
+  const size_t n = std::min<size_t>(static_cast<size_t>(max_floats), kStoreFloats);
+  PNP_CUDA(cudaMemcpyAsync(out_dev, h->store, n * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
+  return 0;
+}
+
+int pnp_kernel_launches(pnp_engine* h, int64_t* out) {
+  PNP_CHECK(h && out, "null argument");
+  *out = h->launches;
+  return 0;
+}
+int pnp_set_use_graph(pnp_engine* h, int enable) {
+  PNP_CHECK(h != nullptr, "null handle");
+  h->use_graph = enable != 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------ stand-alone kernel entry points
+static int test_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+int pnp_test_gemm(const uint16_t* a_dev, int M, int K, int lda, const uint16_t* w_dev, int N, const float* bias_dev,
+                  const uint16_t* residual_dev, uint16_t* out_dev, int ldc, int geglu, int bn, void* stream) {
+  GemmEpilogue ep;
+  ep.bias = bias_dev;
+  ep.residual = reinterpret_cast<const __half*>(residual_dev);
+  ep.ldr = ldc;
+  ep.out = reinterpret_cast<__half*>(out_dev);
+  ep.ldc = ldc;
+  ep.geglu = geglu != 0;
+  ASource s{reinterpret_cast<const __half*>(a_dev), K, lda};
+  GemmPlan gp;
+  int rc = gemm_plan_create(&gp, &s, 1, 1, true, 1, 1, M, reinterpret_cast<const __half*>(w_dev), N, K, ep, bn, test_sms());
+  if (rc) return rc;
+  return gemm_launch(gp, as_stream(stream));
+}
+
+int pnp_test_conv3x3(const uint16_t* x_dev, int B, int H, int W, int C, const uint16_t* w_dev, int N,
+                     const uint16_t* sc0_dev, int sc0_C, const uint16_t* sc1_dev, int sc1_C, const float* bias_dev,
+                     const uint16_t* residual_dev, uint16_t* out_dev, int bn, void* stream) {
+  GemmEpilogue ep;
+  ep.bias = bias_dev;
+  ep.residual = reinterpret_cast<const __half*>(residual_dev);
+  ep.ldr = N;
+  ep.out = reinterpret_cast<__half*>(out_dev);
+  ep.ldc = N;
+  ASource s[3];
+  int ns = 1;
+  s[0] = ASource{reinterpret_cast<const __half*>(x_dev), C, C};
+  int ktot = 9 * C;
+  if (sc0_dev) { s[ns++] = ASource{reinterpret_cast<const __half*>(sc0_dev), sc0_C, sc0_C}; ktot += sc0_C; }
+  if (sc1_dev) { s[ns++] = ASource{reinterpret_cast<const __half*>(sc1_dev), sc1_C, sc1_C}; ktot += sc1_C; }
+  GemmPlan gp;
+  int rc = gemm_plan_create(&gp, s, ns, 9, false, B, H, W, reinterpret_cast<const __half*>(w_dev), N, ktot, ep, bn, test_sms());
+  if (rc) return rc;
+  return gemm_launch(gp, as_stream(stream));
+}
+
+int pnp_test_groupnorm(const uint16_t* x0_dev, int C0, const uint16_t* x1_dev, int C1, int B, int HW,
+                       const float* gamma_dev, const float* beta_dev, float eps, int silu, uint16_t* out_dev,
+                       void* stream) {
+  float* partials = nullptr;
+  PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&partials), groupnorm_partials_floats(B, HW) * sizeof(float)));
+  int rc = groupnorm_launch(reinterpret_cast<const __half*>(x0_dev), C0, reinterpret_cast<const __half*>(x1_dev), C1, B,
+                            HW, gamma_dev, beta_dev, eps, silu != 0, reinterpret_cast<__half*>(out_dev), partials,
+                            as_stream(stream));
+  cudaStreamSynchronize(as_stream(stream));
+  cudaFree(partials);
+  return rc;
+}
+
+int pnp_test_layernorm(const uint16_t* x_dev, int rows, int C, const float* gamma_dev, const float* beta_dev,
+                       float eps, uint16_t* out_dev, void* stream) {
+  return layernorm_launch(reinterpret_cast<const __half*>(x_dev), rows, C, gamma_dev, beta_dev, eps,
+                          reinterpret_cast<__half*>(out_dev), as_stream(stream));
+}
+
+int pnp_test_self_attention(const uint16_t* qkv_dev, int B, int H, int N, int d, const int32_t* q_row_dev,
+                            const int32_t* k_row_dev, const int32_t* v_row_dev, uint16_t* out_dev, void* stream) {
+  const int c = H * d;
+  SelfAttnParams sp;
+  const __half* base = reinterpret_cast<const __half*>(qkv_dev);
+  sp.q = base; sp.k = base + c; sp.v = base + 2 * c; sp.ld = 3 * c;
+  sp.o = reinterpret_cast<__half*>(out_dev); sp.ldo = c;
+  sp.B = B; sp.H = H; sp.N = N; sp.d = d;
+  sp.scale = 1.0f / sqrtf(static_cast<float>(d));
+  sp.q_row = q_row_dev; sp.k_row = k_row_dev; sp.v_row = v_row_dev;
+  return self_attention_launch(sp, as_stream(stream));
+}
+
+int pnp_test_cross_attention(const uint16_t* q_dev, const uint16_t* kv_dev, int B, int H, int N, int d, int nk,
+                             const pnp_attn_ctrl* c, float* store_dev, uint16_t* out_dev, void* stream) {
+  PNP_CHECK(B <= PNP_MAX_BATCH, "batch too large");
+  const int ch = H * d;
+  struct Tab {
+    int base[PNP_MAX_BATCH], slot[PNP_MAX_BATCH], sslot[PNP_MAX_BATCH];
+    int mapper[PNP_MAX_SLOTS][PNP_TOKENS];
+    float alphas[PNP_MAX_SLOTS][PNP_TOKENS], eq[PNP_MAX_SLOTS][PNP_TOKENS], ca[PNP_MAX_SLOTS][PNP_TOKENS];
+  };
+  Tab* d_tab = nullptr;
+  CrossAttnParams cp;
+  memset(&cp, 0, sizeof cp);
+  if (c != nullptr) {
+    Tab t;
+    memcpy(t.base, c->cross_base_row, sizeof t.base);
+    memcpy(t.slot, c->cross_slot, sizeof t.slot);
+    memcpy(t.sslot, c->store_slot, sizeof t.sslot);
+    memcpy(t.mapper, c->mapper, sizeof t.mapper);
+    memcpy(t.alphas, c->alphas, sizeof t.alphas);
+    memcpy(t.eq, c->equalizer, sizeof t.eq);
+    memcpy(t.ca, c->cross_alpha, sizeof t.ca);
+    PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_tab), sizeof(Tab)));
+    PNP_CUDA(cudaMemcpy(d_tab, &t, sizeof(Tab), cudaMemcpyHostToDevice));
+    cp.base_row = d_tab->base; cp.edit_slot = d_tab->slot; cp.store_slot = d_tab->sslot;
+    cp.mapper = &d_tab->mapper[0][0]; cp.alphas = &d_tab->alphas[0][0];
+    cp.equalizer = &d_tab->eq[0][0]; cp.cross_alpha = &d_tab->ca[0][0];
+    cp.store = store_dev;
+  }
+  cp.q = reinterpret_cast<const __half*>(q_dev); cp.ldq = ch;
+  cp.kv = reinterpret_cast<const __half*>(kv_dev); cp.ldkv = 2 * ch;
+  cp.o = reinterpret_cast<__half*>(out_dev); cp.ldo = ch;
+  cp.B = B; cp.H = H; cp.N = N; cp.d = d; cp.nk = nk;
+  cp.scale = 1.0f / sqrtf(static_cast<float>(d));
+  int rc = cross_attention_launch(cp, as_stream(stream));
+  cudaStreamSynchronize(as_stream(stream));
+  if (d_tab) cudaFree(d_tab);
+  return rc;
+}
+
+int pnp_test_upsample2x(const uint16_t* x_dev, int B, int H, int W, int C, uint16_t* out_dev, void* stream) {
+  return upsample2x_launch(reinterpret_cast<const __half*>(x_dev), B, H, W, C, reinterpret_cast<__half*>(out_dev),
+                           as_stream(stream));
+}
+int pnp_test_im2col_s2(const uint16_t* x_dev, int B, int H, int W, int C, uint16_t* out_dev, void* stream) {
+  return im2col_s2_launch(reinterpret_cast<const __half*>(x_dev), B, H, W, C, reinterpret_cast<__half*>(out_dev),
+                          as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[M,N] = A[M,K] . Wt[N,K]^T   fp16 operands, fp32 accumulation in TMEM, fused epilogue.
+//
+// One persistent CTA per SM, 256 threads, warp-specialised:
+//   warp 0 (lane 0)  TMA producer: per 64-wide K block one 4-D box of the NHWC activation (128 pixels x 64 channels,
+//                    shifted by the 3x3 tap, hardware zero fill = the conv padding) and one 2-D box of the weights,
+//                    both landing 128B-swizzled in a STAGES-deep shared-memory ring guarded by full/empty mbarriers.
+//   warp 1 (lane 0)  MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of two TMEM accumulators,
+//                    tcgen05.commit releases the stage / publishes the accumulator.
+//   warp 2           TMEM allocator.
+//   warps 4..7       epilogue: tcgen05.ld 32 lanes x 32 columns, + bias + time-embedding + residual (or GEGLU),
+//                    fp16 pack, 16-byte global stores; overlaps the next tile's MMAs (double-buffered accumulator).
+//
+// This is the only place the library does dense contractions: ResnetBlock2D convs (reference arithmetic:
+// models/edict/my_diffusers/models/resnet.py:331-365), 1x1 proj_in/out, attention projections and the GEGLU
+// feed-forward (models/edict/my_diffusers/models/attention.py:140-151,186-200,253-260,329-333).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "pnp_internal.h"
+#include "pnp_ptx.cuh"
+
+namespace pnp {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 160 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM = STAGES * STAGE + BAR_BYTES + 1024;  // +1024: manual alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a[0]);
+    tma_prefetch_desc(&p.map_b);
+    if (p.chunks1 > 0) tma_prefetch_desc(&p.map_a[1]);
+    if (p.chunks2 > 0) tma_prefetch_desc(&p.map_a[2]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int num_kb = p.num_kb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      uint32_t stage = 0, phase = 0;
+      const int kb0 = p.taps0 * p.chunks0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.m_tiles;
+        const int n_blk = tile / p.m_tiles;
+        const int p0 = m_blk * BM;
+        int x0, y0, b0;
+        if (p.linear) {
+          x0 = p0; y0 = 0; b0 = 0;
+        } else {
+          b0 = p0 / p.HW;
+          y0 = (p0 - b0 * p.HW) / p.W;
+          x0 = 0;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u, p.dbg, 1);
+          uint8_t* sa = smem + stage * C::STAGE;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full[stage], C::STAGE);
+          if (kb < kb0) {
+            const int tap = kb / p.chunks0;
+            const int cc = kb - tap * p.chunks0;
+            int dx = 0, dy = 0;
+            if (p.taps0 == 9) {
+              dy = tap / 3 - 1;
+              dx = tap - (tap / 3) * 3 - 1;
+            }
+            tma_load_4d(sa, &p.map_a[0], &full[stage], cc * BK, x0 + dx, y0 + dy, b0);
+          } else if (kb - kb0 < p.chunks1) {
+            tma_load_4d(sa, &p.map_a[1], &full[stage], (kb - kb0) * BK, x0, y0, b0);
+          } else {
+            tma_load_4d(sa, &p.map_a[2], &full[stage], (kb - kb0 - p.chunks1) * BK, x0, y0, b0);
+          }
+          tma_load_2d(sb, &p.map_b, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1u, p.dbg, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase, p.dbg, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE);
+          const uint64_t adesc = umma_desc_sw128_kmajor(a_addr);
+          const uint64_t bdesc = umma_desc_sw128_kmajor(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-byte swizzle atom
+            umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull[as]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------------------- epilogue
+    const int q = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const float* temb = nullptr;
+    if (p.temb_table != nullptr) temb = p.temb_table + static_cast<size_t>(*p.t_index) * p.temb_stride;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % p.m_tiles;
+      const int n_blk = tile / p.m_tiles;
+      const uint32_t as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull[as], aphase, p.dbg, 4);
+      tc_fence_after();
+      const int m = m_blk * BM + row;
+      const bool valid = m < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      if (!p.geglu) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            }
+          }
+          if (temb != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(temb + n0 + j));
+              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            }
+          }
+          if (valid) {
+            if (p.residual != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(m) * p.ldr + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = rp[j];
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h[e]);
+                  v[j * 8 + e * 2] += f.x;
+                  v[j * 8 + e * 2 + 1] += f.y;
+                }
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_half2(v[j * 8 + 0], v[j * 8 + 1]);
+              u.y = pack_half2(v[j * 8 + 2], v[j * 8 + 3]);
+              u.z = pack_half2(v[j * 8 + 4], v[j * 8 + 5]);
+              u.w = pack_half2(v[j * 8 + 6], v[j * 8 + 7]);
+              op[j] = u;
+            }
+          }
+        }
+      } else {
+        // GEGLU: tile columns [0,BN/2) hold the value projection, [BN/2,BN) the gate projection of the same
+        // output columns (weights are packed that way by the engine).  attention.py:329-333 (erf GELU).
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t rv[32], rg[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, rv);
+          tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, rg);
+          tmem_ld_wait();
+          const int nv = n_blk * BN + c * 32;
+          const int ng = nv + BN / 2;
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float vv = __uint_as_float(rv[j]) + __ldg(p.bias + nv + j);
+            const float gg = __uint_as_float(rg[j]) + __ldg(p.bias + ng + j);
+            o[j] = vv * gelu_erf(gg);
+          }
+          if (valid) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldc + n_blk * (BN / 2) + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_half2(o[j * 8 + 0], o[j * 8 + 1]);
+              u.y = pack_half2(o[j * 8 + 2], o[j * 8 + 3]);
+              u.z = pack_half2(o[j * 8 + 4], o[j * 8 + 5]);
+              u.w = pack_half2(o[j * 8 + 6], o[j * 8 + 7]);
+              op[j] = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // resolved at run time so that the library has no link-time dependency on libcuda (absent on the build box)
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+  });
+  return fn;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  PNP_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
+             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    set_last_error(buf);
+    return -3;
+  }
+  return 0;
+}
+
+template <int BN>
+int launch_t(const GemmPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<BN>::SMEM));
+    attr_set = true;
+  }
+  gemm_tcgen05_kernel<BN><<<plan.grid, 256, Cfg<BN>::SMEM, stream>>>(plan.p);
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int gemm_choose_bn(int M, int N, bool geglu, int num_sms) {
+  const int cands[4] = {256, 160, 128, 64};
+  const int m_tiles = (M + BM - 1) / BM;
+  long best_cost = -1;
+  int best = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (N % bn != 0) continue;
+    if (geglu && bn != 256 && bn != 128) continue;
+    const long tiles = static_cast<long>(m_tiles) * (N / bn);
+    const long waves = (tiles + num_sms - 1) / num_sms;
+    const long per = std::max(2 * bn, 128 + bn);  // tensor-pipe cycles vs shared-memory cycles per 64-wide K block
+    const long cost = waves * per;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, bool linear, int B, int H, int W,
+                     const __half* Wt, int N, int Ktot, const GemmEpilogue& ep, int bn_force, int num_sms) {
+  PNP_CHECK(nsrc >= 1 && nsrc <= 3, "gemm: 1..3 A sources");
+  PNP_CHECK(taps0 == 1 || taps0 == 9, "gemm: taps must be 1 or 9");
+  GemmParams& p = plan->p;
+  memset(&p, 0, sizeof p);
+  const int M = B * H * W;
+  int ksum = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    PNP_CHECK(srcs[i].C % BK == 0, "gemm: every A source needs a multiple of 64 channels");
+    PNP_CHECK(srcs[i].ld % 8 == 0 && (reinterpret_cast<uintptr_t>(srcs[i].ptr) & 15) == 0, "gemm: A alignment");
+    ksum += srcs[i].C * (i == 0 ? taps0 : 1);
+  }
+  PNP_CHECK(ksum == Ktot, "gemm: K of the sources does not match the packed weight");
+  const bool geglu = ep.geglu;
+  int bn = bn_force > 0 ? bn_force : gemm_choose_bn(M, N, geglu, num_sms);
+  PNP_CHECK(bn == 256 || bn == 160 || bn == 128 || bn == 64, "gemm: unsupported BN");
+  PNP_CHECK(N % bn == 0, "gemm: N must be a multiple of the column tile");
+  PNP_CHECK(!geglu || bn == 256 || bn == 128, "gemm: GEGLU epilogue needs BN 128/256");
+  PNP_CHECK(ep.out != nullptr && ep.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0,
+            "gemm: output alignment");
+  PNP_CHECK(ep.residual == nullptr || (ep.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0),
+            "gemm: residual alignment");
+  PNP_CHECK(!geglu || ep.bias != nullptr, "gemm: GEGLU needs a bias");
+
+  // A maps.  Box = 128 consecutive pixels x 64 channels.
+  uint32_t box[4];
+  if (linear) {
+    PNP_CHECK(B == 1 && H == 1, "gemm: linear mode takes M as W");
+    box[0] = BK; box[1] = BM; box[2] = 1; box[3] = 1;
+  } else {
+    PNP_CHECK(W <= 128 && 128 % W == 0, "gemm: conv mode needs W | 128");
+    const int rows = 128 / W;  // image rows per tile
+    if (rows <= H) {
+      PNP_CHECK(H % rows == 0, "gemm: conv tile rows must divide H");
+      box[0] = BK; box[1] = W; box[2] = rows; box[3] = 1;
+    } else {
+      PNP_CHECK(rows % H == 0, "gemm: conv tile must cover whole images");
+      box[0] = BK; box[1] = W; box[2] = H; box[3] = rows / H;
+    }
+  }
+  for (int i = 0; i < nsrc; ++i) {
+    uint64_t dims[4], strides[3];
+    if (linear) {
+      dims[0] = srcs[i].C; dims[1] = M; dims[2] = 1; dims[3] = 1;
+      strides[0] = static_cast<uint64_t>(srcs[i].ld) * 2;
+      strides[1] = strides[0] * M;
+      strides[2] = strides[1];
+    } else {
+      dims[0] = srcs[i].C; dims[1] = W; dims[2] = H; dims[3] = B;
+      strides[0] = static_cast<uint64_t>(srcs[i].ld) * 2;
+      strides[1] = strides[0] * W;
+      strides[2] = strides[1] * H;
+    }
+    int rc = encode_map(&p.map_a[i], srcs[i].ptr, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};
+    uint32_t bbox[2] = {BK, static_cast<uint32_t>(bn)};
+    PNP_CHECK((reinterpret_cast<uintptr_t>(Wt) & 15) == 0 && Ktot % 8 == 0, "gemm: weight alignment");
+    int rc = encode_map(&p.map_b, Wt, 2, dims, strides, bbox);
+    if (rc) return rc;
+  }
+  p.taps0 = taps0;
+  p.chunks0 = srcs[0].C / BK;
+  p.chunks1 = nsrc > 1 ? srcs[1].C / BK : 0;
+  p.chunks2 = nsrc > 2 ? srcs[2].C / BK : 0;
+  p.num_kb = Ktot / BK;
+  p.linear = linear ? 1 : 0;
+  p.W = W;
+  p.HW = H * W;
+  p.M = M;
+  p.N = N;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = N / bn;
+  p.bias = ep.bias;
+  p.temb_table = ep.temb_table;
+  p.t_index = ep.t_index;
+  p.temb_stride = ep.temb_stride;
+  p.residual = ep.residual;
+  p.ldr = ep.ldr;
+  p.out = ep.out;
+  p.ldc = ep.ldc;
+  p.geglu = geglu ? 1 : 0;
+  p.dbg = debug_words_device();
+  plan->bn = bn;
+  plan->grid = std::min(p.m_tiles * p.n_tiles, num_sms);
+  return 0;
+}
+
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  switch (plan.bn) {
+    case 256: return launch_t<256>(plan, stream);
+    case 160: return launch_t<160>(plan, stream);
+    case 128: return launch_t<128>(plan, stream);
+    case 64: return launch_t<64>(plan, stream);
+  }
+  set_last_error("gemm_launch: bad plan");
+  return -2;
+}
+
+}  // namespace pnp

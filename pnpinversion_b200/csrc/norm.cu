@@ -1,0 +1,434 @@
+// HBM-bound helper kernels around the tcgen05 GEMM: GroupNorm(+SiLU) over NHWC, LayerNorm, nearest 2x upsample,
+// stride-2 im2col, and the two tiny edge convolutions (4->320 and 320->4) that are not worth a tensor-core tile.
+// All loads/stores are 16-byte vectors along the contiguous channel dimension.
+//
+// Reference arithmetic: torch.nn.GroupNorm(32, C, eps) / SiLU in models/edict/my_diffusers/models/resnet.py:336-358,
+// GroupNorm(eps=1e-6) in attention.py:123,143; LayerNorm attention.py:195-200; Upsample2D resnet.py:38-52;
+// Downsample2D (stride 2, pad 1) resnet.py:88-97; conv_in / conv_norm_out+conv_out unet_2d_condition.py:230,266-268.
+#include <algorithm>
+
+#include "pnp_internal.h"
+
+namespace pnp {
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __half22float2(h[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+  return u;
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// ------------------------------------------------------------------ GroupNorm
+constexpr int GN_GROUPS = 32;
+constexpr int GN_MAX_VPT = 2;
+
+// partials[b][slice][g] = (mean, M2) over ppc*cpg elements
+__global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                int ppc, int tx_n, int vpt, float* __restrict__ partials) {
+  extern __shared__ float sm[];  // [rows_y][2*C] then reused
+  const int C = C0 + C1;
+  const int nvec0 = C0 >> 3;
+  const int b = blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+  const int rows_y = blockDim.x / tx_n;
+  float s[GN_MAX_VPT][8], ss[GN_MAX_VPT][8];
+#pragma unroll
+  for (int i = 0; i < GN_MAX_VPT; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[i][e] = ss[i][e] = 0.f;
+  if (ty < rows_y) {
+    for (int pix = ty; pix < ppc; pix += rows_y) {
+      const size_t row = static_cast<size_t>(b) * HW + static_cast<size_t>(slice) * ppc + pix;
+#pragma unroll
+      for (int i = 0; i < GN_MAX_VPT; ++i) {
+        if (i < vpt) {
+          const int v = tx + i * tx_n;
+          const uint4 u = (v < nvec0) ? *reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8)
+                                      : *reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8);
+          float f[8];
+          unpack8(u, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            s[i][e] += f[e];
+            ss[i][e] += f[e] * f[e];
+          }
+        }
+      }
+    }
+    float* mine = sm + static_cast<size_t>(ty) * 2 * C;
+#pragma unroll
+    for (int i = 0; i < GN_MAX_VPT; ++i) {
+      if (i < vpt) {
+        const int v = tx + i * tx_n;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          mine[v * 8 + e] = s[i][e];
+          mine[C + v * 8 + e] = ss[i][e];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // reduce over ty into row 0
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float a = sm[c];
+    for (int r = 1; r < rows_y; ++r) a += sm[static_cast<size_t>(r) * 2 * C + c];
+    sm[c] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {
+    const int g = threadIdx.x, cpg = C / GN_GROUPS;
+    float a = 0.f, q = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += sm[c];
+      q += sm[C + c];
+    }
+    const float n = static_cast<float>(ppc) * cpg;
+    const float mean = a / n;
+    const float m2 = fmaxf(q - a * mean, 0.f);
+    float* o = partials + ((static_cast<size_t>(b) * nslices + slice) * GN_GROUPS + g) * 2;
+    o[0] = mean;
+    o[1] = m2;
+  }
+}
+
+__global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                int nslices, int ppc_stats, const float* __restrict__ partials,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int do_silu,
+                                __half* __restrict__ out, int ppc) {
+  extern __shared__ float sm[];  // scale[C], shift[C], mean[32], rstd[32]
+  const int C = C0 + C1;
+  float* scale = sm;
+  float* shift = sm + C;
+  float* gmean = sm + 2 * C;
+  float* grstd = gmean + GN_GROUPS;
+  const int b = blockIdx.y;
+  const int cpg = C / GN_GROUPS;
+  if (threadIdx.x < GN_GROUPS) {
+    const int g = threadIdx.x;
+    const float* pp = partials + (static_cast<size_t>(b) * nslices * GN_GROUPS + g) * 2;
+    float msum = 0.f;
+    for (int s = 0; s < nslices; ++s) msum += pp[static_cast<size_t>(s) * GN_GROUPS * 2];
+    const float mean = msum / nslices;
+    const float n_i = static_cast<float>(ppc_stats) * cpg;
+    float m2 = 0.f;
+    for (int s = 0; s < nslices; ++s) {
+      const float d = pp[static_cast<size_t>(s) * GN_GROUPS * 2] - mean;
+      m2 += pp[static_cast<size_t>(s) * GN_GROUPS * 2 + 1] + n_i * d * d;
+    }
+    const float var = m2 / (n_i * nslices);
+    gmean[g] = mean;
+    grstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = grstd[g] * gamma[c];
+    scale[c] = sc;
+    shift[c] = beta[c] - gmean[g] * sc;
+  }
+  __syncthreads();
+  const int nvec = C >> 3, nvec0 = C0 >> 3;
+  const int total = ppc * nvec;
+  const size_t row0 = static_cast<size_t>(b) * HW + static_cast<size_t>(blockIdx.x) * ppc;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pix = idx / nvec, v = idx - pix * nvec;
+    const size_t row = row0 + pix;
+    const uint4 u = (v < nvec0) ? *reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8)
+                                : *reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8);
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = f[e] * scale[v * 8 + e] + shift[v * 8 + e];
+      f[e] = do_silu ? silu(y) : y;
+    }
+    *reinterpret_cast<uint4*>(out + row * C + v * 8) = pack8(f);
+  }
+}
+
+int gn_ppc(int B, int HW) {
+  // pixels per CTA: aim for >= ~256 CTAs, at least 8 pixels each
+  int ppc = HW;
+  while (ppc > 8 && static_cast<long>(B) * (HW / ppc) < 256) ppc >>= 1;
+  return ppc;
+}
+
+// ------------------------------------------------------------------ LayerNorm: one warp per token
+template <int VPL>  // 16-byte vectors per lane (C = 8*32*VPL at most)
+__global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float eps, __half* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C >> 3;
+  const __half* xr = x + static_cast<size_t>(warp) * C;
+  float f[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += f[i][e];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[i][e] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  __half* orow = out + static_cast<size_t>(warp) * C;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * gamma[v * 8 + e] + beta[v * 8 + e];
+      *reinterpret_cast<uint4*>(orow + v * 8) = pack8(y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ data movement
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int B, int H, int W, int nvec, uint4* __restrict__ out) {
+  const size_t total = static_cast<size_t>(B) * 2 * H * 2 * W * nvec;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = idx % nvec;
+    size_t r = idx / nvec;
+    const int xo = r % (2 * W);
+    r /= (2 * W);
+    const int yo = r % (2 * H);
+    const int b = r / (2 * H);
+    out[idx] = x[((static_cast<size_t>(b) * H + (yo >> 1)) * W + (xo >> 1)) * nvec + v];
+  }
+}
+
+// out[(b,yo,xo)][tap*C + c] = x[b, 2yo+dy-1, 2xo+dx-1, c]  (zero outside), tap = dy*3+dx
+__global__ void im2col_s2_kernel(const uint4* __restrict__ x, int B, int H, int W, int nvec, uint4* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * 9 * nvec;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = idx % nvec;
+    size_t r = idx / nvec;
+    const int tap = r % 9;
+    r /= 9;
+    const int xo = r % Wo;
+    r /= Wo;
+    const int yo = r % Ho;
+    const int b = r / Ho;
+    const int yi = 2 * yo + tap / 3 - 1, xi = 2 * xo + tap % 3 - 1;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (yi >= 0 && yi < H && xi >= 0 && xi < W) u = x[((static_cast<size_t>(b) * H + yi) * W + xi) * nvec + v];
+    out[idx] = u;
+  }
+}
+
+// ------------------------------------------------------------------ conv_in: NCHW fp32 (4 ch) -> NHWC fp16 (320 ch)
+constexpr int CIN_K = 36;
+constexpr int CIN_CO = 320;
+__global__ void conv_in_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w,
+                               const float* __restrict__ bias, __half* __restrict__ out) {
+  __shared__ float ws[CIN_K * CIN_CO];  // [k][co], k = ci*9 + tap
+  for (int i = threadIdx.x; i < CIN_K * CIN_CO; i += blockDim.x) {
+    const int co = i % CIN_CO, k = i / CIN_CO;
+    ws[i] = w[co * CIN_K + k];
+  }
+  __syncthreads();
+  const int nvec = CIN_CO / 8;  // 40
+  const int ppb = blockDim.x / nvec;
+  const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+  if (pl >= ppb) return;
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * ppb + pl; pix < npix; pix += static_cast<size_t>(gridDim.x) * ppb) {
+    const int xx = pix % W;
+    const int yy = (pix / W) % H;
+    const int b = pix / (static_cast<size_t>(W) * H);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias[v * 8 + e];
+    for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yi = yy + tap / 3 - 1, xi = xx + tap % 3 - 1;
+        float a = 0.f;
+        if (yi >= 0 && yi < H && xi >= 0 && xi < W) a = x[((static_cast<size_t>(b) * 4 + ci) * H + yi) * W + xi];
+        const float* wr = ws + (ci * 9 + tap) * CIN_CO + v * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += a * wr[e];
+      }
+    }
+    *reinterpret_cast<uint4*>(out + pix * CIN_CO + v * 8) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------ conv_out: NHWC fp16 (320 ch, already GN+SiLU) -> NCHW fp32 (4 ch)
+__global__ void conv_out_kernel(const __half* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ w,
+                                const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ __half wsh[];  // [co][tap][c]
+  const int K = 9 * C;
+  for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) {
+    const int co = i / K, r = i % K, tap = r / C, c = r % C;
+    wsh[i] = __float2half(w[(co * C + c) * 9 + tap]);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = C >> 3;
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * wpb) {
+    const int xx = pix % W;
+    const int yy = (pix / W) % H;
+    const int b = pix / (static_cast<size_t>(W) * H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < 9 * nvec; i += 32) {
+      const int tap = i / nvec, v = i % nvec;
+      const int yi = yy + tap / 3 - 1, xi = xx + tap % 3 - 1;
+      if (yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + yi) * W + xi) * C + v * 8), f);
+#pragma unroll
+      for (int co = 0; co < 4; ++co) {
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(wsh + co * K + tap * C + v * 8), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[co] += f[e] * g[e];
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+    }
+    if (lane < 4) {
+      const float val = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + bias[lane];
+      out[((static_cast<size_t>(b) * 4 + lane) * H + yy) * W + xx] = val;
+    }
+  }
+}
+
+}  // namespace
+
+size_t groupnorm_partials_floats(int B, int HW) {
+  const int ppc = gn_ppc(B, HW);
+  return static_cast<size_t>(B) * (HW / ppc) * GN_GROUPS * 2;
+}
+
+int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, int HW, const float* gamma,
+                     const float* beta, float eps, bool do_silu, __half* out, float* partials, cudaStream_t s) {
+  const int C = C0 + C1;
+  PNP_CHECK(C % (8 * GN_GROUPS / 8) == 0 && C % GN_GROUPS == 0 && C0 % 8 == 0 && C1 % 8 == 0, "groupnorm: channels");
+  const int nvec = C / 8;
+  const int vpt = (nvec + 255) / 256;
+  PNP_CHECK(vpt <= GN_MAX_VPT && nvec % vpt == 0, "groupnorm: too many channels");
+  const int tx_n = nvec / vpt;
+  const int rows_y = 256 / tx_n;
+  const int threads = tx_n * rows_y;
+  const int ppc = gn_ppc(B, HW);
+  const int nslices = HW / ppc;
+  PNP_CHECK(HW % ppc == 0, "groupnorm: HW split");
+  const size_t sm1 = static_cast<size_t>(rows_y) * 2 * C * sizeof(float);
+  static bool attr1 = false;
+  if (!attr1) {
+    PNP_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr1 = true;
+  }
+  PNP_CHECK(sm1 <= 160 * 1024, "groupnorm: smem");
+  gn_stats_kernel<<<dim3(nslices, B), threads, sm1, s>>>(x0, C0, x1, C1, HW, ppc, tx_n, vpt, partials);
+  PNP_CUDA(cudaGetLastError());
+  const size_t sm2 = (2 * static_cast<size_t>(C) + 2 * GN_GROUPS) * sizeof(float);
+  gn_apply_kernel<<<dim3(nslices, B), 256, sm2, s>>>(x0, C0, x1, C1, HW, nslices, ppc, partials, gamma, beta, eps,
+                                                    do_silu ? 1 : 0, out, ppc);
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int layernorm_launch(const __half* x, int rows, int C, const float* gamma, const float* beta, float eps, __half* out,
+                     cudaStream_t s) {
+  PNP_CHECK(C % 8 == 0 && C <= 8 * 32 * 5, "layernorm: C");
+  const int threads = 256;
+  const int blocks = (rows * 32 + threads - 1) / threads;
+  const int vpl = (C / 8 + 31) / 32;
+  switch (vpl) {
+    case 1: ln_kernel<1><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    case 2: ln_kernel<2><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    case 3: ln_kernel<3><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    case 4: ln_kernel<4><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    default: ln_kernel<5><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+  }
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int upsample2x_launch(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t s) {
+  PNP_CHECK(C % 8 == 0, "upsample: C");
+  const size_t total = static_cast<size_t>(B) * 4 * H * W * (C / 8);
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  upsample2x_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(x), B, H, W, C / 8,
+                                           reinterpret_cast<uint4*>(out));
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int im2col_s2_launch(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t s) {
+  PNP_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col: shape");
+  const size_t total = static_cast<size_t>(B) * (H / 2) * (W / 2) * 9 * (C / 8);
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  im2col_s2_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(x), B, H, W, C / 8,
+                                          reinterpret_cast<uint4*>(out));
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conv_in_launch(const float* x_nchw, int B, int H, int W, const float* w, const float* bias, __half* out,
+                   cudaStream_t s) {
+  const int threads = 240;  // 40 channel-octets x 6 pixels
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const int blocks = static_cast<int>(std::min<size_t>((npix + 5) / 6, 148 * 4));
+  conv_in_kernel<<<blocks, threads, 0, s>>>(x_nchw, B, H, W, w, bias, out);
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conv_out_launch(const __half* x, int B, int H, int W, int C, const float* w, const float* bias, float* out_nchw,
+                    cudaStream_t s) {
+  PNP_CHECK(C % 8 == 0, "conv_out: C");
+  const size_t sm = static_cast<size_t>(4) * 9 * C * sizeof(__half);
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const int blocks = static_cast<int>(std::min<size_t>((npix + 7) / 8, 148 * 8));
+  conv_out_kernel<<<blocks, 256, sm, s>>>(x, B, H, W, C, w, bias, out_nchw);
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace pnp

@@ -1,0 +1,89 @@
+// Parameter blocks of the attention kernels (attention.cu) and of the fused step epilogue (epilogue.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace pnp {
+
+// q/k/v point into one fused [B, N, ld] buffer (ld = 3C): q at +0, k at +C, v at +2C; head h at column h*d.
+// *_row (device, length B, may be null = identity) implement the controllers as batch-row indirection:
+//   P2P self-replace : q_row[tgt]=src, k_row[tgt]=src            (attention_control.py:258-263)
+//   MasaCtrl         : k_row[r]=src(r), v_row[r]=src(r)          (masactrl.py:56-72)
+struct SelfAttnParams {
+  const __half* q;
+  const __half* k;
+  const __half* v;
+  int ld;
+  __half* o;
+  int ldo;
+  int B, H, N, d;
+  float scale;
+  const int* q_row;
+  const int* k_row;
+  const int* v_row;
+};
+
+// q: [B, N, ldq]; kv: [B, nk, ldkv] with K at +0 and V at +C (C = H*d), precomputed once per prompt.
+// Per batch row r: base_row[r] >= 0 marks an edited (target) row whose source row is base_row[r]; edit_slot[r]
+// selects its 77-entry tables (mapper/alphas/equalizer/cross_alpha).  store (may be null): accumulate the final
+// probabilities of rows with store_slot[r] >= 0 into store[slot][h][q][77] (the maps LocalBlend consumes).
+struct CrossAttnParams {
+  const __half* q;
+  int ldq;
+  const __half* kv;
+  int ldkv;
+  __half* o;
+  int ldo;
+  int B, H, N, d, nk;
+  float scale;
+  const int* base_row;
+  const int* edit_slot;
+  const int* mapper;         // [slots][77] int32
+  const float* alphas;       // [slots][77]
+  const float* equalizer;    // [slots][77]
+  const float* cross_alpha;  // [slots][77]  (row cur_step of cross_replace_alpha)
+  float* store;
+  const int* store_slot;
+};
+
+int self_attention_launch(const SelfAttnParams& p, cudaStream_t s);
+int cross_attention_launch(const CrossAttnParams& p, cudaStream_t s);
+
+// ------------------------------------------------------------------ fused step epilogue (epilogue.cu)
+// One launch per diffusion step over `n` latent rows of 4*64*64 fp32:
+//   eps   = eps_u + g * (eps_c - eps_u)                       p2p_guidance_forward.py:111 ; inversion.py:282
+//   x0    = (x - sqrt(1-a_from) * eps) / sqrt(a_from)         inversion.py:252-253 / 266-267 ; scheduler_dev.py:46,51
+//   x_new = sqrt(a_to) * x0 + sqrt(1-a_to) * eps              inversion.py:254-255 / 268-269 ; scheduler_dev.py:91-94
+//   OFFSET  : loss = target - x_new ; x_new = x_new + loss     inversion.py:386-389
+//   RECTIFY : x_new += noise_loss (rows flagged in add_mask)   p2p_guidance_forward.py:113-114
+struct StepParams {
+  const float* x;      // [n, 16384]
+  const float* eps_u;  // [n, 16384] (null: no CFG, eps = eps_c)
+  const float* eps_c;  // [n, 16384]
+  float* x_out;        // [n, 16384]
+  int n;
+  float guidance;
+  // fp32 scalars computed on the host exactly the way the reference does (alphas_cumprod table in fp32)
+  float sqrt_a_from, sqrt_1m_a_from;  // x0 = (x - sqrt_1m_a_from * eps) / sqrt_a_from
+  float sqrt_a_to, sqrt_1m_a_to;      // x_new = sqrt_a_to * x0 + sqrt_1m_a_to * eps
+  const float* target;      // OFFSET: [target_rows, 16384] latent the branch must land on (row r uses r % target_rows)
+  int target_rows;
+  float* loss_out;          // OFFSET: [n, 16384]
+  const float* noise_loss;  // RECTIFY: [n, 16384]
+  unsigned add_mask;        // RECTIFY: bit r set -> add noise_loss row r to x_new row r
+};
+int step_epilogue_launch(const StepParams& p, cudaStream_t s);
+
+// LocalBlend (attention_control.py:97-121): store = accumulated [layers*? ...] see epilogue.cu
+struct LocalBlendParams {
+  const float* store;  // [5 layers][2 prompts][8 heads][256 queries][77] running sum over steps
+  int nwords[2];       // words with alpha_layers != 0 per prompt
+  int words[2][8];
+  float alpha[2][8];
+  float threshold;
+  float* x;         // [2, 4, 64, 64] in/out (row 0 = source, row 1 = target)
+  float* mask_out;  // optional [2][64*64] inspection output (may be null)
+};
+int local_blend_launch(const LocalBlendParams& p, cudaStream_t s);
+
+}  // namespace pnp

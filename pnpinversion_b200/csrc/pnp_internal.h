@@ -1,0 +1,108 @@
+// Internal C++ declarations shared by the kernels and the engine (not part of the C ABI; see include/pnpinv.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace pnp {
+
+// ------------------------------------------------------------------ errors
+void set_last_error(const std::string& msg);
+const char* get_last_error();
+#define PNP_CUDA(call)                                                                                          \
+  do {                                                                                                          \
+    cudaError_t e__ = (call);                                                                                   \
+    if (e__ != cudaSuccess) {                                                                                   \
+      ::pnp::set_last_error(std::string(#call) + " failed: " + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + \
+                            std::to_string(__LINE__));                                                          \
+      return -1;                                                                                                \
+    }                                                                                                           \
+  } while (0)
+#define PNP_CHECK(cond, msg)                                                                    \
+  do {                                                                                          \
+    if (!(cond)) {                                                                              \
+      ::pnp::set_last_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+      return -2;                                                                                \
+    }                                                                                           \
+  } while (0)
+
+// host-mapped debug words written by a kernel that detects a stuck pipeline (see mbar_wait)
+volatile unsigned int* debug_words_device();  // device-visible alias
+const unsigned int* debug_words_host();
+
+// ------------------------------------------------------------------ GEMM / implicit-GEMM convolution
+// D[M,N] = sum_seg A_seg[M,K_seg] . Wt[N,Ktot]^T  (+bias +temb +residual | GEGLU), fp16 operands, fp32 accumulate
+// in TMEM.  A segments: segment 0 is either a plain [M,K] matrix (linear) or an NHWC activation read through
+// `taps0` (1 or 9) shifted TMA boxes with zero fill at the borders (3x3 pad-1 convolution as implicit GEMM);
+// segments 1,2 are extra 1-tap sources appended along K (fused 1x1 shortcut over a skip-concat).
+struct ASource {
+  const __half* ptr = nullptr;  // [rows, ld] fp16, `C` channels used
+  int C = 0;
+  int ld = 0;
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap map_a[3];
+  CUtensorMap map_b;
+  int taps0, chunks0, chunks1, chunks2;
+  int num_kb;
+  int linear;
+  int W, HW;
+  int M, N;
+  int m_tiles, n_tiles;
+  const float* bias;        // [N] (packed order) or null
+  const float* temb_table;  // per-timestep additive vector table or null
+  const int* t_index;       // device pointer to the current row of temb_table
+  int temb_stride;          // floats between rows of temb_table
+  const __half* residual;   // [M, ldr] or null
+  int ldr;
+  __half* out;  // [M, ldc]
+  int ldc;
+  int geglu;  // epilogue: out[:, j] = (v_j) * gelu(g_j), tile columns [0,BN/2) = v, [BN/2,BN) = g
+  volatile unsigned int* dbg;
+};
+
+struct GemmPlan {
+  GemmParams p;
+  int bn = 0;
+  int grid = 0;
+  size_t smem = 0;
+};
+
+struct GemmEpilogue {
+  const float* bias = nullptr;
+  const float* temb_table = nullptr;
+  const int* t_index = nullptr;
+  int temb_stride = 0;
+  const __half* residual = nullptr;
+  int ldr = 0;
+  __half* out = nullptr;
+  int ldc = 0;
+  bool geglu = false;
+};
+
+// conv-mode: srcs[0] is NHWC [B,H,W,C0] with `taps0`=9 (3x3, pad 1) or 1; linear mode: B=H=1, W=M.
+int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, bool linear, int B, int H, int W,
+                     const __half* Wt, int N, int Ktot, const GemmEpilogue& ep, int bn_force, int num_sms);
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+int gemm_choose_bn(int M, int N, bool geglu, int num_sms);
+
+// ------------------------------------------------------------------ normalisation kernels (norm.cu)
+// GroupNorm(32 groups) [+SiLU] over NHWC fp16; optional second source = channel concat (skip connection).
+int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, int HW, const float* gamma,
+                     const float* beta, float eps, bool silu, __half* out, float* partials, cudaStream_t s);
+size_t groupnorm_partials_floats(int B, int HW);
+int layernorm_launch(const __half* x, int rows, int C, const float* gamma, const float* beta, float eps, __half* out,
+                     cudaStream_t s);
+int upsample2x_launch(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t s);
+int im2col_s2_launch(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t s);
+int conv_in_launch(const float* x_nchw, int B, int H, int W, const float* w, const float* bias, __half* out,
+                   cudaStream_t s);
+int conv_out_launch(const __half* x, int B, int H, int W, int C, const float* w, const float* bias, float* out_nchw,
+                    cudaStream_t s);
+int concat_launch(const __half* x0, int C0, const __half* x1, int C1, int rows, __half* out, cudaStream_t s);
+
+}  // namespace pnp

@@ -1,0 +1,143 @@
+"""Attention kernels vs the materialised-softmax algebra of the reference (attention_control.py:20-47,269-282;
+masactrl.py:41-72), evaluated in fp32 with PyTorch on the same fp16 inputs."""
+import ctypes as C
+
+import pytest
+import torch
+
+from pnpinversion_b200 import _lib
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+H = 8
+
+
+def _mk(shape, dev, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.float16).to(dev)
+
+
+def _heads(t, d):  # (B,N,H*d) -> (B,H,N,d)
+    B, N, _ = t.shape
+    return t.reshape(B, N, H, d).permute(0, 2, 1, 3).float()
+
+
+def _self_ref(qkv, d, q_row, k_row, v_row):
+    c = H * d
+    q, k, v = _heads(qkv[..., :c], d), _heads(qkv[..., c:2 * c], d), _heads(qkv[..., 2 * c:], d)
+    q, k, v = q[q_row], k[k_row], v[v_row]
+    p = (q @ k.transpose(-1, -2) * d ** -0.5).softmax(-1)
+    o = p @ v
+    return o.permute(0, 2, 1, 3).reshape(qkv.shape[0], qkv.shape[1], c)
+
+
+@pytest.mark.parametrize("d,N", [(40, 4096), (80, 1024), (160, 256), (160, 64), (40, 64)])
+def test_self_attention_plain(cuda, d, N):
+    lib = _lib.load()
+    B = 2
+    qkv = _mk((B, N, 3 * H * d), cuda, d + N, 1.0)
+    qkv[..., :2 * H * d] *= 1.5  # logits std ~ 2-3
+    out = torch.empty(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention(G.ptr(qkv), B, H, N, d, None, None, None, G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    ident = list(range(B))
+    ref = _self_ref(qkv, d, ident, ident, ident)
+    assert G.rel_l2(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("mode", ["p2p_self_replace", "masactrl"])
+def test_self_attention_row_indirection(cuda, mode):
+    lib = _lib.load()
+    B, N, d = 4, 1024, 80
+    qkv = _mk((B, N, 3 * H * d), cuda, 7, 1.2)
+    ident = list(range(B))
+    if mode == "p2p_self_replace":  # cond target (row 3) uses the cond source's (row 2) Q and K, own V
+        q_row, k_row, v_row = [0, 1, 2, 2], [0, 1, 2, 2], ident
+    else:  # both rows of each CFG half attend to the source image's K,V
+        q_row, k_row, v_row = ident, [0, 0, 2, 2], [0, 0, 2, 2]
+    dq, dk, dv = (torch.tensor(r, dtype=torch.int32, device=cuda) for r in (q_row, k_row, v_row))
+    out = torch.empty(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention(G.ptr(qkv), B, H, N, d, G.ptr(dq), G.ptr(dk), G.ptr(dv), G.ptr(out),
+                                           G.stream()))
+    torch.cuda.synchronize()
+    ref = _self_ref(qkv, d, q_row, k_row, v_row)
+    assert G.rel_l2(out, ref) < 2e-3
+    # known-answer invariant: rows whose indirection is the identity are untouched
+    plain = torch.empty_like(out)
+    _lib.check(lib.pnp_test_self_attention(G.ptr(qkv), B, H, N, d, None, None, None, G.ptr(plain), G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], plain[0]) and torch.equal(out[2], plain[2])
+
+
+def _cross_ref(q, kv, d, ctrl=None):
+    """attention_control.py:34-45 + :269-282 (Refine :319-323, Reweight :340-345) on materialised probabilities."""
+    c = H * d
+    qh, kh, vh = _heads(q, d), _heads(kv[..., :c], d), _heads(kv[..., c:], d)
+    p = (qh @ kh.transpose(-1, -2) * d ** -0.5).softmax(-1)  # (B,H,N,77)
+    store = {}
+    if ctrl is not None:
+        p = p.clone()
+        for r, (base, mapper, alphas, eq, ca) in ctrl["edit"].items():
+            src = p[base][:, :, mapper]
+            refine = src * alphas + p[r] * (1 - alphas)
+            rew = refine * eq
+            p[r] = rew * ca + (1 - ca) * p[r]
+        for r, slot in ctrl.get("store", {}).items():
+            store[slot] = p[r].clone()
+    o = p @ vh
+    return o.permute(0, 2, 1, 3).reshape(q.shape[0], q.shape[1], c), store
+
+
+@pytest.mark.parametrize("d,N", [(40, 4096), (80, 1024), (160, 256), (160, 64)])
+def test_cross_attention_plain(cuda, d, N):
+    lib = _lib.load()
+    B = 2
+    q = _mk((B, N, H * d), cuda, 11, 1.5)
+    kv = _mk((B, 77, 2 * H * d), cuda, 12, 1.5)
+    out = torch.empty(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_cross_attention(G.ptr(q), G.ptr(kv), B, H, N, d, 77, None, None, G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    ref, _ = _cross_ref(q, kv, d)
+    assert G.rel_l2(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("d,N", [(160, 256), (80, 1024)])
+def test_cross_attention_p2p_injection_and_store(cuda, d, N):
+    lib = _lib.load()
+    B = 4
+    q = _mk((B, N, H * d), cuda, 13, 1.5)
+    kv = _mk((B, 77, 2 * H * d), cuda, 14, 1.5)
+    g = torch.Generator().manual_seed(5)
+    mapper = torch.arange(77)
+    mapper[3:40] = torch.arange(2, 39)  # an "inserted word" shift like get_refinement_mapper produces
+    mapper[2] = -1
+    alphas = torch.ones(77)
+    alphas[2] = 0.0
+    eq = torch.ones(77)
+    eq[5] = 2.0
+    ca = (torch.rand(77, generator=g) > 0.3).float()
+    ctrl = _lib.new_ctrl()
+    ctrl.cross_base_row[3] = 2
+    ctrl.cross_slot[3] = 0
+    for i in range(77):
+        ctrl.mapper[0][i] = int(mapper[i])
+        ctrl.alphas[0][i] = float(alphas[i])
+        ctrl.equalizer[0][i] = float(eq[i])
+        ctrl.cross_alpha[0][i] = float(ca[i])
+    ctrl.store_slot[2] = 0
+    ctrl.store_slot[3] = 1
+    store = torch.zeros(2, H, N, 77, device=cuda)
+    out = torch.empty(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_cross_attention(G.ptr(q), G.ptr(kv), B, H, N, d, 77, C.byref(ctrl), G.ptr(store),
+                                            G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    dev = lambda t: t.to(cuda)
+    ref, rstore = _cross_ref(q, kv, d, {"edit": {3: (2, dev(mapper), dev(alphas), dev(eq), dev(ca))},
+                                        "store": {2: 0, 3: 1}})
+    assert G.rel_l2(out, ref) < 2e-3
+    assert G.rel_l2(store[0], rstore[0]) < 1e-4 and G.rel_l2(store[1], rstore[1]) < 1e-4
+    # rows without a controller entry are bit-identical to the plain kernel
+    plain = torch.empty_like(out)
+    _lib.check(lib.pnp_test_cross_attention(G.ptr(q), G.ptr(kv), B, H, N, d, 77, None, None, G.ptr(plain), G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out[:3], plain[:3])

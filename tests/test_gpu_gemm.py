@@ -1,0 +1,99 @@
+"""tcgen05 GEMM / implicit-GEMM conv parity against a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, dev, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.float16).to(dev)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 160, 256])
+@pytest.mark.parametrize("M,K", [(128, 64), (256, 320), (308, 768), (1024, 1280)])
+def test_linear_plain(cuda, bn, M, K):
+    N = {64: 192, 128: 384, 160: 320, 256: 512}[bn]
+    a = _mk((M, K), cuda, 1)
+    w = _mk((N, K), cuda, 2, K ** -0.5)
+    out = G.gemm(a, w, bn=bn)
+    ref = a.float() @ w.float().t()
+    assert G.rel_l2(out, ref) < 1e-3, (bn, M, K)
+
+
+def test_linear_many_tiles_bias_residual(cuda):
+    M, K, N = 16384, 320, 960
+    a = _mk((M, K), cuda, 3)
+    w = _mk((N, K), cuda, 4, K ** -0.5)
+    bias = torch.randn(N, device=cuda)
+    res = _mk((M, N), cuda, 5)
+    out = G.gemm(a, w, bias=bias, residual=res)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    assert G.rel_l2(out, ref) < 1e-3
+
+
+def test_linear_strided_a(cuda):
+    M, K, N = 512, 320, 320
+    big = _mk((M, 3 * K), cuda, 6)
+    a = big[:, K:2 * K]
+    w = _mk((N, K), cuda, 7, K ** -0.5)
+    out = G.gemm(a, w)
+    ref = a.float() @ w.float().t()
+    assert G.rel_l2(out, ref) < 1e-3
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_geglu(cuda, bn):
+    M, K, C4 = 384, 320, 1280
+    a = _mk((M, K), cuda, 8)
+    w = _mk((2 * C4, K), cuda, 9, K ** -0.5)
+    bias = torch.randn(2 * C4, device=cuda) * 0.1
+    # interleave like pnp_finalize_params: per tile of bn packed rows: bn/2 value rows then bn/2 gate rows
+    hb = bn // 2
+    idx = []
+    for t in range(2 * C4 // bn):
+        idx += list(range(t * hb, (t + 1) * hb)) + list(range(C4 + t * hb, C4 + (t + 1) * hb))
+    idx = torch.tensor(idx, device=cuda)
+    out = G.gemm(a, w[idx].contiguous(), bias=bias[idx].contiguous(), geglu=True, bn=bn)
+    y = a.float() @ w.float().t() + bias
+    ref = y[:, :C4] * F.gelu(y[:, C4:])
+    assert G.rel_l2(out, ref) < 1e-3
+
+
+@pytest.mark.parametrize("B,H,C,N", [(1, 64, 64, 64), (2, 32, 128, 128), (2, 16, 320, 160), (1, 8, 64, 64),
+                                      (3, 8, 128, 256), (4, 8, 64, 64), (1, 64, 320, 320)])
+def test_conv3x3(cuda, B, H, C, N):
+    x = _mk((B, H, H, C), cuda, 10)
+    w = _mk((N, C, 3, 3), cuda, 11, (9 * C) ** -0.5)
+    bias = torch.randn(N, device=cuda) * 0.1
+    out = G.conv3x3(x, G.pack_conv3(w), bias=bias)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert G.rel_l2(out, ref) < 1e-3
+
+
+def test_conv3x3_residual(cuda):
+    B, H, C = 2, 16, 128
+    x = _mk((B, H, H, C), cuda, 12)
+    r = _mk((B, H, H, C), cuda, 13)
+    w = _mk((C, C, 3, 3), cuda, 14, (9 * C) ** -0.5)
+    out = G.conv3x3(x, G.pack_conv3(w), residual=r)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), None, padding=1).permute(0, 2, 3, 1) + r.float()
+    assert G.rel_l2(out, ref) < 1e-3
+
+
+def test_conv3x3_fused_shortcut_over_concat(cuda):
+    """conv2 of a ResnetBlock2D whose input was a skip-concat: 3x3 conv on h plus 1x1 shortcut on cat([a, b])."""
+    B, H, C, Ca, Cb = 2, 16, 128, 128, 64
+    hmid = _mk((B, H, H, C), cuda, 15)
+    a = _mk((B, H, H, Ca), cuda, 16)
+    b = _mk((B, H, H, Cb), cuda, 17)
+    w = _mk((C, C, 3, 3), cuda, 18, (9 * C) ** -0.5)
+    ws = _mk((C, Ca + Cb, 1, 1), cuda, 19, (Ca + Cb) ** -0.5)
+    bias = torch.randn(C, device=cuda) * 0.1
+    out = G.conv3x3(hmid, G.pack_conv3(w, ws), bias=bias, sc0=a, sc1=b)
+    cat = torch.cat([a, b], dim=-1).permute(0, 3, 1, 2).float()
+    ref = (F.conv2d(hmid.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1) + F.conv2d(cat, ws.float()))
+    assert G.rel_l2(out, ref.permute(0, 2, 3, 1)) < 1e-3
