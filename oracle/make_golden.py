@@ -1,0 +1,191 @@
+"""TEST INFRASTRUCTURE ONLY -- generates the committed fixtures under tests/golden/ by running the UNMODIFIED reference
+(`/root/reference`, through oracle/ref_shim.py) on the seeded synthetic inputs of pnpinversion_b200/synth.py.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python -m oracle.make_golden tables        # integer/0-1 host tables  (seconds)
+    python -m oracle.make_golden unet          # single UNet forwards, fp64 vendored UNet (minutes)
+    python -m oracle.make_golden pipeline 3    # directinversion+p2p, 3 DDIM steps, full-size UNet (~10 min)
+
+What runs is the reference's own `DirectInversion.invert`, `direct_inversion_p2p_guidance_forward`,
+`AttentionStore / AttentionRefine / AttentionReweight / LocalBlend`, `register_attention_control`,
+`seq_aligner`, `utils.get_word_inds / get_time_words_attention_alpha` against the reference's vendored
+`UNet2DConditionModel` + `DDIMScheduler` (diffusers 0.3.0, fp64) loaded with the synthetic fp16-rounded weights.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+
+from oracle import ref_shim
+from pnpinversion_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+PROMPT_PAIRS = [
+    list(synth.CAT_PROMPTS),
+    ["a cat sitting on a table with a green eyes", "a dog sitting on a table with a green eyes"],
+    ["a photo of a house on a hill", "a photo of a red house on a snowy hill at night"],
+    ["a round cake with orange frosting on a wooden plate", "a square cake with orange frosting on a wooden plate"],
+    ["two birds on a branch", "two colorful birds on a branch"],
+    ["a man riding a horse", "a man riding a horse"],
+    ["the quick brown fox jumps over the lazy dog", "the quick red fox leaps over the sleepy dog quickly"],
+]
+BLEND = [("cat", "cat"), ("cat", "dog"), ("house", "house"), ("cake", "cake"), ("birds", "birds"), ("horse", "horse"),
+         ("fox", "fox")]
+EQ_WORD = ["watercolor", "dog", "red", "square", "colorful", "horse", "red"]
+
+
+def build_model(dtype=torch.float64):
+    md = ref_shim.load_my_diffusers()
+    unet = md.UNet2DConditionModel(sample_size=64, cross_attention_dim=768)
+    sd = synth.synth_unet_state_dict(0)
+    unet.load_state_dict({k: v.to(dtype) for k, v in sd.items()})
+    unet = unet.to(dtype).eval()
+    sched = md.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                             set_alpha_to_one=False)
+
+    class _Vae:  # image2latent passes 4-D tensors through (utils/utils.py:73-74); decode only feeds the unused image_rec
+        def decode(self, z):
+            return {"sample": torch.zeros(z.shape[0], 3, 8, 8, dtype=z.dtype)}
+
+    model = types.SimpleNamespace(unet=unet, scheduler=sched, vae=_Vae(), tokenizer=synth.FakeTokenizer(),
+                                  text_encoder=synth.SynthTextEncoder(dtype=dtype), device=torch.device("cpu"))
+    return model
+
+
+def make_controller_cpu(ref, model, prompts, num_steps, cross=0.4, self_=0.6, blend_word=None, eq_params=None):
+    """make_controller (attention_control.py:366-405) with device='cpu' (it hard-codes 'cuda')."""
+    ac = ref.attention_control
+    tok = model.tokenizer
+    lb = None
+    if blend_word is not None:
+        lb = ac.LocalBlend(prompts, blend_word, tokenizer=tok, device="cpu", num_ddim_steps=num_steps)
+    ctrl = ac.AttentionRefine(prompts, num_steps, cross_replace_steps={"default_": cross}, self_replace_steps=self_,
+                              local_blend=lb, tokenizer=tok, device="cpu")
+    if eq_params is not None:
+        eq = ac.get_equalizer(prompts[1], eq_params["words"], eq_params["values"], tokenizer=tok)
+        ctrl = ac.AttentionReweight(prompts, num_steps, cross_replace_steps={"default_": cross},
+                                    self_replace_steps=self_, equalizer=eq, local_blend=lb, controller=ctrl,
+                                    device="cpu")
+    return ctrl
+
+
+def gen_tables():
+    ref = ref_shim.load_reference_p2p()
+    tok = synth.FakeTokenizer()
+    out = []
+    for (src, tgt), (bs, bt), eqw in zip(PROMPT_PAIRS, BLEND, EQ_WORD):
+        prompts = [src, tgt]
+        mapper, alphas = ref.seq_aligner.get_refinement_mapper(prompts, tok)
+        entry = {"prompts": prompts, "mapper": mapper[0].tolist(), "alphas": alphas[0].tolist()}
+        for n in (50, 20, 3):
+            a = ref.utils.get_time_words_attention_alpha(prompts, n, {"default_": 0.4}, tok)
+            entry[f"cross_alpha_{n}"] = a.reshape(n + 1, 77)[:, 0].tolist()
+        entry["inds_src"] = ref.utils.get_word_inds(src, bs, tok).tolist()
+        entry["inds_tgt"] = ref.utils.get_word_inds(tgt, bt, tok).tolist()
+        entry["blend"] = [bs, bt]
+        entry["eq_word"] = eqw
+        entry["equalizer"] = ref.attention_control.get_equalizer(tgt, (eqw,), (2,), tok)[0].tolist()
+        if len(src.split(" ")) == len(tgt.split(" ")):
+            entry["replace_mapper"] = ref.seq_aligner.get_replacement_mapper(prompts, tok)[0].tolist()
+        out.append(entry)
+    # schedule tables of the vendored scheduler (float64) for 50 / 20 / 3 steps
+    md = ref_shim.load_my_diffusers()
+    sched = md.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                             set_alpha_to_one=False)
+    sch = {"alphas_cumprod_f64_first_last": [float(sched.alphas_cumprod[0]), float(sched.alphas_cumprod[-1])],
+           "alphas_cumprod_f64_every_100": [float(sched.alphas_cumprod[i]) for i in range(0, 1000, 100)],
+           "final_alpha_cumprod": float(sched.final_alpha_cumprod)}
+    for n in (50, 20, 3):
+        sched.set_timesteps(n)
+        sch[f"timesteps_{n}"] = [int(t) for t in sched.timesteps]
+    with open(os.path.join(GOLD, "tables.json"), "w") as f:
+        json.dump({"pairs": out, "schedule": sch}, f)
+    print("tables.json written:", len(out), "pairs")
+
+
+def _ctx(model, prompts):
+    tok, te = model.tokenizer, model.text_encoder
+    un = te(tok([""] * len(prompts)).input_ids)[0]
+    tx = te(tok(prompts).input_ids)[0]
+    return torch.cat([un, tx])
+
+
+def gen_unet():
+    ref = ref_shim.load_reference_p2p()
+    model = build_model()
+    prompts = list(synth.CAT_PROMPTS)
+    ctx = _ctx(model, prompts)  # [uncond, uncond, src, tgt]
+    res = {}
+    with torch.no_grad():
+        # (a) B=1, no controller, the ddim_loop call shape (inversion.py:272-274,315-316)
+        ref.attention_control.register_attention_control(model, None)
+        x = synth.synth_latent(0).double()
+        t0 = time.time()
+        res["a_eps"] = model.unet(x, torch.tensor(981), encoder_hidden_states=ctx[2:3])["sample"].float().numpy()
+        print("case a", time.time() - t0)
+        # (b) B=4, Refine+Reweight+LocalBlend controller at step 0 (cross gate 1, self-replace on)
+        lat = torch.cat([synth.synth_latent(0), synth.synth_latent(1)]).double()
+        for name, step in (("b", 0), ("c", 35)):
+            ctrl = make_controller_cpu(ref, model, prompts, 50, blend_word=(("cat",), ("cat",)),
+                                       eq_params={"words": ("watercolor",), "values": (2,)})
+            ctrl.cur_step = step
+            ref.attention_control.register_attention_control(model, ctrl)
+            t0 = time.time()
+            eps = model.unet(torch.cat([lat] * 2), torch.tensor(601), encoder_hidden_states=ctx)["sample"]
+            print("case", name, time.time() - t0, "cur_step after", ctrl.cur_step)
+            res[f"{name}_eps"] = eps.float().numpy()
+            # what LocalBlend would read after this single step: the five 16x16 maps, reduced like get_mask does
+            maps = ctrl.attention_store["down_cross"][2:4] + ctrl.attention_store["up_cross"][:3]
+            maps = torch.cat([m.reshape(2, -1, 1, 16, 16, 77) for m in maps], dim=1)
+            res[f"{name}_maps_mean"] = maps.mean(1).reshape(2, 16, 16, 77).float().numpy()  # (2,16,16,77)
+    np.savez_compressed(os.path.join(GOLD, "unet_forward.npz"), **res)
+    print("unet_forward.npz written")
+
+
+def gen_pipeline(n_steps: int):
+    ref = ref_shim.load_reference_p2p()
+    model = build_model()
+    prompts = list(synth.CAT_PROMPTS)
+    z0 = synth.synth_latent(0).double()
+    t0 = time.time()
+    inv = ref.inversion.DirectInversion(model=model, num_ddim_steps=n_steps)
+    model.scheduler.set_timesteps(n_steps)
+    _, _, x_stars, noise_loss = inv.invert(image_gt=z0, prompt=prompts, guidance_scale=7.5)
+    print("invert done", time.time() - t0)
+    x_t = x_stars[-1]
+    ctrl = ref.attention_control.AttentionStore()
+    recon, _ = ref.p2p_guidance_forward.direct_inversion_p2p_guidance_forward(
+        model=model, prompt=prompts, controller=ctrl, noise_loss_list=noise_loss, latent=x_t,
+        num_inference_steps=n_steps, guidance_scale=7.5, generator=None)
+    print("recon done", time.time() - t0)
+    ctrl = make_controller_cpu(ref, model, prompts, n_steps, blend_word=(("cat",), ("cat",)),
+                               eq_params={"words": ("watercolor",), "values": (2,)})
+    edit, _ = ref.p2p_guidance_forward.direct_inversion_p2p_guidance_forward(
+        model=model, prompt=prompts, controller=ctrl, noise_loss_list=noise_loss, latent=x_t,
+        num_inference_steps=n_steps, guidance_scale=7.5, generator=None)
+    print("edit done", time.time() - t0)
+    np.savez_compressed(
+        os.path.join(GOLD, f"pipeline_{n_steps}steps.npz"),
+        x_stars=torch.cat(x_stars).float().numpy(), noise_loss=torch.stack(noise_loss).float().numpy(),
+        recon=recon.float().numpy(), edit=edit.float().numpy())
+    print("pipeline fixture written")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_grad_enabled(False)
+    what = sys.argv[1]
+    if what == "tables":
+        gen_tables()
+    elif what == "unet":
+        gen_unet()
+    elif what == "pipeline":
+        gen_pipeline(int(sys.argv[2]))
