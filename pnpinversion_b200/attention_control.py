@@ -1,0 +1,299 @@
+"""Seam C of the reference: Prompt-to-Prompt attention controllers (`models/p2p/attention_control.py`).
+
+The reference invokes `controller(attn, is_cross, place_in_unet)` inside each of the 32 attention layers on a
+*materialised* probability tensor.  Here the same classes (same names, constructor arguments, counters, windows) hold
+the host-side tables and lower themselves, once per UNet call, into a `pnp_attn_ctrl` descriptor that selects the
+kernel modes of csrc/attention.cu.  There is no Python-callback path: unknown controller subclasses are rejected.
+
+Deliberate, disclosed difference: `AttentionStore` keeps only what the hot path consumes -- the five 16x16 cross
+maps `down_cross[2:4] + up_cross[:3]` LocalBlend reads (attention_control.py:112) -- not every <=32^2 map.
+"""
+from __future__ import annotations
+
+import abc
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib, seq_aligner
+from .ptp_utils import get_time_words_attention_alpha, get_word_inds
+
+MAX_NUM_WORDS = 77
+LATENT_SIZE = (64, 64)
+NUM_ATT_LAYERS = 32
+_SELF_REPLACE_MAX_TOKENS = 32 ** 2  # attention_control.py:259
+
+
+def register_attention_control(model, controller):
+    """Replaces the monkey-patching of attention_control.py:12-81: binds the controller to the fused UNet."""
+    model.unet.set_controller(controller)
+    if controller is not None:
+        controller.num_att_layers = NUM_ATT_LAYERS
+        if hasattr(controller, "_bind"):
+            controller._bind(model.unet.handle)
+
+
+def get_equalizer(text, word_select, values, tokenizer=None):
+    if isinstance(word_select, (int, str)):
+        word_select = (word_select,)
+    equalizer = torch.ones(1, MAX_NUM_WORDS)
+    for word, val in zip(word_select, values):
+        inds = get_word_inds(text, word, tokenizer)
+        equalizer[:, inds] = val
+    return equalizer
+
+
+class LocalBlend:
+    """attention_control.py:95-147.  Works on the maps accumulated by the cross-attention kernel (store slots 0,1)."""
+
+    def __init__(self, prompts, words, substruct_words=None, start_blend=0.2, th=(.3, .3), tokenizer=None, device="cuda",
+                 num_ddim_steps=50):
+        if len(prompts) != 2:
+            raise NotImplementedError("LocalBlend is implemented for one (source, target) prompt pair")
+        if substruct_words is not None:
+            raise NotImplementedError("substruct_words is not used on the PnP-inversion path")
+        alpha_layers = torch.zeros(len(prompts), MAX_NUM_WORDS)
+        for i, (prompt, words_) in enumerate(zip(prompts, words)):
+            if isinstance(words_, str):
+                words_ = [words_]
+            for word in words_:
+                alpha_layers[i, get_word_inds(prompt, word, tokenizer)] = 1
+        self.alpha_layers = alpha_layers
+        self.start_blend = int(start_blend * num_ddim_steps)
+        self.counter = 0
+        self.th = th
+        self._engine = None
+        self.last_mask = None
+
+    def __call__(self, x_t, attention_store=None):
+        self.counter += 1
+        if self.counter > self.start_blend:
+            if self._engine is None:
+                raise _lib.PnpError("LocalBlend is not bound to an engine (register_attention_control first)")
+            if not (x_t.is_cuda and x_t.dtype == torch.float32 and x_t.shape[0] == 2):
+                raise _lib.PnpError("LocalBlend expects CUDA float32 latents of shape (2,4,64,64)")
+            x_t = x_t.contiguous()
+            nwords = (C.c_int32 * 2)()
+            words = (C.c_int32 * 16)()
+            alpha = (C.c_float * 16)()
+            for p in range(2):
+                nz = torch.nonzero(self.alpha_layers[p]).flatten().tolist()
+                if len(nz) > 8:
+                    raise NotImplementedError("at most 8 blend tokens per prompt")
+                nwords[p] = len(nz)
+                for j, w in enumerate(nz):
+                    words[p * 8 + j] = w
+                    alpha[p * 8 + j] = float(self.alpha_layers[p, w])
+            _lib.check(_lib.load().pnp_local_blend(self._engine, C.c_void_p(x_t.data_ptr()), nwords, words, alpha,
+                                                   float(self.th[0]), None, _lib.current_stream_ptr()))
+        return x_t
+
+
+class EmptyControl:
+    def step_callback(self, x_t):
+        return x_t
+
+    def between_steps(self):
+        return
+
+    def descriptor(self, batch):
+        return None
+
+    def after_unet_call(self):
+        return
+
+
+class AttentionControl(abc.ABC):
+    def __init__(self):
+        self.cur_step = 0
+        self.num_att_layers = -1
+        self.cur_att_layer = 0
+        self._engine = None
+
+    def _bind(self, engine):
+        self._engine = engine
+        if self.cur_step == 0:
+            _lib.check(_lib.load().pnp_store_reset(engine, _lib.current_stream_ptr()))
+
+    def step_callback(self, x_t):
+        return x_t
+
+    def between_steps(self):
+        return
+
+    def reset(self):
+        self.cur_step = 0
+        self.cur_att_layer = 0
+
+    # one UNet call == 32 invocations of the reference's __call__ (attention_control.py:178-190)
+    def after_unet_call(self):
+        self.cur_att_layer = 0
+        self.cur_step += 1
+        self.between_steps()
+
+    @abc.abstractmethod
+    def descriptor(self, batch) -> Optional[_lib.AttnCtrl]:
+        raise NotImplementedError
+
+    def __call__(self, attn, is_cross, place_in_unet):
+        raise _lib.PnpError("controllers are compiled into kernel modes; there is no materialised-attention callback")
+
+
+class AttentionStore(AttentionControl):
+    """attention_control.py:214-248 (only the maps LocalBlend consumes are accumulated, on the device)."""
+
+    def __init__(self):
+        super().__init__()
+        self._want_store = False
+
+    def descriptor(self, batch):
+        if not self._want_store:
+            return None
+        c = _lib.new_ctrl()
+        n = batch // 2
+        c.store_slot[n] = 0
+        if n > 1:
+            c.store_slot[n + 1] = 1
+        return c
+
+    def get_average_attention(self):
+        raise NotImplementedError("only the five 16x16 cross maps LocalBlend reads are kept (see DESIGN.md)")
+
+    def reset(self):
+        super().reset()
+        if self._engine is not None:
+            _lib.check(_lib.load().pnp_store_reset(self._engine, _lib.current_stream_ptr()))
+
+
+class AttentionControlEdit(AttentionStore, abc.ABC):
+    def __init__(self, prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend, tokenizer=None,
+                 device="cuda"):
+        super().__init__()
+        self.batch_size = len(prompts)
+        if not 2 <= self.batch_size <= 1 + _lib.PNP_MAX_SLOTS:
+            raise ValueError("need one source prompt and 1..8 target prompts")
+        self.cross_replace_alpha = get_time_words_attention_alpha(prompts, num_steps, cross_replace_steps, tokenizer)
+        if isinstance(self_replace_steps, float):
+            self_replace_steps = 0, self_replace_steps
+        self.num_self_replace = int(num_steps * self_replace_steps[0]), int(num_steps * self_replace_steps[1])
+        self.local_blend = local_blend
+        self._want_store = local_blend is not None
+
+    def _bind(self, engine):
+        super()._bind(engine)
+        if self.local_blend is not None:
+            self.local_blend._engine = engine
+
+    def step_callback(self, x_t):
+        if self.local_blend is not None:
+            x_t = self.local_blend(x_t, None)
+        return x_t
+
+    # subclasses fill mapper / alphas / equalizer of one target slot
+    @abc.abstractmethod
+    def _fill_tables(self, c: _lib.AttnCtrl, slot: int):
+        raise NotImplementedError
+
+    def descriptor(self, batch):
+        n = self.batch_size
+        if batch != 2 * n:
+            raise _lib.PnpError(f"controller built for {n} prompts expects a UNet batch of {2 * n}, got {batch}")
+        c = _lib.new_ctrl()
+        src = n  # first cond row; the controller only touches attn[h//2:] (attention_control.py:184)
+        gate = self.cross_replace_alpha[self.cur_step]  # (n-1,1,1,77)
+        self_on = self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1]
+        if self_on:
+            c.self_layer_lo, c.self_layer_hi, c.self_max_tokens = 0, 16, _SELF_REPLACE_MAX_TOKENS
+        for i in range(1, n):
+            r, slot = n + i, i - 1
+            c.cross_base_row[r] = src
+            c.cross_slot[r] = slot
+            self._fill_tables(c, slot)
+            g = gate[slot].reshape(-1)
+            for w in range(MAX_NUM_WORDS):
+                c.cross_alpha[slot][w] = float(g[w])
+            if self_on:
+                c.self_q_row[r] = src
+                c.self_k_row[r] = src
+        if self._want_store:
+            c.store_slot[n] = 0
+            c.store_slot[n + 1] = 1
+        return c
+
+
+def _set_row(arr, values):
+    for w in range(MAX_NUM_WORDS):
+        arr[w] = values[w]
+
+
+class AttentionReplace(AttentionControlEdit):
+    """attention_control.py:301-314: P_src @ mapper.  Lowered to a gather when every target token takes its
+    probability from exactly one source token (the word-swap case); fractional splits are not implemented."""
+
+    def __init__(self, prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend=None, tokenizer=None,
+                 device="cuda"):
+        super().__init__(prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend, tokenizer, device)
+        self.mapper = seq_aligner.get_replacement_mapper(prompts, tokenizer)  # (n-1,77,77)
+        self._gather = []
+        for m in self.mapper:
+            cols_ok = ((m == 0) | (m == 1)).all() and (m.sum(0) == 1).all()
+            if not bool(cols_ok):
+                raise NotImplementedError("AttentionReplace with fractional token splits is not implemented")
+            self._gather.append(m.argmax(0).tolist())
+
+    def _fill_tables(self, c, slot):
+        _set_row(c.mapper[slot], self._gather[slot])
+        _set_row(c.alphas[slot], [1.0] * MAX_NUM_WORDS)
+        _set_row(c.equalizer[slot], [1.0] * MAX_NUM_WORDS)
+
+
+class AttentionRefine(AttentionControlEdit):
+    """attention_control.py:317-335."""
+
+    def __init__(self, prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend=None, tokenizer=None,
+                 device="cuda"):
+        super().__init__(prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend, tokenizer, device)
+        self.mapper, alphas = seq_aligner.get_refinement_mapper(prompts, tokenizer)
+        self.alphas = alphas.reshape(alphas.shape[0], 1, 1, alphas.shape[1])
+
+    def _fill_tables(self, c, slot):
+        _set_row(c.mapper[slot], self.mapper[slot].tolist())
+        _set_row(c.alphas[slot], self.alphas[slot].reshape(-1).tolist())
+        _set_row(c.equalizer[slot], [1.0] * MAX_NUM_WORDS)
+
+
+class AttentionReweight(AttentionControlEdit):
+    """attention_control.py:338-363: scales the (optionally refined/replaced) source probabilities per token."""
+
+    def __init__(self, prompts, num_steps, cross_replace_steps, self_replace_steps, equalizer, local_blend=None,
+                 controller=None, device="cuda", tokenizer=None):
+        super().__init__(prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend, tokenizer, device)
+        self.equalizer = equalizer
+        self.prev_controller = controller
+
+    def _fill_tables(self, c, slot):
+        if self.prev_controller is not None:
+            self.prev_controller._fill_tables(c, slot)
+        else:
+            _set_row(c.mapper[slot], list(range(MAX_NUM_WORDS)))
+            _set_row(c.alphas[slot], [1.0] * MAX_NUM_WORDS)
+        eq = self.equalizer[slot if self.equalizer.shape[0] > 1 else 0].reshape(-1).tolist()
+        _set_row(c.equalizer[slot], eq)
+
+
+def make_controller(pipeline, prompts, is_replace_controller, cross_replace_steps, self_replace_steps, blend_words=None,
+                    equilizer_params=None, num_ddim_steps=50, device="cuda") -> AttentionControlEdit:
+    """attention_control.py:366-405 (same argument names, including the reference's `equilizer_params` spelling)."""
+    tok = pipeline.tokenizer
+    lb = None if blend_words is None else LocalBlend(prompts, blend_words, tokenizer=tok, device=device,
+                                                      num_ddim_steps=num_ddim_steps)
+    cls = AttentionReplace if is_replace_controller else AttentionRefine
+    controller = cls(prompts, num_ddim_steps, cross_replace_steps=cross_replace_steps,
+                     self_replace_steps=self_replace_steps, local_blend=lb, tokenizer=tok)
+    if equilizer_params is not None:
+        eq = get_equalizer(prompts[1], equilizer_params["words"], equilizer_params["values"], tokenizer=tok)
+        controller = AttentionReweight(prompts, num_ddim_steps, cross_replace_steps=cross_replace_steps,
+                                       self_replace_steps=self_replace_steps, equalizer=eq, local_blend=lb,
+                                       controller=controller, tokenizer=tok)
+    return controller

@@ -1,0 +1,83 @@
+"""The guided denoising loops with the source-branch latent rectification -- part 3 of the "3 lines".
+
+Mirror of `models/p2p/p2p_guidance_forward.py` (:103-116 step, :135-173 loop).  Per step: one fused-UNet call
+(B = 2 * prompts, controller compiled into the attention kernels) and one fused epilogue launch that performs
+    noise_pred = uncond + g * (text - uncond)                       (:111)
+    latents    = scheduler.step(noise_pred, t, latents).prev_sample (:112)
+    latents    = cat(latents[:1] + noise_loss[:1], latents[1:])     (:113-114, the rectification)
+followed by `controller.step_callback` (LocalBlend, one more launch when active).
+"""
+from __future__ import annotations
+
+import torch
+
+from .attention_control import register_attention_control
+from .ptp_utils import init_latent
+from .scheduler import fused_step, step_coefficients
+
+
+def _encode(model, prompt):
+    tok, enc, dev = model.tokenizer, model.text_encoder, model.device
+    text_input = tok(prompt, padding="max_length", max_length=tok.model_max_length, truncation=True,
+                     return_tensors="pt")
+    text_embeddings = enc(text_input.input_ids.to(dev))[0]
+    max_length = text_input.input_ids.shape[-1]
+    uncond_input = tok([""] * len(prompt), padding="max_length", max_length=max_length, return_tensors="pt")
+    uncond_embeddings = enc(uncond_input.input_ids.to(dev))[0]
+    return torch.cat([uncond_embeddings, text_embeddings]).to(dev, torch.float32).contiguous()
+
+
+def direct_inversion_p2p_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale, noise_loss,
+                                                 low_resource=False, add_offset=True, add_target=False):
+    if low_resource:
+        raise NotImplementedError("low_resource (two B=n UNet calls) is not on the hot path")
+    n = latents.shape[0]
+    noise_pred = model.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context)["sample"]
+    sched = model.scheduler
+    tt = int(t)
+    co = step_coefficients(sched.alphas_cumprod, sched.final_alpha_cumprod, tt,
+                           tt - sched.config.num_train_timesteps // sched.num_inference_steps)
+    mask = 0
+    if add_offset:
+        mask = (1 << n) - 1 if add_target else 1
+    latents = fused_step(model.unet.handle, latents.contiguous(), noise_pred[n:], co, eps_u=noise_pred[:n],
+                         guidance=guidance_scale, noise_loss=noise_loss.contiguous() if add_offset else None,
+                         add_mask=mask)
+    if controller is not None:
+        latents = controller.step_callback(latents)
+    return latents
+
+
+@torch.no_grad()
+def direct_inversion_p2p_guidance_forward(model, prompt, controller, latent=None, num_inference_steps: int = 50,
+                                          guidance_scale=7.5, generator=None, noise_loss_list=None, add_offset=True):
+    batch_size = len(prompt)
+    register_attention_control(model, controller)
+    height = width = 512
+    context = _encode(model, prompt)
+    latent, latents = init_latent(latent, model, height, width, generator, batch_size)
+    latents = latents.to(torch.float32).contiguous()
+    model.scheduler.set_timesteps(num_inference_steps)
+    for i, t in enumerate(model.scheduler.timesteps):
+        latents = direct_inversion_p2p_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale,
+                                                               noise_loss_list[i], low_resource=False,
+                                                               add_offset=add_offset)
+    return latents, latent
+
+
+@torch.no_grad()
+def direct_inversion_p2p_guidance_forward_add_target(model, prompt, controller, latent=None,
+                                                     num_inference_steps: int = 50, guidance_scale=7.5, generator=None,
+                                                     noise_loss_list=None, add_offset=True):
+    """p2p_guidance_forward.py:119-132,175-213: the ablation that also rectifies the target branch."""
+    batch_size = len(prompt)
+    register_attention_control(model, controller)
+    context = _encode(model, prompt)
+    latent, latents = init_latent(latent, model, 512, 512, generator, batch_size)
+    latents = latents.to(torch.float32).contiguous()
+    model.scheduler.set_timesteps(num_inference_steps)
+    for i, t in enumerate(model.scheduler.timesteps):
+        latents = direct_inversion_p2p_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale,
+                                                               noise_loss_list[i], add_offset=add_offset,
+                                                               add_target=True)
+    return latents, latent

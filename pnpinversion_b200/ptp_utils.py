@@ -1,0 +1,93 @@
+"""Host-side glue mirroring the reference's `utils/utils.py` (init_latent :48-55, latent2image :58-66,
+image2latent :68-80, get_word_inds :84-102, get_time_words_attention_alpha :117-135, load_512 :27-46)."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .seq_aligner import get_word_inds  # noqa: F401  (re-exported, the reference has it in both modules)
+
+
+def load_512(image_path, left=0, right=0, top=0, bottom=0):
+    """Path or HWC uint8 array -> centre-cropped 512x512x3 uint8 (utils/utils.py:27-46)."""
+    from PIL import Image
+
+    if isinstance(image_path, str):
+        image = np.array(Image.open(image_path))[:, :, :3]
+    else:
+        image = image_path
+    h, w, _ = image.shape
+    left = min(left, w - 1)
+    right = min(right, w - left - 1)
+    top = min(top, h - left - 1)
+    bottom = min(bottom, h - top - 1)
+    image = image[top:h - bottom, left:w - right]
+    h, w, _ = image.shape
+    if h < w:
+        off = (w - h) // 2
+        image = image[:, off:off + h]
+    elif w < h:
+        off = (h - w) // 2
+        image = image[off:off + w]
+    return np.array(Image.fromarray(image).resize((512, 512)))
+
+
+def init_latent(latent, model, height, width, generator, batch_size):
+    if latent is None:
+        latent = torch.randn((1, model.unet.in_channels, height // 8, width // 8), generator=generator)
+    latents = latent.expand(batch_size, model.unet.in_channels, height // 8, width // 8).to(model.device)
+    return latent, latents
+
+
+@torch.no_grad()
+def latent2image(model, latents, return_type="np"):
+    latents = 1 / 0.18215 * latents.detach()
+    image = model.decode(latents)["sample"]
+    if return_type == "np":
+        image = (image / 2 + 0.5).clamp(0, 1)
+        image = image.cpu().permute(0, 2, 3, 1).numpy()
+        image = (image * 255).astype(np.uint8)  # truncation like the reference
+    return image
+
+
+@torch.no_grad()
+def image2latent(model, image):
+    if isinstance(image, torch.Tensor) and image.dim() == 4:
+        return image  # already a latent (synthetic-latent path)
+    image = torch.from_numpy(np.asarray(image)).float() / 127.5 - 1
+    image = image.permute(2, 0, 1).unsqueeze(0).to(model.device)
+    return model.encode(image)["latent_dist"].mean * 0.18215
+
+
+def _set_window(alpha, bounds, prompt_ind, word_inds=None):
+    if isinstance(bounds, float):
+        bounds = (0, bounds)
+    start, end = int(bounds[0] * alpha.shape[0]), int(bounds[1] * alpha.shape[0])
+    if word_inds is None:
+        word_inds = torch.arange(alpha.shape[2])
+    alpha[:start, prompt_ind, word_inds] = 0
+    alpha[start:end, prompt_ind, word_inds] = 1
+    alpha[end:, prompt_ind, word_inds] = 0
+    return alpha
+
+
+def get_time_words_attention_alpha(prompts: Sequence[str], num_steps: int,
+                                   cross_replace_steps: Union[float, Dict[str, object]], tokenizer,
+                                   max_num_words: int = 77) -> torch.Tensor:
+    """(num_steps+1, len(prompts)-1, 1, 1, 77) gate table: NB num_steps+1 rows, so the window is int(f*(n+1))."""
+    if not isinstance(cross_replace_steps, dict):
+        cross_replace_steps = {"default_": cross_replace_steps}
+    if "default_" not in cross_replace_steps:
+        cross_replace_steps["default_"] = (0.0, 1.0)
+    table = torch.zeros(num_steps + 1, len(prompts) - 1, max_num_words)
+    for i in range(len(prompts) - 1):
+        table = _set_window(table, cross_replace_steps["default_"], i)
+    for word, bounds in cross_replace_steps.items():
+        if word == "default_":
+            continue
+        for i, ind in enumerate(get_word_inds(prompts[k], word, tokenizer) for k in range(1, len(prompts))):
+            if len(ind) > 0:
+                table = _set_window(table, bounds, i, ind)
+    return table.reshape(num_steps + 1, len(prompts) - 1, 1, 1, max_num_words)
