@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: 512x512, 50-step DDIM-inversion + PnP-rectified P2P edit, images/sec.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (libpnpinv.so, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+A "step" is one whole image: `P2PEditor("directinversion+p2p")` on one synthetic 4x64x64 latent with the cat prompt
+pair, i.e. the faithful 650 UNet sample-forwards (50 x B1 inversion + 3 x 50 x B4) + 200 fused epilogues
+(BASELINE.md section 2).  Weak scaling: every rank edits its own K images (image-parallel);
+NCCL only broadcasts the inputs and gathers the output latents.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+UNET_GFLOP = 803.27          # per sample-forward, SURVEY.md section 8d
+FWD_PER_IMAGE = 650          # faithful directinversion+p2p
+N_B4_CALLS, N_B1_CALLS = 150, 50
+BLEND = (("cat",), ("cat",))
+EQ = {"words": ("watercolor",), "values": (2,)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()  # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_unet_times(state_dict, threads, reps=1):
+    """Times the CPU oracle port (oracle/unet_ref.py, fp32 like the reference's P2P path) on the host cores."""
+    from oracle import unet_ref
+    from pnpinversion_b200 import synth
+
+    torch.set_num_threads(threads)
+    ref = unet_ref.UNetRef(state_dict, dtype=torch.float32)
+    tok, te = synth.FakeTokenizer(), synth.SynthTextEncoder()
+    prompts = list(synth.CAT_PROMPTS)
+    ctx = torch.cat([te(tok([""] * 2).input_ids)[0], te(tok(prompts).input_ids)[0]])
+    lat = torch.cat([synth.synth_latent(0), synth.synth_latent(1)])
+    out = {}
+    with torch.no_grad():
+        for name, x, c in (("b4", torch.cat([lat] * 2), ctx), ("b1", lat[:1], ctx[2:3])):
+            ref(x, 501, c)  # warm-up (page-in, thread pool)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ref(x, 501, c)
+            out[name] = (time.perf_counter() - t0) / reps
+    return out
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the reference's own algorithm on the host CPU (oracle port, there is no compiled reference).
+    Each step = one B=4 and one B=1 UNet forward (a bounded sample of the 150 + 50 calls one image needs); images/sec
+    is the extrapolation 1 / (150 t_b4 + 50 t_b1).  The fused epilogues are negligible on the CPU as well."""
+    if rank != 0:
+        return
+    from pnpinversion_b200 import synth
+
+    threads = os.cpu_count() or 1
+    sd = synth.synth_unet_state_dict(0)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_unet_times(sd, threads)
+    vals = []
+    t_all0 = time.perf_counter()
+    for _ in range(args.steps):
+        t = cpu_unet_times(sd, threads)
+        vals.append(1.0 / (N_B4_CALLS * t["b4"] + N_B1_CALLS * t["b1"]))
+    wall = time.perf_counter() - t_all0
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "images_per_sec_512x512_50step_invert_edit", "value": v, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "directinversion+p2p 50 steps, 1 image (B=4 edit batch), faithful 650 UNet forwards",
+                   "timing": "host wall clock; extrapolated from 1xB4 + 1xB1 UNet forward per step"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": "per step: one B=4 and one B=1 fp32 UNet forward of oracle/unet_ref.py; "
+                                   "x150 / x50 extrapolation to one image"},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: W >= 3
+
+    from pnpinversion_b200 import _lib, synth
+    from pnpinversion_b200.model import FusedModel
+    from pnpinversion_b200.p2p_editor import P2PEditor
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    sd = synth.synth_unet_state_dict(0)
+    model = FusedModel(sd, device=str(dev), max_batch=4, tokenizer=synth.FakeTokenizer(),
+                       text_encoder=synth.SynthTextEncoder())
+    editor = P2PEditor(["directinversion+p2p"], dev, num_ddim_steps=50, model=model)
+    src, tgt = synth.CAT_PROMPTS
+
+    def edit(z):
+        return editor("directinversion+p2p", image_path=z, prompt_src=src, prompt_tar=tgt, guidance_scale=7.5,
+                      cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
+
+    total = args.warmup + args.steps
+    # inputs: rank 0 draws the seeded latents for everybody and broadcasts them (the image-parallel scatter)
+    z_all = torch.empty(world, total, 1, 4, 64, 64, device=dev)
+    if rank == 0:
+        for r in range(world):
+            for i in range(total):
+                z_all[r, i] = synth.synth_latent(r * total + i).to(dev)
+    if dist is not None:
+        dist.broadcast(z_all, src=0)
+    z_dev = z_all[rank]
+
+    # ---------------- warm-up
+    for i in range(args.warmup):
+        edit(z_dev[i])
+    torch.cuda.synchronize()
+    lib = _lib.load()
+    l0 = model.unet.kernel_launches()
+
+    # ---------------- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    outs = []
+    for i in range(args.steps):
+        outs.append(edit(z_dev[args.warmup + i]).latents)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        gathered = [torch.empty_like(torch.stack(outs)) for _ in range(world)]
+        dist.all_gather(gathered, torch.stack(outs))  # the image-parallel gather of the edited latents
+    ms = float(ms.item())
+    launches = model.unet.kernel_launches() - l0
+    value = world * args.steps / (ms / 1000.0)
+
+    # ---------------- timed region 2: end to end through the public API with HOST buffers
+    z_host = [z_dev[args.warmup + i].cpu().pin_memory() for i in range(args.steps)]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    host_results = []
+    for i in range(args.steps):
+        res = edit(z_host[i])                      # H2D of the latent + context embeddings inside
+        host_results.append(res.latents.cpu())     # D2H of the result latents
+    t1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms2 = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / (float(ms2.item()) / 1000.0)
+    ctx_bytes = 4 * 77 * 768 * 4
+    h2d = 4 * 64 * 64 * 4 + 3 * ctx_bytes  # latent + the three context uploads (invert, reconstruct, edit)
+    d2h = 2 * 4 * 64 * 64 * 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (tcgen05 GEMM / implicit conv), CUDA events around every op
+    sustained, burst, hbm, peak_src = peaks()
+    maxops = 1024
+    ms_op = (C.c_float * maxops)()
+    kind = (C.c_int32 * maxops)()
+    fl = (C.c_double * maxops)()
+    n = C.c_int()
+    kinds = {0: "tcgen05_gemm_conv", 1: "groupnorm", 2: "layernorm", 3: "self_attention", 4: "cross_attention",
+             5: "other"}
+    agg = {k: [0.0, 0.0, 0] for k in kinds.values()}
+    reps = 5
+    for _ in range(reps):
+        _lib.check(lib.pnp_unet_profile(model.unet.handle, 4, 501, ms_op, kind, fl, maxops, C.byref(n)))
+        for i in range(n.value):
+            a = agg[kinds[kind[i]]]
+            a[0] += ms_op[i] / reps
+            a[1] += fl[i] / reps
+            a[2] += 1
+    tot_ms = sum(a[0] for a in agg.values())
+    g = agg["tcgen05_gemm_conv"]
+    n_gemm = g[2] // reps
+    achieved = g[1] / (g[0] * 1e-3) / 1e12 if g[0] > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tcgen05_kernel<BN> (all GEMM / implicit-conv launches of one B=4 UNet call)",
+        "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+        "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
+        "launches_per_unet_call": n_gemm, "gflop_per_launch_avg": g[1] / max(n_gemm, 1) / 1e9,
+        "avg_launch_us": 1000.0 * g[0] / max(n_gemm, 1), "share_of_unet_time": g[0] / tot_ms if tot_ms else None,
+        "traffic": None,
+        "by_kernel_ms_per_b4_unet_call": {k: round(v[0], 4) for k, v in agg.items()},
+        "unet_b4_eager_ms": tot_ms,
+        "whole_job_tflops": value * FWD_PER_IMAGE * UNET_GFLOP / 1e3,
+        "whole_job_frac_of_sustained_peak": value * FWD_PER_IMAGE * UNET_GFLOP / 1e3 / (sustained * world),
+    }
+    prof = os.path.join(ROOT, "profiles", "traffic_latest.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("gemm_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t = cpu_unet_times(sd, threads)
+        v = 1.0 / (N_B4_CALLS * t["b4"] + N_B1_CALLS * t["b1"])
+        cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "dtype": "f32",
+               "sample": f"one B=4 ({t['b4']:.2f} s) and one B=1 ({t['b1']:.2f} s) UNet forward of oracle/unet_ref.py "
+                         f"on {threads} host threads; extrapolated x150 / x50 to one image"}
+
+    line = {
+        "metric": "images_per_sec_512x512_50step_invert_edit", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "directinversion+p2p 50 steps, 1 image per step (UNet B=1 inversion, B=4 offset/"
+                               "reconstruct/edit), faithful 650 UNet forwards, SD-1.x random-init UNet, cat prompts",
+                   "images_per_step_per_gpu": 1, "parallelism": f"image-parallel x{world}",
+                   "l2": "each step streams 1.72 GB of fp16 weights per UNet call (> 126 MB L2), no flush needed",
+                   "accumulate": "fp32", "unet_step_ms_b4": ms / args.steps / (N_B4_CALLS + N_B1_CALLS * 0.4)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

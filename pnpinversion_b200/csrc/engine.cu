@@ -249,9 +249,17 @@ struct DevCtrl {  // device-resident controller state for one forward
   int t_index;
 };
 
+struct OpInfo {
+  int kind;      // 0 tcgen05 gemm/conv, 1 groupnorm, 2 layernorm, 3 self-attention, 4 cross-attention, 5 other
+  double flops;  // algorithmic 2*MAC of the op (0 for memory-bound ops)
+  int kernels;   // kernel launches the op issues
+};
+
 struct Plan {
   int B = 0;
   std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<OpInfo> info;
+  int kernels_per_forward = 0;
   std::vector<std::unique_ptr<GemmPlan>> gemms;
   std::vector<void*> bufs;
   float* x_in = nullptr;    // [B,4,64,64]
@@ -279,7 +287,8 @@ struct pnp_engine {
   std::vector<ResnetW> resnets;  // execution order
   std::vector<XfmrW> xf;         // execution order (16)
   SampW down[3], up[3];
-  float *conv_in_w = nullptr, *conv_in_b = nullptr, *conv_out_w = nullptr, *conv_out_b = nullptr;
+  float *conv_in_w = nullptr, *conv_in_b = nullptr, *conv_out_b = nullptr;
+  __half* conv_out_w = nullptr;
   float *norm_out_g = nullptr, *norm_out_b = nullptr;
   __half *te1 = nullptr, *te2 = nullptr, *temb_proj = nullptr;  // temb_proj: [sum cout, 1280]
   float *te1_b = nullptr, *te2_b = nullptr, *temb_proj_b = nullptr;
@@ -293,6 +302,9 @@ struct pnp_engine {
   float* gn_partials = nullptr;
   int ctx_batch = 0;
   std::map<int, std::unique_ptr<Plan>> plans;
+  // private stream: graphs cannot be captured on the legacy default stream the caller may hand us
+  cudaStream_t es = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
   template <typename T>
   T* dalloc(size_t n) {
@@ -497,9 +509,16 @@ static int finalize(pnp_engine* e) {
     e->up[i].w = upload_f16(e, pack_conv3(*find_param(e, u + ".weight"), rev[i], rev[i], nullptr, 0));
     e->up[i].b = up_vec(e, u + ".bias");
   }
-  e->conv_in_w = up_vec(e, "conv_in.weight");
+  {
+    // conv_in weights [co][ci][tap] -> [k = ci*9+tap][co] fp32 (coalesced shared-memory fill)
+    const std::vector<float> w = to_f32(*find_param(e, "conv_in.weight"));
+    std::vector<float> p(w.size());
+    for (int co = 0; co < 320; ++co)
+      for (int k = 0; k < 36; ++k) p[static_cast<size_t>(k) * 320 + co] = w[static_cast<size_t>(co) * 36 + k];
+    e->conv_in_w = upload_f32(e, p);
+  }
   e->conv_in_b = up_vec(e, "conv_in.bias");
-  e->conv_out_w = up_vec(e, "conv_out.weight");
+  e->conv_out_w = upload_f16(e, pack_conv3(*find_param(e, "conv_out.weight"), 4, 320, nullptr, 0));  // [co][tap][c]
   e->conv_out_b = up_vec(e, "conv_out.bias");
   e->norm_out_g = up_vec(e, "conv_norm_out.weight");
   e->norm_out_b = up_vec(e, "conv_norm_out.bias");
@@ -510,8 +529,9 @@ static int finalize(pnp_engine* e) {
   e->store = e->dalloc<float>(kStoreFloats);
   PNP_CHECK(e->d_ctrl && e->store, "alloc failed");
   PNP_CUDA(cudaMemset(e->store, 0, kStoreFloats * sizeof(float)));
-  e->gn_partials = e->dalloc<float>(static_cast<size_t>(PNP_MAX_BATCH) * 64 * 32 * 2 * 4);
+  e->gn_partials = e->dalloc<float>(groupnorm_workspace_floats(PNP_MAX_BATCH, 4096) + 4096);
   PNP_CHECK(e->gn_partials != nullptr, "alloc failed");
+  PNP_CUDA(cudaMemset(e->gn_partials, 0, (groupnorm_workspace_floats(PNP_MAX_BATCH, 4096) + 4096) * sizeof(float)));
   e->temb_table = e->dalloc<float>(static_cast<size_t>(kMaxTimesteps) * e->temb_total);
   PNP_CHECK(e->temb_table != nullptr, "alloc failed");
   e->finalized = true;
@@ -535,7 +555,11 @@ struct PlanBuilder {
     pl->bufs.push_back(p);
     return static_cast<__half*>(p);
   }
-  void op(std::function<int(cudaStream_t)> f) { pl->ops.push_back(std::move(f)); }
+  void op(int kind, double flops, int kernels, std::function<int(cudaStream_t)> f) {
+    pl->ops.push_back(std::move(f));
+    pl->info.push_back(OpInfo{kind, flops, kernels});
+    pl->kernels_per_forward += kernels;
+  }
 
   void gemm(std::vector<std::function<int(cudaStream_t)>>& ops, const ASource* srcs, int nsrc, int taps, bool linear,
             int b, int h, int w, const __half* wt, int n, int ktot, const GemmEpilogue& ep) {
@@ -546,6 +570,10 @@ struct PlanBuilder {
     GemmPlan* raw = gp.get();
     pl->gemms.push_back(std::move(gp));
     ops.push_back([raw](cudaStream_t s) { return gemm_launch(*raw, s); });
+    if (&ops == &pl->ops) {
+      pl->info.push_back(OpInfo{0, 2.0 * static_cast<double>(raw->p.M) * n * ktot, 1});
+      pl->kernels_per_forward += 1;
+    }
   }
   void linear(const __half* a, int M, int K, int lda, const __half* wt, int N, const GemmEpilogue& ep) {
     ASource s{a, K, lda};
@@ -555,10 +583,10 @@ struct PlanBuilder {
                  bool silu, __half* out) {
     pnp_engine* en = e;
     const int Bn = B;
-    op([=](cudaStream_t s) { return groupnorm_launch(x0, c0, x1, c1, Bn, hw, g, b, eps, silu, out, en->gn_partials, s); });
+    op(1, 0.0, 2, [=](cudaStream_t s) { return groupnorm_launch(x0, c0, x1, c1, Bn, hw, g, b, eps, silu, out, en->gn_partials, s); });
   }
   void layernorm(const __half* x, int rows, int c, const float* g, const float* b, __half* out) {
-    op([=](cudaStream_t s) { return layernorm_launch(x, rows, c, g, b, 1e-5f, out, s); });
+    op(2, 0.0, 1, [=](cudaStream_t s) { return layernorm_launch(x, rows, c, g, b, 1e-5f, out, s); });
   }
 };
 
@@ -666,7 +694,7 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
       sp.o = T_ATT; sp.ldo = c; sp.B = B; sp.H = kHeads; sp.N = N; sp.d = d;
       sp.scale = 1.0f / sqrtf(static_cast<float>(d));
       sp.q_row = e->d_ctrl->self_q[layer]; sp.k_row = e->d_ctrl->self_k[layer]; sp.v_row = e->d_ctrl->self_v[layer];
-      pb.op([sp](cudaStream_t s) { return self_attention_launch(sp, s); });
+      pb.op(3, 4.0 * B * kHeads * static_cast<double>(N) * N * d, 1, [sp](cudaStream_t s) { return self_attention_launch(sp, s); });
     }
     { GemmEpilogue ep; ep.bias = w.o1_b; ep.residual = T_H; ep.ldr = c; ep.out = T_H; ep.ldc = c;
       pb.linear(T_ATT, M, c, c, w.o1, c, ep); }
@@ -687,7 +715,7 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
       else if (layer == 7) store_layer = 2; else if (layer == 8) store_layer = 3; else if (layer == 9) store_layer = 4;
       cp.store = store_layer >= 0 ? e->store + static_cast<size_t>(store_layer) * 2 * PNP_MAX_SLOTS * 8 * 256 * 77 : nullptr;
       cp.store_slot = e->d_ctrl->store_slot;
-      pb.op([cp](cudaStream_t s) { return cross_attention_launch(cp, s); });
+      pb.op(4, 4.0 * B * kHeads * static_cast<double>(N) * 77 * d, 1, [cp](cudaStream_t s) { return cross_attention_launch(cp, s); });
     }
     { GemmEpilogue ep; ep.bias = w.o2_b; ep.residual = T_H; ep.ldr = c; ep.out = T_H; ep.ldc = c;
       pb.linear(T_ATT, M, c, c, w.o2, c, ep); }
@@ -699,7 +727,8 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
         auto gp = std::make_unique<GemmPlan>();
         pb.rc = gemm_plan_create(gp.get(), &s, 1, 1, true, 1, 1, M, w.geglu, 8 * c, c, ep, 256, e->num_sms);
         if (!pb.rc) { GemmPlan* raw = gp.get(); pl->gemms.push_back(std::move(gp));
-          pl->ops.push_back([raw](cudaStream_t st) { return gemm_launch(*raw, st); }); }
+          pl->ops.push_back([raw](cudaStream_t st) { return gemm_launch(*raw, st); });
+          pl->info.push_back(OpInfo{0, 2.0 * M * 8.0 * c * c, 1}); pl->kernels_per_forward += 1; }
       } }
     { GemmEpilogue ep; ep.bias = w.ff2_b; ep.residual = T_H; ep.ldr = c; ep.out = T_H; ep.ldc = c;
       pb.linear(T_FF, M, 4 * c, 4 * c, w.ff2, c, ep); }
@@ -711,7 +740,7 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
   {
     float* xin = pl->x_in;
     const float* wi = e->conv_in_w; const float* bi = e->conv_in_b; __half* o = SK[0];
-    pb.op([=](cudaStream_t s) { return conv_in_launch(xin, B, 64, 64, wi, bi, o, s); });
+    pb.op(5, 2.0 * B * 4096 * 320 * 36, 1, [=](cudaStream_t s) { return conv_in_launch(xin, B, 64, 64, wi, bi, o, s); });
   }
   // ---- down blocks
   const __half* h = SK[0];
@@ -731,7 +760,7 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
     }
     if (i < 3) {
       const __half* src = h; const int c = cout, hh = hw;
-      pb.op([=](cudaStream_t s) { return im2col_s2_launch(src, B, hh, hh, c, IM2, s); });
+      pb.op(5, 0.0, 1, [=](cudaStream_t s) { return im2col_s2_launch(src, B, hh, hh, c, IM2, s); });
       GemmEpilogue ep; ep.bias = e->down[i].b; ep.out = SK[sk]; ep.ldc = cout;
       pb.linear(IM2, B * (hw / 2) * (hw / 2), 9 * cout, 9 * cout, e->down[i].w, cout, ep);
       h = SK[sk++];
@@ -769,7 +798,7 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
     }
     if (i < 3) {
       const __half* src = h; const int c = cout, hh = hw;
-      pb.op([=](cudaStream_t s) { return upsample2x_launch(src, B, hh, hh, c, UPS, s); });
+      pb.op(5, 0.0, 1, [=](cudaStream_t s) { return upsample2x_launch(src, B, hh, hh, c, UPS, s); });
       hw *= 2;
       __half* o = (h == HA) ? HB : HA;
       GemmEpilogue ep; ep.bias = e->up[i].b; ep.out = o; ep.ldc = cout;
@@ -782,8 +811,8 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
   // ---- out
   pb.groupnorm(h, 320, nullptr, 0, 4096, e->norm_out_g, e->norm_out_b, 1e-5f, true, NRM);
   {
-    const float* wo = e->conv_out_w; const float* bo = e->conv_out_b; float* o = pl->eps_out;
-    pb.op([=](cudaStream_t s) { return conv_out_launch(NRM, B, 64, 64, 320, wo, bo, o, s); });
+    const __half* wo = e->conv_out_w; const float* bo = e->conv_out_b; float* o = pl->eps_out;
+    pb.op(5, 2.0 * B * 4096 * 4 * 2880, 1, [=](cudaStream_t s) { return conv_out_launch(NRM, B, 64, 64, 320, wo, bo, o, s); });
   }
   (void)H1;
   return pb.rc;
@@ -811,6 +840,17 @@ static int get_plan(pnp_engine* e, int B, Plan** out) {
 using namespace pnp;
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+// engine stream <- caller stream ordering
+static int enter(pnp_engine* h, cudaStream_t caller) {
+  PNP_CUDA(cudaEventRecord(h->ev_in, caller));
+  PNP_CUDA(cudaStreamWaitEvent(h->es, h->ev_in, 0));
+  return 0;
+}
+static int leave(pnp_engine* h, cudaStream_t caller) {
+  PNP_CUDA(cudaEventRecord(h->ev_out, h->es));
+  PNP_CUDA(cudaStreamWaitEvent(caller, h->ev_out, 0));
+  return 0;
+}
 
 extern "C" {
 
@@ -842,6 +882,9 @@ int pnp_create(int device_ordinal, int max_batch, pnp_engine** out) {
   e->num_sms = prop.multiProcessorCount;
   e->max_batch = max_batch;
   debug_words_device();
+  PNP_CUDA(cudaStreamCreateWithFlags(&e->es, cudaStreamNonBlocking));
+  PNP_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+  PNP_CUDA(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
   *out = e;
   return 0;
 }
@@ -856,6 +899,9 @@ void pnp_destroy(pnp_engine* h) {
   }
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_ctrl_ring) cudaFreeHost(h->h_ctrl_ring);
+  if (h->es) cudaStreamDestroy(h->es);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
   delete h;
 }
 
@@ -935,7 +981,10 @@ int pnp_set_context(pnp_engine* h, const float* ctx_dev, int batch, void* stream
   Plan* pl = nullptr;
   int rc = get_plan(h, batch, &pl);
   if (rc) return rc;
-  cudaStream_t s = as_stream(stream);
+  cudaStream_t caller = as_stream(stream);
+  rc = enter(h, caller);
+  if (rc) return rc;
+  cudaStream_t s = h->es;
   const size_t n = static_cast<size_t>(batch) * 77 * kCrossDim;
   f32_to_f16_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 2048)), 256, 0, s>>>(ctx_dev, pl->ctx16, n);
   PNP_CUDA(cudaGetLastError());
@@ -943,6 +992,8 @@ int pnp_set_context(pnp_engine* h, const float* ctx_dev, int batch, void* stream
     rc = f(s);
     if (rc) return rc;
   }
+  rc = leave(h, caller);
+  if (rc) return rc;
   h->launches += 1 + static_cast<int64_t>(pl->ctx_ops.size());
   h->ctx_batch = batch;
   return 0;
@@ -1016,7 +1067,10 @@ int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, 
   Plan* pl = nullptr;
   int rc = get_plan(h, batch, &pl);
   if (rc) return rc;
-  cudaStream_t s = as_stream(stream);
+  cudaStream_t caller = as_stream(stream);
+  rc = enter(h, caller);
+  if (rc) return rc;
+  cudaStream_t s = h->es;
   rc = push_ctrl(h, batch, t_index, ctrl_host, s);
   if (rc) return rc;
   const size_t bytes = static_cast<size_t>(batch) * PNP_LATENT_ELEMS * sizeof(float);
@@ -1030,7 +1084,7 @@ int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, 
       }
       PNP_CUDA(cudaStreamSynchronize(s));
       cudaGraph_t g = nullptr;
-      PNP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      PNP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
       for (auto& f : pl->ops) {
         rc = f(s);
         if (rc) {
@@ -1051,8 +1105,42 @@ int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, 
     }
   }
   // groupnorm = 2 kernels per op; count them
-  h->launches += static_cast<int64_t>(pl->ops.size());
+  h->launches += pl->kernels_per_forward;
   PNP_CUDA(cudaMemcpyAsync(eps_out_dev, pl->eps_out, bytes, cudaMemcpyDeviceToDevice, s));
+  return leave(h, caller);
+}
+
+int pnp_unet_profile(pnp_engine* h, int batch, int t_index, float* ms_out, int32_t* kind_out, double* flops_out,
+                     int max_ops, int* n_out) {
+  PNP_CHECK(h && h->finalized && ms_out && kind_out && flops_out && n_out, "pnp_unet_profile: bad argument");
+  PNP_CHECK(h->ctx_batch == batch, "pnp_unet_profile: call pnp_set_context for this batch first");
+  PNP_CHECK(t_index >= 0 && t_index < h->n_t, "pnp_unet_profile: t_index");
+  Plan* pl = nullptr;
+  int rc = get_plan(h, batch, &pl);
+  if (rc) return rc;
+  const int n = static_cast<int>(pl->ops.size());
+  PNP_CHECK(n <= max_ops, "pnp_unet_profile: output arrays too small");
+  cudaStream_t s = h->es;
+  PNP_CUDA(cudaDeviceSynchronize());
+  rc = push_ctrl(h, batch, t_index, nullptr, s);
+  if (rc) return rc;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) PNP_CUDA(cudaEventCreate(&e));
+  // x_in keeps whatever the last forward left there; the timing does not depend on the values
+  PNP_CUDA(cudaEventRecord(ev[0], s));
+  for (int i = 0; i < n; ++i) {
+    rc = pl->ops[i](s);
+    if (rc) return rc;
+    PNP_CUDA(cudaEventRecord(ev[i + 1], s));
+  }
+  PNP_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < n; ++i) {
+    PNP_CUDA(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]));
+    kind_out[i] = pl->info[i].kind;
+    flops_out[i] = pl->info[i].flops;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  *n_out = n;
   return 0;
 }
 
@@ -1164,7 +1252,8 @@ int pnp_test_groupnorm(const uint16_t* x0_dev, int C0, const uint16_t* x1_dev, i
                        const float* gamma_dev, const float* beta_dev, float eps, int silu, uint16_t* out_dev,
                        void* stream) {
   float* partials = nullptr;
-  PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&partials), groupnorm_partials_floats(B, HW) * sizeof(float)));
+  PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&partials), groupnorm_workspace_floats(B, HW) * sizeof(float)));
+  PNP_CUDA(cudaMemset(partials, 0, groupnorm_workspace_floats(B, HW) * sizeof(float)));
   int rc = groupnorm_launch(reinterpret_cast<const __half*>(x0_dev), C0, reinterpret_cast<const __half*>(x1_dev), C1, B,
                             HW, gamma_dev, beta_dev, eps, silu != 0, reinterpret_cast<__half*>(out_dev), partials,
                             as_stream(stream));

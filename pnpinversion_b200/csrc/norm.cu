@@ -36,13 +36,13 @@ constexpr int GN_MAX_VPT = 2;
 
 // partials[b][slice][g] = (mean, M2) over ppc*cpg elements
 __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
-                                int ppc, int tx_n, int vpt, float* __restrict__ partials) {
+                                int ppc, int tx_n, int rows_y, int vpt, float* __restrict__ partials, float eps,
+                                float* __restrict__ mean_rstd, int* __restrict__ counters) {
   extern __shared__ float sm[];  // [rows_y][2*C] then reused
   const int C = C0 + C1;
   const int nvec0 = C0 >> 3;
   const int b = blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
-  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
-  const int rows_y = blockDim.x / tx_n;
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;  // blockDim is always 256; rows ty >= rows_y idle
   float s[GN_MAX_VPT][8], ss[GN_MAX_VPT][8];
 #pragma unroll
   for (int i = 0; i < GN_MAX_VPT; ++i)
@@ -102,12 +102,50 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
     o[0] = mean;
     o[1] = m2;
   }
+  // last CTA of this batch row merges the per-slice (mean, M2) pairs (Chan et al., equal counts) into (mean, rstd)
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(&counters[b], 1);
+    is_last = (done == nslices - 1);
+    if (is_last) counters[b] = 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  {
+    // 8 lanes per group
+    const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    if (g < GN_GROUPS) {
+      const int cpg = C / GN_GROUPS;
+      const float* pp = partials + (static_cast<size_t>(b) * nslices * GN_GROUPS + g) * 2;
+      float msum = 0.f;
+      for (int s2 = sub; s2 < nslices; s2 += 8) msum += __ldcg(pp + static_cast<size_t>(s2) * GN_GROUPS * 2);
+      msum += __shfl_xor_sync(0xffffffffu, msum, 1);
+      msum += __shfl_xor_sync(0xffffffffu, msum, 2);
+      msum += __shfl_xor_sync(0xffffffffu, msum, 4);
+      const float mean = msum / nslices;
+      const float n_i = static_cast<float>(ppc) * cpg;
+      float m2 = 0.f;
+      for (int s2 = sub; s2 < nslices; s2 += 8) {
+        const float d = __ldcg(pp + static_cast<size_t>(s2) * GN_GROUPS * 2) - mean;
+        m2 += __ldcg(pp + static_cast<size_t>(s2) * GN_GROUPS * 2 + 1) + n_i * d * d;
+      }
+      m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
+      if (sub == 0) {
+        mean_rstd[(b * GN_GROUPS + g) * 2] = mean;
+        mean_rstd[(b * GN_GROUPS + g) * 2 + 1] = rsqrtf(m2 / (n_i * nslices) + eps);
+      }
+    }
+  }
 }
 
 __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
-                                int nslices, int ppc_stats, const float* __restrict__ partials,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int do_silu,
-                                __half* __restrict__ out, int ppc) {
+                                const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int do_silu, __half* __restrict__ out, int ppc) {
   extern __shared__ float sm[];  // scale[C], shift[C], mean[32], rstd[32]
   const int C = C0 + C1;
   float* scale = sm;
@@ -117,20 +155,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
   const int b = blockIdx.y;
   const int cpg = C / GN_GROUPS;
   if (threadIdx.x < GN_GROUPS) {
-    const int g = threadIdx.x;
-    const float* pp = partials + (static_cast<size_t>(b) * nslices * GN_GROUPS + g) * 2;
-    float msum = 0.f;
-    for (int s = 0; s < nslices; ++s) msum += pp[static_cast<size_t>(s) * GN_GROUPS * 2];
-    const float mean = msum / nslices;
-    const float n_i = static_cast<float>(ppc_stats) * cpg;
-    float m2 = 0.f;
-    for (int s = 0; s < nslices; ++s) {
-      const float d = pp[static_cast<size_t>(s) * GN_GROUPS * 2] - mean;
-      m2 += pp[static_cast<size_t>(s) * GN_GROUPS * 2 + 1] + n_i * d * d;
-    }
-    const float var = m2 / (n_i * nslices);
-    gmean[g] = mean;
-    grstd[g] = rsqrtf(var + eps);
+    gmean[threadIdx.x] = mean_rstd[(b * GN_GROUPS + threadIdx.x) * 2];
+    grstd[threadIdx.x] = mean_rstd[(b * GN_GROUPS + threadIdx.x) * 2 + 1];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -170,49 +196,62 @@ int gn_ppc(int B, int HW) {
 template <int VPL>  // 16-byte vectors per lane (C = 8*32*VPL at most)
 __global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float eps, __half* __restrict__ out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = C >> 3;
-  const __half* xr = x + static_cast<size_t>(warp) * C;
-  float f[VPL][8];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[i]);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s += f[i][e];
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  float q = 0.f;
+  float gam[VPL][8], bet[VPL][8];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + i * 32;
     if (v < nvec) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float d = f[i][e] - mean;
-        q += d * d;
+        gam[i][e] = gamma[v * 8 + e];
+        bet[i][e] = beta[v * 8 + e];
       }
     }
   }
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps) {
+    const __half* xr = x + static_cast<size_t>(row) * C;
+    float f[VPL][8];
+    float s = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + eps);
-  __half* orow = out + static_cast<size_t>(warp) * C;
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[i]);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      float y[8];
+        for (int e = 0; e < 8; ++e) s += f[i][e];
+      }
+    }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * gamma[v * 8 + e] + beta[v * 8 + e];
-      *reinterpret_cast<uint4*>(orow + v * 8) = pack8(y);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = f[i][e] - mean;
+          q += d * d;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + eps);
+    __half* orow = out + static_cast<size_t>(row) * C;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * gam[i][e] + bet[i][e];
+        *reinterpret_cast<uint4*>(orow + v * 8) = pack8(y);
+      }
     }
   }
 }
@@ -259,10 +298,7 @@ constexpr int CIN_CO = 320;
 __global__ void conv_in_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w,
                                const float* __restrict__ bias, __half* __restrict__ out) {
   __shared__ float ws[CIN_K * CIN_CO];  // [k][co], k = ci*9 + tap
-  for (int i = threadIdx.x; i < CIN_K * CIN_CO; i += blockDim.x) {
-    const int co = i % CIN_CO, k = i / CIN_CO;
-    ws[i] = w[co * CIN_K + k];
-  }
+  for (int i = threadIdx.x; i < CIN_K * CIN_CO; i += blockDim.x) ws[i] = w[i];  // prepacked [k][co]
   __syncthreads();
   const int nvec = CIN_CO / 8;  // 40
   const int ppb = blockDim.x / nvec;
@@ -292,14 +328,11 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int B, int H, int W,
 }
 
 // ------------------------------------------------------------------ conv_out: NHWC fp16 (320 ch, already GN+SiLU) -> NCHW fp32 (4 ch)
-__global__ void conv_out_kernel(const __half* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ w,
+__global__ void conv_out_kernel(const __half* __restrict__ x, int B, int H, int W, int C, const __half* __restrict__ w,
                                 const float* __restrict__ bias, float* __restrict__ out) {
   extern __shared__ __half wsh[];  // [co][tap][c]
   const int K = 9 * C;
-  for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) {
-    const int co = i / K, r = i % K, tap = r / C, c = r % C;
-    wsh[i] = __float2half(w[(co * C + c) * 9 + tap]);
-  }
+  for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) wsh[i] = w[i];  // prepacked fp16 [co][tap][c]
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -364,20 +397,35 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
     attr1 = true;
   }
   PNP_CHECK(sm1 <= 160 * 1024, "groupnorm: smem");
-  gn_stats_kernel<<<dim3(nslices, B), threads, sm1, s>>>(x0, C0, x1, C1, HW, ppc, tx_n, vpt, partials);
+  // workspace layout (fixed offsets so that the self-resetting counters are never overwritten by another shape):
+  //   [0,64) ints: per-batch arrival counters | [64, 64+64*64) floats: (mean, rstd) | partials
+  int* counters = reinterpret_cast<int*>(partials);
+  float* mean_rstd = partials + 64;
+  float* parts = partials + 64 + 64 * GN_GROUPS * 2;
+  PNP_CHECK(B <= 64, "groupnorm: batch");
+  (void)threads;
+  gn_stats_kernel<<<dim3(nslices, B), 256, sm1, s>>>(x0, C0, x1, C1, HW, ppc, tx_n, rows_y, vpt, parts, eps, mean_rstd,
+                                                         counters);
   PNP_CUDA(cudaGetLastError());
   const size_t sm2 = (2 * static_cast<size_t>(C) + 2 * GN_GROUPS) * sizeof(float);
-  gn_apply_kernel<<<dim3(nslices, B), 256, sm2, s>>>(x0, C0, x1, C1, HW, nslices, ppc, partials, gamma, beta, eps,
-                                                    do_silu ? 1 : 0, out, ppc);
+  // the apply pass is pure streaming: fewer, fatter CTAs than the statistics pass
+  int ppa = ppc;
+  while (ppa < HW && static_cast<long>(B) * (HW / ppa) > 2 * 148) ppa <<= 1;
+  gn_apply_kernel<<<dim3(HW / ppa, B), 256, sm2, s>>>(x0, C0, x1, C1, HW, mean_rstd, gamma, beta, do_silu ? 1 : 0, out,
+                                                      ppa);
   PNP_CUDA(cudaGetLastError());
   return 0;
+}
+
+size_t groupnorm_workspace_floats(int B, int HW) {
+  return groupnorm_partials_floats(B, HW) + 64 + 64 * GN_GROUPS * 2;
 }
 
 int layernorm_launch(const __half* x, int rows, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t s) {
   PNP_CHECK(C % 8 == 0 && C <= 8 * 32 * 5, "layernorm: C");
   const int threads = 256;
-  const int blocks = (rows * 32 + threads - 1) / threads;
+  const int blocks = std::min((rows * 32 + threads - 1) / threads, 148 * 8);
   const int vpl = (C / 8 + 31) / 32;
   switch (vpl) {
     case 1: ln_kernel<1><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
@@ -414,18 +462,18 @@ int conv_in_launch(const float* x_nchw, int B, int H, int W, const float* w, con
                    cudaStream_t s) {
   const int threads = 240;  // 40 channel-octets x 6 pixels
   const size_t npix = static_cast<size_t>(B) * H * W;
-  const int blocks = static_cast<int>(std::min<size_t>((npix + 5) / 6, 148 * 4));
+  const int blocks = static_cast<int>(std::min<size_t>((npix + 5) / 6, 148 * 2));
   conv_in_kernel<<<blocks, threads, 0, s>>>(x_nchw, B, H, W, w, bias, out);
   PNP_CUDA(cudaGetLastError());
   return 0;
 }
 
-int conv_out_launch(const __half* x, int B, int H, int W, int C, const float* w, const float* bias, float* out_nchw,
+int conv_out_launch(const __half* x, int B, int H, int W, int C, const __half* w, const float* bias, float* out_nchw,
                     cudaStream_t s) {
   PNP_CHECK(C % 8 == 0, "conv_out: C");
   const size_t sm = static_cast<size_t>(4) * 9 * C * sizeof(__half);
   const size_t npix = static_cast<size_t>(B) * H * W;
-  const int blocks = static_cast<int>(std::min<size_t>((npix + 7) / 8, 148 * 8));
+  const int blocks = static_cast<int>(std::min<size_t>((npix + 7) / 8, 148 * 4));
   conv_out_kernel<<<blocks, 256, sm, s>>>(x, B, H, W, C, w, bias, out_nchw);
   PNP_CUDA(cudaGetLastError());
   return 0;

@@ -95,13 +95,14 @@ int gemm_choose_bn(int M, int N, bool geglu, int num_sms);
 int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, int HW, const float* gamma,
                      const float* beta, float eps, bool silu, __half* out, float* partials, cudaStream_t s);
 size_t groupnorm_partials_floats(int B, int HW);
+size_t groupnorm_workspace_floats(int B, int HW);  // partials + mean/rstd + per-batch counters (zero-initialised)
 int layernorm_launch(const __half* x, int rows, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t s);
 int upsample2x_launch(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t s);
 int im2col_s2_launch(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t s);
 int conv_in_launch(const float* x_nchw, int B, int H, int W, const float* w, const float* bias, __half* out,
                    cudaStream_t s);
-int conv_out_launch(const __half* x, int B, int H, int W, int C, const float* w, const float* bias, float* out_nchw,
+int conv_out_launch(const __half* x, int B, int H, int W, int C, const __half* w, const float* bias, float* out_nchw,
                     cudaStream_t s);
 int concat_launch(const __half* x0, int C0, const __half* x1, int C1, int rows, __half* out, cudaStream_t s);
 

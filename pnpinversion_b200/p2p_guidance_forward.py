@@ -81,3 +81,30 @@ def direct_inversion_p2p_guidance_forward_add_target(model, prompt, controller, 
                                                                noise_loss_list[i], add_offset=add_offset,
                                                                add_target=True)
     return latents, latent
+
+
+def p2p_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale, low_resource=False):
+    """p2p_guidance_forward.py:6-18 (no rectification: the plain DDIM+P2P baseline)."""
+    return direct_inversion_p2p_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale, None,
+                                                        low_resource=low_resource, add_offset=False)
+
+
+@torch.no_grad()
+def p2p_guidance_forward(model, prompt, controller, num_inference_steps: int = 50, guidance_scale=7.5, generator=None,
+                         latent=None, uncond_embeddings=None):
+    """p2p_guidance_forward.py:21-62."""
+    batch_size = len(prompt)
+    register_attention_control(model, controller)
+    context_default = _encode(model, prompt)
+    text_embeddings = context_default[batch_size:]
+    latent, latents = init_latent(latent, model, 512, 512, generator, batch_size)
+    latents = latents.to(torch.float32).contiguous()
+    model.scheduler.set_timesteps(num_inference_steps)
+    for i, t in enumerate(model.scheduler.timesteps):
+        if uncond_embeddings is not None:
+            context = torch.cat([uncond_embeddings[i].to(text_embeddings).expand(*text_embeddings.shape),
+                                 text_embeddings]).contiguous()
+        else:
+            context = context_default
+        latents = p2p_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale)
+    return latents, latent

@@ -110,10 +110,16 @@ class SynthTextEncoder:
     def __init__(self, seed: int = 7, dtype=torch.float32):
         self.seed = seed
         self.dtype = dtype
+        self._cache: Dict[tuple, torch.Tensor] = {}
 
     def _row(self, tok: int, pos: int) -> torch.Tensor:
-        g = torch.Generator().manual_seed((self.seed * 77_003 + tok) * 131 + pos)
-        return torch.randn(CROSS_DIM, generator=g)
+        key = (tok, pos)
+        r = self._cache.get(key)
+        if r is None:
+            g = torch.Generator().manual_seed((self.seed * 77_003 + tok) * 131 + pos)
+            r = torch.randn(CROSS_DIM, generator=g)
+            self._cache[key] = r
+        return r
 
     def __call__(self, input_ids: torch.Tensor):
         ids = input_ids.cpu()

@@ -1,0 +1,53 @@
+"""End-to-end parity of the hot loops against the REFERENCE pipeline fixture (tests/golden/pipeline_4steps.npz:
+the reference's own DirectInversion.invert + direct_inversion_p2p_guidance_forward with AttentionStore and with
+AttentionRefine+AttentionReweight+LocalBlend, fp64 vendored UNet, 4 DDIM steps, full-size SD-1.x UNet).
+
+Stated tolerances (fp16 operands / fp32 accumulate vs fp64): per-latent rel-L2 <= 5e-3 over the 4-step loops; the
+rectified source branch must land on x_stars[0] to fp32 rounding (the exactness invariant)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pnpinversion_b200 import synth
+from pnpinversion_b200.model import FusedModel
+from pnpinversion_b200.p2p_editor import P2PEditor
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "pipeline_4steps.npz")
+TOL = 5e-3
+
+
+def test_directinversion_p2p_4_steps_matches_reference(cuda):
+    if not os.path.exists(GOLD):
+        pytest.fail("tests/golden/pipeline_4steps.npz missing (python -m oracle.make_golden pipeline 4)")
+    g = np.load(GOLD)
+    # the fixture was produced with the vendored (float64-table) scheduler
+    model = FusedModel.synthetic(device="cuda:0", max_batch=4, table_dtype="float64")
+    editor = P2PEditor(["directinversion+p2p"], "cuda:0", num_ddim_steps=4, model=model)
+    src, tgt = synth.CAT_PROMPTS
+    res = editor("directinversion+p2p", image_path=synth.synth_latent(0), prompt_src=src, prompt_tar=tgt,
+                 guidance_scale=7.5, cross_replace_steps=0.4, self_replace_steps=0.6,
+                 blend_word=(("cat",), ("cat",)), eq_params={"words": ("watercolor",), "values": (2,)})
+    torch.cuda.synchronize()
+    x_stars = torch.cat(res.x_stars).cpu()
+    nl = torch.stack(res.noise_loss_list).cpu()
+    ref_xs, ref_nl = torch.from_numpy(g["x_stars"]), torch.from_numpy(g["noise_loss"])
+    errs = {"x_stars": [G.rel_l2(x_stars[i], ref_xs[i]) for i in range(1, 5)],
+            "recon_tgt": G.rel_l2(res.reconstruct_latent[1].cpu(), torch.from_numpy(g["recon"][1])),
+            "edit_tgt": G.rel_l2(res.latents[1].cpu(), torch.from_numpy(g["edit"][1]))}
+    # noise_loss is a small difference of large numbers: compare it relative to the latent scale
+    errs["noise_loss_abs_over_latent_norm"] = float((nl - ref_nl).norm() / ref_xs[1:].norm())
+    print("pipeline parity:", errs)
+    assert max(errs["x_stars"]) < TOL
+    assert errs["recon_tgt"] < TOL and errs["edit_tgt"] < TOL
+    assert errs["noise_loss_abs_over_latent_norm"] < TOL
+    # exactness invariant: the rectified source branch reproduces x_stars[0] = z0 in both passes
+    z0 = synth.synth_latent(0)[0]
+    assert (res.reconstruct_latent[0].cpu() - z0).abs().max() < 2e-5
+    assert (res.latents[0].cpu() - z0).abs().max() < 2e-5
+    # and the edit differs from the reconstruction (the controller did something)
+    assert G.rel_l2(res.latents[1].cpu(), res.reconstruct_latent[1].cpu()) > 1e-2
+    model.unet.close()

@@ -1,5 +1,6 @@
 """Quick device-side timing of the fused UNet forward (CUDA events), used while optimising."""
-import sys, time
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pnpinversion_b200 import synth
 from pnpinversion_b200.model import FusedModel
