@@ -261,13 +261,22 @@ def main():
              5: "other"}
     agg = {k: [0.0, 0.0, 0] for k in kinds.values()}
     reps = 5
+    per_op = None
     for _ in range(reps):
         _lib.check(lib.pnp_unet_profile(model.unet.handle, 4, 501, ms_op, kind, fl, maxops, C.byref(n)))
+        if per_op is None:
+            per_op = [[kind[i], fl[i], 0.0] for i in range(n.value)]
+        for i in range(n.value):
+            per_op[i][2] += ms_op[i] / reps
         for i in range(n.value):
             a = agg[kinds[kind[i]]]
             a[0] += ms_op[i] / reps
             a[1] += fl[i] / reps
             a[2] += 1
+    dump = os.environ.get("PNP_PROFILE_DUMP")
+    if dump:
+        with open(dump, "w") as f:
+            json.dump(per_op, f)
     tot_ms = sum(a[0] for a in agg.values())
     g = agg["tcgen05_gemm_conv"]
     n_gemm = g[2] // reps

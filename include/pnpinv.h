@@ -128,10 +128,11 @@ int pnp_set_use_graph(pnp_engine* h, int enable);     /* capture each UNet forwa
 /* D[M,N] = A[M,K].W[N,K]^T (+bias)(+residual) ; mode 0 plain, 1 GEGLU (N = 2*out columns, weights pre-interleaved by
  * pnp_test_pack_geglu) ; conv3x3: A is NHWC [B,H,W,C], W packed (N, 9*C) tap-major */
 int pnp_test_gemm(const uint16_t* a_dev, int M, int K, int lda, const uint16_t* w_dev, int N, const float* bias_dev,
-                  const uint16_t* residual_dev, uint16_t* out_dev, int ldc, int geglu, int bn, void* stream);
+                  const uint16_t* residual_dev, uint16_t* out_dev, int ldc, int geglu, int bn, int split,
+                  void* stream); /* split: 0 auto, 1 off, n>1 force n K-splits */
 int pnp_test_conv3x3(const uint16_t* x_dev, int B, int H, int W, int C, const uint16_t* w_dev, int N,
                      const uint16_t* sc0_dev, int sc0_C, const uint16_t* sc1_dev, int sc1_C, const float* bias_dev,
-                     const uint16_t* residual_dev, uint16_t* out_dev, int bn, void* stream);
+                     const uint16_t* residual_dev, uint16_t* out_dev, int bn, int split, void* stream);
 int pnp_test_groupnorm(const uint16_t* x0_dev, int C0, const uint16_t* x1_dev, int C1, int B, int HW,
                        const float* gamma_dev, const float* beta_dev, float eps, int silu, uint16_t* out_dev,
                        void* stream);

@@ -87,8 +87,8 @@ SIGNATURES = {
     "pnp_unet_profile": (_i, [_vp, _i, _i, C.POINTER(_f), C.POINTER(C.c_int32), C.POINTER(C.c_double), _i, C.POINTER(_i)]),
     "pnp_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
     "pnp_set_use_graph": (_i, [_vp, _i]),
-    "pnp_test_gemm": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "pnp_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "pnp_test_gemm": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pnp_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "pnp_test_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp]),
     "pnp_test_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "pnp_test_self_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

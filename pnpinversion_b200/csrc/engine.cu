@@ -268,6 +268,8 @@ struct Plan {
   std::vector<std::function<int(cudaStream_t)>> ctx_ops;  // context K/V projection for this batch
   __half* ctx16 = nullptr;
   __half* ctxkv[16] = {nullptr};
+  float* gemm_ws = nullptr;      // shared split-K workspace
+  int* gemm_counters = nullptr;  // zero-initialised, self-resetting
 };
 
 constexpr int kStoreLayers = 5;
@@ -815,6 +817,18 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
     pb.op(5, 2.0 * B * 4096 * 4 * 2880, 1, [=](cudaStream_t s) { return conv_out_launch(NRM, B, 64, 64, 320, wo, bo, o, s); });
   }
   (void)H1;
+  if (pb.rc) return pb.rc;
+  // one split-K workspace shared by all GEMMs of this plan (they run back to back on one stream)
+  size_t ws_floats = 0;
+  for (auto& g : pl->gemms) ws_floats = std::max(ws_floats, gemm_ws_floats(*g));
+  if (ws_floats > 0) {
+    PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl->gemm_ws), ws_floats * sizeof(float)));
+    pl->bufs.push_back(pl->gemm_ws);
+    PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl->gemm_counters), kGemmMaxCounters * sizeof(int)));
+    pl->bufs.push_back(pl->gemm_counters);
+    PNP_CUDA(cudaMemset(pl->gemm_counters, 0, kGemmMaxCounters * sizeof(int)));
+    for (auto& g : pl->gemms) gemm_set_workspace(g.get(), pl->gemm_ws, pl->gemm_counters);
+  }
   return pb.rc;
 }
 
@@ -1075,14 +1089,17 @@ int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, 
   if (rc) return rc;
   const size_t bytes = static_cast<size_t>(batch) * PNP_LATENT_ELEMS * sizeof(float);
   PNP_CUDA(cudaMemcpyAsync(pl->x_in, x_dev, bytes, cudaMemcpyDeviceToDevice, s));
-  if (h->use_graph) {
-    if (pl->graph == nullptr) {
-      // warm-up run outside capture (sets function attributes, catches launch errors with a readable message)
-      for (auto& f : pl->ops) {
-        rc = f(s);
-        if (rc) return rc;
-      }
-      PNP_CUDA(cudaStreamSynchronize(s));
+  if (h->use_graph && pl->graph != nullptr) {
+    PNP_CUDA(cudaGraphLaunch(pl->graph, s));
+  } else {
+    // eager execution (also the first call of a plan: it sets the function attributes and surfaces launch errors
+    // with a readable message); the graph for the following calls is captured right after, without being launched,
+    // so that side effects (the AttentionStore accumulation) happen exactly once per call
+    for (auto& f : pl->ops) {
+      rc = f(s);
+      if (rc) return rc;
+    }
+    if (h->use_graph) {
       cudaGraph_t g = nullptr;
       PNP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
       for (auto& f : pl->ops) {
@@ -1096,12 +1113,6 @@ int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, 
       PNP_CUDA(cudaStreamEndCapture(s, &g));
       PNP_CUDA(cudaGraphInstantiate(&pl->graph, g, 0));
       cudaGraphDestroy(g);
-    }
-    PNP_CUDA(cudaGraphLaunch(pl->graph, s));
-  } else {
-    for (auto& f : pl->ops) {
-      rc = f(s);
-      if (rc) return rc;
     }
   }
   // groupnorm = 2 kernels per op; count them
@@ -1164,6 +1175,8 @@ int pnp_local_blend(pnp_engine* h, float* x_dev, const int32_t* nwords2, const i
   LocalBlendParams p;
   // slots 0 (source prompt) and 1 (target prompt) of each of the five layers
   p.store = h->store;
+  p.layer_stride = static_cast<long long>(2) * PNP_MAX_SLOTS * 8 * 256 * 77;
+  p.slot_stride = 8LL * 256 * 77;
   for (int i = 0; i < 2; ++i) {
     p.nwords[i] = nwords2[i];
     PNP_CHECK(nwords2[i] >= 0 && nwords2[i] <= 8, "pnp_local_blend: at most 8 blend words per prompt");
@@ -1211,8 +1224,25 @@ static int test_sms() {
   return sms;
 }
 
+static int test_launch_with_ws(GemmPlan* gp, cudaStream_t s) {
+  float* ws = nullptr;
+  int* cnt = nullptr;
+  if (gemm_ws_floats(*gp) > 0) {
+    PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws), gemm_ws_floats(*gp) * sizeof(float)));
+    PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&cnt), kGemmMaxCounters * sizeof(int)));
+    PNP_CUDA(cudaMemset(cnt, 0, kGemmMaxCounters * sizeof(int)));
+    gemm_set_workspace(gp, ws, cnt);
+  }
+  int rc = gemm_launch(*gp, s);
+  PNP_CUDA(cudaStreamSynchronize(s));
+  if (ws) cudaFree(ws);
+  if (cnt) cudaFree(cnt);
+  return rc;
+}
+
 int pnp_test_gemm(const uint16_t* a_dev, int M, int K, int lda, const uint16_t* w_dev, int N, const float* bias_dev,
-                  const uint16_t* residual_dev, uint16_t* out_dev, int ldc, int geglu, int bn, void* stream) {
+                  const uint16_t* residual_dev, uint16_t* out_dev, int ldc, int geglu, int bn, int split,
+                  void* stream) {
   GemmEpilogue ep;
   ep.bias = bias_dev;
   ep.residual = reinterpret_cast<const __half*>(residual_dev);
@@ -1222,14 +1252,15 @@ int pnp_test_gemm(const uint16_t* a_dev, int M, int K, int lda, const uint16_t* 
   ep.geglu = geglu != 0;
   ASource s{reinterpret_cast<const __half*>(a_dev), K, lda};
   GemmPlan gp;
-  int rc = gemm_plan_create(&gp, &s, 1, 1, true, 1, 1, M, reinterpret_cast<const __half*>(w_dev), N, K, ep, bn, test_sms());
+  int rc = gemm_plan_create(&gp, &s, 1, 1, true, 1, 1, M, reinterpret_cast<const __half*>(w_dev), N, K, ep, bn, test_sms(),
+                            split);
   if (rc) return rc;
-  return gemm_launch(gp, as_stream(stream));
+  return test_launch_with_ws(&gp, as_stream(stream));
 }
 
 int pnp_test_conv3x3(const uint16_t* x_dev, int B, int H, int W, int C, const uint16_t* w_dev, int N,
                      const uint16_t* sc0_dev, int sc0_C, const uint16_t* sc1_dev, int sc1_C, const float* bias_dev,
-                     const uint16_t* residual_dev, uint16_t* out_dev, int bn, void* stream) {
+                     const uint16_t* residual_dev, uint16_t* out_dev, int bn, int split, void* stream) {
   GemmEpilogue ep;
   ep.bias = bias_dev;
   ep.residual = reinterpret_cast<const __half*>(residual_dev);
@@ -1243,9 +1274,10 @@ int pnp_test_conv3x3(const uint16_t* x_dev, int B, int H, int W, int C, const ui
   if (sc0_dev) { s[ns++] = ASource{reinterpret_cast<const __half*>(sc0_dev), sc0_C, sc0_C}; ktot += sc0_C; }
   if (sc1_dev) { s[ns++] = ASource{reinterpret_cast<const __half*>(sc1_dev), sc1_C, sc1_C}; ktot += sc1_C; }
   GemmPlan gp;
-  int rc = gemm_plan_create(&gp, s, ns, 9, false, B, H, W, reinterpret_cast<const __half*>(w_dev), N, ktot, ep, bn, test_sms());
+  int rc = gemm_plan_create(&gp, s, ns, 9, false, B, H, W, reinterpret_cast<const __half*>(w_dev), N, ktot, ep, bn, test_sms(),
+                            split);
   if (rc) return rc;
-  return gemm_launch(gp, as_stream(stream));
+  return test_launch_with_ws(&gp, as_stream(stream));
 }
 
 int pnp_test_groupnorm(const uint16_t* x0_dev, int C0, const uint16_t* x1_dev, int C1, int B, int HW,

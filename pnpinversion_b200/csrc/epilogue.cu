@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) local_blend_kernel(const LocalBlendParams
     float acc = 0.f;
     for (int lh = 0; lh < 40; ++lh) {
       const int layer = lh / 8, h = lh % 8;
-      const float* row = p.store + ((((static_cast<size_t>(layer) * 2 + pr) * 8 + h) * 256) + pos) * 77;
+      const float* row = p.store + layer * p.layer_stride + pr * p.slot_stride + (static_cast<size_t>(h) * 256 + pos) * 77;
       float s = 0.f;
       for (int w = 0; w < p.nwords[pr]; ++w) s += row[p.words[pr][w]] * p.alpha[pr][w];
       acc += s;

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  volatile int* split_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_work = total_tiles * p.splits;
   const int num_kb = p.num_kb;
 
   if (warp == 0) {
@@ -93,7 +95,11 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
       // ------------------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
       const int kb0 = p.taps0 * p.chunks0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work % total_tiles;
+        const int split = work / total_tiles;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
         const int m_blk = tile % p.m_tiles;
         const int n_blk = tile / p.m_tiles;
         const int p0 = m_blk * BM;
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
           y0 = (p0 - b0 * p.HW) / p.W;
           x0 = 0;
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, p.dbg, 1);
           uint8_t* sa = smem + stage * C::STAGE;
           uint8_t* sb = sa + A_BYTES;
@@ -135,13 +141,16 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+        const int split = work / total_tiles;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
         const uint32_t as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1u, p.dbg, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full[stage], phase, p.dbg, 3);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE);
@@ -150,10 +159,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128-byte swizzle atom
-            umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull[as]);
+          if (kb == kb_end - 1) umma_commit(&tfull[as]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -165,7 +174,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
     const float* temb = nullptr;
     if (p.temb_table != nullptr) temb = p.temb_table + static_cast<size_t>(*p.t_index) * p.temb_stride;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+      const int tile = work % total_tiles;
+      const int split = work / total_tiles;
       const int m_blk = tile % p.m_tiles;
       const int n_blk = tile / p.m_tiles;
       const uint32_t as = it & 1;
@@ -175,16 +186,64 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
       const int m = m_blk * BM + row;
       const bool valid = m < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      if (!p.geglu) {
+      bool from_ws = false;
+      if (p.splits > 1) {
+        // dump the raw fp32 partial of this K range, release the accumulator, then elect the last arrival
+        float* wrow = p.ws + (static_cast<size_t>(split) * p.M + (valid ? m : 0)) * p.N + n_blk * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              __stcg(reinterpret_cast<float4*>(wrow + c * 32 + j),
+                     make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3])));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[as]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          const int old = atomicAdd(&p.counters[tile], 1);
+          *split_flag = (old == p.splits - 1) ? 1 : 0;
+          if (old == p.splits - 1) p.counters[tile] = 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool last = *split_flag != 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone has read the flag before it can be rewritten
+        if (!last) continue;
+        __threadfence();
+        from_ws = true;
+      }
+      if (!p.geglu) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
           const int n0 = n_blk * BN + c * 32;
           float v[32];
+          if (!from_ws) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            if (valid) {
+              for (int sp = 0; sp < p.splits; ++sp) {
+                const float* wr = p.ws + (static_cast<size_t>(sp) * p.M + m) * p.N + n0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 t4 = __ldcg(reinterpret_cast<const float4*>(wr + j));
+                  v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                }
+              }
+            }
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -258,8 +317,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      if (!from_ws) {
+        tc_fence_before();
+        mbar_arrive(&tempty[as]);
+      }
     }
   }
 
@@ -355,7 +416,8 @@ int gemm_choose_bn(int M, int N, bool geglu, int num_sms) {
 }
 
 int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, bool linear, int B, int H, int W,
-                     const __half* Wt, int N, int Ktot, const GemmEpilogue& ep, int bn_force, int num_sms) {
+                     const __half* Wt, int N, int Ktot, const GemmEpilogue& ep, int bn_force, int num_sms,
+                     int split_force) {
   PNP_CHECK(nsrc >= 1 && nsrc <= 3, "gemm: 1..3 A sources");
   PNP_CHECK(taps0 == 1 || taps0 == 9, "gemm: taps must be 1 or 9");
   GemmParams& p = plan->p;
@@ -441,12 +503,37 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   p.ldc = ep.ldc;
   p.geglu = geglu ? 1 : 0;
   p.dbg = debug_words_device();
+  // split-K when the output has too few tiles to occupy the chip (8x8 / 16x16 levels: weight streaming)
+  p.splits = 1;
+  p.kb_per_split = p.num_kb;
+  const int tiles = p.m_tiles * p.n_tiles;
+  if (!geglu && split_force != 1 && tiles <= kGemmMaxCounters) {
+    int want = split_force > 1 ? split_force : (tiles * 2 <= num_sms ? num_sms / tiles : 1);
+    want = std::min(want, 16);
+    while (want > 1 && p.num_kb / want < 4) --want;
+    if (want > 1) {
+      p.kb_per_split = (p.num_kb + want - 1) / want;
+      p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    }
+  }
   plan->bn = bn;
-  plan->grid = std::min(p.m_tiles * p.n_tiles, num_sms);
+  plan->grid = std::min(tiles * p.splits, num_sms);
   return 0;
 }
 
+size_t gemm_ws_floats(const GemmPlan& plan) {
+  return plan.p.splits > 1 ? static_cast<size_t>(plan.p.splits) * plan.p.M * plan.p.N : 0;
+}
+void gemm_set_workspace(GemmPlan* plan, float* ws, int* counters) {
+  plan->p.ws = ws;
+  plan->p.counters = counters;
+}
+
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  if (plan.p.splits > 1 && (plan.p.ws == nullptr || plan.p.counters == nullptr)) {
+    set_last_error("gemm_launch: split-K plan without workspace");
+    return -2;
+  }
   switch (plan.bn) {
     case 256: return launch_t<256>(plan, stream);
     case 160: return launch_t<160>(plan, stream);

@@ -76,7 +76,8 @@ int step_epilogue_launch(const StepParams& p, cudaStream_t s);
 
 // LocalBlend (attention_control.py:97-121): store = accumulated [layers*? ...] see epilogue.cu
 struct LocalBlendParams {
-  const float* store;  // [5 layers][2 prompts][8 heads][256 queries][77] running sum over steps
+  const float* store;  // [5 layers][slots][8 heads][256 queries][77] running sum over steps; slots 0,1 are read
+  long long layer_stride, slot_stride;  // floats
   int nwords[2];       // words with alpha_layers != 0 per prompt
   int words[2][8];
   float alpha[2][8];

@@ -62,6 +62,11 @@ struct alignas(64) GemmParams {
   __half* out;  // [M, ldc]
   int ldc;
   int geglu;  // epilogue: out[:, j] = (v_j) * gelu(g_j), tile columns [0,BN/2) = v, [BN/2,BN) = g
+  // split-K (small-M, weight-streaming layers): `splits` CTAs share one output tile, each reduces a K range into
+  // ws[split][M][N] (fp32); the last CTA to arrive (counters[tile]) sums the slices in index order and runs the epilogue
+  int splits, kb_per_split;
+  float* ws;
+  int* counters;
   volatile unsigned int* dbg;
 };
 
@@ -86,9 +91,14 @@ struct GemmEpilogue {
 
 // conv-mode: srcs[0] is NHWC [B,H,W,C0] with `taps0`=9 (3x3, pad 1) or 1; linear mode: B=H=1, W=M.
 int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, bool linear, int B, int H, int W,
-                     const __half* Wt, int N, int Ktot, const GemmEpilogue& ep, int bn_force, int num_sms);
+                     const __half* Wt, int N, int Ktot, const GemmEpilogue& ep, int bn_force, int num_sms,
+                     int split_force = 0);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 int gemm_choose_bn(int M, int N, bool geglu, int num_sms);
+// shared split-K workspace (all GEMMs of a stream run back to back): floats / ints needed by a plan
+size_t gemm_ws_floats(const GemmPlan& plan);
+void gemm_set_workspace(GemmPlan* plan, float* ws, int* counters);
+constexpr int kGemmMaxCounters = 4096;
 
 // ------------------------------------------------------------------ normalisation kernels (norm.cu)
 // GroupNorm(32 groups) [+SiLU] over NHWC fp16; optional second source = channel concat (skip connection).

@@ -20,14 +20,14 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def gemm(a, w, bias=None, residual=None, geglu=False, bn=0):
+def gemm(a, w, bias=None, residual=None, geglu=False, bn=0, split=1):
     lib = _lib.load()
     M, K = a.shape
     N = w.shape[0]
     n_out = N // 2 if geglu else N
     out = torch.empty(M, n_out, dtype=torch.float16, device=a.device)
     _lib.check(lib.pnp_test_gemm(ptr(a), M, K, a.stride(0), ptr(w), N, ptr(bias), ptr(residual), ptr(out), n_out,
-                                 1 if geglu else 0, bn, stream()))
+                                 1 if geglu else 0, bn, split, stream()))
     torch.cuda.synchronize()
     return out
 
@@ -41,7 +41,7 @@ def pack_conv3(w_oihw, shortcut=None):
     return p.contiguous()
 
 
-def conv3x3(x_nhwc, w_packed, bias=None, residual=None, sc0=None, sc1=None, bn=0):
+def conv3x3(x_nhwc, w_packed, bias=None, residual=None, sc0=None, sc1=None, bn=0, split=1):
     lib = _lib.load()
     B, H, W, Cc = x_nhwc.shape
     N = w_packed.shape[0]
@@ -49,6 +49,6 @@ def conv3x3(x_nhwc, w_packed, bias=None, residual=None, sc0=None, sc1=None, bn=0
     _lib.check(lib.pnp_test_conv3x3(ptr(x_nhwc), B, H, W, Cc, ptr(w_packed), N, ptr(sc0),
                                     0 if sc0 is None else sc0.shape[-1], ptr(sc1),
                                     0 if sc1 is None else sc1.shape[-1], ptr(bias), ptr(residual), ptr(out), bn,
-                                    stream()))
+                                    split, stream()))
     torch.cuda.synchronize()
     return out

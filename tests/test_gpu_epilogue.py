@@ -84,3 +84,43 @@ def test_offset_mode(engine, cuda):
     assert G.rel_l2(loss.cpu(), loss_ref) < 1e-6 and G.rel_l2(cur.cpu(), cur_ref) < 1e-6
     # the branch lands on the target up to one rounding (rec + (target - rec))
     assert (cur.cpu() - target).abs().max() < 1e-5
+
+
+def test_local_blend_kernel_vs_oracle_via_pipeline_store(cuda):
+    """Drive one real UNet call with store slots on, read the store back, run the LocalBlend kernel and compare with the
+    oracle's LocalBlend applied to the very same maps."""
+    from pnpinversion_b200 import synth
+    from pnpinversion_b200.attention_control import make_controller, register_attention_control
+    from pnpinversion_b200.model import FusedModel
+
+    model = FusedModel.synthetic(device="cuda:0", max_batch=4)
+    prompts = list(synth.CAT_PROMPTS)
+    tok, te = model.tokenizer, model.text_encoder
+    ctx = torch.cat([te(tok([""] * 2).input_ids)[0], te(tok(prompts).input_ids)[0]]).to(cuda, torch.float32)
+    ctrl = make_controller(model, prompts, False, {"default_": 0.4}, 0.6, blend_words=(("cat",), ("cat",)),
+                           num_ddim_steps=4)
+    register_attention_control(model, ctrl)
+    lat = torch.cat([synth.synth_latent(0), synth.synth_latent(1)]).to(cuda)
+    model.unet(torch.cat([lat] * 2), 500, encoder_hidden_states=ctx)
+    store = torch.empty(5, 2 * _lib.PNP_MAX_SLOTS, 8, 256, 77, device=cuda)
+    _lib.check(_lib.load().pnp_store_read(model.unet.handle, C.c_void_p(store.data_ptr()), store.numel(),
+                                          _lib.current_stream_ptr()))
+    x = torch.randn(2, 4, 64, 64, generator=torch.Generator().manual_seed(4)).to(cuda)
+    got = ctrl.step_callback(x.clone())  # counter 1 > start_blend 0 -> blends
+    torch.cuda.synchronize()
+    # oracle LocalBlend on the same maps
+    maps = store[:, :2].cpu().double()  # (5,2,8,256,77)
+    maps = maps.permute(1, 0, 2, 3, 4).reshape(2, 40, 1, 16, 16, 77)
+    alpha = ctrl.local_blend.alpha_layers.double().reshape(2, 1, 1, 1, 1, 77)
+    m = (maps * alpha).sum(-1).mean(1)
+    m = F.max_pool2d(m, (3, 3), (1, 1), padding=(1, 1))
+    mask = F.interpolate(m, size=(64, 64))
+    mask = mask / mask.max(2, keepdim=True)[0].max(3, keepdim=True)[0]
+    mask = mask.gt(0.3)
+    mask = (mask[:1] + mask).float()
+    xc = x.cpu()
+    ref = xc[:1] + mask * (xc - xc[:1])
+    frac = float(mask[1].mean())
+    assert 0.0 < frac < 1.0, frac  # a non-trivial mask
+    assert torch.equal(got.cpu(), ref)
+    model.unet.close()

@@ -97,3 +97,26 @@ def test_conv3x3_fused_shortcut_over_concat(cuda):
     cat = torch.cat([a, b], dim=-1).permute(0, 3, 1, 2).float()
     ref = (F.conv2d(hmid.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1) + F.conv2d(cat, ws.float()))
     assert G.rel_l2(out, ref.permute(0, 2, 3, 1)) < 1e-3
+
+
+@pytest.mark.parametrize("split", [0, 2, 5, 9])
+def test_split_k_conv_small_m(cuda, split):
+    """8x8 / 16x16 levels: few output tiles, K split across CTAs, deterministic last-arrival reduction."""
+    B, H, C, N = 4, 8, 1280, 1280
+    x = _mk((B, H, H, C), cuda, 20)
+    w = _mk((N, C, 3, 3), cuda, 21, (9 * C) ** -0.5)
+    bias = torch.randn(N, device=cuda) * 0.1
+    r = _mk((B, H, H, N), cuda, 22)
+    out = G.conv3x3(x, G.pack_conv3(w), bias=bias, residual=r, split=split)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1) + r.float()
+    assert G.rel_l2(out, ref) < 1e-3
+    out2 = G.conv3x3(x, G.pack_conv3(w), bias=bias, residual=r, split=split)
+    assert torch.equal(out, out2)  # bit-reproducible
+
+
+def test_split_k_linear(cuda):
+    M, K, N = 308, 768, 2560
+    a = _mk((M, K), cuda, 23)
+    w = _mk((N, K), cuda, 24, K ** -0.5)
+    out = G.gemm(a, w, split=3)
+    assert G.rel_l2(out, a.float() @ w.float().t()) < 1e-3
