@@ -53,6 +53,13 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// 2^x on a packed pair of fp16 (one MUFU op for two exponentials); the result is directly an mma A-fragment register
+__device__ __forceinline__ uint32_t ex2_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  uint32_t x = *reinterpret_cast<uint32_t*>(&h), y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -138,6 +145,31 @@ __device__ __forceinline__ void pv_tile(float (&o)[Geo<D>::NT][4], const float (
   }
 }
 
+// O[16 x D] += P . V and l[16] += P . 1 with P given as packed fp16 A-fragments (pa[kt] = 16 keys)
+template <int D, int KT>
+__device__ __forceinline__ void pv_tile_packed(float (&o)[Geo<D>::NT][4], float (&lacc)[4], const uint32_t (&pa)[KT][4],
+                                               const uint8_t* sV, int lane) {
+  using G = Geo<D>;
+  const uint32_t base = s_u32(sV) + ((lane & 7) + ((lane >> 3) & 1) * 8) * G::PITCH + ((lane >> 4) * 8) * 2;
+  constexpr uint32_t ONES = 0x3C003C00u;  // half2(1, 1): row sums through the tensor core, in fp32
+#pragma unroll
+  for (int kt = 0; kt < KT; ++kt) {
+#pragma unroll
+    for (int dp = 0; dp < G::NT / 2; ++dp) {
+      uint32_t vb[4];
+      ldsm_x4_t(vb, base + kt * 16 * G::PITCH + dp * 32);
+      mma16816(o[2 * dp], pa[kt], vb[0], vb[1]);
+      mma16816(o[2 * dp + 1], pa[kt], vb[2], vb[3]);
+    }
+    if (G::NT & 1) {
+      uint32_t vb[2];
+      ldsm_x2_t(vb, base + kt * 16 * G::PITCH + (G::NT - 1) * 16);
+      mma16816(o[G::NT - 1], pa[kt], vb[0], vb[1]);
+    }
+    mma16816(lacc, pa[kt], ONES, ONES);
+  }
+}
+
 template <int D>
 __device__ __forceinline__ void load_q_frags(uint32_t (&qf)[Geo<D>::KS][4], const uint8_t* sQ, int warp, int lane) {
   using G = Geo<D>;
@@ -189,7 +221,8 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnParams p) 
   float o[G::NT][4];
 #pragma unroll
   for (int i = 0; i < G::NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  float lacc[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t qf[G::KS][4];
 
   const int ntiles = p.N / 64;
@@ -222,29 +255,25 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnParams p) 
     m0 = mn0;
     m1 = mn1;
     const float off0 = mn0 * sl2, off1 = mn1 * sl2;
-    float rs0 = 0.f, rs1 = 0.f;
+    // p = 2^(s*scale*log2e - max): argument in fp32 (one FFMA), exponential on packed fp16 pairs
+    uint32_t pa[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] * sl2 - off0);
-      s[nt][1] = exp2f(s[nt][1] * sl2 - off0);
-      s[nt][2] = exp2f(s[nt][2] * sl2 - off1);
-      s[nt][3] = exp2f(s[nt][3] * sl2 - off1);
-      rs0 += s[nt][0] + s[nt][1];
-      rs1 += s[nt][2] + s[nt][3];
+      const uint32_t h01 = ex2_h2(fmaf(s[nt][0], sl2, -off0), fmaf(s[nt][1], sl2, -off0));
+      const uint32_t h23 = ex2_h2(fmaf(s[nt][2], sl2, -off1), fmaf(s[nt][3], sl2, -off1));
+      pa[nt >> 1][(nt & 1) * 2] = h01;
+      pa[nt >> 1][(nt & 1) * 2 + 1] = h23;
     }
-    l0 = l0 * a0 + rs0;
-    l1 = l1 * a1 + rs1;
 #pragma unroll
     for (int nt = 0; nt < G::NT; ++nt) {
       o[nt][0] *= a0; o[nt][1] *= a0;
       o[nt][2] *= a1; o[nt][3] *= a1;
     }
-    pv_tile<D, 8>(o, s, cV, lane);
+    lacc[0] *= a0; lacc[1] *= a0;
+    lacc[2] *= a1; lacc[3] *= a1;
+    pv_tile_packed<D, 4>(o, lacc, pa, cV, lane);
   }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float l0 = lacc[0], l1 = lacc[2];  // every column of the ones-MMA holds the row sum
   __half* og = p.o + static_cast<size_t>(b) * p.N * p.ldo + h * D;
   store_o<D>(o, 1.f / l0, 1.f / l1, og, p.ldo, qt * 64 + warp * 16, lane);
 }

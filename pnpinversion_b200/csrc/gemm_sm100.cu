@@ -394,25 +394,56 @@ int launch_t(const GemmPlan& plan, cudaStream_t stream) {
 
 }  // namespace
 
+// Cost model (cycles) behind the tile-shape / split-K choice.  Measured on B200 (profiles/r1_per_op_*.md): most GEMMs of
+// this UNet are bound by L2->SM operand traffic (~5 KB/cycle chip-wide), not by the tensor pipe, so the model weighs
+//   tensor   : waves * k_blocks * max(2*BN, 128+BN)        (4 MMAs of 128xBNx16 vs shared-memory feed, per 64-wide K block)
+//   L2       : tiles * k_blocks * (16 KB + BN*128 B) / 5000
+//   epilogue : waves * (BN/32) * 700  (+ the split-K round trip through the fp32 workspace)
+static long gemm_cost(int M, int N, int num_kb, int bn, int splits, int num_sms) {
+  const long m_tiles = (M + BM - 1) / BM;
+  const long tiles = m_tiles * (N / bn);
+  const long kb_per = (num_kb + splits - 1) / splits;
+  const long ctas = tiles * splits;
+  const long waves = (ctas + num_sms - 1) / num_sms;
+  const long tensor = waves * kb_per * std::max(2 * bn, 128 + bn);
+  const long l2 = tiles * num_kb * (16384L + bn * 128L) / 5000;
+  long epi = waves * (bn / 32) * 700;
+  if (splits > 1) epi += waves * (bn / 32) * 300 + (bn / 32) * 200L * splits + 2000;
+  return std::max(tensor, l2) + epi + 4000;
+}
+
 int gemm_choose_bn(int M, int N, bool geglu, int num_sms) {
+  int bn = 0, sp = 0;
+  gemm_choose(M, N, 64, geglu, num_sms, 0, 1, &bn, &sp);
+  return bn;
+}
+
+void gemm_choose(int M, int N, int num_kb, bool geglu, int num_sms, int bn_force, int split_force, int* bn_out,
+                 int* splits_out) {
   const int cands[4] = {256, 160, 128, 64};
-  const int m_tiles = (M + BM - 1) / BM;
-  long best_cost = -1;
-  int best = 0;
+  long best = -1;
+  *bn_out = 0;
+  *splits_out = 1;
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
+    if (bn_force > 0 && bn != bn_force) continue;
     if (N % bn != 0) continue;
     if (geglu && bn != 256 && bn != 128) continue;
-    const long tiles = static_cast<long>(m_tiles) * (N / bn);
-    const long waves = (tiles + num_sms - 1) / num_sms;
-    const long per = std::max(2 * bn, 128 + bn);  // tensor-pipe cycles vs shared-memory cycles per 64-wide K block
-    const long cost = waves * per;
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = bn;
+    const long tiles = static_cast<long>((M + BM - 1) / BM) * (N / bn);
+    for (int sp = 1; sp <= 16; ++sp) {
+      if (split_force > 0 && sp != split_force) continue;
+      if (sp > 1 && (geglu || tiles > kGemmMaxCounters || num_kb / sp < 4)) continue;
+      // a split must not leave an empty K range
+      const int kb_per = (num_kb + sp - 1) / sp;
+      if ((sp - 1) * kb_per >= num_kb) continue;
+      const long c = gemm_cost(M, N, num_kb, bn, sp, num_sms);
+      if (best < 0 || c < best) {
+        best = c;
+        *bn_out = bn;
+        *splits_out = sp;
+      }
     }
   }
-  return best;
 }
 
 int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, bool linear, int B, int H, int W,
@@ -431,7 +462,10 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   }
   PNP_CHECK(ksum == Ktot, "gemm: K of the sources does not match the packed weight");
   const bool geglu = ep.geglu;
-  int bn = bn_force > 0 ? bn_force : gemm_choose_bn(M, N, geglu, num_sms);
+  int bn = 0, splits = 1;
+  gemm_choose(M, N, Ktot / BK, geglu, num_sms, bn_force, split_force, &bn, &splits);
+  if (bn == 0 && split_force > 1) gemm_choose(M, N, Ktot / BK, geglu, num_sms, bn_force, 0, &bn, &splits);
+  PNP_CHECK(bn != 0, "gemm: no valid tile shape for this N");
   PNP_CHECK(bn == 256 || bn == 160 || bn == 128 || bn == 64, "gemm: unsupported BN");
   PNP_CHECK(N % bn == 0, "gemm: N must be a multiple of the column tile");
   PNP_CHECK(!geglu || bn == 256 || bn == 128, "gemm: GEGLU epilogue needs BN 128/256");
@@ -504,18 +538,9 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   p.geglu = geglu ? 1 : 0;
   p.dbg = debug_words_device();
   // split-K when the output has too few tiles to occupy the chip (8x8 / 16x16 levels: weight streaming)
-  p.splits = 1;
-  p.kb_per_split = p.num_kb;
+  p.splits = splits;
+  p.kb_per_split = (p.num_kb + splits - 1) / splits;
   const int tiles = p.m_tiles * p.n_tiles;
-  if (!geglu && split_force != 1 && tiles <= kGemmMaxCounters) {
-    int want = split_force > 1 ? split_force : (tiles * 2 <= num_sms ? num_sms / tiles : 1);
-    want = std::min(want, 16);
-    while (want > 1 && p.num_kb / want < 4) --want;
-    if (want > 1) {
-      p.kb_per_split = (p.num_kb + want - 1) / want;
-      p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
-    }
-  }
   plan->bn = bn;
   plan->grid = std::min(tiles * p.splits, num_sms);
   return 0;

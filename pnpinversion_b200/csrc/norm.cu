@@ -49,20 +49,35 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[i][e] = ss[i][e] = 0.f;
   if (ty < rows_y) {
-    for (int pix = ty; pix < ppc; pix += rows_y) {
-      const size_t row = static_cast<size_t>(b) * HW + static_cast<size_t>(slice) * ppc + pix;
+    constexpr int U = 4;  // pixels in flight per thread (memory-level parallelism: these kernels are latency-bound)
+    for (int pix0 = ty; pix0 < ppc; pix0 += U * rows_y) {
+      uint4 u[U][GN_MAX_VPT];
 #pragma unroll
-      for (int i = 0; i < GN_MAX_VPT; ++i) {
-        if (i < vpt) {
-          const int v = tx + i * tx_n;
-          const uint4 u = (v < nvec0) ? *reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8)
-                                      : *reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8);
-          float f[8];
-          unpack8(u, f);
+      for (int j = 0; j < U; ++j) {
+        const int pix = pix0 + j * rows_y;
+        const size_t row = static_cast<size_t>(b) * HW + static_cast<size_t>(slice) * ppc + pix;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            s[i][e] += f[e];
-            ss[i][e] += f[e] * f[e];
+        for (int i = 0; i < GN_MAX_VPT; ++i) {
+          u[j][i] = make_uint4(0, 0, 0, 0);
+          if (i < vpt && pix < ppc) {
+            const int v = tx + i * tx_n;
+            u[j][i] = (v < nvec0) ? __ldg(reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8))
+                                  : __ldg(reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8));
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+#pragma unroll
+        for (int i = 0; i < GN_MAX_VPT; ++i) {
+          if (i < vpt) {
+            float f[8];
+            unpack8(u[j][i], f);  // out-of-range pixels were loaded as zeros: they add nothing
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              s[i][e] += f[e];
+              ss[i][e] += f[e] * f[e];
+            }
           }
         }
       }
@@ -169,19 +184,37 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
   const int nvec = C >> 3, nvec0 = C0 >> 3;
   const int total = ppc * nvec;
   const size_t row0 = static_cast<size_t>(b) * HW + static_cast<size_t>(blockIdx.x) * ppc;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int pix = idx / nvec, v = idx - pix * nvec;
-    const size_t row = row0 + pix;
-    const uint4 u = (v < nvec0) ? *reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8)
-                                : *reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8);
-    float f[8];
-    unpack8(u, f);
+  constexpr int U = 4;
+  for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
+    uint4 u[U];
+    int pixs[U], vs[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float y = f[e] * scale[v * 8 + e] + shift[v * 8 + e];
-      f[e] = do_silu ? silu(y) : y;
+    for (int j = 0; j < U; ++j) {
+      const int idx = base + j * blockDim.x;
+      const int pix = idx / nvec, v = idx - pix * nvec;
+      pixs[j] = pix;
+      vs[j] = v;
+      if (idx < total) {
+        const size_t row = row0 + pix;
+        u[j] = (v < nvec0) ? __ldg(reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8))
+                           : __ldg(reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8));
+      }
     }
-    *reinterpret_cast<uint4*>(out + row * C + v * 8) = pack8(f);
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int idx = base + j * blockDim.x;
+      if (idx < total) {
+        float f[8];
+        unpack8(u[j], f);
+        const int v = vs[j];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float y = f[e] * scale[v * 8 + e] + shift[v * 8 + e];
+          f[e] = do_silu ? silu(y) : y;
+        }
+        *reinterpret_cast<uint4*>(out + (row0 + pixs[j]) * C + v * 8) = pack8(f);
+      }
+    }
   }
 }
 
@@ -193,64 +226,68 @@ int gn_ppc(int B, int HW) {
 }
 
 // ------------------------------------------------------------------ LayerNorm: one warp per token
-template <int VPL>  // 16-byte vectors per lane (C = 8*32*VPL at most)
+template <int VPL, int R>  // VPL 16-byte vectors per lane (C <= 8*32*VPL), R rows in flight per warp
 __global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float eps, __half* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = C >> 3;
-  float gam[VPL][8], bet[VPL][8];
+  for (int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; row0 < rows; row0 += nwarps * R) {
+    uint4 u[R][VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        gam[i][e] = gamma[v * 8 + e];
-        bet[i][e] = beta[v * 8 + e];
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + i * 32;
+        u[r][i] = make_uint4(0, 0, 0, 0);
+        if (v < nvec && row0 + r < rows)
+          u[r][i] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(row0 + r) * C + v * 8));
       }
     }
-  }
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps) {
-    const __half* xr = x + static_cast<size_t>(row) * C;
-    float f[VPL][8];
-    float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
-        unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f[i]);
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r >= rows) break;
+      float f[VPL][8];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        unpack8(u[r][i], f[i]);  // lanes beyond nvec hold zeros
 #pragma unroll
         for (int e = 0; e < 8; ++e) s += f[i][e];
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / C;
-    float q = 0.f;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / C;
+      float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
+      for (int i = 0; i < VPL; ++i) {
+        if (lane + i * 32 < nvec) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float d = f[i][e] - mean;
-          q += d * d;
+          for (int e = 0; e < 8; ++e) {
+            const float d = f[i][e] - mean;
+            q += d * d;
+          }
         }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / C + eps);
-    __half* orow = out + static_cast<size_t>(row) * C;
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / C + eps);
+      __half* orow = out + static_cast<size_t>(row0 + r) * C;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
-        float y[8];
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float y[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * gam[i][e] + bet[i][e];
-        *reinterpret_cast<uint4*>(orow + v * 8) = pack8(y);
+          for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * gg[e] + bb[e];
+          *reinterpret_cast<uint4*>(orow + v * 8) = pack8(y);
+        }
       }
     }
   }
@@ -297,7 +334,7 @@ constexpr int CIN_K = 36;
 constexpr int CIN_CO = 320;
 __global__ void conv_in_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w,
                                const float* __restrict__ bias, __half* __restrict__ out) {
-  __shared__ float ws[CIN_K * CIN_CO];  // [k][co], k = ci*9 + tap
+  __shared__ __align__(16) float ws[CIN_K * CIN_CO];  // [k][co], k = ci*9 + tap
   for (int i = threadIdx.x; i < CIN_K * CIN_CO; i += blockDim.x) ws[i] = w[i];  // prepacked [k][co]
   __syncthreads();
   const int nvec = CIN_CO / 8;  // 40
@@ -318,9 +355,10 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int B, int H, int W,
         const int yi = yy + tap / 3 - 1, xi = xx + tap % 3 - 1;
         float a = 0.f;
         if (yi >= 0 && yi < H && xi >= 0 && xi < W) a = x[((static_cast<size_t>(b) * 4 + ci) * H + yi) * W + xi];
-        const float* wr = ws + (ci * 9 + tap) * CIN_CO + v * 8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += a * wr[e];
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * CIN_CO + v * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * CIN_CO + v * 8 + 4);
+        acc[0] += a * w0.x; acc[1] += a * w0.y; acc[2] += a * w0.z; acc[3] += a * w0.w;
+        acc[4] += a * w1.x; acc[5] += a * w1.y; acc[6] += a * w1.z; acc[7] += a * w1.w;
       }
     }
     *reinterpret_cast<uint4*>(out + pix * CIN_CO + v * 8) = pack8(acc);
@@ -409,8 +447,9 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   PNP_CUDA(cudaGetLastError());
   const size_t sm2 = (2 * static_cast<size_t>(C) + 2 * GN_GROUPS) * sizeof(float);
   // the apply pass is pure streaming: fewer, fatter CTAs than the statistics pass
+  // one pass of 4 vectors per thread per CTA where possible (1024 vectors per CTA)
   int ppa = ppc;
-  while (ppa < HW && static_cast<long>(B) * (HW / ppa) > 2 * 148) ppa <<= 1;
+  while (ppa > 1 && ppa * (C / 8) > 1024 && HW % (ppa / 2) == 0) ppa >>= 1;
   gn_apply_kernel<<<dim3(HW / ppa, B), 256, sm2, s>>>(x0, C0, x1, C1, HW, mean_rstd, gamma, beta, do_silu ? 1 : 0, out,
                                                       ppa);
   PNP_CUDA(cudaGetLastError());
@@ -425,14 +464,16 @@ int layernorm_launch(const __half* x, int rows, int C, const float* gamma, const
                      cudaStream_t s) {
   PNP_CHECK(C % 8 == 0 && C <= 8 * 32 * 5, "layernorm: C");
   const int threads = 256;
-  const int blocks = std::min((rows * 32 + threads - 1) / threads, 148 * 8);
   const int vpl = (C / 8 + 31) / 32;
+  const int R = vpl <= 2 ? 4 : 2;
+  const int warps = (rows + R - 1) / R;
+  const int blocks = std::max(1, std::min((warps * 32 + threads - 1) / threads, 148 * 8));
   switch (vpl) {
-    case 1: ln_kernel<1><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
-    case 2: ln_kernel<2><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
-    case 3: ln_kernel<3><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
-    case 4: ln_kernel<4><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
-    default: ln_kernel<5><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    case 1: ln_kernel<1, 4><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    case 2: ln_kernel<2, 4><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    case 3: ln_kernel<3, 2><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    case 4: ln_kernel<4, 2><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    default: ln_kernel<5, 2><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
   }
   PNP_CUDA(cudaGetLastError());
   return 0;

@@ -95,6 +95,8 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
                      int split_force = 0);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 int gemm_choose_bn(int M, int N, bool geglu, int num_sms);
+void gemm_choose(int M, int N, int num_kb, bool geglu, int num_sms, int bn_force, int split_force, int* bn_out,
+                 int* splits_out);
 // shared split-K workspace (all GEMMs of a stream run back to back): floats / ints needed by a plan
 size_t gemm_ws_floats(const GemmPlan& plan);
 void gemm_set_workspace(GemmPlan* plan, float* ws, int* counters);
