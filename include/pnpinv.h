@@ -119,8 +119,8 @@ int pnp_store_read(pnp_engine* h, float* out_dev, int64_t max_floats, void* stre
 /* runs one UNet forward eagerly with a CUDA event pair around every op of the plan (on the engine's stream);
  * kind: 0 tcgen05 gemm/conv, 1 groupnorm, 2 layernorm, 3 self-attention, 4 cross-attention, 5 other;
  * flops: algorithmic 2*MAC of the op.  Used by bench.py for the roofline of the dominant kernel. */
-int pnp_unet_profile(pnp_engine* h, int batch, int t_index, float* ms_out, int32_t* kind_out, double* flops_out,
-                     int max_ops, int* n_out);
+int pnp_unet_profile(pnp_engine* h, int batch, int t_index, int reps, float* ms_out, int32_t* kind_out,
+                     double* flops_out, int max_ops, int* n_out); /* each op launched `reps` times back to back */
 int pnp_kernel_launches(pnp_engine* h, int64_t* out); /* kernels launched by this handle so far (graph nodes count) */
 int pnp_set_use_graph(pnp_engine* h, int enable);     /* capture each UNet forward into a CUDA graph (default on) */
 

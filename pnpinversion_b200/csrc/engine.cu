@@ -1121,8 +1121,8 @@ int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, 
   return leave(h, caller);
 }
 
-int pnp_unet_profile(pnp_engine* h, int batch, int t_index, float* ms_out, int32_t* kind_out, double* flops_out,
-                     int max_ops, int* n_out) {
+int pnp_unet_profile(pnp_engine* h, int batch, int t_index, int reps, float* ms_out, int32_t* kind_out,
+                     double* flops_out, int max_ops, int* n_out) {
   PNP_CHECK(h && h->finalized && ms_out && kind_out && flops_out && n_out, "pnp_unet_profile: bad argument");
   PNP_CHECK(h->ctx_batch == batch, "pnp_unet_profile: call pnp_set_context for this batch first");
   PNP_CHECK(t_index >= 0 && t_index < h->n_t, "pnp_unet_profile: t_index");
@@ -1139,14 +1139,21 @@ int pnp_unet_profile(pnp_engine* h, int batch, int t_index, float* ms_out, int32
   for (auto& e : ev) PNP_CUDA(cudaEventCreate(&e));
   // x_in keeps whatever the last forward left there; the timing does not depend on the values
   PNP_CUDA(cudaEventRecord(ev[0], s));
+  // every op is launched `reps` times back to back between two events: that amortises the host launch cost, which
+  // would otherwise dominate the microsecond-scale kernels (in-place residual updates make the VALUES meaningless
+  // after repetition; the timing is unaffected)
+  if (reps < 1) reps = 1;
   for (int i = 0; i < n; ++i) {
-    rc = pl->ops[i](s);
-    if (rc) return rc;
+    for (int r = 0; r < reps; ++r) {
+      rc = pl->ops[i](s);
+      if (rc) return rc;
+    }
     PNP_CUDA(cudaEventRecord(ev[i + 1], s));
   }
   PNP_CUDA(cudaStreamSynchronize(s));
   for (int i = 0; i < n; ++i) {
     PNP_CUDA(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]));
+    ms_out[i] /= reps;
     kind_out[i] = pl->info[i].kind;
     flops_out[i] = pl->info[i].flops;
   }

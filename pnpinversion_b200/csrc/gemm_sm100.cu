@@ -2,14 +2,14 @@
 //
 //   D[M,N] = A[M,K] . Wt[N,K]^T   fp16 operands, fp32 accumulation in TMEM, fused epilogue.
 //
-// One persistent CTA per SM, 256 threads, warp-specialised:
+// One persistent CTA per SM, 384 threads, warp-specialised:
 //   warp 0 (lane 0)  TMA producer: per 64-wide K block one 4-D box of the NHWC activation (128 pixels x 64 channels,
 //                    shifted by the 3x3 tap, hardware zero fill = the conv padding) and one 2-D box of the weights,
 //                    both landing 128B-swizzled in a STAGES-deep shared-memory ring guarded by full/empty mbarriers.
 //   warp 1 (lane 0)  MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of two TMEM accumulators,
 //                    tcgen05.commit releases the stage / publishes the accumulator.
 //   warp 2           TMEM allocator.
-//   warps 4..7       epilogue: tcgen05.ld 32 lanes x 32 columns, + bias + time-embedding + residual (or GEGLU),
+//   warps 4..11      epilogue (two warps per TMEM lane quarter): tcgen05.ld 32 lanes x 32 columns, + bias + time-embedding + residual (or GEGLU),
 //                    fp16 pack, 16-byte global stores; overlaps the next tile's MMAs (double-buffered accumulator).
 //
 // This is the only place the library does dense contractions: ResnetBlock2D convs (reference arithmetic:
@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 256);
     }
     fence_barrier_init();
   }
@@ -168,8 +168,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // -------------------------------------------------------------- epilogue
-    const int q = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
+    // -------------------------------------------------------------- epilogue (8 warps: 2 per TMEM lane quarter)
+    const int q = warp & 3;            // TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 4) >> 2;  // which half of the 32-column chunks this warp owns
     const int row = q * 32 + lane;
     const float* temb = nullptr;
     if (p.temb_table != nullptr) temb = p.temb_table + static_cast<size_t>(*p.t_index) * p.temb_stride;
@@ -181,17 +182,25 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
       const int n_blk = tile / p.m_tiles;
       const uint32_t as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tfull[as], aphase, p.dbg, 4);
-      tc_fence_after();
       const int m = m_blk * BM + row;
       const bool valid = m < p.M;
+      // the residual does not depend on the accumulator: fetch the first chunk before waiting for the MMAs
+      uint4 rcur[4], rnext[4];
+      const bool has_res = p.residual != nullptr && valid && !p.geglu;
+      const __half* res_row = has_res ? p.residual + static_cast<size_t>(m) * p.ldr + n_blk * BN : nullptr;
+      if (has_res && half < BN / 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(res_row + half * 32) + j);
+      }
+      mbar_wait(&tfull[as], aphase, p.dbg, 4);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       bool from_ws = false;
       if (p.splits > 1) {
         // dump the raw fp32 partial of this K range, release the accumulator, then elect the last arrival
         float* wrow = p.ws + (static_cast<size_t>(split) * p.M + (valid ? m : 0)) * p.N + n_blk * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -206,82 +215,93 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
         tc_fence_before();
         mbar_arrive(&tempty[as]);
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 128) {
           const int old = atomicAdd(&p.counters[tile], 1);
           *split_flag = (old == p.splits - 1) ? 1 : 0;
           if (old == p.splits - 1) p.counters[tile] = 0;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const bool last = *split_flag != 0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone has read the flag before it can be rewritten
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read the flag before it can be rewritten
         if (!last) continue;
         __threadfence();
         from_ws = true;
       }
       if (!p.geglu) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int n0 = n_blk * BN + c * 32;
-          float v[32];
-          if (!from_ws) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(taddr + c * 32, r);
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          } else {
+        for (int c0 = 0; c0 < BN / 32; c0 += 2) {
+          const int c = c0 + half;
+          if (c < BN / 32) {
+            const int n0 = n_blk * BN + c * 32;
+            float v[32];
+            if (!from_ws) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(taddr + c * 32, r);
+              if (has_res && c + 2 < BN / 32) {  // prefetch the next chunk's residual under the TMEM load
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            if (valid) {
-              for (int sp = 0; sp < p.splits; ++sp) {
-                const float* wr = p.ws + (static_cast<size_t>(sp) * p.M + m) * p.N + n0;
+                for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 2) * 32) + j);
+              }
+              tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 t4 = __ldcg(reinterpret_cast<const float4*>(wr + j));
-                  v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            } else {
+              if (has_res && c + 2 < BN / 32) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 2) * 32) + j);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              if (valid) {
+                for (int sp = 0; sp < p.splits; ++sp) {
+                  const float* wr = p.ws + (static_cast<size_t>(sp) * p.M + m) * p.N + n0;
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    const float4 t4 = __ldcg(reinterpret_cast<const float4*>(wr + j));
+                    v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                  }
                 }
               }
             }
-          }
-          if (p.bias != nullptr) {
+            if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              }
             }
-          }
-          if (temb != nullptr) {
+            if (temb != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(temb + n0 + j));
-              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(temb + n0 + j));
+                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              }
             }
-          }
-          if (valid) {
-            if (p.residual != nullptr) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(m) * p.ldr + n0);
+            if (valid) {
+              if (has_res) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __half2* h = reinterpret_cast<const __half2*>(&rcur[j]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(h[e]);
+                    v[j * 8 + e * 2] += f.x;
+                    v[j * 8 + e * 2 + 1] += f.y;
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+              }
+              uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldc + n0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint4 u = rp[j];
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __half22float2(h[e]);
-                  v[j * 8 + e * 2] += f.x;
-                  v[j * 8 + e * 2 + 1] += f.y;
-                }
+                uint4 u;
+                u.x = pack_half2(v[j * 8 + 0], v[j * 8 + 1]);
+                u.y = pack_half2(v[j * 8 + 2], v[j * 8 + 3]);
+                u.z = pack_half2(v[j * 8 + 4], v[j * 8 + 5]);
+                u.w = pack_half2(v[j * 8 + 6], v[j * 8 + 7]);
+                op[j] = u;
               }
-            }
-            uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldc + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack_half2(v[j * 8 + 0], v[j * 8 + 1]);
-              u.y = pack_half2(v[j * 8 + 2], v[j * 8 + 3]);
-              u.z = pack_half2(v[j * 8 + 4], v[j * 8 + 5]);
-              u.w = pack_half2(v[j * 8 + 6], v[j * 8 + 7]);
-              op[j] = u;
             }
           }
         }
@@ -289,7 +309,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
         // GEGLU: tile columns [0,BN/2) hold the value projection, [BN/2,BN) the gate projection of the same
         // output columns (weights are packed that way by the engine).  attention.py:329-333 (erf GELU).
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = half; c < BN / 64; c += 2) {
           uint32_t rv[32], rg[32];
           tmem_ld_32x32b_x32(taddr + c * 32, rv);
           tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, rg);
@@ -387,7 +407,7 @@ int launch_t(const GemmPlan& plan, cudaStream_t stream) {
                                   Cfg<BN>::SMEM));
     attr_set = true;
   }
-  gemm_tcgen05_kernel<BN><<<plan.grid, 256, Cfg<BN>::SMEM, stream>>>(plan.p);
+  gemm_tcgen05_kernel<BN><<<plan.grid, 384, Cfg<BN>::SMEM, stream>>>(plan.p);
   PNP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -405,7 +425,9 @@ static long gemm_cost(int M, int N, int num_kb, int bn, int splits, int num_sms)
   const long kb_per = (num_kb + splits - 1) / splits;
   const long ctas = tiles * splits;
   const long waves = (ctas + num_sms - 1) / num_sms;
-  const long tensor = waves * kb_per * std::max(2 * bn, 128 + bn);
+  // per CTA and 64-wide K block: tensor pipe, shared-memory feed, and the ~64 B/cycle one SM can pull from L2
+  const long per_kb = std::max<long>(std::max(2 * bn, 128 + bn), (16384L + bn * 128L) / 64);
+  const long tensor = waves * kb_per * per_kb;
   const long l2 = tiles * num_kb * (16384L + bn * 128L) / 5000;
   long epi = waves * (bn / 32) * 700;
   if (splits > 1) epi += waves * (bn / 32) * 300 + (bn / 32) * 200L * splits + 2000;
