@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(128) self_attn_kernel(const SelfAttnParams p) 
   uint8_t* sQ = sm;
   uint8_t* sK = sm + TILE;      // 2 stages
   uint8_t* sV = sm + 3 * TILE;  // 2 stages
+  pdl_sync();
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bq = p.q_row ? p.q_row[b] : b;
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnParams p
   uint8_t* sKs = sQs + QT;  // source-row K
   float* sP = reinterpret_cast<float*>(sKs + KT);  // [4 warps][16][XK]
   float* sTab = sP + 4 * 16 * XK;                  // alphas[80], eq[80], ca[80], then int mapper[80]
+  pdl_sync();
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -468,8 +470,7 @@ int launch_self(const SelfAttnParams& p, cudaStream_t s) {
                                   static_cast<int>(self_smem<D>())));
     attr = true;
   }
-  self_attn_kernel<D><<<dim3(p.N / 64, p.H, p.B), 128, self_smem<D>(), s>>>(p);
-  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(launch_k(self_attn_kernel<D>, dim3(p.N / 64, p.H, p.B), dim3(128), self_smem<D>(), s, p));
   return 0;
 }
 template <int D>
@@ -480,8 +481,7 @@ int launch_cross(const CrossAttnParams& p, cudaStream_t s) {
                                   static_cast<int>(cross_smem<D>())));
     attr = true;
   }
-  cross_attn_kernel<D><<<dim3((p.N + 63) / 64, p.H, p.B), 128, cross_smem<D>(), s>>>(p);
-  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(launch_k(cross_attn_kernel<D>, dim3((p.N + 63) / 64, p.H, p.B), dim3(128), cross_smem<D>(), s, p));
   return 0;
 }
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -38,6 +39,10 @@ volatile unsigned int* debug_words_device() {
   return g_dbg_dev;
 }
 const unsigned int* debug_words_host() { return g_dbg_host; }
+
+static bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl_enabled(bool on) { g_pdl = on; }
 
 // ------------------------------------------------------------------ architecture table (mirrors pnpinversion_b200/arch.py)
 static const int kBlockOut[4] = {320, 640, 1280, 1280};
@@ -896,6 +901,7 @@ int pnp_create(int device_ordinal, int max_batch, pnp_engine** out) {
   e->num_sms = prop.multiProcessorCount;
   e->max_batch = max_batch;
   debug_words_device();
+  if (const char* ev = getenv("PNP_PDL")) set_pdl_enabled(atoi(ev) != 0);
   PNP_CUDA(cudaStreamCreateWithFlags(&e->es, cudaStreamNonBlocking));
   PNP_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
   PNP_CUDA(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // set-up done: let the successor start its own, then wait for the predecessor's results
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int total_work = total_tiles * p.splits;
@@ -407,8 +408,7 @@ int launch_t(const GemmPlan& plan, cudaStream_t stream) {
                                   Cfg<BN>::SMEM));
     attr_set = true;
   }
-  gemm_tcgen05_kernel<BN><<<plan.grid, 384, Cfg<BN>::SMEM, stream>>>(plan.p);
-  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(launch_k(gemm_tcgen05_kernel<BN>, dim3(plan.grid), dim3(384), Cfg<BN>::SMEM, stream, plan.p));
   return 0;
 }
 

@@ -39,6 +39,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
                                 int ppc, int tx_n, int rows_y, int vpt, float* __restrict__ partials, float eps,
                                 float* __restrict__ mean_rstd, int* __restrict__ counters) {
   extern __shared__ float sm[];  // [rows_y][2*C] then reused
+  pdl_sync();
   const int C = C0 + C1;
   const int nvec0 = C0 >> 3;
   const int b = blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
@@ -135,17 +136,30 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
     if (g < GN_GROUPS) {
       const int cpg = C / GN_GROUPS;
       const float* pp = partials + (static_cast<size_t>(b) * nslices * GN_GROUPS + g) * 2;
+      // all (mean, M2) pairs of this lane are fetched up front (one memory latency instead of a dependent chain)
+      constexpr int MAXS = 16;  // nslices <= 128
+      float2 pr[MAXS];
+#pragma unroll
+      for (int j = 0; j < MAXS; ++j) {
+        const int s2 = sub + j * 8;
+        pr[j] = make_float2(0.f, 0.f);
+        if (s2 < nslices) pr[j] = __ldcg(reinterpret_cast<const float2*>(pp + static_cast<size_t>(s2) * GN_GROUPS * 2));
+      }
       float msum = 0.f;
-      for (int s2 = sub; s2 < nslices; s2 += 8) msum += __ldcg(pp + static_cast<size_t>(s2) * GN_GROUPS * 2);
+#pragma unroll
+      for (int j = 0; j < MAXS; ++j) msum += pr[j].x;  // missing slices contribute 0
       msum += __shfl_xor_sync(0xffffffffu, msum, 1);
       msum += __shfl_xor_sync(0xffffffffu, msum, 2);
       msum += __shfl_xor_sync(0xffffffffu, msum, 4);
       const float mean = msum / nslices;
       const float n_i = static_cast<float>(ppc) * cpg;
       float m2 = 0.f;
-      for (int s2 = sub; s2 < nslices; s2 += 8) {
-        const float d = __ldcg(pp + static_cast<size_t>(s2) * GN_GROUPS * 2) - mean;
-        m2 += __ldcg(pp + static_cast<size_t>(s2) * GN_GROUPS * 2 + 1) + n_i * d * d;
+#pragma unroll
+      for (int j = 0; j < MAXS; ++j) {
+        if (sub + j * 8 < nslices) {
+          const float d = pr[j].x - mean;
+          m2 += pr[j].y + n_i * d * d;
+        }
       }
       m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
       m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
@@ -162,6 +176,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
                                 const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int do_silu, __half* __restrict__ out, int ppc) {
   extern __shared__ float sm[];  // scale[C], shift[C], mean[32], rstd[32]
+  pdl_sync();
   const int C = C0 + C1;
   float* scale = sm;
   float* shift = sm + C;
@@ -229,9 +244,25 @@ int gn_ppc(int B, int HW) {
 template <int VPL, int R>  // VPL 16-byte vectors per lane (C <= 8*32*VPL), R rows in flight per warp
 __global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float eps, __half* __restrict__ out) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = C >> 3;
+  float gam[VPL][8], bet[VPL][8];  // issued before the activations are needed: one latency, not two in series
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      gam[i][0] = g0.x; gam[i][1] = g0.y; gam[i][2] = g0.z; gam[i][3] = g0.w;
+      gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
+      bet[i][0] = b0.x; bet[i][1] = b0.y; bet[i][2] = b0.z; bet[i][3] = b0.w;
+      bet[i][4] = b1.x; bet[i][5] = b1.y; bet[i][6] = b1.z; bet[i][7] = b1.w;
+    }
+  }
   for (int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; row0 < rows; row0 += nwarps * R) {
     uint4 u[R][VPL];
 #pragma unroll
@@ -277,12 +308,8 @@ __global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const f
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float* gg = gam[i];
+          const float* bb = bet[i];
           float y[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * gg[e] + bb[e];
@@ -295,6 +322,7 @@ __global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const f
 
 // ------------------------------------------------------------------ data movement
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, int B, int H, int W, int nvec, uint4* __restrict__ out) {
+  pdl_sync();
   const size_t total = static_cast<size_t>(B) * 2 * H * 2 * W * nvec;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -310,6 +338,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int B, int H, int
 
 // out[(b,yo,xo)][tap*C + c] = x[b, 2yo+dy-1, 2xo+dx-1, c]  (zero outside), tap = dy*3+dx
 __global__ void im2col_s2_kernel(const uint4* __restrict__ x, int B, int H, int W, int nvec, uint4* __restrict__ out) {
+  pdl_sync();
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * 9 * nvec;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -337,6 +366,7 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int B, int H, int W,
   __shared__ __align__(16) float ws[CIN_K * CIN_CO];  // [k][co], k = ci*9 + tap
   for (int i = threadIdx.x; i < CIN_K * CIN_CO; i += blockDim.x) ws[i] = w[i];  // prepacked [k][co]
   __syncthreads();
+  pdl_sync();  // the weights are constants: staged before waiting for the predecessor
   const int nvec = CIN_CO / 8;  // 40
   const int ppb = blockDim.x / nvec;
   const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
@@ -372,6 +402,7 @@ __global__ void conv_out_kernel(const __half* __restrict__ x, int B, int H, int 
   const int K = 9 * C;
   for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) wsh[i] = w[i];  // prepacked fp16 [co][tap][c]
   __syncthreads();
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = C >> 3;
@@ -427,7 +458,7 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   const int threads = tx_n * rows_y;
   const int ppc = gn_ppc(B, HW);
   const int nslices = HW / ppc;
-  PNP_CHECK(HW % ppc == 0, "groupnorm: HW split");
+  PNP_CHECK(HW % ppc == 0 && nslices <= 128, "groupnorm: HW split");
   const size_t sm1 = static_cast<size_t>(rows_y) * 2 * C * sizeof(float);
   static bool attr1 = false;
   if (!attr1) {
@@ -442,17 +473,15 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   float* parts = partials + 64 + 64 * GN_GROUPS * 2;
   PNP_CHECK(B <= 64, "groupnorm: batch");
   (void)threads;
-  gn_stats_kernel<<<dim3(nslices, B), 256, sm1, s>>>(x0, C0, x1, C1, HW, ppc, tx_n, rows_y, vpt, parts, eps, mean_rstd,
-                                                         counters);
-  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(launch_k(gn_stats_kernel, dim3(nslices, B), dim3(256), sm1, s, x0, C0, x1, C1, HW, ppc, tx_n, rows_y, vpt, parts,
+                    eps, mean_rstd, counters));
   const size_t sm2 = (2 * static_cast<size_t>(C) + 2 * GN_GROUPS) * sizeof(float);
   // the apply pass is pure streaming: fewer, fatter CTAs than the statistics pass
   // one pass of 4 vectors per thread per CTA where possible (1024 vectors per CTA)
   int ppa = ppc;
   while (ppa > 1 && ppa * (C / 8) > 1024 && HW % (ppa / 2) == 0) ppa >>= 1;
-  gn_apply_kernel<<<dim3(HW / ppa, B), 256, sm2, s>>>(x0, C0, x1, C1, HW, mean_rstd, gamma, beta, do_silu ? 1 : 0, out,
-                                                      ppa);
-  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(launch_k(gn_apply_kernel, dim3(HW / ppa, B), dim3(256), sm2, s, x0, C0, x1, C1, HW, mean_rstd, gamma, beta,
+                    do_silu ? 1 : 0, out, ppa));
   return 0;
 }
 
@@ -469,11 +498,11 @@ int layernorm_launch(const __half* x, int rows, int C, const float* gamma, const
   const int warps = (rows + R - 1) / R;
   const int blocks = std::max(1, std::min((warps * 32 + threads - 1) / threads, 148 * 8));
   switch (vpl) {
-    case 1: ln_kernel<1, 4><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
-    case 2: ln_kernel<2, 4><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
-    case 3: ln_kernel<3, 2><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
-    case 4: ln_kernel<4, 2><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
-    default: ln_kernel<5, 2><<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, eps, out); break;
+    case 1: PNP_CUDA(launch_k(ln_kernel<1, 4>, dim3(blocks), dim3(threads), 0, s, x, rows, C, gamma, beta, eps, out)); break;
+    case 2: PNP_CUDA(launch_k(ln_kernel<2, 4>, dim3(blocks), dim3(threads), 0, s, x, rows, C, gamma, beta, eps, out)); break;
+    case 3: PNP_CUDA(launch_k(ln_kernel<3, 2>, dim3(blocks), dim3(threads), 0, s, x, rows, C, gamma, beta, eps, out)); break;
+    case 4: PNP_CUDA(launch_k(ln_kernel<4, 2>, dim3(blocks), dim3(threads), 0, s, x, rows, C, gamma, beta, eps, out)); break;
+    default: PNP_CUDA(launch_k(ln_kernel<5, 2>, dim3(blocks), dim3(threads), 0, s, x, rows, C, gamma, beta, eps, out)); break;
   }
   PNP_CUDA(cudaGetLastError());
   return 0;
@@ -483,9 +512,8 @@ int upsample2x_launch(const __half* x, int B, int H, int W, int C, __half* out, 
   PNP_CHECK(C % 8 == 0, "upsample: C");
   const size_t total = static_cast<size_t>(B) * 4 * H * W * (C / 8);
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
-  upsample2x_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(x), B, H, W, C / 8,
-                                           reinterpret_cast<uint4*>(out));
-  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(launch_k(upsample2x_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint4*>(x), B, H, W, C / 8,
+                    reinterpret_cast<uint4*>(out)));
   return 0;
 }
 
@@ -493,9 +521,8 @@ int im2col_s2_launch(const __half* x, int B, int H, int W, int C, __half* out, c
   PNP_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col: shape");
   const size_t total = static_cast<size_t>(B) * (H / 2) * (W / 2) * 9 * (C / 8);
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
-  im2col_s2_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(x), B, H, W, C / 8,
-                                          reinterpret_cast<uint4*>(out));
-  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(launch_k(im2col_s2_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint4*>(x), B, H, W, C / 8,
+                    reinterpret_cast<uint4*>(out)));
   return 0;
 }
 
@@ -504,8 +531,7 @@ int conv_in_launch(const float* x_nchw, int B, int H, int W, const float* w, con
   const int threads = 240;  // 40 channel-octets x 6 pixels
   const size_t npix = static_cast<size_t>(B) * H * W;
   const int blocks = static_cast<int>(std::min<size_t>((npix + 5) / 6, 148 * 2));
-  conv_in_kernel<<<blocks, threads, 0, s>>>(x_nchw, B, H, W, w, bias, out);
-  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(launch_k(conv_in_kernel, dim3(blocks), dim3(threads), 0, s, x_nchw, B, H, W, w, bias, out));
   return 0;
 }
 
@@ -515,8 +541,7 @@ int conv_out_launch(const __half* x, int B, int H, int W, int C, const __half* w
   const size_t sm = static_cast<size_t>(4) * 9 * C * sizeof(__half);
   const size_t npix = static_cast<size_t>(B) * H * W;
   const int blocks = static_cast<int>(std::min<size_t>((npix + 7) / 8, 148 * 4));
-  conv_out_kernel<<<blocks, 256, sm, s>>>(x, B, H, W, C, w, bias, out_nchw);
-  PNP_CUDA(cudaGetLastError());
+  PNP_CUDA(launch_k(conv_out_kernel, dim3(blocks), dim3(256), sm, s, x, B, H, W, C, w, bias, out_nchw));
   return 0;
 }
 

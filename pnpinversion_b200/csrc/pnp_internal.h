@@ -33,6 +33,34 @@ const char* get_last_error();
 volatile unsigned int* debug_words_device();  // device-visible alias
 const unsigned int* debug_words_host();
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel of the UNet plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization and executes
+// `griddepcontrol.launch_dependents` + `griddepcontrol.wait` after its own set-up (barrier init, TMEM allocation,
+// constant-weight staging) and before its first access to global memory produced by a predecessor, so the ~330
+// launches of one UNet call overlap their prologues with the predecessor's tail (also inside the captured graph).
+bool pdl_enabled();
+void set_pdl_enabled(bool on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 // ------------------------------------------------------------------ GEMM / implicit-GEMM convolution
 // D[M,N] = sum_seg A_seg[M,K_seg] . Wt[N,Ktot]^T  (+bias +temb +residual | GEGLU), fp16 operands, fp32 accumulate
 // in TMEM.  A segments: segment 0 is either a plain [M,K] matrix (linear) or an NHWC activation read through
