@@ -140,6 +140,9 @@ int pnp_test_layernorm(const uint16_t* x_dev, int rows, int C, const float* gamm
                        float eps, uint16_t* out_dev, void* stream);
 int pnp_test_self_attention(const uint16_t* qkv_dev, int B, int H, int N, int d, const int32_t* q_row_dev,
                             const int32_t* k_row_dev, const int32_t* v_row_dev, uint16_t* out_dev, void* stream);
+/* tcgen05 path (8 heads of dim 40, N % 128 == 0); qkv_dev: [B,N,960] */
+int pnp_test_self_attention_tc(const uint16_t* qkv_dev, int B, int N, const int32_t* q_row_dev, const int32_t* k_row_dev,
+                               const int32_t* v_row_dev, uint16_t* out_dev, void* stream);
 int pnp_test_cross_attention(const uint16_t* q_dev, const uint16_t* kv_dev, int B, int H, int N, int d, int nk,
                              const pnp_attn_ctrl* ctrl_host, float* store_dev, uint16_t* out_dev, void* stream);
 int pnp_test_upsample2x(const uint16_t* x_dev, int B, int H, int W, int C, uint16_t* out_dev, void* stream);

@@ -92,6 +92,7 @@ SIGNATURES = {
     "pnp_test_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp]),
     "pnp_test_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "pnp_test_self_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pnp_test_self_attention_tc": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pnp_test_cross_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(AttnCtrl), _vp, _vp, _vp]),
     "pnp_test_upsample2x": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "pnp_test_im2col_s2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),

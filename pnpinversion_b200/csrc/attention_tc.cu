@@ -1,0 +1,375 @@
+// tcgen05 flash self-attention for the 4096-token layers (head dim 40), the second-largest cost of the UNet step.
+//
+//   O = softmax(Q K^T / sqrt(d)) V      per (batch row, head), N = 4096 (any multiple of 128), d = 40
+//
+// One CTA = 128 queries of one (b, h); keys stream through in tiles of 128.  Two passes over the keys, both on the tensor
+// core, so that no accumulator ever has to be rescaled:
+//   pass A : S = Q K^T (tcgen05.mma, 128x128x48 per tile, fp32 in TMEM) -> row maxima
+//   pass B : S again (recomputing it costs 192 tensor cycles per tile, far cheaper than a rescale round trip through
+//            TMEM), P = 2^((S - max) * scale * log2 e) on packed fp16 pairs (MUFU.EX2.F16x2), written 128B-swizzled to
+//            shared memory as the A operand of O += P V^T' (tcgen05.mma 128x48x128 per tile).
+// V is consumed as V^T (keys contiguous = K-major B operand) from a [B][H][41][N] buffer written by a small transpose
+// kernel; row 40 of that buffer is all ones, so column 40 of O is the softmax denominator, accumulated in fp32 by the
+// same MMAs from exactly the fp16 probabilities that multiply V.  Zero padding of the head dimension (40 -> 64 columns
+// of the 128-byte swizzle atom) and of the V^T rows (41 -> 48) is TMA out-of-bounds fill: no padded copies exist.
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..11 softmax
+// (two warps per TMEM lane quarter, 64 keys each).  All hand-offs are mbarriers; every wait is bounded (mbar_wait).
+//
+// Controllers (same semantics as attention.cu): per-batch-row source indirection for Q / K / V.
+// Reference algebra: models/p2p/attention_control.py:34-45 (sim = q k^T * scale; softmax; attn @ v).
+#include <algorithm>
+
+#include "pnp_attn.h"
+#include "pnp_internal.h"
+#include "pnp_ptx.cuh"
+
+namespace pnp {
+namespace {
+
+constexpr int D = 40;
+constexpr int QT = 128;  // queries per CTA
+constexpr int KT = 128;  // keys per tile
+constexpr int Q_BYTES = QT * 128;        // 128 rows x 64 halves
+constexpr int K_BYTES = KT * 128;
+constexpr int VT_ROWS = 48;              // 40 d + ones row + zero rows
+constexpr int VT_ATOM = VT_ROWS * 128;   // 64 keys x 48 rows
+constexpr int VT_BYTES = 2 * VT_ATOM;    // 128 keys
+constexpr int P_ATOM = QT * 128;         // 128 rows x 64 keys
+constexpr int P_BYTES = 2 * P_ATOM;
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + Q_BYTES;            // 2 stages
+constexpr int OFF_VT = OFF_K + 2 * K_BYTES;       // 2 stages
+constexpr int OFF_P = OFF_VT + 2 * VT_BYTES;      // 2 stages
+constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;  // barriers + row-max exchange, + alignment slack
+constexpr int TMEM_COLS = 512;
+constexpr int COL_S = 0;    // two S accumulators of 128 columns
+constexpr int COL_O = 256;  // O: 48 columns
+
+__device__ __forceinline__ uint32_t ex2_pair(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  uint32_t x = *reinterpret_cast<uint32_t*>(&h), y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_constant__ SelfAttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 11;
+  uint64_t* p_full = bars + 13;
+  uint64_t* p_empty = bars + 15;
+  uint64_t* o_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* rowmax_x = reinterpret_cast<float*>(smem + OFF_BAR + 256);  // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int T = p.N / KT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_qk);
+    tma_prefetch_desc(&p.map_vt);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 256);
+      mbar_init(&p_full[i], 256);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      const int bq = p.q_row ? p.q_row[b] : b;
+      const int bk = p.k_row ? p.k_row[b] : b;
+      const int bv = p.v_row ? p.v_row[b] : b;
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      tma_load_4d(smem + OFF_Q, &p.map_qk, q_full, 0, h, 0, bq * p.N + qt * QT);
+      int kc = 0, vc = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < T; ++j, ++kc) {
+          const int ks = kc & 1;
+          mbar_wait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u, p.dbg, 11);
+          mbar_arrive_expect_tx(&k_full[ks], K_BYTES);
+          tma_load_4d(smem + OFF_K + ks * K_BYTES, &p.map_qk, &k_full[ks], 0, h, 1, bk * p.N + j * KT);
+          if (pass == 1) {
+            const int vs = vc & 1;
+            mbar_wait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u, p.dbg, 12);
+            mbar_arrive_expect_tx(&v_full[vs], VT_BYTES);
+            tma_load_4d(smem + OFF_VT + vs * VT_BYTES, &p.map_vt, &v_full[vs], j * KT, 0, h, bv);
+            tma_load_4d(smem + OFF_VT + vs * VT_BYTES + VT_ATOM, &p.map_vt, &v_full[vs], j * KT + 64, 0, h, bv);
+            ++vc;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_qk = umma_idesc_f16(QT, KT);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, VT_ROWS);
+      const uint32_t q_addr = smem_u32(smem + OFF_Q);
+      int kc = 0, sc = 0, pc = 0, vc = 0;
+      auto issue_qk = [&]() {
+        const int ks = kc & 1, ss = sc & 1;
+        mbar_wait(&k_full[ks], (kc >> 1) & 1, p.dbg, 21);
+        mbar_wait(&s_empty[ss], ((sc >> 1) & 1) ^ 1u, p.dbg, 22);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128_kmajor(q_addr);
+        const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + OFF_K + ks * K_BYTES));
+#pragma unroll
+        for (int k = 0; k < 3; ++k)  // head dim 40 -> 48 = three K=16 steps (columns 40..63 are TMA zero fill)
+          umma_f16_ss(tmem_base + COL_S + ss * KT, adesc + 2u * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
+        umma_commit(&k_empty[ks]);
+        umma_commit(&s_full[ss]);
+        ++kc;
+        ++sc;
+      };
+      mbar_wait(q_full, 0, p.dbg, 20);
+      for (int j = 0; j < T; ++j) issue_qk();  // pass A
+      issue_qk();                              // pass B, tile 0
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_qk();  // S of the next tile is computed while the softmax warps work on this one
+        const int ps = pc & 1, vs = vc & 1;
+        mbar_wait(&p_full[ps], (pc >> 1) & 1, p.dbg, 23);
+        mbar_wait(&v_full[vs], (vc >> 1) & 1, p.dbg, 24);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + OFF_P + ps * P_BYTES);
+        const uint32_t v_addr = smem_u32(smem + OFF_VT + vs * VT_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 128 keys = 8 K=16 steps over two 64-key swizzle atoms
+          const uint64_t adesc = umma_desc_sw128_kmajor(p_addr + (k >> 2) * P_ATOM) + 2u * (k & 3);
+          const uint64_t bdesc = umma_desc_sw128_kmajor(v_addr + (k >> 2) * VT_ATOM) + 2u * (k & 3);
+          umma_f16_ss(tmem_base + COL_O, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&p_empty[ps]);
+        umma_commit(&v_empty[vs]);
+        ++pc;
+        ++vc;
+      }
+      umma_commit(o_full);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax warps
+    const int q = warp & 3;            // TMEM lane quarter
+    const int hf = (warp - 4) >> 2;    // which 64 keys of each 128-key tile
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    int sc = 0, pc = 0;
+    // pass A: row maxima of the raw scores
+    float mx = -INFINITY;
+    for (int j = 0; j < T; ++j, ++sc) {
+      const int ss = sc & 1;
+      mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 31);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + hf * 64 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[ss]);
+    }
+    rowmax_x[hf * 128 + row] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(rowmax_x[row], rowmax_x[128 + row]);
+    const float off = mx * p.sl2;
+    // pass B: probabilities -> shared memory (A operand of the PV MMA)
+    for (int j = 0; j < T; ++j, ++sc, ++pc) {
+      const int ss = sc & 1, ps = pc & 1;
+      mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 32);
+      mbar_wait(&p_empty[ps], ((pc >> 1) & 1) ^ 1u, p.dbg, 33);
+      tc_fence_after();
+      uint8_t* prow = smem + OFF_P + ps * P_BYTES + hf * P_ATOM + row * 128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + hf * 64 + c * 32, r);
+        tmem_ld_wait();
+        uint32_t ph[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          ph[i] = ex2_pair(fmaf(__uint_as_float(r[2 * i]), p.sl2, -off), fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -off));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = (c * 4 + i) ^ (row & 7);  // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(&p_full[ps]);
+      tc_fence_before();
+      mbar_arrive(&s_empty[ss]);
+    }
+    // epilogue: O / l  (column 40 of O is the row sum of the probabilities)
+    mbar_wait(o_full, 0, p.dbg, 34);
+    tc_fence_after();
+    uint32_t hi[16];
+    tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + 32, hi);
+    __half* orow = p.o + (static_cast<size_t>(b) * p.N + qt * QT + row) * p.ldo + h * D;
+    if (hf == 0) {
+      uint32_t lo[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + COL_O, lo);
+      tmem_ld_wait();
+      const float inv = 1.0f / __uint_as_float(hi[8]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        __half2 t0 = __floats2half2_rn(__uint_as_float(lo[8 * i + 0]) * inv, __uint_as_float(lo[8 * i + 1]) * inv);
+        __half2 t1 = __floats2half2_rn(__uint_as_float(lo[8 * i + 2]) * inv, __uint_as_float(lo[8 * i + 3]) * inv);
+        __half2 t2 = __floats2half2_rn(__uint_as_float(lo[8 * i + 4]) * inv, __uint_as_float(lo[8 * i + 5]) * inv);
+        __half2 t3 = __floats2half2_rn(__uint_as_float(lo[8 * i + 6]) * inv, __uint_as_float(lo[8 * i + 7]) * inv);
+        u.x = *reinterpret_cast<uint32_t*>(&t0);
+        u.y = *reinterpret_cast<uint32_t*>(&t1);
+        u.z = *reinterpret_cast<uint32_t*>(&t2);
+        u.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(orow + 8 * i) = u;
+      }
+    } else {
+      tmem_ld_wait();
+      const float inv = 1.0f / __uint_as_float(hi[8]);
+      uint4 u;
+      __half2 t0 = __floats2half2_rn(__uint_as_float(hi[0]) * inv, __uint_as_float(hi[1]) * inv);
+      __half2 t1 = __floats2half2_rn(__uint_as_float(hi[2]) * inv, __uint_as_float(hi[3]) * inv);
+      __half2 t2 = __floats2half2_rn(__uint_as_float(hi[4]) * inv, __uint_as_float(hi[5]) * inv);
+      __half2 t3 = __floats2half2_rn(__uint_as_float(hi[6]) * inv, __uint_as_float(hi[7]) * inv);
+      u.x = *reinterpret_cast<uint32_t*>(&t0);
+      u.y = *reinterpret_cast<uint32_t*>(&t1);
+      u.z = *reinterpret_cast<uint32_t*>(&t2);
+      u.w = *reinterpret_cast<uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(orow + 32) = u;
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// V part of the fused QKV activation [B*N, ld] -> V^T [B][H][41][N] (row 40 is pre-filled with ones by the owner of the
+// buffer).  One CTA: 64 tokens of one (b, h); shared-memory tile transpose, 128-byte coalesced on both sides.
+__global__ void __launch_bounds__(256) vt_transpose_kernel(const __half* __restrict__ v, int ld, int N,
+                                                           __half* __restrict__ vt) {
+  __shared__ __half tile[D][64 + 2];
+  pdl_sync();
+  const int t0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 64 * D; i += blockDim.x) {
+    const int tok = i / D, j = i - tok * D;
+    tile[j][tok] = v[(static_cast<size_t>(b) * N + t0 + tok) * ld + h * D + j];
+  }
+  __syncthreads();
+  __half* dst = vt + (static_cast<size_t>(b) * 8 + h) * 41 * N + t0;
+  for (int i = threadIdx.x; i < D * 64; i += blockDim.x) {
+    const int j = i / 64, tok = i - j * 64;
+    dst[static_cast<size_t>(j) * N + tok] = tile[j][tok];
+  }
+}
+
+__global__ void vt_fill_ones_kernel(__half* __restrict__ vt, int B, int N) {
+  const size_t total = static_cast<size_t>(B) * 8 * N;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t bh = i / N, tok = i - bh * N;
+    vt[(bh * 41 + 40) * N + tok] = __float2half(1.0f);
+  }
+}
+
+}  // namespace
+
+size_t self_attention_tc_vt_elems(int B, int N) { return static_cast<size_t>(B) * 8 * 41 * N; }
+
+int self_attention_tc_init_vt(__half* vt, int B, int N, cudaStream_t s) {
+  vt_fill_ones_kernel<<<256, 256, 0, s>>>(vt, B, N);
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int self_attention_tc_plan(SelfAttnTcParams* p, const __half* qkv, int ld, __half* vt, __half* o, int ldo, int B, int N,
+                           const int* q_row, const int* k_row, const int* v_row) {
+  PNP_CHECK(N % 128 == 0 && ld == 3 * 8 * D, "tc self-attention: N % 128 == 0 and 8 heads of dim 40");
+  memset(p, 0, sizeof *p);
+  {
+    // the fused QKV activation viewed as [rows = B*N][3][8 heads][40]; box = 64 (zero-filled past 40) x 1 x 1 x 128 rows
+    const uint64_t dims[4] = {D, 8, 3, static_cast<uint64_t>(B) * N};
+    const uint64_t strides[3] = {D * 2, 8 * D * 2, static_cast<uint64_t>(ld) * 2};
+    const uint32_t box[4] = {64, 1, 1, 128};
+    int rc = encode_tensor_map_f16(&p->map_qk, qkv, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    // V^T [B][H][41][N]; box = 64 keys x 48 rows (rows 41..47 zero-filled)
+    const uint64_t dims[4] = {static_cast<uint64_t>(N), 41, 8, static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(N) * 2, static_cast<uint64_t>(N) * 41 * 2,
+                                 static_cast<uint64_t>(N) * 41 * 8 * 2};
+    const uint32_t box[4] = {64, VT_ROWS, 1, 1};
+    int rc = encode_tensor_map_f16(&p->map_vt, vt, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  p->v_src = qkv + 2 * 8 * D;
+  p->ld = ld;
+  p->vt = vt;
+  p->o = o;
+  p->ldo = ldo;
+  p->B = B;
+  p->N = N;
+  p->sl2 = (1.0f / sqrtf(static_cast<float>(D))) * 1.4426950408889634f;
+  p->q_row = q_row;
+  p->k_row = k_row;
+  p->v_row = v_row;
+  p->dbg = debug_words_device();
+  return 0;
+}
+
+int self_attention_tc_launch(const SelfAttnTcParams& p, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    PNP_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  PNP_CUDA(launch_k(vt_transpose_kernel, dim3(p.N / 64, 8, p.B), dim3(256), 0, s, p.v_src, p.ld, p.N, p.vt));
+  PNP_CUDA(launch_k(self_attn_tc_kernel, dim3(p.N / QT, 8, p.B), dim3(384), SMEM_BYTES, s, p));
+  return 0;
+}
+
+}  // namespace pnp

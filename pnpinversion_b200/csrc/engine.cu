@@ -40,6 +40,8 @@ volatile unsigned int* debug_words_device() {
 }
 const unsigned int* debug_words_host() { return g_dbg_host; }
 
+static bool g_tc_attn = true;
+bool use_tc_attention() { return g_tc_attn; }
 static bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl_enabled(bool on) { g_pdl = on; }
@@ -266,6 +268,8 @@ struct Plan {
   std::vector<OpInfo> info;
   int kernels_per_forward = 0;
   std::vector<std::unique_ptr<GemmPlan>> gemms;
+  std::vector<std::unique_ptr<SelfAttnTcParams>> tc_attn;
+  __half* vt_scratch = nullptr;
   std::vector<void*> bufs;
   float* x_in = nullptr;    // [B,4,64,64]
   float* eps_out = nullptr;  // [B,4,64,64]
@@ -620,6 +624,13 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
   __half* T_ATT = pb.buf(rows64 * 320);
   __half* T_Q = pb.buf(rows64 * 320);
   __half* T_FF = pb.buf(rows64 * 1280);
+  pl->vt_scratch = pb.buf(self_attention_tc_vt_elems(B, 4096));
+  if (pb.rc) return pb.rc;
+  {
+    int rc = self_attention_tc_init_vt(pl->vt_scratch, B, 4096, nullptr);
+    if (rc) return rc;
+    PNP_CUDA(cudaDeviceSynchronize());
+  }
   // the 12 skip tensors
   const int skip_c[12] = {320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280};
   const int skip_hw[12] = {64, 64, 64, 32, 32, 32, 16, 16, 16, 8, 8, 8};
@@ -695,7 +706,17 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
     // attn1 (self)
     pb.layernorm(T_H, M, c, w.ln1_g, w.ln1_b, T_LN);
     { GemmEpilogue ep; ep.out = T_QKV; ep.ldc = 3 * c; pb.linear(T_LN, M, c, c, w.qkv, 3 * c, ep); }
-    {
+    if (d == 40 && N % 128 == 0 && use_tc_attention()) {
+      // 4096-token layers: tcgen05 flash attention (attention_tc.cu)
+      auto tp = std::make_unique<SelfAttnTcParams>();
+      if (!pb.rc)
+        pb.rc = self_attention_tc_plan(tp.get(), T_QKV, 3 * c, pl->vt_scratch, T_ATT, c, B, N, e->d_ctrl->self_q[layer],
+                                       e->d_ctrl->self_k[layer], e->d_ctrl->self_v[layer]);
+      SelfAttnTcParams* raw = tp.get();
+      pl->tc_attn.push_back(std::move(tp));
+      pb.op(3, 4.0 * B * kHeads * static_cast<double>(N) * N * d, 2,
+            [raw](cudaStream_t s) { return self_attention_tc_launch(*raw, s); });
+    } else {
       SelfAttnParams sp;
       sp.q = T_QKV; sp.k = T_QKV + c; sp.v = T_QKV + 2 * c; sp.ld = 3 * c;
       sp.o = T_ATT; sp.ldo = c; sp.B = B; sp.H = kHeads; sp.N = N; sp.d = d;
@@ -902,6 +923,7 @@ int pnp_create(int device_ordinal, int max_batch, pnp_engine** out) {
   e->max_batch = max_batch;
   debug_words_device();
   if (const char* ev = getenv("PNP_PDL")) set_pdl_enabled(atoi(ev) != 0);
+  if (const char* ev = getenv("PNP_TC_ATTN")) g_tc_attn = atoi(ev) != 0;
   PNP_CUDA(cudaStreamCreateWithFlags(&e->es, cudaStreamNonBlocking));
   PNP_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
   PNP_CUDA(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
@@ -1324,6 +1346,30 @@ int pnp_test_self_attention(const uint16_t* qkv_dev, int B, int H, int N, int d,
   sp.scale = 1.0f / sqrtf(static_cast<float>(d));
   sp.q_row = q_row_dev; sp.k_row = k_row_dev; sp.v_row = v_row_dev;
   return self_attention_launch(sp, as_stream(stream));
+}
+
+int pnp_test_self_attention_tc(const uint16_t* qkv_dev, int B, int N, const int32_t* q_row_dev, const int32_t* k_row_dev,
+                               const int32_t* v_row_dev, uint16_t* out_dev, void* stream) {
+  __half* vt = nullptr;
+  PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&vt), self_attention_tc_vt_elems(B, N) * sizeof(__half)));
+  PNP_CUDA(cudaMemset(vt, 0, self_attention_tc_vt_elems(B, N) * sizeof(__half)));
+  int rc = self_attention_tc_init_vt(vt, B, N, as_stream(stream));
+  SelfAttnTcParams tp;
+  if (!rc)
+    rc = self_attention_tc_plan(&tp, reinterpret_cast<const __half*>(qkv_dev), 960, vt, reinterpret_cast<__half*>(out_dev),
+                                320, B, N, q_row_dev, k_row_dev, v_row_dev);
+  if (!rc) rc = self_attention_tc_launch(tp, as_stream(stream));
+  cudaError_t e2 = cudaStreamSynchronize(as_stream(stream));
+  cudaFree(vt);
+  if (!rc && e2 != cudaSuccess) {
+    const unsigned int* dw = debug_words_host();
+    char buf[256];
+    snprintf(buf, sizeof buf, "tc self-attention failed: %s (debug words %08x %u %u %u)", cudaGetErrorString(e2),
+             dw ? dw[0] : 0, dw ? dw[1] : 0, dw ? dw[2] : 0, dw ? dw[3] : 0);
+    set_last_error(buf);
+    return -1;
+  }
+  return rc;
 }
 
 int pnp_test_cross_attention(const uint16_t* q_dev, const uint16_t* kv_dev, int B, int H, int N, int d, int nk,

@@ -373,8 +373,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box) {
+}  // namespace
+
+int encode_tensor_map_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   PNP_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -399,6 +401,8 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
   }
   return 0;
 }
+
+namespace {
 
 template <int BN>
 int launch_t(const GemmPlan& plan, cudaStream_t stream) {
@@ -526,7 +530,7 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
       strides[1] = strides[0] * W;
       strides[2] = strides[1] * H;
     }
-    int rc = encode_map(&p.map_a[i], srcs[i].ptr, 4, dims, strides, box);
+    int rc = encode_tensor_map_f16(&p.map_a[i], srcs[i].ptr, 4, dims, strides, box);
     if (rc) return rc;
   }
   {
@@ -534,7 +538,7 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
     uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};
     uint32_t bbox[2] = {BK, static_cast<uint32_t>(bn)};
     PNP_CHECK((reinterpret_cast<uintptr_t>(Wt) & 15) == 0 && Ktot % 8 == 0, "gemm: weight alignment");
-    int rc = encode_map(&p.map_b, Wt, 2, dims, strides, bbox);
+    int rc = encode_tensor_map_f16(&p.map_b, Wt, 2, dims, strides, bbox);
     if (rc) return rc;
   }
   p.taps0 = taps0;

@@ -236,7 +236,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
 int gn_ppc(int B, int HW) {
   // pixels per CTA: aim for >= ~256 CTAs, at least 8 pixels each
   int ppc = HW;
-  while (ppc > 8 && static_cast<long>(B) * (HW / ppc) < 256) ppc >>= 1;
+  while (ppc > 8 && HW / ppc < 128 && static_cast<long>(B) * (HW / ppc) < 256) ppc >>= 1;  // <= 128 slices
   return ppc;
 }
 

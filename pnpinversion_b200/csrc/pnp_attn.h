@@ -1,5 +1,6 @@
 // Parameter blocks of the attention kernels (attention.cu) and of the fused step epilogue (epilogue.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -47,6 +48,28 @@ struct CrossAttnParams {
 };
 
 int self_attention_launch(const SelfAttnParams& p, cudaStream_t s);
+
+// tcgen05 path for the 4096-token layers (8 heads of dim 40), attention_tc.cu
+struct alignas(64) SelfAttnTcParams {
+  CUtensorMap map_qk;  // fused QKV activation viewed as [B*N][3][8][40]
+  CUtensorMap map_vt;  // V^T scratch [B][8][41][N] (row 40 = ones)
+  const __half* v_src;  // V part of the fused activation (transpose source)
+  int ld;
+  __half* vt;
+  __half* o;
+  int ldo;
+  int B, N;
+  float sl2;  // scale * log2(e)
+  const int* q_row;
+  const int* k_row;
+  const int* v_row;
+  volatile unsigned int* dbg;
+};
+size_t self_attention_tc_vt_elems(int B, int N);
+int self_attention_tc_init_vt(__half* vt, int B, int N, cudaStream_t s);
+int self_attention_tc_plan(SelfAttnTcParams* p, const __half* qkv, int ld, __half* vt, __half* o, int ldo, int B, int N,
+                           const int* q_row, const int* k_row, const int* v_row);
+int self_attention_tc_launch(const SelfAttnTcParams& p, cudaStream_t s);
 int cross_attention_launch(const CrossAttnParams& p, cudaStream_t s);
 
 // ------------------------------------------------------------------ fused step epilogue (epilogue.cu)

@@ -38,6 +38,7 @@ const unsigned int* debug_words_host();
 // `griddepcontrol.launch_dependents` + `griddepcontrol.wait` after its own set-up (barrier init, TMEM allocation,
 // constant-weight staging) and before its first access to global memory produced by a predecessor, so the ~330
 // launches of one UNet call overlap their prologues with the predecessor's tail (also inside the captured graph).
+bool use_tc_attention();
 bool pdl_enabled();
 void set_pdl_enabled(bool on);
 template <typename... KArgs, typename... Args>
@@ -116,6 +117,10 @@ struct GemmEpilogue {
   int ldc = 0;
   bool geglu = false;
 };
+
+// fp16 tiled tensor map with 128-byte swizzle and zero out-of-bounds fill (rank 2..4); strides in bytes for dims 1..
+int encode_tensor_map_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box);
 
 // conv-mode: srcs[0] is NHWC [B,H,W,C0] with `taps0`=9 (3x3, pad 1) or 1; linear mode: B=H=1, W=M.
 int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, bool linear, int B, int H, int W,

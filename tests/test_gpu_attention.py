@@ -141,3 +141,32 @@ def test_cross_attention_p2p_injection_and_store(cuda, d, N):
     _lib.check(lib.pnp_test_cross_attention(G.ptr(q), G.ptr(kv), B, H, N, d, 77, None, None, G.ptr(plain), G.stream()))
     torch.cuda.synchronize()
     assert torch.equal(out[:3], plain[:3])
+
+
+@pytest.mark.parametrize("N,B", [(128, 1), (256, 2), (4096, 2)])
+def test_self_attention_tcgen05_d40(cuda, N, B):
+    """tcgen05 flash attention (attention_tc.cu): two-pass softmax on the tensor core, 8 heads of dim 40."""
+    lib = _lib.load()
+    d = 40
+    qkv = _mk((B, N, 3 * H * d), cuda, 31 + N, 1.0)
+    qkv[..., :2 * H * d] *= 1.5
+    out = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    ident = list(range(B))
+    ref = _self_ref(qkv, d, ident, ident, ident)
+    err = G.rel_l2(out, ref)
+    print(f"tc attention N={N} B={B}: rel-L2 {err:.3e}")
+    assert err < 2e-3
+
+
+def test_self_attention_tcgen05_row_indirection(cuda):
+    lib = _lib.load()
+    B, N, d = 4, 1024, 40
+    qkv = _mk((B, N, 3 * H * d), cuda, 77, 1.2)
+    q_row, k_row, v_row = [0, 1, 2, 2], [0, 0, 2, 2], [0, 0, 2, 3]
+    dq, dk, dv = (torch.tensor(r, dtype=torch.int32, device=cuda) for r in (q_row, k_row, v_row))
+    out = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, G.ptr(dq), G.ptr(dk), G.ptr(dv), G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    assert G.rel_l2(out, _self_ref(qkv, d, q_row, k_row, v_row)) < 2e-3
