@@ -179,6 +179,40 @@ def gen_pipeline(n_steps: int):
     print("pipeline fixture written")
 
 
+def gen_masactrl():
+    """One B=4 UNet forward with the reference's own MutualSelfAttentionControl (models/masactrl/masactrl.py:14-72)
+    registered through its own regiter_attention_editor_diffusers (masactrl_utils.py:79-144) on the vendored UNet.
+    The registration matches the class name 'Attention' (diffusers >= 0.15); the vendored class is named
+    CrossAttention, so the harness renames it -- no reference code is modified."""
+    import importlib
+    import sys as _sys
+
+    if ref_shim.REF not in _sys.path:
+        _sys.path.insert(0, ref_shim.REF)
+    masactrl = importlib.import_module("models.masactrl.masactrl")
+    mutils = importlib.import_module("models.masactrl.masactrl_utils")
+    model = build_model()
+    md = ref_shim.load_my_diffusers()
+    md.CrossAttention.__name__ = "Attention"
+    prompts = ["", synth.CAT_PROMPTS[1]]
+    ctx = _ctx(model, prompts)
+    lat = torch.cat([synth.synth_latent(0), synth.synth_latent(1)]).double()
+    res = {}
+    with torch.no_grad():
+        for name, step in (("on", 10), ("off", 2)):
+            editor = masactrl.MutualSelfAttentionControl(4, 10)
+            mutils.regiter_attention_editor_diffusers(model, editor)
+            assert editor.num_att_layers == 32
+            editor.cur_step = step
+            t0 = time.time()
+            eps = model.unet(torch.cat([lat] * 2), torch.tensor(401), encoder_hidden_states=ctx)["sample"]
+            print("masactrl", name, time.time() - t0, "cur_step after", editor.cur_step)
+            res[f"{name}_eps"] = eps.float().numpy()
+    md.CrossAttention.__name__ = "CrossAttention"
+    np.savez_compressed(os.path.join(GOLD, "masactrl_forward.npz"), **res)
+    print("masactrl_forward.npz written")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
@@ -189,3 +223,5 @@ if __name__ == "__main__":
         gen_unet()
     elif what == "pipeline":
         gen_pipeline(int(sys.argv[2]))
+    elif what == "masactrl":
+        gen_masactrl()

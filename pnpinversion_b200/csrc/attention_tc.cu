@@ -19,6 +19,8 @@
 // Controllers (same semantics as attention.cu): per-batch-row source indirection for Q / K / V.
 // Reference algebra: models/p2p/attention_control.py:34-45 (sim = q k^T * scale; softmax; attn @ v).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "pnp_attn.h"
 #include "pnp_internal.h"
@@ -64,6 +66,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+template <bool CL2>
 __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_constant__ SelfAttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -88,14 +91,16 @@ __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_qk);
     tma_prefetch_desc(&p.map_vt);
+    if (CL2) tma_prefetch_desc(&p.map_k64);
   }
+  const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], CL2 ? 2 : 1);  // with a cluster both CTAs' MMAs must release a stage: the peer writes into it
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], CL2 ? 2 : 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 256);
       mbar_init(&p_full[i], 256);
@@ -107,6 +112,7 @@ __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_const
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();  // the peer's barriers exist before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();
@@ -125,13 +131,23 @@ __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_const
           const int ks = kc & 1;
           mbar_wait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u, p.dbg, 11);
           mbar_arrive_expect_tx(&k_full[ks], K_BYTES);
-          tma_load_4d(smem + OFF_K + ks * K_BYTES, &p.map_qk, &k_full[ks], 0, h, 1, bk * p.N + j * KT);
+          if (CL2) {  // this CTA fetches half of the key tile and multicasts it to both CTAs of the cluster
+            tma_load_4d_mc(smem + OFF_K + ks * K_BYTES + crank * (K_BYTES / 2), &p.map_k64, &k_full[ks], 0x3, 0, h, 1,
+                           bk * p.N + j * KT + crank * 64);
+          } else {
+            tma_load_4d(smem + OFF_K + ks * K_BYTES, &p.map_qk, &k_full[ks], 0, h, 1, bk * p.N + j * KT);
+          }
           if (pass == 1) {
             const int vs = vc & 1;
             mbar_wait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u, p.dbg, 12);
             mbar_arrive_expect_tx(&v_full[vs], VT_BYTES);
-            tma_load_4d(smem + OFF_VT + vs * VT_BYTES, &p.map_vt, &v_full[vs], j * KT, 0, h, bv);
-            tma_load_4d(smem + OFF_VT + vs * VT_BYTES + VT_ATOM, &p.map_vt, &v_full[vs], j * KT + 64, 0, h, bv);
+            if (CL2) {
+              tma_load_4d_mc(smem + OFF_VT + vs * VT_BYTES + crank * VT_ATOM, &p.map_vt, &v_full[vs], 0x3,
+                             j * KT + crank * 64, 0, h, bv);
+            } else {
+              tma_load_4d(smem + OFF_VT + vs * VT_BYTES, &p.map_vt, &v_full[vs], j * KT, 0, h, bv);
+              tma_load_4d(smem + OFF_VT + vs * VT_BYTES + VT_ATOM, &p.map_vt, &v_full[vs], j * KT + 64, 0, h, bv);
+            }
             ++vc;
           }
         }
@@ -154,7 +170,7 @@ __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_const
 #pragma unroll
         for (int k = 0; k < 3; ++k)  // head dim 40 -> 48 = three K=16 steps (columns 40..63 are TMA zero fill)
           umma_f16_ss(tmem_base + COL_S + ss * KT, adesc + 2u * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
-        umma_commit(&k_empty[ks]);
+        if (CL2) umma_commit_mc(&k_empty[ks], 0x3); else umma_commit(&k_empty[ks]);
         umma_commit(&s_full[ss]);
         ++kc;
         ++sc;
@@ -177,7 +193,7 @@ __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_const
           umma_f16_ss(tmem_base + COL_O, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&p_empty[ps]);
-        umma_commit(&v_empty[vs]);
+        if (CL2) umma_commit_mc(&v_empty[vs], 0x3); else umma_commit(&v_empty[vs]);
         ++pc;
         ++vc;
       }
@@ -281,6 +297,7 @@ __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -336,6 +353,9 @@ int self_attention_tc_plan(SelfAttnTcParams* p, const __half* qkv, int ld, __hal
     const uint32_t box[4] = {64, 1, 1, 128};
     int rc = encode_tensor_map_f16(&p->map_qk, qkv, 4, dims, strides, box);
     if (rc) return rc;
+    const uint32_t box64[4] = {64, 1, 1, 64};
+    rc = encode_tensor_map_f16(&p->map_k64, qkv, 4, dims, strides, box64);
+    if (rc) return rc;
   }
   {
     // V^T [B][H][41][N]; box = 64 keys x 48 rows (rows 41..47 zero-filled)
@@ -358,17 +378,23 @@ int self_attention_tc_plan(SelfAttnTcParams* p, const __half* qkv, int ld, __hal
   p->k_row = k_row;
   p->v_row = v_row;
   p->dbg = debug_words_device();
+  p->cluster = ((N / QT) % 2 == 0) ? 2 : 1;
+  if (const char* ev = getenv("PNP_ATTN_CLUSTER")) p->cluster = (atoi(ev) == 2 && (N / QT) % 2 == 0) ? 2 : 1;
   return 0;
 }
 
 int self_attention_tc_launch(const SelfAttnTcParams& p, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    PNP_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PNP_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    PNP_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
   PNP_CUDA(launch_k(vt_transpose_kernel, dim3(p.N / 64, 8, p.B), dim3(256), 0, s, p.v_src, p.ld, p.N, p.vt));
-  PNP_CUDA(launch_k(self_attn_tc_kernel, dim3(p.N / QT, 8, p.B), dim3(384), SMEM_BYTES, s, p));
+  if (p.cluster == 2)
+    PNP_CUDA(launch_kc(self_attn_tc_kernel<true>, dim3(p.N / QT, 8, p.B), dim3(384), SMEM_BYTES, s, 2, p));
+  else
+    PNP_CUDA(launch_k(self_attn_tc_kernel<false>, dim3(p.N / QT, 8, p.B), dim3(384), SMEM_BYTES, s, p));
   return 0;
 }
 

@@ -42,7 +42,7 @@ const unsigned int* debug_words_host() { return g_dbg_host; }
 
 static bool g_tc_attn = true;
 bool use_tc_attention() { return g_tc_attn; }
-static bool g_pdl = true;
+static bool g_pdl = false;  // measured on B200: no gain for this plan (PNP_PDL=1 enables it)
 bool pdl_enabled() { return g_pdl; }
 void set_pdl_enabled(bool on) { g_pdl = on; }
 

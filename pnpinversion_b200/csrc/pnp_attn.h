@@ -53,6 +53,8 @@ int self_attention_launch(const SelfAttnParams& p, cudaStream_t s);
 struct alignas(64) SelfAttnTcParams {
   CUtensorMap map_qk;  // fused QKV activation viewed as [B*N][3][8][40]
   CUtensorMap map_vt;  // V^T scratch [B][8][41][N] (row 40 = ones)
+  CUtensorMap map_k64;  // same view as map_qk with a 64-row box (cluster-of-2 multicast: each CTA loads half a K tile)
+  int cluster;          // 1 or 2
   const __half* v_src;  // V part of the fused activation (transpose source)
   int ld;
   __half* vt;

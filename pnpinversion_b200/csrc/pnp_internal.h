@@ -42,18 +42,31 @@ bool use_tc_attention();
 bool pdl_enabled();
 void set_pdl_enabled(bool on);
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
+                             Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  int na = 1;
+  if (cluster_x > 1) {
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = cluster_x;
+    at[1].val.clusterDim.y = 1;
+    at[1].val.clusterDim.z = 1;
+    na = 2;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  return launch_kc(kernel, grid, block, smem, s, 1, static_cast<Args&&>(args)...);
 }
 #if defined(__CUDACC__)
 __device__ __forceinline__ void pdl_sync() {
