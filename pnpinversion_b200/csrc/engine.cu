@@ -924,6 +924,7 @@ int pnp_create(int device_ordinal, int max_batch, pnp_engine** out) {
   debug_words_device();
   if (const char* ev = getenv("PNP_PDL")) set_pdl_enabled(atoi(ev) != 0);
   if (const char* ev = getenv("PNP_TC_ATTN")) g_tc_attn = atoi(ev) != 0;
+  if (const char* ev = getenv("PNP_GEMM_CLUSTER")) set_cluster_allowed(atoi(ev) != 0);
   PNP_CUDA(cudaStreamCreateWithFlags(&e->es, cudaStreamNonBlocking));
   PNP_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
   PNP_CUDA(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));

@@ -17,6 +17,7 @@
 // feed-forward (models/edict/my_diffusers/models/attention.py:140-151,186-200,253-260,329-333).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -48,7 +49,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN>
+template <int BN, bool CL2>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -68,11 +69,13 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     tma_prefetch_desc(&p.map_b);
     if (p.chunks1 > 0) tma_prefetch_desc(&p.map_a[1]);
     if (p.chunks2 > 0) tma_prefetch_desc(&p.map_a[2]);
+    if (CL2) tma_prefetch_desc(&p.map_b_half);
   }
+  const int crank = CL2 ? static_cast<int>(cluster_ctarank()) : 0;
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CL2 ? 2 : 1);  // cluster: the peer multicasts its half of the weight tile into this stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -83,26 +86,42 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();  // peer barriers are initialised before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();  // set-up done: let the successor start its own, then wait for the predecessor's results
 
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int total_work = total_tiles * p.splits;
   const int num_kb = p.num_kb;
+  // work items: (tile, K split) for a lone CTA; (pair of vertically adjacent M tiles, same N tile) for a cluster of 2
+  const int half_m = p.m_tiles >> 1;
+  const int total_work = CL2 ? half_m * p.n_tiles : total_tiles * p.splits;
+  const int work_begin = CL2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int work_stride = CL2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  auto decode = [&](int work, int& tile, int& split, int& m_blk, int& n_blk) {
+    if (CL2) {
+      n_blk = work / half_m;
+      m_blk = 2 * (work - n_blk * half_m) + crank;
+      tile = n_blk * p.m_tiles + m_blk;
+      split = 0;
+    } else {
+      tile = work % total_tiles;
+      split = work / total_tiles;
+      m_blk = tile % p.m_tiles;
+      n_blk = tile / p.m_tiles;
+    }
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
       const int kb0 = p.taps0 * p.chunks0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        const int tile = work % total_tiles;
-        const int split = work / total_tiles;
+      for (int work = work_begin; work < total_work; work += work_stride) {
+        int tile, split, m_blk, n_blk;
+        decode(work, tile, split, m_blk, n_blk);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
-        const int m_blk = tile % p.m_tiles;
-        const int n_blk = tile / p.m_tiles;
         const int p0 = m_blk * BM;
         int x0, y0, b0;
         if (p.linear) {
@@ -131,7 +150,12 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           } else {
             tma_load_4d(sa, &p.map_a[2], &full[stage], (kb - kb0 - p.chunks1) * BK, x0, y0, b0);
           }
-          tma_load_2d(sb, &p.map_b, &full[stage], kb * BK, n_blk * BN);
+          if (CL2) {  // fetch half of the weight tile, deliver it to both CTAs of the cluster
+            tma_load_2d_mc(sb + crank * (C::B_BYTES / 2), &p.map_b_half, &full[stage], 0x3, kb * BK,
+                           n_blk * BN + crank * (BN / 2));
+          } else {
+            tma_load_2d(sb, &p.map_b, &full[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -142,8 +166,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
-        const int split = work / total_tiles;
+      for (int work = work_begin; work < total_work; work += work_stride, ++it) {
+        int tile, split, m_blk, n_blk;
+        decode(work, tile, split, m_blk, n_blk);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
         const uint32_t as = it & 1;
@@ -162,7 +187,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             // +32 bytes per K=16 step inside the 128-byte swizzle atom
             umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (CL2) umma_commit_mc(&empty[stage], 0x3); else umma_commit(&empty[stage]);
           if (kb == kb_end - 1) umma_commit(&tfull[as]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -176,11 +201,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     const float* temb = nullptr;
     if (p.temb_table != nullptr) temb = p.temb_table + static_cast<size_t>(*p.t_index) * p.temb_stride;
     int it = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
-      const int tile = work % total_tiles;
-      const int split = work / total_tiles;
-      const int m_blk = tile % p.m_tiles;
-      const int n_blk = tile / p.m_tiles;
+    for (int work = work_begin; work < total_work; work += work_stride, ++it) {
+      int tile, split, m_blk, n_blk;
+      decode(work, tile, split, m_blk, n_blk);
       const uint32_t as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m = m_blk * BM + row;
@@ -347,6 +370,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -408,11 +432,16 @@ template <int BN>
 int launch_t(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<BN>::SMEM));
+    PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg<BN>::SMEM));
     attr_set = true;
   }
-  PNP_CUDA(launch_k(gemm_tcgen05_kernel<BN>, dim3(plan.grid), dim3(384), Cfg<BN>::SMEM, stream, plan.p));
+  if (plan.cluster == 2)
+    PNP_CUDA(launch_kc(gemm_tcgen05_kernel<BN, true>, dim3(plan.grid), dim3(384), Cfg<BN>::SMEM, stream, 2, plan.p));
+  else
+    PNP_CUDA(launch_k(gemm_tcgen05_kernel<BN, false>, dim3(plan.grid), dim3(384), Cfg<BN>::SMEM, stream, plan.p));
   return 0;
 }
 
@@ -423,20 +452,25 @@ int launch_t(const GemmPlan& plan, cudaStream_t stream) {
 //   tensor   : waves * k_blocks * max(2*BN, 128+BN)        (4 MMAs of 128xBNx16 vs shared-memory feed, per 64-wide K block)
 //   L2       : tiles * k_blocks * (16 KB + BN*128 B) / 5000
 //   epilogue : waves * (BN/32) * 700  (+ the split-K round trip through the fp32 workspace)
-static long gemm_cost(int M, int N, int num_kb, int bn, int splits, int num_sms) {
+static long gemm_cost(int M, int N, int num_kb, int bn, int splits, int num_sms, bool cl2 = false) {
   const long m_tiles = (M + BM - 1) / BM;
   const long tiles = m_tiles * (N / bn);
   const long kb_per = (num_kb + splits - 1) / splits;
   const long ctas = tiles * splits;
   const long waves = (ctas + num_sms - 1) / num_sms;
   // per CTA and 64-wide K block: tensor pipe, shared-memory feed, and the ~64 B/cycle one SM can pull from L2
-  const long per_kb = std::max<long>(std::max(2 * bn, 128 + bn), (16384L + bn * 128L) / 64);
+  const long stage_l2 = 16384L + (cl2 ? bn * 64L : bn * 128L);  // a cluster fetches each weight tile once for two CTAs
+  const long per_kb = std::max<long>(std::max(2 * bn, 128 + bn), stage_l2 / 64);
   const long tensor = waves * kb_per * per_kb;
-  const long l2 = tiles * num_kb * (16384L + bn * 128L) / 5000;
+  const long l2 = tiles * num_kb * stage_l2 / 5000;
   long epi = waves * (bn / 32) * 700;
   if (splits > 1) epi += waves * (bn / 32) * 300 + (bn / 32) * 200L * splits + 2000;
   return std::max(tensor, l2) + epi + 4000;
 }
+
+static bool g_cluster_ok = true;
+bool cluster_allowed() { return g_cluster_ok; }
+void set_cluster_allowed(bool on) { g_cluster_ok = on; }
 
 int gemm_choose_bn(int M, int N, bool geglu, int num_sms) {
   int bn = 0, sp = 0;
@@ -462,7 +496,8 @@ void gemm_choose(int M, int N, int num_kb, bool geglu, int num_sms, int bn_force
       // a split must not leave an empty K range
       const int kb_per = (num_kb + sp - 1) / sp;
       if ((sp - 1) * kb_per >= num_kb) continue;
-      const long c = gemm_cost(M, N, num_kb, bn, sp, num_sms);
+      const bool cl2 = cluster_allowed() && sp == 1 && ((M + BM - 1) / BM) % 2 == 0 && tiles >= 4;
+      const long c = gemm_cost(M, N, num_kb, bn, sp, num_sms, cl2);
       if (best < 0 || c < best) {
         best = c;
         *bn_out = bn;
@@ -475,6 +510,7 @@ void gemm_choose(int M, int N, int num_kb, bool geglu, int num_sms, int bn_force
 int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, bool linear, int B, int H, int W,
                      const __half* Wt, int N, int Ktot, const GemmEpilogue& ep, int bn_force, int num_sms,
                      int split_force) {
+  if (const char* ev = getenv("PNP_GEMM_CLUSTER")) set_cluster_allowed(atoi(ev) != 0);
   PNP_CHECK(nsrc >= 1 && nsrc <= 3, "gemm: 1..3 A sources");
   PNP_CHECK(taps0 == 1 || taps0 == 9, "gemm: taps must be 1 or 9");
   GemmParams& p = plan->p;
@@ -569,6 +605,18 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   const int tiles = p.m_tiles * p.n_tiles;
   plan->bn = bn;
   plan->grid = std::min(tiles * p.splits, num_sms);
+  // cluster of 2 (vertically adjacent M tiles share one weight tile through TMA multicast) whenever it applies
+  plan->cluster = 1;
+  if (cluster_allowed() && splits == 1 && p.m_tiles % 2 == 0 && tiles >= 4) {
+    plan->cluster = 2;
+    const int pairs = tiles / 2;
+    plan->grid = 2 * std::min(pairs, num_sms / 2);
+    uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};
+    uint32_t hbox[2] = {BK, static_cast<uint32_t>(bn / 2)};
+    int rc = encode_tensor_map_f16(&p.map_b_half, Wt, 2, dims, strides, hbox);
+    if (rc) return rc;
+  }
   return 0;
 }
 

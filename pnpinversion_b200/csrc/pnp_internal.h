@@ -39,6 +39,8 @@ const unsigned int* debug_words_host();
 // constant-weight staging) and before its first access to global memory produced by a predecessor, so the ~330
 // launches of one UNet call overlap their prologues with the predecessor's tail (also inside the captured graph).
 bool use_tc_attention();
+bool cluster_allowed();
+void set_cluster_allowed(bool on);
 bool pdl_enabled();
 void set_pdl_enabled(bool on);
 template <typename... KArgs, typename... Args>
@@ -89,6 +91,7 @@ struct ASource {
 struct alignas(64) GemmParams {
   CUtensorMap map_a[3];
   CUtensorMap map_b;
+  CUtensorMap map_b_half;  // box of BN/2 weight rows (cluster-of-2 multicast)
   int taps0, chunks0, chunks1, chunks2;
   int num_kb;
   int linear;
@@ -115,6 +118,7 @@ struct alignas(64) GemmParams {
 struct GemmPlan {
   GemmParams p;
   int bn = 0;
+  int cluster = 1;
   int grid = 0;
   size_t smem = 0;
 };

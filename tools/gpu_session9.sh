@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for f in gemm unet; do
+  timeout 900 python -m pytest tests/test_gpu_$f.py -m gpu -q -s --timeout 600 -p no:cacheprovider > gpurun_out/test_$f.log 2>&1
+  echo "exit code $?" >> gpurun_out/test_$f.log
+done
+PNP_GEMM_CLUSTER=0 timeout 600 python tools/time_unet.py 20 4 > gpurun_out/time_unet_nocluster.log 2>&1
+PNP_PROFILE_DUMP=gpurun_out/per_op.json timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1
+timeout 600 python tools/time_unet.py 20 1,4 > gpurun_out/time_unet.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"self_attn_tc_kernel|vt_transpose" -s 4 -c 3 -o gpurun_out/prof_attn_tc python tools/time_unet.py 1 4 > gpurun_out/ncu_attn.log 2>&1
+grep -E "passed|failed|rel-L2" gpurun_out/test_*.log; cat gpurun_out/time_unet_nocluster.log gpurun_out/time_unet.log; tail -c 700 gpurun_out/bench.log
