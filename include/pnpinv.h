@@ -111,6 +111,9 @@ int pnp_step_epilogue(pnp_engine* h, const pnp_step_args* a, void* stream);
  * entries of alpha_layers per prompt (<= 8 each). mask_out_dev: optional [2,4096] floats. */
 int pnp_local_blend(pnp_engine* h, float* x_dev, const int32_t* nwords2_host, const int32_t* words2x8_host,
                     const float* alpha2x8_host, float threshold, float* mask_out_dev, void* stream);
+/* replaces the EDICT mixing layers on the coupled latent pair, in place (models/edict/edict_functions.py:854-859 when
+ * reverse != 0, :931-936 otherwise); x_dev, y_dev: [n_rows,16384] */
+int pnp_edict_mix(pnp_engine* h, float* x_dev, float* y_dev, int n_rows, float mix_weight, int reverse, void* stream);
 int pnp_store_reset(pnp_engine* h, void* stream);          /* AttentionStore.reset() */
 /* debug/inspection: copy the accumulated maps [5][2*PNP_MAX_SLOTS... see DESIGN.md] */
 int pnp_store_read(pnp_engine* h, float* out_dev, int64_t max_floats, void* stream);

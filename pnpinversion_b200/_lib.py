@@ -82,6 +82,7 @@ SIGNATURES = {
     "pnp_unet_forward": (_i, [_vp, _vp, _i, _i, C.POINTER(AttnCtrl), _vp, _vp]),
     "pnp_step_epilogue": (_i, [_vp, C.POINTER(StepArgs), _vp]),
     "pnp_local_blend": (_i, [_vp, _vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_f), _f, _vp, _vp]),
+    "pnp_edict_mix": (_i, [_vp, _vp, _vp, _i, _f, _i, _vp]),
     "pnp_store_reset": (_i, [_vp, _vp]),
     "pnp_store_read": (_i, [_vp, _vp, _i64, _vp]),
     "pnp_unet_profile": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(C.c_int32), C.POINTER(C.c_double), _i, C.POINTER(_i)]),

@@ -13,8 +13,8 @@
 // same MMAs from exactly the fp16 probabilities that multiply V.  Zero padding of the head dimension (40 -> 64 columns
 // of the 128-byte swizzle atom) and of the V^T rows (41 -> 48) is TMA out-of-bounds fill: no padded copies exist.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..11 softmax
-// (two warps per TMEM lane quarter, 64 keys each).  All hand-offs are mbarriers; every wait is bounded (mbar_wait).
+// Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..19 softmax
+// (four warps per TMEM lane quarter, 32 keys each).  All hand-offs are mbarriers; every wait is bounded (mbar_wait).
 //
 // Controllers (same semantics as attention.cu): per-batch-row source indirection for Q / K / V.
 // Reference algebra: models/p2p/attention_control.py:34-45 (sim = q k^T * scale; softmax; attn @ v).
@@ -44,7 +44,7 @@ constexpr int OFF_K = OFF_Q + Q_BYTES;            // 2 stages
 constexpr int OFF_VT = OFF_K + 2 * K_BYTES;       // 2 stages
 constexpr int OFF_P = OFF_VT + 2 * VT_BYTES;      // 2 stages
 constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;  // barriers + row-max exchange, + alignment slack
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 2048 + 1024;  // barriers, row-max exchange [4][128], alignment slack
 constexpr int TMEM_COLS = 512;
 constexpr int COL_S = 0;    // two S accumulators of 128 columns
 constexpr int COL_O = 256;  // O: 48 columns
@@ -67,7 +67,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 }
 
 template <bool CL2>
-__global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_constant__ SelfAttnTcParams p) {
+__global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_constant__ SelfAttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_const
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], CL2 ? 2 : 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 256);
-      mbar_init(&p_full[i], 256);
+      mbar_init(&s_empty[i], 512);
+      mbar_init(&p_full[i], 512);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
@@ -201,8 +201,11 @@ __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_const
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax warps
-    const int q = warp & 3;            // TMEM lane quarter
-    const int hf = (warp - 4) >> 2;    // which 64 keys of each 128-key tile
+    // 16 warps: 4 per TMEM lane quarter, each owning 32 of the 128 keys of a tile.  The per-element work is a chain of
+    // long-latency ops (TMEM load, FFMA, F2FP, MUFU, STS); measured with 8 warps the kernel was latency-bound (no
+    // eligible warp 72 % of the time), so the parallelism comes from more warps with less work each.
+    const int q = warp & 3;           // TMEM lane quarter
+    const int cg = (warp - 4) >> 2;   // column group: keys [cg*32, cg*32+32) of each tile
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     int sc = 0, pc = 0;
@@ -212,85 +215,81 @@ __global__ void __launch_bounds__(384, 1) self_attn_tc_kernel(const __grid_const
       const int ss = sc & 1;
       mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 31);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + hf * 64 + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&s_empty[ss]);
+      mbar_arrive(&s_empty[ss]);  // the values are in registers: hand the accumulator back before reducing
+      float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+      for (int i = 4; i < 32; i += 4) {
+        m0 = fmaxf(m0, __uint_as_float(r[i]));
+        m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+        m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
+        m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+      }
+      mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
     }
-    rowmax_x[hf * 128 + row] = mx;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    mx = fmaxf(rowmax_x[row], rowmax_x[128 + row]);
+    rowmax_x[cg * 128 + row] = mx;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    mx = fmaxf(fmaxf(rowmax_x[row], rowmax_x[128 + row]), fmaxf(rowmax_x[256 + row], rowmax_x[384 + row]));
     const float off = mx * p.sl2;
     // pass B: probabilities -> shared memory (A operand of the PV MMA)
     for (int j = 0; j < T; ++j, ++sc, ++pc) {
       const int ss = sc & 1, ps = pc & 1;
       mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 32);
-      mbar_wait(&p_empty[ps], ((pc >> 1) & 1) ^ 1u, p.dbg, 33);
       tc_fence_after();
-      uint8_t* prow = smem + OFF_P + ps * P_BYTES + hf * P_ATOM + row * 128;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[ss]);
+      uint32_t ph[16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + hf * 64 + c * 32, r);
-        tmem_ld_wait();
-        uint32_t ph[16];
+      for (int i = 0; i < 16; ++i)
+        ph[i] = ex2_pair(fmaf(__uint_as_float(r[2 * i]), p.sl2, -off), fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -off));
+      mbar_wait(&p_empty[ps], ((pc >> 1) & 1) ^ 1u, p.dbg, 33);
+      // keys [cg*32, +32) live in swizzle atom cg/2 (64 keys each), 16-byte chunks (cg&1)*4 .. +3 of the row
+      uint8_t* prow = smem + OFF_P + ps * P_BYTES + (cg >> 1) * P_ATOM + row * 128;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          ph[i] = ex2_pair(fmaf(__uint_as_float(r[2 * i]), p.sl2, -off), fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -off));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int chunk = (c * 4 + i) ^ (row & 7);  // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-        }
+      for (int i = 0; i < 4; ++i) {
+        const int chunk = ((cg & 1) * 4 + i) ^ (row & 7);  // 128-byte swizzle: chunk index XOR (row mod 8)
+        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(&p_full[ps]);
-      tc_fence_before();
-      mbar_arrive(&s_empty[ss]);
     }
     // epilogue: O / l  (column 40 of O is the row sum of the probabilities)
     mbar_wait(o_full, 0, p.dbg, 34);
     tc_fence_after();
-    uint32_t hi[16];
-    tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + 32, hi);
-    __half* orow = p.o + (static_cast<size_t>(b) * p.N + qt * QT + row) * p.ldo + h * D;
-    if (hf == 0) {
-      uint32_t lo[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + COL_O, lo);
-      tmem_ld_wait();
-      const float inv = 1.0f / __uint_as_float(hi[8]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
+    if (cg < 3) {
+      uint32_t hi[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + 32, hi);
+      __half* orow = p.o + (static_cast<size_t>(b) * p.N + qt * QT + row) * p.ldo + h * D;
+      auto pack8 = [](const uint32_t* v, float inv) {
         uint4 u;
-        __half2 t0 = __floats2half2_rn(__uint_as_float(lo[8 * i + 0]) * inv, __uint_as_float(lo[8 * i + 1]) * inv);
-        __half2 t1 = __floats2half2_rn(__uint_as_float(lo[8 * i + 2]) * inv, __uint_as_float(lo[8 * i + 3]) * inv);
-        __half2 t2 = __floats2half2_rn(__uint_as_float(lo[8 * i + 4]) * inv, __uint_as_float(lo[8 * i + 5]) * inv);
-        __half2 t3 = __floats2half2_rn(__uint_as_float(lo[8 * i + 6]) * inv, __uint_as_float(lo[8 * i + 7]) * inv);
+        __half2 t0 = __floats2half2_rn(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+        __half2 t1 = __floats2half2_rn(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+        __half2 t2 = __floats2half2_rn(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+        __half2 t3 = __floats2half2_rn(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
         u.x = *reinterpret_cast<uint32_t*>(&t0);
         u.y = *reinterpret_cast<uint32_t*>(&t1);
         u.z = *reinterpret_cast<uint32_t*>(&t2);
         u.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(orow + 8 * i) = u;
+        return u;
+      };
+      if (cg < 2) {
+        uint32_t lo[16];
+        tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + cg * 16, lo);
+        tmem_ld_wait();
+        const float inv = 1.0f / __uint_as_float(hi[8]);
+        *reinterpret_cast<uint4*>(orow + cg * 16) = pack8(lo, inv);
+        *reinterpret_cast<uint4*>(orow + cg * 16 + 8) = pack8(lo + 8, inv);
+      } else {
+        tmem_ld_wait();
+        const float inv = 1.0f / __uint_as_float(hi[8]);
+        *reinterpret_cast<uint4*>(orow + 32) = pack8(hi, inv);
       }
-    } else {
-      tmem_ld_wait();
-      const float inv = 1.0f / __uint_as_float(hi[8]);
-      uint4 u;
-      __half2 t0 = __floats2half2_rn(__uint_as_float(hi[0]) * inv, __uint_as_float(hi[1]) * inv);
-      __half2 t1 = __floats2half2_rn(__uint_as_float(hi[2]) * inv, __uint_as_float(hi[3]) * inv);
-      __half2 t2 = __floats2half2_rn(__uint_as_float(hi[4]) * inv, __uint_as_float(hi[5]) * inv);
-      __half2 t3 = __floats2half2_rn(__uint_as_float(hi[6]) * inv, __uint_as_float(hi[7]) * inv);
-      u.x = *reinterpret_cast<uint32_t*>(&t0);
-      u.y = *reinterpret_cast<uint32_t*>(&t1);
-      u.z = *reinterpret_cast<uint32_t*>(&t2);
-      u.w = *reinterpret_cast<uint32_t*>(&t3);
-      *reinterpret_cast<uint4*>(orow + 32) = u;
     }
     tc_fence_before();
   }
@@ -392,9 +391,9 @@ int self_attention_tc_launch(const SelfAttnTcParams& p, cudaStream_t s) {
   }
   PNP_CUDA(launch_k(vt_transpose_kernel, dim3(p.N / 64, 8, p.B), dim3(256), 0, s, p.v_src, p.ld, p.N, p.vt));
   if (p.cluster == 2)
-    PNP_CUDA(launch_kc(self_attn_tc_kernel<true>, dim3(p.N / QT, 8, p.B), dim3(384), SMEM_BYTES, s, 2, p));
+    PNP_CUDA(launch_kc(self_attn_tc_kernel<true>, dim3(p.N / QT, 8, p.B), dim3(640), SMEM_BYTES, s, 2, p));
   else
-    PNP_CUDA(launch_k(self_attn_tc_kernel<false>, dim3(p.N / QT, 8, p.B), dim3(384), SMEM_BYTES, s, p));
+    PNP_CUDA(launch_k(self_attn_tc_kernel<false>, dim3(p.N / QT, 8, p.B), dim3(640), SMEM_BYTES, s, p));
   return 0;
 }
 

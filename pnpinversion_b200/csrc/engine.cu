@@ -1229,6 +1229,12 @@ int pnp_local_blend(pnp_engine* h, float* x_dev, const int32_t* nwords2, const i
   return local_blend_launch(p, as_stream(stream));
 }
 
+int pnp_edict_mix(pnp_engine* h, float* x_dev, float* y_dev, int n_rows, float mix_weight, int reverse, void* stream) {
+  PNP_CHECK(h != nullptr && n_rows >= 1, "pnp_edict_mix: bad argument");
+  h->launches += 1;
+  return edict_mix_launch(x_dev, y_dev, n_rows * PNP_LATENT_ELEMS, mix_weight, reverse != 0, as_stream(stream));
+}
+
 int pnp_store_reset(pnp_engine* h, void* stream) {
   PNP_CHECK(h && h->finalized, "pnp_store_reset: engine not ready");
   PNP_CUDA(cudaMemsetAsync(h->store, 0, kStoreFloats * sizeof(float), as_stream(stream)));

@@ -111,7 +111,35 @@ __global__ void __launch_bounds__(256) local_blend_kernel(const LocalBlendParams
   }
 }
 
+// EDICT mixing layers (models/edict/edict_functions.py:854-859 reverse, :931-936 forward), in place on the coupled pair
+__global__ void edict_mix_kernel(float* __restrict__ x, float* __restrict__ y, int n4, float w, int reverse) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(x)[i];
+    float4 b = reinterpret_cast<float4*>(y)[i];
+    float xs[4] = {a.x, a.y, a.z, a.w}, ys[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (reverse) {
+        ys[k] = __fdiv_rn(__fsub_rn(ys[k], __fmul_rn(1.f - w, xs[k])), w);
+        xs[k] = __fdiv_rn(__fsub_rn(xs[k], __fmul_rn(1.f - w, ys[k])), w);
+      } else {
+        xs[k] = __fadd_rn(__fmul_rn(w, xs[k]), __fmul_rn(1.f - w, ys[k]));
+        ys[k] = __fadd_rn(__fmul_rn(1.f - w, xs[k]), __fmul_rn(w, ys[k]));
+      }
+    }
+    reinterpret_cast<float4*>(x)[i] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+    reinterpret_cast<float4*>(y)[i] = make_float4(ys[0], ys[1], ys[2], ys[3]);
+  }
+}
+
 }  // namespace
+
+int edict_mix_launch(float* x, float* y, int n_elems, float w, bool reverse, cudaStream_t s) {
+  PNP_CHECK(n_elems % 4 == 0 && x != nullptr && y != nullptr, "edict mix: bad arguments");
+  edict_mix_kernel<<<(n_elems / 4 + 255) / 256, 256, 0, s>>>(x, y, n_elems / 4, w, reverse ? 1 : 0);
+  PNP_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int step_epilogue_launch(const StepParams& p, cudaStream_t s) {
   PNP_CHECK(p.n >= 1 && p.n <= 32, "step epilogue: 1..32 latent rows");

@@ -98,6 +98,7 @@ struct StepParams {
   unsigned add_mask;        // RECTIFY: bit r set -> add noise_loss row r to x_new row r
 };
 int step_epilogue_launch(const StepParams& p, cudaStream_t s);
+int edict_mix_launch(float* x, float* y, int n_elems, float w, bool reverse, cudaStream_t s);
 
 // LocalBlend (attention_control.py:97-121): store = accumulated [layers*? ...] see epilogue.cu
 struct LocalBlendParams {

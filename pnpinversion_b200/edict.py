@@ -1,0 +1,180 @@
+"""EDICT coupled dual-latent exact inversion (+ its Prompt-to-Prompt variant) -- SURVEY.md section 8 row a15.
+
+Mirror of `models/edict/edict_functions.py`: `coupled_stablediffusion` (:707-956; loop :851-936, leapfrog order :862-880,
+mixing layers :854-859 / :931-936), `forward_step` (:621-650), `reverse_step` (:653-684), `get_alpha_and_beta` (:599-617),
+`init_attention_edit` (:225-247, difflib opcodes -> mask / indices), `EDICT_editing` (:56-115) and
+`run_editing_edict.py::edit_image_edict_p2p` (:32-61).
+
+The reference runs three sequential B=1 fp64 UNet calls per coupled latent (uncond, cond, cond_edit) and passes the
+source pass's attention probabilities to the edit pass through module attributes.  Here the three passes are ONE fused
+UNet call of batch 3 on the same latent, and "reuse the saved probabilities" is the kernel mode the P2P controllers
+already use: self-attention of the edit row takes Q,K of the source row in every layer (:269-270), cross-attention
+becomes P*(1-mask) + P_src[..., indices]*mask (:266-268).  The DDIM algebra is the fused step epilogue with the
+alpha-quotient coefficients; the mixing layers are `pnp_edict_mix`.  Arithmetic is fp16/fp32 (the reference is fp64):
+tolerances are stated in tests/test_gpu_edict.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from difflib import SequenceMatcher
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .scheduler import fused_step
+
+MAX_TOKENS = 77
+
+
+def attention_edit_tables(tokens: Sequence[int], tokens_edit: Sequence[int]):
+    """init_attention_edit (edict_functions.py:225-247): mask[j]=1 and indices[j]=source position for target tokens in an
+    'equal' block or an equal-length 'replace' block of the difflib alignment."""
+    mask = torch.zeros(MAX_TOKENS)
+    indices = torch.zeros(MAX_TOKENS, dtype=torch.long)
+    target = torch.arange(MAX_TOKENS, dtype=torch.long)
+    for name, a0, a1, b0, b1 in SequenceMatcher(None, list(tokens), list(tokens_edit)).get_opcodes():
+        if b0 < MAX_TOKENS:
+            if name == "equal" or (name == "replace" and a1 - a0 == b1 - b0):
+                mask[b0:b1] = 1
+                indices[b0:b1] = target[a0:a1]
+    return mask, indices
+
+
+class EdictP2PController:
+    """Batch rows [uncond, cond(source prompt), cond(edit prompt)] on one latent."""
+
+    def __init__(self, mask, indices, weights=None):
+        self.mask, self.indices = mask, indices
+        self.weights = weights if weights is not None else torch.ones(MAX_TOKENS)
+        self.num_att_layers = 32
+
+    def descriptor(self, batch):
+        if batch != 3:
+            raise _lib.PnpError("EDICT P2P expects the batch [uncond, cond, cond_edit]")
+        c = _lib.new_ctrl()
+        c.self_layer_lo, c.self_layer_hi, c.self_max_tokens = 0, 16, 1 << 30  # attn1 reused wholesale in every layer
+        c.self_q_row[2] = 1
+        c.self_k_row[2] = 1
+        c.cross_base_row[2] = 1
+        c.cross_slot[2] = 0
+        for w in range(MAX_TOKENS):
+            c.mapper[0][w] = int(self.indices[w])
+            c.alphas[0][w] = float(self.mask[w])
+            c.equalizer[0][w] = float(self.weights[w])
+            c.cross_alpha[0][w] = 1.0
+        return c
+
+    def after_unet_call(self):
+        pass
+
+
+def _alpha(sched, t: int):
+    """get_alpha_and_beta (:599-617) for integer-valued timesteps; t < 0 selects final_alpha_cumprod."""
+    return sched.alphas_cumprod[t] if t >= 0 else sched.final_alpha_cumprod
+
+
+def step_coeffs(sched, t: int, ratio: int, reverse: bool):
+    """forward_step (:646-650): x' = (x - sqrt(1-a_t) e)/q + sqrt(1-a_prev) e ;  reverse_step (:679-684):
+    x' = q (x - sqrt(1-a_prev) e) + sqrt(1-a_t) e, with q = sqrt(a_t / a_prev).  Expressed as the fused epilogue's
+    (sqrt_a_from, sqrt_1m_a_from, sqrt_a_to, sqrt_1m_a_to)."""
+    a_t, a_p = _alpha(sched, t), _alpha(sched, t - ratio)
+    q = float((a_t / a_p) ** 0.5)
+    if reverse:
+        return (1.0, float((1 - a_p) ** 0.5), q, float((1 - a_t) ** 0.5))
+    return (q, float((1 - a_t) ** 0.5), 1.0, float((1 - a_p) ** 0.5))
+
+
+def _embed(model, text: str):
+    tok, enc = model.tokenizer, model.text_encoder
+    ids = tok(text, padding="max_length", max_length=tok.model_max_length, truncation=True, return_tensors="pt")
+    return ids, enc(ids.input_ids.to(model.device))[0].to(model.device, torch.float32)
+
+
+@torch.no_grad()
+def coupled_stablediffusion(model, prompt="", prompt_edit=None, null_prompt="", guidance_scale=7.0, steps=50,
+                            init_image=None, init_image_strength=1.0, reverse=False, fixed_starting_latent=None,
+                            mix_weight=0.93, leapfrog_steps=True, run_baseline=False):
+    """Returns the coupled latent pair [x, y] (the reference returns it for reverse=True / return_latents=True; the
+    VAE decode of the forward direction is outside this library)."""
+    if run_baseline:
+        raise NotImplementedError("run_baseline=True is plain DDIM, covered by the P2P / MasaCtrl paths")
+    dev = model.device
+    if init_image is not None:
+        assert reverse, "want to be performing deterministic noising"
+        lat = [t.clone() for t in init_image] if isinstance(init_image, (list, tuple)) else init_image
+        t_limit = steps - int(steps * init_image_strength)
+    else:
+        assert not reverse, "Need image to reverse from"
+        assert fixed_starting_latent is not None, "random starts are not part of the editing path"
+        lat = [l.clone() for l in fixed_starting_latent] if isinstance(fixed_starting_latent, (list, tuple)) \
+            else fixed_starting_latent.clone()
+        t_limit = steps - int(steps * init_image_strength)
+    pair = list(lat) if isinstance(lat, list) else [lat.clone(), lat.clone()]
+    pair = [p.to(dev, torch.float32).contiguous() for p in pair]
+    sched = model.scheduler
+    sched.set_timesteps(steps)
+    ratio = sched.config.num_train_timesteps // steps
+
+    ids_c, emb_c = _embed(model, prompt)
+    _, emb_u = _embed(model, null_prompt)
+    controller = None
+    if prompt_edit is not None:
+        ids_e, emb_e = _embed(model, prompt_edit)
+        mask, indices = attention_edit_tables(ids_c.input_ids[0].tolist(), ids_e.input_ids[0].tolist())
+        controller = EdictP2PController(mask, indices)
+        context = torch.cat([emb_u, emb_c, emb_e]).contiguous()
+    else:
+        context = torch.cat([emb_u, emb_c]).contiguous()
+    nb = context.shape[0]
+    model.unet.set_controller(controller)
+    lib, h = _lib.load(), model.unet.handle
+
+    timesteps = sched.timesteps[t_limit:]
+    if reverse:
+        timesteps = timesteps.flip(0)
+    n = len(timesteps)
+    for i, t in enumerate(timesteps):
+        tt = int(t)
+        if reverse:
+            _lib.check(lib.pnp_edict_mix(h, C.c_void_p(pair[0].data_ptr()), C.c_void_p(pair[1].data_ptr()),
+                                         pair[0].shape[0], float(mix_weight), 1, _lib.current_stream_ptr()))
+        for k in range(2):
+            if reverse:
+                latent_i = (k + ((n - (i + 1)) + 1) % 2) % 2 if leapfrog_steps else (k + 1) % 2
+            else:
+                latent_i = (k + i % 2) % 2 if leapfrog_steps else k
+            latent_j = (latent_i + 1) % 2
+            x_in = pair[latent_j].expand(nb, -1, -1, -1).contiguous()
+            eps = model.unet(x_in, tt, encoder_hidden_states=context)["sample"]
+            eps_c = eps[nb - 1:nb]  # cond (or cond_edit when P2P is on) -- edict_functions.py:913-915
+            co = step_coeffs(sched, tt, ratio, reverse)
+            pair[latent_i] = fused_step(h, pair[latent_i], eps_c.contiguous(), co, eps_u=eps[0:1].contiguous(),
+                                        guidance=guidance_scale)
+        if not reverse:
+            _lib.check(lib.pnp_edict_mix(h, C.c_void_p(pair[0].data_ptr()), C.c_void_p(pair[1].data_ptr()),
+                                         pair[0].shape[0], float(mix_weight), 0, _lib.current_stream_ptr()))
+    model.unet.set_controller(None)
+    return pair
+
+
+def EDICT_editing(model, latent, base_prompt, edit_prompt, use_p2p=False, steps=50, mix_weight=0.93,
+                  init_image_strength=0.8, guidance_scale=3):
+    """edict_functions.py:56-115."""
+    latents = coupled_stablediffusion(model, base_prompt, reverse=True, init_image=latent,
+                                      init_image_strength=init_image_strength, steps=steps, mix_weight=mix_weight,
+                                      guidance_scale=guidance_scale)
+    return coupled_stablediffusion(model, edit_prompt if not use_p2p else base_prompt,
+                                   None if not use_p2p else edit_prompt, fixed_starting_latent=latents,
+                                   init_image_strength=init_image_strength, steps=steps, mix_weight=mix_weight,
+                                   guidance_scale=guidance_scale)
+
+
+def edit_image_edict_p2p(model, image_path, prompt_src, prompt_tar, use_p2p, steps=50):
+    """run_editing_edict.py:32-61 on latents: returns (reconstruction pair, edit pair)."""
+    if not (isinstance(image_path, torch.Tensor) and image_path.dim() == 4):
+        raise _lib.PnpError("pass the (1,4,64,64) image latent (the VAE is outside this library)")
+    latents = coupled_stablediffusion(model, prompt_src, reverse=True, init_image=image_path, steps=steps)
+    recon = coupled_stablediffusion(model, prompt_src, reverse=False, fixed_starting_latent=latents, steps=steps)
+    edit = EDICT_editing(model, image_path, prompt_src, prompt_tar, use_p2p=use_p2p, steps=steps)
+    return recon, edit
