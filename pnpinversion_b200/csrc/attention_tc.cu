@@ -2,8 +2,10 @@
 //
 //   O = softmax(Q K^T / sqrt(d)) V      per (batch row, head), N = 4096 (any multiple of 128), d = 40
 //
-// One CTA = 128 queries of one (b, h); keys stream through in tiles of 128.  Two passes over the keys, both on the tensor
-// core, so that no accumulator ever has to be rescaled:
+// One CTA = 128 queries of one (b, h); keys stream through in tiles of 128.  The exact schedule is two passes over the keys
+// (below); the kernel first tries an optimistic single pass whose softmax offset comes from the first key tile and falls
+// back to the two-pass schedule only if a probability would overflow fp16 (see the attempt loop).  Two passes, both on the
+// tensor core, so that no accumulator ever has to be rescaled:
 //   pass A : S = Q K^T (tcgen05.mma, 128x128x48 per tile, fp32 in TMEM) -> row maxima
 //   pass B : S again (recomputing it costs 192 tensor cycles per tile, far cheaper than a rescale round trip through
 //            TMEM), P = 2^((S - max) * scale * log2 e) on packed fp16 pairs (MUFU.EX2.F16x2), written 128B-swizzled to
@@ -82,7 +84,8 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
   uint64_t* p_empty = bars + 15;
   uint64_t* o_full = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  float* rowmax_x = reinterpret_cast<float*>(smem + OFF_BAR + 256);  // [2][128]
+  volatile int* ovf_flag = reinterpret_cast<volatile int*>(bars + 19);
+  float* rowmax_x = reinterpret_cast<float*>(smem + OFF_BAR + 256);  // [4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
+    *ovf_flag = 0;
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -117,181 +121,210 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      const int bq = p.q_row ? p.q_row[b] : b;
-      const int bk = p.k_row ? p.k_row[b] : b;
-      const int bv = p.v_row ? p.v_row[b] : b;
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_4d(smem + OFF_Q, &p.map_qk, q_full, 0, h, 0, bq * p.N + qt * QT);
-      int kc = 0, vc = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < T; ++j, ++kc) {
-          const int ks = kc & 1;
-          mbar_wait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u, p.dbg, 11);
-          mbar_arrive_expect_tx(&k_full[ks], K_BYTES);
-          if (CL2) {  // this CTA fetches half of the key tile and multicasts it to both CTAs of the cluster
-            tma_load_4d_mc(smem + OFF_K + ks * K_BYTES + crank * (K_BYTES / 2), &p.map_k64, &k_full[ks], 0x3, 0, h, 1,
-                           bk * p.N + j * KT + crank * 64);
-          } else {
-            tma_load_4d(smem + OFF_K + ks * K_BYTES, &p.map_qk, &k_full[ks], 0, h, 1, bk * p.N + j * KT);
-          }
-          if (pass == 1) {
-            const int vs = vc & 1;
-            mbar_wait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u, p.dbg, 12);
-            mbar_arrive_expect_tx(&v_full[vs], VT_BYTES);
-            if (CL2) {
-              tma_load_4d_mc(smem + OFF_VT + vs * VT_BYTES + crank * VT_ATOM, &p.map_vt, &v_full[vs], 0x3,
-                             j * KT + crank * 64, 0, h, bv);
+  // Optimistic single pass.  Attempt 0 takes the softmax offset from the FIRST key tile only (pass A over one tile) and
+  // streams all tiles once through pass B; the probabilities are then 2^(s - m_first) instead of 2^(s - m_row), which is
+  // exact after the final division by the row sum as long as nothing overflows fp16.  Every thread tracks its largest
+  // exponent; if any exceeds 15 (|P| would pass 2^15) the whole CTA (and its cluster peer) repeats with the full
+  // two-pass schedule (attempt 1: pass A over all tiles).  Reading S from TMEM costs ~1000 cycles per 128x128 tile
+  // (TMEM read bandwidth), as much as the exponentials, so skipping pass A nearly halves the kernel.
+  int kc = 0, vc = 0, sc = 0, pc = 0;  // ring counters (each role advances the ones it uses)
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int TA = (attempt == 0) ? 1 : T;
+    if (warp == 0) {
+      if (lane == 0) {
+        // -------------------------------------------------------------- TMA producer
+        const int bq = p.q_row ? p.q_row[b] : b;
+        const int bk = p.k_row ? p.k_row[b] : b;
+        const int bv = p.v_row ? p.v_row[b] : b;
+        if (attempt == 0) {
+          mbar_arrive_expect_tx(q_full, Q_BYTES);
+          tma_load_4d(smem + OFF_Q, &p.map_qk, q_full, 0, h, 0, bq * p.N + qt * QT);
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+          const int nt = pass == 0 ? TA : T;
+          for (int j = 0; j < nt; ++j, ++kc) {
+            const int ks = kc & 1;
+            mbar_wait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u, p.dbg, 11);
+            mbar_arrive_expect_tx(&k_full[ks], K_BYTES);
+            if (CL2) {  // this CTA fetches half of the key tile and multicasts it to both CTAs of the cluster
+              tma_load_4d_mc(smem + OFF_K + ks * K_BYTES + crank * (K_BYTES / 2), &p.map_k64, &k_full[ks], 0x3, 0, h, 1,
+                             bk * p.N + j * KT + crank * 64);
             } else {
-              tma_load_4d(smem + OFF_VT + vs * VT_BYTES, &p.map_vt, &v_full[vs], j * KT, 0, h, bv);
-              tma_load_4d(smem + OFF_VT + vs * VT_BYTES + VT_ATOM, &p.map_vt, &v_full[vs], j * KT + 64, 0, h, bv);
+              tma_load_4d(smem + OFF_K + ks * K_BYTES, &p.map_qk, &k_full[ks], 0, h, 1, bk * p.N + j * KT);
             }
-            ++vc;
+            if (pass == 1) {
+              const int vs = vc & 1;
+              mbar_wait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u, p.dbg, 12);
+              mbar_arrive_expect_tx(&v_full[vs], VT_BYTES);
+              if (CL2) {
+                tma_load_4d_mc(smem + OFF_VT + vs * VT_BYTES + crank * VT_ATOM, &p.map_vt, &v_full[vs], 0x3,
+                               j * KT + crank * 64, 0, h, bv);
+              } else {
+                tma_load_4d(smem + OFF_VT + vs * VT_BYTES, &p.map_vt, &v_full[vs], j * KT, 0, h, bv);
+                tma_load_4d(smem + OFF_VT + vs * VT_BYTES + VT_ATOM, &p.map_vt, &v_full[vs], j * KT + 64, 0, h, bv);
+              }
+              ++vc;
+            }
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc_qk = umma_idesc_f16(QT, KT);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(QT, VT_ROWS);
-      const uint32_t q_addr = smem_u32(smem + OFF_Q);
-      int kc = 0, sc = 0, pc = 0, vc = 0;
-      auto issue_qk = [&]() {
-        const int ks = kc & 1, ss = sc & 1;
-        mbar_wait(&k_full[ks], (kc >> 1) & 1, p.dbg, 21);
-        mbar_wait(&s_empty[ss], ((sc >> 1) & 1) ^ 1u, p.dbg, 22);
-        tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128_kmajor(q_addr);
-        const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + OFF_K + ks * K_BYTES));
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // -------------------------------------------------------------- MMA issuer
+        constexpr uint32_t idesc_qk = umma_idesc_f16(QT, KT);
+        constexpr uint32_t idesc_pv = umma_idesc_f16(QT, VT_ROWS);
+        const uint32_t q_addr = smem_u32(smem + OFF_Q);
+        auto issue_qk = [&]() {
+          const int ks = kc & 1, ss = sc & 1;
+          mbar_wait(&k_full[ks], (kc >> 1) & 1, p.dbg, 21);
+          mbar_wait(&s_empty[ss], ((sc >> 1) & 1) ^ 1u, p.dbg, 22);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128_kmajor(q_addr);
+          const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + OFF_K + ks * K_BYTES));
 #pragma unroll
-        for (int k = 0; k < 3; ++k)  // head dim 40 -> 48 = three K=16 steps (columns 40..63 are TMA zero fill)
-          umma_f16_ss(tmem_base + COL_S + ss * KT, adesc + 2u * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
-        if (CL2) umma_commit_mc(&k_empty[ks], 0x3); else umma_commit(&k_empty[ks]);
-        umma_commit(&s_full[ss]);
-        ++kc;
-        ++sc;
-      };
-      mbar_wait(q_full, 0, p.dbg, 20);
-      for (int j = 0; j < T; ++j) issue_qk();  // pass A
-      issue_qk();                              // pass B, tile 0
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_qk();  // S of the next tile is computed while the softmax warps work on this one
-        const int ps = pc & 1, vs = vc & 1;
-        mbar_wait(&p_full[ps], (pc >> 1) & 1, p.dbg, 23);
-        mbar_wait(&v_full[vs], (vc >> 1) & 1, p.dbg, 24);
-        tc_fence_after();
-        const uint32_t p_addr = smem_u32(smem + OFF_P + ps * P_BYTES);
-        const uint32_t v_addr = smem_u32(smem + OFF_VT + vs * VT_BYTES);
+          for (int k = 0; k < 3; ++k)  // head dim 40 -> 48 = three K=16 steps (columns 40..63 are TMA zero fill)
+            umma_f16_ss(tmem_base + COL_S + ss * KT, adesc + 2u * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
+          if (CL2) umma_commit_mc(&k_empty[ks], 0x3); else umma_commit(&k_empty[ks]);
+          umma_commit(&s_full[ss]);
+          ++kc;
+          ++sc;
+        };
+        if (attempt == 0) mbar_wait(q_full, 0, p.dbg, 20);
+        for (int j = 0; j < TA; ++j) issue_qk();  // pass A
+        issue_qk();                               // pass B, tile 0
+        for (int j = 0; j < T; ++j) {
+          if (j + 1 < T) issue_qk();  // S of the next tile is computed while the softmax warps work on this one
+          const int ps = pc & 1, vs = vc & 1;
+          mbar_wait(&p_full[ps], (pc >> 1) & 1, p.dbg, 23);
+          mbar_wait(&v_full[vs], (vc >> 1) & 1, p.dbg, 24);
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(smem + OFF_P + ps * P_BYTES);
+          const uint32_t v_addr = smem_u32(smem + OFF_VT + vs * VT_BYTES);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // 128 keys = 8 K=16 steps over two 64-key swizzle atoms
-          const uint64_t adesc = umma_desc_sw128_kmajor(p_addr + (k >> 2) * P_ATOM) + 2u * (k & 3);
-          const uint64_t bdesc = umma_desc_sw128_kmajor(v_addr + (k >> 2) * VT_ATOM) + 2u * (k & 3);
-          umma_f16_ss(tmem_base + COL_O, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {  // 128 keys = 8 K=16 steps over two 64-key swizzle atoms
+            const uint64_t adesc = umma_desc_sw128_kmajor(p_addr + (k >> 2) * P_ATOM) + 2u * (k & 3);
+            const uint64_t bdesc = umma_desc_sw128_kmajor(v_addr + (k >> 2) * VT_ATOM) + 2u * (k & 3);
+            umma_f16_ss(tmem_base + COL_O, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&p_empty[ps]);
+          if (CL2) umma_commit_mc(&v_empty[vs], 0x3); else umma_commit(&v_empty[vs]);
+          ++pc;
+          ++vc;
         }
-        umma_commit(&p_empty[ps]);
-        if (CL2) umma_commit_mc(&v_empty[vs], 0x3); else umma_commit(&v_empty[vs]);
-        ++pc;
-        ++vc;
+        umma_commit(o_full);
       }
-      umma_commit(o_full);
-    }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax warps
-    // 16 warps: 4 per TMEM lane quarter, each owning 32 of the 128 keys of a tile.  The per-element work is a chain of
-    // long-latency ops (TMEM load, FFMA, F2FP, MUFU, STS); measured with 8 warps the kernel was latency-bound (no
-    // eligible warp 72 % of the time), so the parallelism comes from more warps with less work each.
-    const int q = warp & 3;           // TMEM lane quarter
-    const int cg = (warp - 4) >> 2;   // column group: keys [cg*32, cg*32+32) of each tile
-    const int row = q * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    int sc = 0, pc = 0;
-    // pass A: row maxima of the raw scores
-    float mx = -INFINITY;
-    for (int j = 0; j < T; ++j, ++sc) {
-      const int ss = sc & 1;
-      mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 31);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_empty[ss]);  // the values are in registers: hand the accumulator back before reducing
-      float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+    } else if (warp >= 4) {
+      // ---------------------------------------------------------------- softmax warps
+      // 16 warps: 4 per TMEM lane quarter, each owning 32 of the 128 keys of a tile.  The per-element work is a chain of
+      // long-latency ops (TMEM load, FFMA, F2FP, MUFU, STS); with 8 warps the kernel was latency-bound (no eligible
+      // warp 72 % of the time), so the parallelism comes from more warps with less work each.
+      const int q = warp & 3;           // TMEM lane quarter
+      const int cg = (warp - 4) >> 2;   // column group: keys [cg*32, cg*32+32) of each tile
+      const int row = q * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+      auto max32 = [](const uint32_t (&r)[32]) {
+        float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
 #pragma unroll
-      for (int i = 4; i < 32; i += 4) {
-        m0 = fmaxf(m0, __uint_as_float(r[i]));
-        m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
-        m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
-        m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
-      }
-      mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-    }
-    rowmax_x[cg * 128 + row] = mx;
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    mx = fmaxf(fmaxf(rowmax_x[row], rowmax_x[128 + row]), fmaxf(rowmax_x[256 + row], rowmax_x[384 + row]));
-    const float off = mx * p.sl2;
-    // pass B: probabilities -> shared memory (A operand of the PV MMA)
-    for (int j = 0; j < T; ++j, ++sc, ++pc) {
-      const int ss = sc & 1, ps = pc & 1;
-      mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 32);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_empty[ss]);
-      uint32_t ph[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        ph[i] = ex2_pair(fmaf(__uint_as_float(r[2 * i]), p.sl2, -off), fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -off));
-      mbar_wait(&p_empty[ps], ((pc >> 1) & 1) ^ 1u, p.dbg, 33);
-      // keys [cg*32, +32) live in swizzle atom cg/2 (64 keys each), 16-byte chunks (cg&1)*4 .. +3 of the row
-      uint8_t* prow = smem + OFF_P + ps * P_BYTES + (cg >> 1) * P_ATOM + row * 128;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int chunk = ((cg & 1) * 4 + i) ^ (row & 7);  // 128-byte swizzle: chunk index XOR (row mod 8)
-        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-      }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(&p_full[ps]);
-    }
-    // epilogue: O / l  (column 40 of O is the row sum of the probabilities)
-    mbar_wait(o_full, 0, p.dbg, 34);
-    tc_fence_after();
-    if (cg < 3) {
-      uint32_t hi[16];
-      tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + 32, hi);
-      __half* orow = p.o + (static_cast<size_t>(b) * p.N + qt * QT + row) * p.ldo + h * D;
-      auto pack8 = [](const uint32_t* v, float inv) {
-        uint4 u;
-        __half2 t0 = __floats2half2_rn(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-        __half2 t1 = __floats2half2_rn(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-        __half2 t2 = __floats2half2_rn(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-        __half2 t3 = __floats2half2_rn(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-        u.x = *reinterpret_cast<uint32_t*>(&t0);
-        u.y = *reinterpret_cast<uint32_t*>(&t1);
-        u.z = *reinterpret_cast<uint32_t*>(&t2);
-        u.w = *reinterpret_cast<uint32_t*>(&t3);
-        return u;
+        for (int i = 4; i < 32; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(r[i]));
+          m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
+          m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+        }
+        return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       };
-      if (cg < 2) {
-        uint32_t lo[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + cg * 16, lo);
+      // pass A: row maxima of the raw scores (first tile only in the optimistic attempt)
+      float mx = -INFINITY;
+      for (int j = 0; j < TA; ++j, ++sc) {
+        const int ss = sc & 1;
+        mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 31);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
         tmem_ld_wait();
-        const float inv = 1.0f / __uint_as_float(hi[8]);
-        *reinterpret_cast<uint4*>(orow + cg * 16) = pack8(lo, inv);
-        *reinterpret_cast<uint4*>(orow + cg * 16 + 8) = pack8(lo + 8, inv);
-      } else {
-        tmem_ld_wait();
-        const float inv = 1.0f / __uint_as_float(hi[8]);
-        *reinterpret_cast<uint4*>(orow + 32) = pack8(hi, inv);
+        tc_fence_before();
+        mbar_arrive(&s_empty[ss]);  // the values are in registers: hand the accumulator back before reducing
+        mx = fmaxf(mx, max32(r));
       }
+      rowmax_x[cg * 128 + row] = mx;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      mx = fmaxf(fmaxf(rowmax_x[row], rowmax_x[128 + row]), fmaxf(rowmax_x[256 + row], rowmax_x[384 + row]));
+      asm volatile("bar.sync 1, 512;" ::: "memory");  // rowmax_x may be rewritten by a second attempt
+      const float off = mx * p.sl2;
+      float smax = -INFINITY;  // largest raw score seen in pass B (overflow check of the optimistic attempt)
+      // pass B: probabilities -> shared memory (A operand of the PV MMA)
+      for (int j = 0; j < T; ++j, ++sc, ++pc) {
+        const int ss = sc & 1, ps = pc & 1;
+        mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 32);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[ss]);
+        if (attempt == 0) smax = fmaxf(smax, max32(r));
+        uint32_t ph[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          ph[i] = ex2_pair(fmaf(__uint_as_float(r[2 * i]), p.sl2, -off), fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -off));
+        mbar_wait(&p_empty[ps], ((pc >> 1) & 1) ^ 1u, p.dbg, 33);
+        // keys [cg*32, +32) live in swizzle atom cg/2 (64 keys each), 16-byte chunks (cg&1)*4 .. +3 of the row
+        uint8_t* prow = smem + OFF_P + ps * P_BYTES + (cg >> 1) * P_ATOM + row * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = ((cg & 1) * 4 + i) ^ (row & 7);  // 128-byte swizzle: chunk index XOR (row mod 8)
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+        }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&p_full[ps]);
+      }
+      if (attempt == 0 && fmaf(smax, p.sl2, -off) > 15.0f) *ovf_flag = 1;
+      // epilogue: O / l  (column 40 of O is the row sum of the probabilities)
+      mbar_wait(o_full, attempt & 1, p.dbg, 34);
+      tc_fence_after();
+      if (cg < 3) {
+        uint32_t hi[16];
+        tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + 32, hi);
+        __half* orow = p.o + (static_cast<size_t>(b) * p.N + qt * QT + row) * p.ldo + h * D;
+        auto pack8 = [](const uint32_t* v, float inv) {
+          uint4 u;
+          __half2 t0 = __floats2half2_rn(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+          __half2 t1 = __floats2half2_rn(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+          __half2 t2 = __floats2half2_rn(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+          __half2 t3 = __floats2half2_rn(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+          u.x = *reinterpret_cast<uint32_t*>(&t0);
+          u.y = *reinterpret_cast<uint32_t*>(&t1);
+          u.z = *reinterpret_cast<uint32_t*>(&t2);
+          u.w = *reinterpret_cast<uint32_t*>(&t3);
+          return u;
+        };
+        if (cg < 2) {
+          uint32_t lo[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + cg * 16, lo);
+          tmem_ld_wait();
+          const float inv = 1.0f / __uint_as_float(hi[8]);
+          *reinterpret_cast<uint4*>(orow + cg * 16) = pack8(lo, inv);
+          *reinterpret_cast<uint4*>(orow + cg * 16 + 8) = pack8(lo + 8, inv);
+        } else {
+          tmem_ld_wait();
+          const float inv = 1.0f / __uint_as_float(hi[8]);
+          *reinterpret_cast<uint4*>(orow + 32) = pack8(hi, inv);
+        }
+      }
+      tc_fence_before();
     }
-    tc_fence_before();
+    // all roles have finished this attempt: decide (cluster-wide) whether the exact two-pass schedule is needed
+    __syncthreads();
+    int again = *ovf_flag;
+    if (CL2) {
+      cluster_sync_all();
+      uint32_t peer_addr, peer_val;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_addr) : "r"(smem_u32(const_cast<int*>(ovf_flag))), "r"(crank ^ 1u));
+      asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(peer_val) : "r"(peer_addr) : "memory");
+      again |= static_cast<int>(peer_val);
+    }
+    if (attempt == 1 || again == 0 || T == 1) break;
+    tc_fence_after();
   }
 
   tc_fence_before();

@@ -170,3 +170,23 @@ def test_self_attention_tcgen05_row_indirection(cuda):
     _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, G.ptr(dq), G.ptr(dk), G.ptr(dv), G.ptr(out), G.stream()))
     torch.cuda.synchronize()
     assert G.rel_l2(out, _self_ref(qkv, d, q_row, k_row, v_row)) < 2e-3
+
+
+def test_self_attention_tcgen05_optimistic_pass_falls_back_when_fp16_would_overflow(cuda):
+    """The kernel first runs a single pass with the softmax offset of the first key tile; here later keys have far larger
+    scores than the first 128, so the probabilities 2^(s - m_first) would overflow fp16 and the exact two-pass schedule
+    must take over (attention_tc.cu, attempt loop).  The result must still match the reference."""
+    lib = _lib.load()
+    B, N, d = 2, 1024, 40
+    qkv = _mk((B, N, 3 * H * d), cuda, 91, 1.0)
+    c = H * d
+    qkv[:, 256:, c:2 * c] *= 12.0  # keys beyond the second tile: logits ~12x larger
+    out = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    ident = list(range(B))
+    ref = _self_ref(qkv, d, ident, ident, ident)
+    assert torch.isfinite(out.float()).all()
+    err = G.rel_l2(out, ref)
+    print("tc attention with forced fallback: rel-L2", err)
+    assert err < 3e-3
