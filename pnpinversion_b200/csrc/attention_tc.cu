@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], CL2 ? 2 : 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 512);
-      mbar_init(&p_full[i], 512);
+      mbar_init(&s_empty[i], 16);  // one arrival per softmax warp (512 per-thread arrivals on one
+      mbar_init(&p_full[i], 16);   // mbarrier serialise in the shared-memory atomic unit: ~2x the whole tile time)
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_empty[ss]);  // the values are in registers: hand the accumulator back before reducing
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[ss]);  // the values are in registers: hand the accumulator back before reducing
         mx = fmaxf(mx, max32(r));
       }
       rowmax_x[cg * 128 + row] = mx;
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_empty[ss]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[ss]);
         if (attempt == 0) smax = fmaxf(smax, max32(r));
         uint32_t ph[16];
 #pragma unroll
@@ -276,7 +278,8 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(&p_full[ps]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[ps]);
       }
       if (attempt == 0 && fmaf(smax, p.sl2, -off) > 15.0f) *ovf_flag = 1;
       // epilogue: O / l  (column 40 of O is the row sum of the probabilities)

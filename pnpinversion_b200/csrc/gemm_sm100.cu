@@ -32,11 +32,15 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 
-template <int BN>
+// PAIR: two CTAs (one thread-block cluster, two SMs) compute one 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA
+// stages its own 128 rows of A and only HALF of the weight tile; the tensor cores read the other half from the peer's
+// shared memory.  What bounds these GEMMs is the ~64 B/cycle one SM can pull in from L2, so halving the weight bytes
+// per SM raises the arithmetic intensity per ingested byte from 73 to 100 (BN=160) / 85 to 131 FLOP/B (BN=256).
+template <int BN, bool PAIR>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // bytes of the weight tile staged by THIS CTA
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 160 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
   static constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM = STAGES * STAGE + BAR_BYTES + 1024;  // +1024: manual alignment slack
@@ -49,9 +53,9 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN, bool CL2>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
@@ -69,41 +73,45 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     tma_prefetch_desc(&p.map_b);
     if (p.chunks1 > 0) tma_prefetch_desc(&p.map_a[1]);
     if (p.chunks2 > 0) tma_prefetch_desc(&p.map_a[2]);
-    if (CL2) tma_prefetch_desc(&p.map_b_half);
+    if (PAIR) tma_prefetch_desc(&p.map_b_half);
   }
-  const int crank = CL2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int crank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], CL2 ? 2 : 1);  // cluster: the peer multicasts its half of the weight tile into this stage
+      mbar_init(&empty[i], 1);  // PAIR: the leader's commit is multicast to this offset in both CTAs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 256);
+      mbar_init(&tempty[i], PAIR ? 16 : 8);  // one arrival per epilogue warp; PAIR: both CTAs' warps arrive on the leader
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_cg2(tmem_slot, C::TMEM_COLS); else tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();  // peer barriers are initialised before anything is multicast into this CTA
+  if (PAIR) cluster_sync_all();  // the peer's barriers and TMEM exist before any copy / commit / MMA reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();  // set-up done: let the successor start its own, then wait for the predecessor's results
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int num_kb = p.num_kb;
-  // work items: (tile, K split) for a lone CTA; (pair of vertically adjacent M tiles, same N tile) for a cluster of 2
+  // work items: (tile, K split) for a lone CTA; (two vertically adjacent M tiles, same N tile, K split) for a pair
   const int half_m = p.m_tiles >> 1;
-  const int total_work = CL2 ? half_m * p.n_tiles : total_tiles * p.splits;
-  const int work_begin = CL2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int work_stride = CL2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_work = PAIR ? half_m * p.n_tiles * p.splits : total_tiles * p.splits;
+  const int work_begin = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int work_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   auto decode = [&](int work, int& tile, int& split, int& m_blk, int& n_blk) {
-    if (CL2) {
-      n_blk = work / half_m;
-      m_blk = 2 * (work - n_blk * half_m) + crank;
+    if (PAIR) {
+      const int pairs = half_m * p.n_tiles;
+      split = work / pairs;
+      const int pw = work - split * pairs;
+      n_blk = pw / half_m;
+      m_blk = 2 * (pw - n_blk * half_m) + crank;
       tile = n_blk * p.m_tiles + m_blk;
-      split = 0;
     } else {
       tile = work % total_tiles;
       split = work / total_tiles;
@@ -135,25 +143,32 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           mbar_wait(&empty[stage], phase ^ 1u, p.dbg, 1);
           uint8_t* sa = smem + stage * C::STAGE;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full[stage], C::STAGE);
+          // PAIR: the boxes of BOTH CTAs complete on the leader's barrier (only the leader's MMA thread waits on it)
+          if (!PAIR) mbar_arrive_expect_tx(&full[stage], C::STAGE);
+          else if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE);
+          const CUtensorMap* am;
+          int c0, dx = 0, dy = 0;
           if (kb < kb0) {
             const int tap = kb / p.chunks0;
             const int cc = kb - tap * p.chunks0;
-            int dx = 0, dy = 0;
             if (p.taps0 == 9) {
               dy = tap / 3 - 1;
               dx = tap - (tap / 3) * 3 - 1;
             }
-            tma_load_4d(sa, &p.map_a[0], &full[stage], cc * BK, x0 + dx, y0 + dy, b0);
+            am = &p.map_a[0];
+            c0 = cc * BK;
           } else if (kb - kb0 < p.chunks1) {
-            tma_load_4d(sa, &p.map_a[1], &full[stage], (kb - kb0) * BK, x0, y0, b0);
+            am = &p.map_a[1];
+            c0 = (kb - kb0) * BK;
           } else {
-            tma_load_4d(sa, &p.map_a[2], &full[stage], (kb - kb0 - p.chunks1) * BK, x0, y0, b0);
+            am = &p.map_a[2];
+            c0 = (kb - kb0 - p.chunks1) * BK;
           }
-          if (CL2) {  // fetch half of the weight tile, deliver it to both CTAs of the cluster
-            tma_load_2d_mc(sb + crank * (C::B_BYTES / 2), &p.map_b_half, &full[stage], 0x3, kb * BK,
-                           n_blk * BN + crank * (BN / 2));
+          if (PAIR) {
+            tma_load_4d_cg2(sa, am, &full[stage], c0, x0 + dx, y0 + dy, b0);
+            tma_load_2d_cg2(sb, &p.map_b_half, &full[stage], kb * BK, n_blk * BN + crank * (BN / 2));
           } else {
+            tma_load_4d(sa, am, &full[stage], c0, x0 + dx, y0 + dy, b0);
             tma_load_2d(sb, &p.map_b, &full[stage], kb * BK, n_blk * BN);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -161,9 +176,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    if (lane == 0 && crank == 0) {
+      // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA drives both SMs)
+      constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int work = work_begin; work < total_work; work += work_stride, ++it) {
@@ -185,10 +200,13 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128-byte swizzle atom
-            umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            if (PAIR) umma_f16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            else umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          if (CL2) umma_commit_mc(&empty[stage], 0x3); else umma_commit(&empty[stage]);
-          if (kb == kb_end - 1) umma_commit(&tfull[as]);
+          if (PAIR) umma_commit_mc_cg2(&empty[stage], 0x3); else umma_commit(&empty[stage]);
+          if (kb == kb_end - 1) {
+            if (PAIR) umma_commit_mc_cg2(&tfull[as], 0x3); else umma_commit(&tfull[as]);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -237,7 +255,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           }
         }
         tc_fence_before();
-        mbar_arrive(&tempty[as]);
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+        }
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 128) {
@@ -363,17 +384,20 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       }
       if (!from_ws) {
         tc_fence_before();
-        mbar_arrive(&tempty[as]);
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
+  if (PAIR) cluster_sync_all();  // nobody leaves while the peer may still commit to / arrive on / read from this CTA
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (PAIR) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -433,15 +457,15 @@ int launch_t(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg<BN>::SMEM));
+                                  Cfg<BN, false>::SMEM));
     PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg<BN>::SMEM));
+                                  Cfg<BN, true>::SMEM));
     attr_set = true;
   }
   if (plan.cluster == 2)
-    PNP_CUDA(launch_kc(gemm_tcgen05_kernel<BN, true>, dim3(plan.grid), dim3(384), Cfg<BN>::SMEM, stream, 2, plan.p));
+    PNP_CUDA(launch_kc(gemm_tcgen05_kernel<BN, true>, dim3(plan.grid), dim3(384), Cfg<BN, true>::SMEM, stream, 2, plan.p));
   else
-    PNP_CUDA(launch_k(gemm_tcgen05_kernel<BN, false>, dim3(plan.grid), dim3(384), Cfg<BN>::SMEM, stream, plan.p));
+    PNP_CUDA(launch_k(gemm_tcgen05_kernel<BN, false>, dim3(plan.grid), dim3(384), Cfg<BN, false>::SMEM, stream, plan.p));
   return 0;
 }
 
@@ -459,8 +483,8 @@ static long gemm_cost(int M, int N, int num_kb, int bn, int splits, int num_sms,
   const long ctas = tiles * splits;
   const long waves = (ctas + num_sms - 1) / num_sms;
   // per CTA and 64-wide K block: tensor pipe, shared-memory feed, and the ~64 B/cycle one SM can pull from L2
-  const long stage_l2 = 16384L + (cl2 ? bn * 64L : bn * 128L);  // a cluster fetches each weight tile once for two CTAs
-  const long per_kb = std::max<long>(std::max(2 * bn, 128 + bn), stage_l2 / 64);
+  const long stage_l2 = 16384L + (cl2 ? bn * 64L : bn * 128L);  // a pair stages half of the weight tile per SM
+  const long per_kb = std::max<long>(std::max(2 * bn, 128 + (cl2 ? bn / 2 : bn)), stage_l2 / 64);
   const long tensor = waves * kb_per * per_kb;
   const long l2 = tiles * num_kb * stage_l2 / 5000;
   long epi = waves * (bn / 32) * 700;
@@ -496,7 +520,7 @@ void gemm_choose(int M, int N, int num_kb, bool geglu, int num_sms, int bn_force
       // a split must not leave an empty K range
       const int kb_per = (num_kb + sp - 1) / sp;
       if ((sp - 1) * kb_per >= num_kb) continue;
-      const bool cl2 = cluster_allowed() && sp == 1 && ((M + BM - 1) / BM) % 2 == 0 && tiles >= 4;
+      const bool cl2 = cluster_allowed() && ((M + BM - 1) / BM) % 2 == 0;
       const long c = gemm_cost(M, N, num_kb, bn, sp, num_sms, cl2);
       if (best < 0 || c < best) {
         best = c;
@@ -605,11 +629,11 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   const int tiles = p.m_tiles * p.n_tiles;
   plan->bn = bn;
   plan->grid = std::min(tiles * p.splits, num_sms);
-  // cluster of 2 (vertically adjacent M tiles share one weight tile through TMA multicast) whenever it applies
+  // pair mode (cta_group::2: two vertically adjacent M tiles, each SM stages half of the weight tile) whenever it applies
   plan->cluster = 1;
-  if (cluster_allowed() && splits == 1 && p.m_tiles % 2 == 0 && tiles >= 4) {
+  if (cluster_allowed() && p.m_tiles % 2 == 0) {
     plan->cluster = 2;
-    const int pairs = tiles / 2;
+    const int pairs = tiles / 2 * p.splits;
     plan->grid = 2 * std::min(pairs, num_sms / 2);
     uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N)};
     uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};

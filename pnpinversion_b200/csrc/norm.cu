@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "pnp_internal.h"
+#include "pnp_ptx.cuh"
 
 namespace pnp {
 namespace {
@@ -231,6 +232,192 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
       }
     }
   }
+}
+
+// Single-launch GroupNorm: one thread-block cluster per image.  Each CTA owns HW/CS pixels, reduces them to per-group
+// (mean, M2), the CTAs exchange those 64 floats through distributed shared memory, and every CTA then normalises its
+// own pixels (second read is an L2 hit).  Replaces stats + atomics/last-block + apply: the dependent chain is
+// load -> block reduce -> cluster barrier -> load -> store, with no global round trip for the statistics.
+__global__ void gn_cluster_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                  int tx_n, int rows_y, int vpt, float eps, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, int do_silu, __half* __restrict__ out) {
+  extern __shared__ float sm[];  // [rows_y][2*C] reduction scratch, then scale[C] | shift[C]
+  __shared__ __align__(8) float part[GN_GROUPS * 2];
+  __shared__ float gstat[GN_GROUPS * 2];
+  pdl_sync();
+  uint32_t CS;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(CS));
+  const uint32_t rank = cluster_ctarank();
+  const int C = C0 + C1;
+  const int nvec = C >> 3, nvec0 = C0 >> 3;
+  const int b = blockIdx.y;
+  const int ppc = HW / static_cast<int>(CS);
+  const size_t row0 = static_cast<size_t>(b) * HW + static_cast<size_t>(rank) * ppc;
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+  const int cpg = C / GN_GROUPS;
+  float s[GN_MAX_VPT][8], ss[GN_MAX_VPT][8];
+#pragma unroll
+  for (int i = 0; i < GN_MAX_VPT; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[i][e] = ss[i][e] = 0.f;
+  if (ty < rows_y) {
+    constexpr int U = 4;
+    for (int pix0 = ty; pix0 < ppc; pix0 += U * rows_y) {
+      uint4 u[U][GN_MAX_VPT];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int pix = pix0 + j * rows_y;
+        const size_t row = row0 + pix;
+#pragma unroll
+        for (int i = 0; i < GN_MAX_VPT; ++i) {
+          u[j][i] = make_uint4(0, 0, 0, 0);
+          if (i < vpt && pix < ppc) {
+            const int v = tx + i * tx_n;
+            u[j][i] = (v < nvec0) ? __ldg(reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8))
+                                  : __ldg(reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8));
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+#pragma unroll
+        for (int i = 0; i < GN_MAX_VPT; ++i) {
+          if (i < vpt) {
+            float f[8];
+            unpack8(u[j][i], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              s[i][e] += f[e];
+              ss[i][e] += f[e] * f[e];
+            }
+          }
+        }
+      }
+    }
+    float* mine = sm + static_cast<size_t>(ty) * 2 * C;
+#pragma unroll
+    for (int i = 0; i < GN_MAX_VPT; ++i) {
+      if (i < vpt) {
+        const int v = tx + i * tx_n;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          mine[v * 8 + e] = s[i][e];
+          mine[C + v * 8 + e] = ss[i][e];
+        }
+      }
+    }
+  }
+  // affine parameters are fetched while the reduction runs (their latency must not sit behind the cluster barrier)
+  constexpr int CPT = 10;  // C <= 2560 (checked by the launcher) -> at most 10 channels per thread
+  float gam[CPT], bet[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int c = threadIdx.x + i * 256;
+    gam[i] = c < C ? __ldg(gamma + c) : 0.f;
+    bet[i] = c < C ? __ldg(beta + c) : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float a = sm[c];
+    for (int r = 1; r < rows_y; ++r) a += sm[static_cast<size_t>(r) * 2 * C + c];
+    sm[c] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {
+    const int g = threadIdx.x;
+    float a = 0.f, q = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += sm[c];
+      q += sm[C + c];
+    }
+    const float n = static_cast<float>(ppc) * cpg;
+    const float mean = a / n;
+    part[g * 2] = mean;
+    part[g * 2 + 1] = fmaxf(q - a * mean, 0.f);
+  }
+  cluster_sync_all();
+  if (threadIdx.x < GN_GROUPS) {
+    // Chan et al. merge with equal counts, same order in every CTA -> identical statistics cluster-wide
+    const int g = threadIdx.x;
+    const uint32_t local = smem_u32(&part[g * 2]);
+    float2 pr[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      pr[r] = make_float2(0.f, 0.f);
+      if (r < static_cast<int>(CS)) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(pr[r].x), "=f"(pr[r].y) : "r"(remote));
+      }
+    }
+    float msum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) msum += pr[r].x;
+    const float mean = msum / static_cast<float>(CS);
+    const float n_i = static_cast<float>(ppc) * cpg;
+    float m2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (r < static_cast<int>(CS)) {
+        const float d = pr[r].x - mean;
+        m2 += pr[r].y + n_i * d * d;
+      }
+    }
+    gstat[g * 2] = mean;
+    gstat[g * 2 + 1] = rsqrtf(m2 / (n_i * static_cast<float>(CS)) + eps);
+  }
+  // peers may still be reading part[]: arrive now, wait just before exit
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  __syncthreads();
+  float* scale = sm;
+  float* shift = sm + C;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < C) {
+      const int g = c / cpg;
+      const float sc = gstat[g * 2 + 1] * gam[i];
+      scale[c] = sc;
+      shift[c] = bet[i] - gstat[g * 2] * sc;
+    }
+  }
+  __syncthreads();
+  {
+    const int total = ppc * nvec;
+    constexpr int U = 4;
+    for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
+      uint4 u[U];
+      int pixs[U], vs[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int idx = base + j * blockDim.x;
+        const int pix = idx / nvec, v = idx - pix * nvec;
+        pixs[j] = pix;
+        vs[j] = v;
+        if (idx < total) {
+          const size_t row = row0 + pix;
+          u[j] = (v < nvec0) ? __ldg(reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8))
+                             : __ldg(reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int idx = base + j * blockDim.x;
+        if (idx < total) {
+          float f[8];
+          unpack8(u[j], f);
+          const int v = vs[j];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float y = f[e] * scale[v * 8 + e] + shift[v * 8 + e];
+            f[e] = do_silu ? silu(y) : y;
+          }
+          *reinterpret_cast<uint4*>(out + (row0 + pixs[j]) * C + v * 8) = pack8(f);
+        }
+      }
+    }
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 int gn_ppc(int B, int HW) {
@@ -473,6 +660,44 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   float* parts = partials + 64 + 64 * GN_GROUPS * 2;
   PNP_CHECK(B <= 64, "groupnorm: batch");
   (void)threads;
+  // single-launch cluster kernel (one cluster of 16 or 8 CTAs per image) when the device can co-schedule it
+  static int cluster_cs = -1;
+  if (cluster_cs < 0) {
+    cluster_cs = 0;
+    const char* e = getenv("PNP_GN_CLUSTER");
+    const int want = e ? atoi(e) : 16;
+    if (want >= 2) {
+      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      for (int cs = want; cs >= 2 && !cluster_cs; cs >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs, 1);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = 64 * 1024;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_kernel, &cfg) == cudaSuccess && nclusters >= 4)
+          cluster_cs = cs;
+        else
+          (void)cudaGetLastError();
+      }
+    }
+  }
+  if (cluster_cs && C <= 2560 && sm1 <= 64 * 1024) {
+    int cs = cluster_cs;
+    while (cs > 1 && (HW % cs != 0 || HW / cs < 1)) cs >>= 1;
+    if (cs >= 2) {
+      PNP_CUDA(launch_kc(gn_cluster_kernel, dim3(cs, B), dim3(256), sm1 > 2 * C * sizeof(float) ? sm1 : 2 * C * sizeof(float),
+                         s, cs, x0, C0, x1, C1, HW, tx_n, rows_y, vpt, eps, gamma, beta, do_silu ? 1 : 0, out));
+      return 0;
+    }
+  }
   PNP_CUDA(launch_k(gn_stats_kernel, dim3(nslices, B), dim3(256), sm1, s, x0, C0, x1, C1, HW, ppc, tx_n, rows_y, vpt, parts,
                     eps, mean_rstd, counters));
   const size_t sm2 = (2 * static_cast<size_t>(C) + 2 * GN_GROUPS) * sizeof(float);

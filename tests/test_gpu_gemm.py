@@ -8,6 +8,14 @@ from tests import gpu_util as G
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["pair", "single"])
+def tile_mode(request, monkeypatch):
+    """Every case runs twice: with the two-SM tiles (tcgen05.mma.cta_group::2, 256 x BN per CTA pair; taken whenever the
+    number of 128-row tiles is even) and with one CTA per 128 x BN tile (PNP_GEMM_CLUSTER=0, read at plan creation)."""
+    monkeypatch.setenv("PNP_GEMM_CLUSTER", "1" if request.param == "pair" else "0")
+    return request.param
+
+
 def _mk(shape, dev, seed, scale=1.0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(torch.float16).to(dev)

@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for f in attention norm unet; do
+  timeout 1500 python -m pytest tests/test_gpu_$f.py -m gpu -q -s --timeout 1200 -p no:cacheprovider > gpurun_out/test_$f.log 2>&1
+  echo "exit code $?" >> gpurun_out/test_$f.log
+done
+PNP_GEMM_CLUSTER=0 PNP_PROFILE_DUMP=gpurun_out/per_op.json timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1
+PNP_GEMM_CLUSTER=0 timeout 600 python tools/time_unet.py 20 1,4 > gpurun_out/time_unet.log 2>&1
+PNP_GEMM_CLUSTER=0 PNP_GN_CLUSTER=0 timeout 600 python tools/time_unet.py 20 1,4 > gpurun_out/time_unet_gn0.log 2>&1
+PNP_GEMM_CLUSTER=0 PNP_GN_CLUSTER=8 timeout 600 python tools/time_unet.py 20 4 > gpurun_out/time_unet_gn8.log 2>&1
+grep -E "passed|failed|rel-L2|tc attention|Error|error" gpurun_out/test_*.log | cut -c1-300; tail -3 gpurun_out/time_unet*.log; tail -c 700 gpurun_out/bench.log
