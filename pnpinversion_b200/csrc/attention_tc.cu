@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], CL2 ? 2 : 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 16);  // one arrival per softmax warp (512 per-thread arrivals on one
-      mbar_init(&p_full[i], 16);   // mbarrier serialise in the shared-memory atomic unit: ~2x the whole tile time)
+      mbar_init(&s_empty[i], 8);  // one arrival per warp of the softmax group that owns this buffer
+      mbar_init(&p_full[i], 8);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
@@ -127,24 +127,30 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
   // exponent; if any exceeds 15 (|P| would pass 2^15) the whole CTA (and its cluster peer) repeats with the full
   // two-pass schedule (attempt 1: pass A over all tiles).  Reading S from TMEM costs ~1000 cycles per 128x128 tile
   // (TMEM read bandwidth), as much as the exponentials, so skipping pass A nearly halves the kernel.
-  int kc = 0, vc = 0, sc = 0, pc = 0;  // ring counters (each role advances the ones it uses)
+  int kc = 0, vc = 0;       // K / V^T ring counters (producer and MMA issuer each advance their own copy)
+  int su[2] = {0, 0};       // uses so far of S accumulator b (MMA issuer: both; a softmax warp: su[0] = its group's buffer)
+  int pu[2] = {0, 0};       // uses so far of probability buffer b (same convention)
   for (int attempt = 0; attempt < 2; ++attempt) {
     const int TA = (attempt == 0) ? 1 : T;
     if (warp == 0) {
-      if (lane == 0) {
+      {
         // -------------------------------------------------------------- TMA producer
+        // (whole warp in the loop, one elected lane issues: inside `if (lane == 0)` every UTMALDG / UTCHMMA / UTCBAR is
+        // wrapped in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop, ~100 cycles of serial latency per instruction)
         const int bq = p.q_row ? p.q_row[b] : b;
         const int bk = p.k_row ? p.k_row[b] : b;
         const int bv = p.v_row ? p.v_row[b] : b;
         if (attempt == 0) {
-          mbar_arrive_expect_tx(q_full, Q_BYTES);
-          tma_load_4d(smem + OFF_Q, &p.map_qk, q_full, 0, h, 0, bq * p.N + qt * QT);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, Q_BYTES);
+            tma_load_4d(smem + OFF_Q, &p.map_qk, q_full, 0, h, 0, bq * p.N + qt * QT);
+          }
+          __syncwarp();
         }
-        for (int pass = 0; pass < 2; ++pass) {
-          const int nt = pass == 0 ? TA : T;
-          for (int j = 0; j < nt; ++j, ++kc) {
-            const int ks = kc & 1;
-            mbar_wait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u, p.dbg, 11);
+        auto load_k = [&](int j) {
+          const int ks = kc & 1;
+          mbar_wait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u, p.dbg, 11);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&k_full[ks], K_BYTES);
             if (CL2) {  // this CTA fetches half of the key tile and multicasts it to both CTAs of the cluster
               tma_load_4d_mc(smem + OFF_K + ks * K_BYTES + crank * (K_BYTES / 2), &p.map_k64, &k_full[ks], 0x3, 0, h, 1,
@@ -152,76 +158,102 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
             } else {
               tma_load_4d(smem + OFF_K + ks * K_BYTES, &p.map_qk, &k_full[ks], 0, h, 1, bk * p.N + j * KT);
             }
-            if (pass == 1) {
-              const int vs = vc & 1;
-              mbar_wait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u, p.dbg, 12);
-              mbar_arrive_expect_tx(&v_full[vs], VT_BYTES);
-              if (CL2) {
-                tma_load_4d_mc(smem + OFF_VT + vs * VT_BYTES + crank * VT_ATOM, &p.map_vt, &v_full[vs], 0x3,
-                               j * KT + crank * 64, 0, h, bv);
-              } else {
-                tma_load_4d(smem + OFF_VT + vs * VT_BYTES, &p.map_vt, &v_full[vs], j * KT, 0, h, bv);
-                tma_load_4d(smem + OFF_VT + vs * VT_BYTES + VT_ATOM, &p.map_vt, &v_full[vs], j * KT + 64, 0, h, bv);
-              }
-              ++vc;
+          }
+          __syncwarp();
+          ++kc;
+        };
+        auto load_v = [&](int j) {
+          const int vs = vc & 1;
+          mbar_wait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u, p.dbg, 12);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&v_full[vs], VT_BYTES);
+            if (CL2) {
+              tma_load_4d_mc(smem + OFF_VT + vs * VT_BYTES + crank * VT_ATOM, &p.map_vt, &v_full[vs], 0x3,
+                             j * KT + crank * 64, 0, h, bv);
+            } else {
+              tma_load_4d(smem + OFF_VT + vs * VT_BYTES, &p.map_vt, &v_full[vs], j * KT, 0, h, bv);
+              tma_load_4d(smem + OFF_VT + vs * VT_BYTES + VT_ATOM, &p.map_vt, &v_full[vs], j * KT + 64, 0, h, bv);
             }
           }
+          __syncwarp();
+          ++vc;
+        };
+        for (int j = 0; j < TA; ++j) load_k(j);  // pass A
+        // pass B: the key tiles run one ahead of the value tiles -- S(j+2) is issued before P(j) V(j), and a V^T slot
+        // only frees when P(j-2) V(j-2) has completed, which must not hold back the keys
+        for (int j = 0; j <= T; ++j) {
+          if (j < T) load_k(j);
+          if (j >= 1) load_v(j - 1);
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        // -------------------------------------------------------------- MMA issuer
+      {
+        // -------------------------------------------------------------- MMA issuer (whole warp, elected lane issues)
         constexpr uint32_t idesc_qk = umma_idesc_f16(QT, KT);
         constexpr uint32_t idesc_pv = umma_idesc_f16(QT, VT_ROWS);
         const uint32_t q_addr = smem_u32(smem + OFF_Q);
-        auto issue_qk = [&]() {
-          const int ks = kc & 1, ss = sc & 1;
+        auto issue_qk = [&](int buf) {  // S tile into accumulator `buf` (pass-B tile j lives in buffer j & 1)
+          const int ks = kc & 1;
           mbar_wait(&k_full[ks], (kc >> 1) & 1, p.dbg, 21);
-          mbar_wait(&s_empty[ss], ((sc >> 1) & 1) ^ 1u, p.dbg, 22);
+          mbar_wait(&s_empty[buf], (su[buf] & 1) ^ 1u, p.dbg, 22);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128_kmajor(q_addr);
           const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + OFF_K + ks * K_BYTES));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k)  // head dim 40 -> 48 = three K=16 steps (columns 40..63 are TMA zero fill)
-            umma_f16_ss(tmem_base + COL_S + ss * KT, adesc + 2u * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
-          if (CL2) umma_commit_mc(&k_empty[ks], 0x3); else umma_commit(&k_empty[ks]);
-          umma_commit(&s_full[ss]);
+            for (int k = 0; k < 3; ++k)  // head dim 40 -> 48 = three K=16 steps (columns 40..63 are TMA zero fill)
+              umma_f16_ss(tmem_base + COL_S + buf * KT, adesc + 2u * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
+            if (CL2) umma_commit_mc(&k_empty[ks], 0x3); else umma_commit(&k_empty[ks]);
+            umma_commit(&s_full[buf]);
+          }
+          __syncwarp();
           ++kc;
-          ++sc;
+          ++su[buf];
         };
         if (attempt == 0) mbar_wait(q_full, 0, p.dbg, 20);
-        for (int j = 0; j < TA; ++j) issue_qk();  // pass A
-        issue_qk();                               // pass B, tile 0
+        for (int j = 0; j < TA; ++j) issue_qk(j & 1);  // pass A
+        issue_qk(0);                                    // pass B, tiles 0 and 1
+        if (T > 1) issue_qk(1);
         for (int j = 0; j < T; ++j) {
-          if (j + 1 < T) issue_qk();  // S of the next tile is computed while the softmax warps work on this one
-          const int ps = pc & 1, vs = vc & 1;
-          mbar_wait(&p_full[ps], (pc >> 1) & 1, p.dbg, 23);
+          // S(j+2) goes into the buffer S(j) came from as soon as its softmax group has pulled S(j) into registers:
+          // each group always has its next tile waiting, and the two groups run half a tile apart
+          if (j + 2 < T) issue_qk(j & 1);
+          const int pb = j & 1, vs = vc & 1;
+          mbar_wait(&p_full[pb], pu[pb] & 1, p.dbg, 23);
           mbar_wait(&v_full[vs], (vc >> 1) & 1, p.dbg, 24);
           tc_fence_after();
-          const uint32_t p_addr = smem_u32(smem + OFF_P + ps * P_BYTES);
+          const uint32_t p_addr = smem_u32(smem + OFF_P + pb * P_BYTES);
           const uint32_t v_addr = smem_u32(smem + OFF_VT + vs * VT_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 128 keys = 8 K=16 steps over two 64-key swizzle atoms
-            const uint64_t adesc = umma_desc_sw128_kmajor(p_addr + (k >> 2) * P_ATOM) + 2u * (k & 3);
-            const uint64_t bdesc = umma_desc_sw128_kmajor(v_addr + (k >> 2) * VT_ATOM) + 2u * (k & 3);
-            umma_f16_ss(tmem_base + COL_O, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 8; ++k) {  // 128 keys = 8 K=16 steps over two 64-key swizzle atoms
+              const uint64_t adesc = umma_desc_sw128_kmajor(p_addr + (k >> 2) * P_ATOM) + 2u * (k & 3);
+              const uint64_t bdesc = umma_desc_sw128_kmajor(v_addr + (k >> 2) * VT_ATOM) + 2u * (k & 3);
+              umma_f16_ss(tmem_base + COL_O, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&p_empty[pb]);
+            if (CL2) umma_commit_mc(&v_empty[vs], 0x3); else umma_commit(&v_empty[vs]);
           }
-          umma_commit(&p_empty[ps]);
-          if (CL2) umma_commit_mc(&v_empty[vs], 0x3); else umma_commit(&v_empty[vs]);
-          ++pc;
+          __syncwarp();
+          ++pu[pb];
           ++vc;
         }
-        umma_commit(o_full);
+        if (elect_one()) umma_commit(o_full);
+        __syncwarp();
       }
     } else if (warp >= 4) {
       // ---------------------------------------------------------------- softmax warps
-      // 16 warps: 4 per TMEM lane quarter, each owning 32 of the 128 keys of a tile.  The per-element work is a chain of
-      // long-latency ops (TMEM load, FFMA, F2FP, MUFU, STS); with 8 warps the kernel was latency-bound (no eligible
-      // warp 72 % of the time), so the parallelism comes from more warps with less work each.
-      const int q = warp & 3;           // TMEM lane quarter
-      const int cg = (warp - 4) >> 2;   // column group: keys [cg*32, cg*32+32) of each tile
+      // 16 warps in two GROUPS of 8 (two warps per TMEM lane quarter, 64 keys each).  Group g owns accumulator g and
+      // probability buffer g and processes tiles g, g+2, ...  All four warps of an SM sub-partition used to work on the
+      // same tile in lockstep: first all in the FFMA/F2FP phase (MUFU idle), then all queued on MUFU (issue slots idle),
+      // 2700 cycles per tile against a MUFU floor of 1024 (ncu: XU 47 %, issue 39 %).  With the groups half a tile apart
+      // one group's conversions and stores overlap the other group's exponentials.
+      const int q = warp & 3;                 // TMEM lane quarter
+      const int g = (warp - 4) >> 3;          // softmax group = S / P buffer index
+      const int cg = ((warp - 4) >> 2) & 1;   // keys [cg*64, cg*64+64) of each tile = swizzle atom cg of the P tile
       const int row = q * 32 + lane;
       const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+      const uint32_t s_addr = tmem_base + lane_off + COL_S + g * KT + cg * 64;
       auto max32 = [](const uint32_t (&r)[32]) {
         float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
 #pragma unroll
@@ -235,57 +267,63 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
       };
       // pass A: row maxima of the raw scores (first tile only in the optimistic attempt)
       float mx = -INFINITY;
-      for (int j = 0; j < TA; ++j, ++sc) {
-        const int ss = sc & 1;
-        mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 31);
+      for (int j = g; j < TA; j += 2, ++su[0]) {
+        mbar_wait(&s_full[g], su[0] & 1, p.dbg, 31);
         tc_fence_after();
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
-        tmem_ld_wait();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(s_addr + hf * 32, r);
+          tmem_ld_wait();
+          mx = fmaxf(mx, max32(r));
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[ss]);  // the values are in registers: hand the accumulator back before reducing
-        mx = fmaxf(mx, max32(r));
+        if (lane == 0) mbar_arrive(&s_empty[g]);
       }
-      rowmax_x[cg * 128 + row] = mx;
+      rowmax_x[(g * 2 + cg) * 128 + row] = mx;
       asm volatile("bar.sync 1, 512;" ::: "memory");
       mx = fmaxf(fmaxf(rowmax_x[row], rowmax_x[128 + row]), fmaxf(rowmax_x[256 + row], rowmax_x[384 + row]));
       asm volatile("bar.sync 1, 512;" ::: "memory");  // rowmax_x may be rewritten by a second attempt
       const float off = mx * p.sl2;
       float smax = -INFINITY;  // largest raw score seen in pass B (overflow check of the optimistic attempt)
       // pass B: probabilities -> shared memory (A operand of the PV MMA)
-      for (int j = 0; j < T; ++j, ++sc, ++pc) {
-        const int ss = sc & 1, ps = pc & 1;
-        mbar_wait(&s_full[ss], (sc >> 1) & 1, p.dbg, 32);
+      for (int j = g; j < T; j += 2, ++su[0], ++pu[0]) {
+        mbar_wait(&s_full[g], su[0] & 1, p.dbg, 32);
         tc_fence_after();
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + COL_S + ss * KT + cg * 32, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[ss]);
-        if (attempt == 0) smax = fmaxf(smax, max32(r));
-        uint32_t ph[16];
+        uint8_t* prow = smem + OFF_P + g * P_BYTES + cg * P_ATOM + row * 128;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          ph[i] = ex2_pair(fmaf(__uint_as_float(r[2 * i]), p.sl2, -off), fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -off));
-        mbar_wait(&p_empty[ps], ((pc >> 1) & 1) ^ 1u, p.dbg, 33);
-        // keys [cg*32, +32) live in swizzle atom cg/2 (64 keys each), 16-byte chunks (cg&1)*4 .. +3 of the row
-        uint8_t* prow = smem + OFF_P + ps * P_BYTES + (cg >> 1) * P_ATOM + row * 128;
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(s_addr + hf * 32, r);
+          tmem_ld_wait();
+          if (hf == 1) {  // both halves are in registers: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[g]);
+          }
+          if (attempt == 0) smax = fmaxf(smax, max32(r));
+          uint32_t ph[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int chunk = ((cg & 1) * 4 + i) ^ (row & 7);  // 128-byte swizzle: chunk index XOR (row mod 8)
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+          for (int i = 0; i < 16; ++i)
+            ph[i] = ex2_pair(fmaf(__uint_as_float(r[2 * i]), p.sl2, -off), fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -off));
+          if (hf == 0) mbar_wait(&p_empty[g], (pu[0] & 1) ^ 1u, p.dbg, 33);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int chunk = (hf * 4 + i) ^ (row & 7);  // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+          }
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[ps]);
+        if (lane == 0) mbar_arrive(&p_full[g]);
       }
       if (attempt == 0 && fmaf(smax, p.sl2, -off) > 15.0f) *ovf_flag = 1;
       // epilogue: O / l  (column 40 of O is the row sum of the probabilities)
       mbar_wait(o_full, attempt & 1, p.dbg, 34);
       tc_fence_after();
-      if (cg < 3) {
+      const int part = g * 2 + cg;  // 0,1: output columns [part*16, +16); 2: columns 32..39; 3: idle
+      if (part < 3) {
         uint32_t hi[16];
         tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + 32, hi);
         __half* orow = p.o + (static_cast<size_t>(b) * p.N + qt * QT + row) * p.ldo + h * D;
@@ -301,13 +339,13 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           u.w = *reinterpret_cast<uint32_t*>(&t3);
           return u;
         };
-        if (cg < 2) {
+        if (part < 2) {
           uint32_t lo[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + cg * 16, lo);
+          tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + part * 16, lo);
           tmem_ld_wait();
           const float inv = 1.0f / __uint_as_float(hi[8]);
-          *reinterpret_cast<uint4*>(orow + cg * 16) = pack8(lo, inv);
-          *reinterpret_cast<uint4*>(orow + cg * 16 + 8) = pack8(lo + 8, inv);
+          *reinterpret_cast<uint4*>(orow + part * 16) = pack8(lo, inv);
+          *reinterpret_cast<uint4*>(orow + part * 16 + 8) = pack8(lo + 8, inv);
         } else {
           tmem_ld_wait();
           const float inv = 1.0f / __uint_as_float(hi[8]);

@@ -4,6 +4,7 @@
 // (models/edict/my_diffusers/models/unet_2d_condition.py:189-273, unet_blocks.py, resnet.py:331-365,
 // attention.py:140-151,186-200,250-288,329-333, embeddings.py:21-80); see DESIGN.md for the kernel map.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -316,6 +317,11 @@ struct pnp_engine {
   // private stream: graphs cannot be captured on the legacy default stream the caller may hand us
   cudaStream_t es = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // GEMM tile autotuning (plan build time): shape key -> (tile columns, K splits); scratch for the timed trial launches
+  std::map<std::array<int, 7>, std::pair<int, int>> gemm_tuned;
+  float* tune_ws = nullptr;
+  int* tune_counters = nullptr;
+  static constexpr size_t kTuneWsFloats = 24u << 20;  // 96 MB
 
   template <typename T>
   T* dalloc(size_t n) {
@@ -572,11 +578,81 @@ struct PlanBuilder {
     pl->kernels_per_forward += kernels;
   }
 
+  // Tile shape and K split of one GEMM: the cost model ranks the candidates, the best few are TIMED on the device with
+  // the real operands (plan build happens once per batch size, outside any capture), the fastest wins and is remembered
+  // per shape so that equal layers get equal numerics.  PNP_GEMM_AUTOTUNE=0 keeps the model's first choice.
+  void tune(const ASource* srcs, int nsrc, int taps, bool linear, int b, int h, int w, const __half* wt, int n, int ktot,
+            const GemmEpilogue& ep, int* bnt_out, int* splits_out) {
+    const int M = b * h * w, num_kb = ktot / 64;
+    const std::array<int, 7> key = {M, n, ktot, taps, nsrc, ep.residual != nullptr ? 1 : 0, linear ? 1 : 0};
+    auto it = e->gemm_tuned.find(key);
+    if (it != e->gemm_tuned.end()) {
+      *bnt_out = it->second.first;
+      *splits_out = it->second.second;
+      return;
+    }
+    struct Cand { long cost; int bnt, sp; };
+    std::vector<Cand> cands;
+    const int tiles_opt[5] = {320, 256, 160, 128, 64};
+    for (int bnt : tiles_opt)
+      for (int sp = 1; sp <= 12; ++sp) {
+        if (static_cast<size_t>(sp) * M * n > pnp_engine::kTuneWsFloats && sp > 1) continue;
+        const long c = gemm_model_cost(M, n, num_kb, false, bnt, sp, e->num_sms);
+        if (c >= 0) cands.push_back(Cand{c, bnt, sp});
+      }
+    if (cands.empty()) { rc = -2; set_last_error("plan: no valid GEMM tile for N=" + std::to_string(n)); return; }
+    std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& c) { return a.cost < c.cost; });
+    static const bool autotune = [] { const char* v = getenv("PNP_GEMM_AUTOTUNE"); return v == nullptr || atoi(v) != 0; }();
+    int best = 0;
+    if (autotune && cands.size() > 1) {
+      if (e->tune_ws == nullptr) {
+        if (cudaMalloc(reinterpret_cast<void**>(&e->tune_ws), pnp_engine::kTuneWsFloats * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&e->tune_counters), kGemmMaxCounters * sizeof(int)) != cudaSuccess) {
+          rc = -1; set_last_error("plan: autotune workspace"); return;
+        }
+        cudaMemset(e->tune_counters, 0, kGemmMaxCounters * sizeof(int));
+        e->allocs.push_back(e->tune_ws);
+        e->allocs.push_back(e->tune_counters);
+      }
+      // at most one candidate per (tile, split) among the model's best 8, and always the un-split version of each tile
+      const size_t ntry = std::min<size_t>(cands.size(), 8);
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      float best_ms = 1e30f;
+      for (size_t i = 0; i < ntry; ++i) {
+        GemmPlan gp;
+        if (gemm_plan_create(&gp, srcs, nsrc, taps, linear, b, h, w, wt, n, ktot, ep, cands[i].bnt, e->num_sms, cands[i].sp)) continue;
+        gemm_set_workspace(&gp, e->tune_ws, e->tune_counters);
+        bool ok = true;
+        for (int r = 0; r < 2 && ok; ++r) ok = gemm_launch(gp, e->es) == 0;
+        cudaEventRecord(e0, e->es);
+        for (int r = 0; r < 5 && ok; ++r) ok = gemm_launch(gp, e->es) == 0;
+        cudaEventRecord(e1, e->es);
+        if (cudaStreamSynchronize(e->es) != cudaSuccess || !ok) { rc = -1; set_last_error("plan: autotune launch failed"); break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best_ms) { best_ms = ms; best = static_cast<int>(i); }
+      }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      if (getenv("PNP_GEMM_AUTOTUNE_LOG"))
+        fprintf(stderr, "[gemm tune] M=%d N=%d K=%d taps=%d -> tile %d splits %d (%.1f us; model first choice %d/%d)\n", M, n, ktot,
+                taps, cands[best].bnt, cands[best].sp, best_ms * 200.0f, cands[0].bnt, cands[0].sp);
+    }
+    *bnt_out = cands[best].bnt;
+    *splits_out = cands[best].sp;
+    e->gemm_tuned[key] = {cands[best].bnt, cands[best].sp};
+  }
+
   void gemm(std::vector<std::function<int(cudaStream_t)>>& ops, const ASource* srcs, int nsrc, int taps, bool linear,
             int b, int h, int w, const __half* wt, int n, int ktot, const GemmEpilogue& ep) {
     if (rc) return;
+    int bnt = ep.geglu ? 256 : 0, splits = 0;
+    if (!ep.geglu) tune(srcs, nsrc, taps, linear, b, h, w, wt, n, ktot, ep, &bnt, &splits);
+    if (rc) return;
     auto gp = std::make_unique<GemmPlan>();
-    rc = gemm_plan_create(gp.get(), srcs, nsrc, taps, linear, b, h, w, wt, n, ktot, ep, 0, e->num_sms);
+    rc = gemm_plan_create(gp.get(), srcs, nsrc, taps, linear, b, h, w, wt, n, ktot, ep, bnt, e->num_sms, splits);
     if (rc) return;
     GemmPlan* raw = gp.get();
     pl->gemms.push_back(std::move(gp));
@@ -1277,6 +1353,42 @@ static int test_launch_with_ws(GemmPlan* gp, cudaStream_t s) {
   }
   int rc = gemm_launch(*gp, s);
   PNP_CUDA(cudaStreamSynchronize(s));
+  if (rc == 0 && getenv("PNP_GEMM_PROF") != nullptr) {
+    // where do the three roles wait?  (cycle counters of thread 0 / 32 / 128 of every CTA, averaged over the grid)
+    long long* prof = nullptr;
+    PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&prof), gp->grid * 8 * sizeof(long long)));
+    PNP_CUDA(cudaMemset(prof, 0, gp->grid * 8 * sizeof(long long)));
+    gp->p.prof = prof;
+    if (const char* ex = getenv("PNP_GEMM_EXP")) gp->p.exp = atoi(ex);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    rc = gemm_launch(*gp, s);
+    cudaEventRecord(e1, s);
+    PNP_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> h(gp->grid * 8);
+    PNP_CUDA(cudaMemcpy(h.data(), prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    double a[8] = {0};
+    int nm = 0;
+    for (int c = 0; c < gp->grid; ++c) {
+      if (h[c * 8 + 0] > 0) ++nm;
+      for (int j = 0; j < 8; ++j) a[j] += static_cast<double>(h[c * 8 + j]);
+    }
+    const double g = gp->grid, gm = nm > 0 ? nm : 1;
+    fprintf(stderr,
+            "[gemm prof] M=%d N=%d kb=%d taps=%d bn=%dx%d splits=%d pair=%d grid=%d  %.1f us | mma: total %.0f cyc, wait full "
+            "%.0f (%.0f%%), wait tempty %.0f | producer: total %.0f, wait empty %.0f (%.0f%%) | epilogue: total %.0f, wait "
+            "tfull %.0f\n",
+            gp->p.M, gp->p.N, gp->p.num_kb, gp->p.taps0, gp->bn, gp->nsub, gp->p.splits, gp->cluster == 2 ? 1 : 0, gp->grid,
+            ms * 1000.0, a[0] / gm, a[1] / gm, 100.0 * a[1] / (a[0] > 0 ? a[0] : 1), a[2] / gm, a[3] / g, a[4] / g,
+            100.0 * a[4] / (a[3] > 0 ? a[3] : 1), a[5] / g, a[6] / g);
+    cudaFree(prof);
+    gp->p.prof = nullptr;
+    gp->p.exp = 0;
+  }
   if (ws) cudaFree(ws);
   if (cnt) cudaFree(cnt);
   return rc;

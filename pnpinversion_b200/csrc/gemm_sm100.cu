@@ -36,12 +36,21 @@ constexpr int A_BYTES = BM * BK * 2;
 // stages its own 128 rows of A and only HALF of the weight tile; the tensor cores read the other half from the peer's
 // shared memory.  What bounds these GEMMs is the ~64 B/cycle one SM can pull in from L2, so halving the weight bytes
 // per SM raises the arithmetic intensity per ingested byte from 73 to 100 (BN=160) / 85 to 131 FLOP/B (BN=256).
-template <int BN, bool PAIR>
+//
+// NSUB: the CTA tile is 128 x (NSUB*BN); every K=16 step issues NSUB MMAs of N=BN into NSUB different accumulators.
+// Measured (in-kernel cycle counters, profiles/README.md): back-to-back MMAs that accumulate into the SAME TMEM tile
+// issue no faster than one per ~112-128 cycles whatever N is, so a lone accumulator runs the tensor pipe at full rate
+// only for N=256; two interleaved accumulators of N=160 (a 128x320 tile) hide that latency and read the A tile once
+// for twice the columns.
+template <int BN, int NSUB, bool PAIR>
 struct Cfg {
-  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // bytes of the weight tile staged by THIS CTA
+  static constexpr int BNT = BN * NSUB;                            // columns of the CTA tile
+  static constexpr int B_BYTES = (PAIR ? BNT / 2 : BNT) * BK * 2;  // bytes of the weight tile staged by THIS CTA
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
-  static constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
+  static constexpr int STAGES = (225 * 1024) / STAGE > 8 ? 8 : (225 * 1024) / STAGE;
+  static constexpr int NACC = 2 * BNT <= 512 ? 2 : 1;  // accumulator sets in TMEM (2 = epilogue overlaps the next tile)
+  static constexpr int ACC_COLS = NACC * BNT;
+  static constexpr int TMEM_COLS = ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512));
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM = STAGES * STAGE + BAR_BYTES + 1024;  // +1024: manual alignment slack
 };
@@ -53,9 +62,11 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN, bool PAIR>
+template <int BN, int NSUB, bool PAIR>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN, PAIR>;
+  using C = Cfg<BN, NSUB, PAIR>;
+  constexpr int BNT = C::BNT;
+  static_assert(!PAIR || NSUB == 1, "pair mode has one accumulator per tile");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
@@ -121,10 +132,16 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------------------ TMA producer
+      // The WHOLE warp runs the loop (uniform control flow, operands in uniform registers) and one elected lane issues
+      // the copies.  With the loop inside `if (lane == 0)` the compiler treats every operand as divergent and wraps each
+      // UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop: ~570 cycles of serial latency per
+      // 64-wide K block, more than the tensor pipe needs for any tile narrower than 256 columns.
       uint32_t stage = 0, phase = 0;
       const int kb0 = p.taps0 * p.chunks0;
+      const bool prof = p.prof != nullptr;
+      long long pr_t0 = prof ? clock64() : 0, pr_wait = 0;
       for (int work = work_begin; work < total_work; work += work_stride) {
         int tile, split, m_blk, n_blk;
         decode(work, tile, split, m_blk, n_blk);
@@ -139,76 +156,142 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           y0 = (p0 - b0 * p.HW) / p.W;
           x0 = 0;
         }
+        // K-block cursor kept incrementally (segment, tap offsets, channel chunk): an integer division per K block put
+        // a ~150-cycle dependent chain into this loop, which has nothing else to overlap it with
+        int seg, cc, dx = 0, dy = 0, tap = 0;
+        if (kb_begin < kb0) {
+          seg = 0;
+          tap = kb_begin / p.chunks0;
+          cc = kb_begin - tap * p.chunks0;
+          if (p.taps0 == 9) {
+            dy = tap / 3 - 1;
+            dx = tap - (tap / 3) * 3 - 1;
+          }
+        } else if (kb_begin - kb0 < p.chunks1) {
+          seg = 1;
+          cc = kb_begin - kb0;
+        } else {
+          seg = 2;
+          cc = kb_begin - kb0 - p.chunks1;
+        }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u, p.dbg, 1);
+          // operands of this K block, computed before the wait
+          const CUtensorMap* am = &p.map_a[seg];
+          const int c0 = cc * BK, cx = x0 + (seg == 0 ? dx : 0), cy = y0 + (seg == 0 ? dy : 0);
+          ++cc;
+          if (seg == 0) {
+            if (cc == p.chunks0) {
+              cc = 0;
+              ++tap;
+              if (++dx == 2) { dx = -1; ++dy; }
+              if (tap == p.taps0) { seg = 1; dx = dy = 0; }
+            }
+          } else if (seg == 1 && cc == p.chunks1) {
+            seg = 2;
+            cc = 0;
+          }
+          if (prof) {
+            const long long t = clock64();
+            mbar_wait(&empty[stage], phase ^ 1u, p.dbg, 1);
+            pr_wait += clock64() - t;
+          } else {
+            mbar_wait(&empty[stage], phase ^ 1u, p.dbg, 1);
+          }
           uint8_t* sa = smem + stage * C::STAGE;
           uint8_t* sb = sa + A_BYTES;
-          // PAIR: the boxes of BOTH CTAs complete on the leader's barrier (only the leader's MMA thread waits on it)
-          if (!PAIR) mbar_arrive_expect_tx(&full[stage], C::STAGE);
-          else if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE);
-          const CUtensorMap* am;
-          int c0, dx = 0, dy = 0;
-          if (kb < kb0) {
-            const int tap = kb / p.chunks0;
-            const int cc = kb - tap * p.chunks0;
-            if (p.taps0 == 9) {
-              dy = tap / 3 - 1;
-              dx = tap - (tap / 3) * 3 - 1;
+          if (p.exp & 1) {  // experiment: no copies at all (the MMAs read whatever is in shared memory)
+            if ((!PAIR || crank == 0) && lane == 0) mbar_arrive(&full[stage]);
+            __syncwarp();
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          if (elect_one()) {
+            // PAIR: the boxes of BOTH CTAs complete on the leader's barrier (only the leader's MMA warp waits on it)
+            if (!PAIR) mbar_arrive_expect_tx(&full[stage], C::STAGE);
+            else if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE);
+            if (PAIR) {
+              tma_load_4d_cg2(sa, am, &full[stage], c0, cx, cy, b0);
+              tma_load_2d_cg2(sb, &p.map_b_half, &full[stage], kb * BK, n_blk * BNT + crank * (BNT / 2));
+            } else {
+              tma_load_4d(sa, am, &full[stage], c0, cx, cy, b0);
+#pragma unroll
+              for (int sub = 0; sub < NSUB; ++sub)  // one box (<= 256 rows) per accumulator
+                tma_load_2d(sb + sub * BN * BK * 2, &p.map_b, &full[stage], kb * BK, n_blk * BNT + sub * BN);
             }
-            am = &p.map_a[0];
-            c0 = cc * BK;
-          } else if (kb - kb0 < p.chunks1) {
-            am = &p.map_a[1];
-            c0 = (kb - kb0) * BK;
-          } else {
-            am = &p.map_a[2];
-            c0 = (kb - kb0 - p.chunks1) * BK;
           }
-          if (PAIR) {
-            tma_load_4d_cg2(sa, am, &full[stage], c0, x0 + dx, y0 + dy, b0);
-            tma_load_2d_cg2(sb, &p.map_b_half, &full[stage], kb * BK, n_blk * BN + crank * (BN / 2));
-          } else {
-            tma_load_4d(sa, am, &full[stage], c0, x0 + dx, y0 + dy, b0);
-            tma_load_2d(sb, &p.map_b, &full[stage], kb * BK, n_blk * BN);
-          }
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      if (prof && lane == 0) {
+        p.prof[blockIdx.x * 8 + 3] = clock64() - pr_t0;
+        p.prof[blockIdx.x * 8 + 4] = pr_wait;
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
+    if (crank == 0) {
       // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA drives both SMs)
+      // whole warp in the loop, one elected lane issues MMAs and commits (see the producer)
       constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
+      const bool prof = p.prof != nullptr;
+      long long mm_t0 = prof ? clock64() : 0, mm_wfull = 0, mm_wtempty = 0;
       for (int work = work_begin; work < total_work; work += work_stride, ++it) {
         int tile, split, m_blk, n_blk;
         decode(work, tile, split, m_blk, n_blk);
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
-        const uint32_t as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty[as], aphase ^ 1u, p.dbg, 2);
+        const uint32_t as = C::NACC == 2 ? (it & 1) : 0;
+        const uint32_t aphase = C::NACC == 2 ? ((it >> 1) & 1) : (it & 1);
+        if (prof) {
+          const long long t = clock64();
+          mbar_wait(&tempty[as], aphase ^ 1u, p.dbg, 2);
+          mm_wtempty += clock64() - t;
+        } else {
+          mbar_wait(&tempty[as], aphase ^ 1u, p.dbg, 2);
+        }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * BNT;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&full[stage], phase, p.dbg, 3);
+          if (prof) {
+            const long long t = clock64();
+            mbar_wait(&full[stage], phase, p.dbg, 3);
+            mm_wfull += clock64() - t;
+          } else {
+            mbar_wait(&full[stage], phase, p.dbg, 3);
+          }
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE);
           const uint64_t adesc = umma_desc_sw128_kmajor(a_addr);
           const uint64_t bdesc = umma_desc_sw128_kmajor(a_addr + A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes per K=16 step inside the 128-byte swizzle atom
-            if (PAIR) umma_f16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-            else umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              if ((p.exp & 2) && !(kb == kb_begin && k == 0)) continue;  // experiment: one MMA per tile, copies only
+              // +32 bytes per K=16 step inside the 128-byte swizzle atom
+              if (PAIR) {
+                umma_f16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub)  // consecutive MMAs go to different accumulators
+                  umma_f16_ss(d_tmem + sub * BN, adesc + 2u * k, bdesc + static_cast<uint64_t>(sub * ((BN * BK * 2) >> 4)) + 2u * k,
+                              idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              }
+            }
+            if (PAIR) umma_commit_mc_cg2(&empty[stage], 0x3); else umma_commit(&empty[stage]);
+            if (kb == kb_end - 1) {
+              if (PAIR) umma_commit_mc_cg2(&tfull[as], 0x3); else umma_commit(&tfull[as]);
+            }
           }
-          if (PAIR) umma_commit_mc_cg2(&empty[stage], 0x3); else umma_commit(&empty[stage]);
-          if (kb == kb_end - 1) {
-            if (PAIR) umma_commit_mc_cg2(&tfull[as], 0x3); else umma_commit(&tfull[as]);
-          }
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
+      }
+      if (prof && lane == 0) {
+        p.prof[blockIdx.x * 8 + 0] = clock64() - mm_t0;
+        p.prof[blockIdx.x * 8 + 1] = mm_wfull;
+        p.prof[blockIdx.x * 8 + 2] = mm_wtempty;
       }
     }
   } else if (warp >= 4) {
@@ -219,30 +302,38 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     const float* temb = nullptr;
     if (p.temb_table != nullptr) temb = p.temb_table + static_cast<size_t>(*p.t_index) * p.temb_stride;
     int it = 0;
+    const bool prof = p.prof != nullptr && threadIdx.x == 128;
+    long long ep_t0 = prof ? clock64() : 0, ep_wait = 0;
     for (int work = work_begin; work < total_work; work += work_stride, ++it) {
       int tile, split, m_blk, n_blk;
       decode(work, tile, split, m_blk, n_blk);
-      const uint32_t as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t as = C::NACC == 2 ? (it & 1) : 0;
+      const uint32_t aphase = C::NACC == 2 ? ((it >> 1) & 1) : (it & 1);
       const int m = m_blk * BM + row;
       const bool valid = m < p.M;
       // the residual does not depend on the accumulator: fetch the first chunk before waiting for the MMAs
       uint4 rcur[4], rnext[4];
       const bool has_res = p.residual != nullptr && valid && !p.geglu;
-      const __half* res_row = has_res ? p.residual + static_cast<size_t>(m) * p.ldr + n_blk * BN : nullptr;
-      if (has_res && half < BN / 32) {
+      const __half* res_row = has_res ? p.residual + static_cast<size_t>(m) * p.ldr + n_blk * BNT : nullptr;
+      if (has_res && half < BNT / 32) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(res_row + half * 32) + j);
       }
-      mbar_wait(&tfull[as], aphase, p.dbg, 4);
+      if (prof) {
+        const long long t = clock64();
+        mbar_wait(&tfull[as], aphase, p.dbg, 4);
+        ep_wait += clock64() - t;
+      } else {
+        mbar_wait(&tfull[as], aphase, p.dbg, 4);
+      }
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BNT;
       bool from_ws = false;
       if (p.splits > 1) {
         // dump the raw fp32 partial of this K range, release the accumulator, then elect the last arrival
-        float* wrow = p.ws + (static_cast<size_t>(split) * p.M + (valid ? m : 0)) * p.N + n_blk * BN;
+        float* wrow = p.ws + (static_cast<size_t>(split) * p.M + (valid ? m : 0)) * p.N + n_blk * BNT;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BNT / 32; c += 2) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -275,15 +366,15 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       }
       if (!p.geglu) {
 #pragma unroll
-        for (int c0 = 0; c0 < BN / 32; c0 += 2) {
+        for (int c0 = 0; c0 < BNT / 32; c0 += 2) {
           const int c = c0 + half;
-          if (c < BN / 32) {
-            const int n0 = n_blk * BN + c * 32;
+          if (c < BNT / 32) {
+            const int n0 = n_blk * BNT + c * 32;
             float v[32];
             if (!from_ws) {
               uint32_t r[32];
               tmem_ld_32x32b_x32(taddr + c * 32, r);
-              if (has_res && c + 2 < BN / 32) {  // prefetch the next chunk's residual under the TMEM load
+              if (has_res && c + 2 < BNT / 32) {  // prefetch the next chunk's residual under the TMEM load
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 2) * 32) + j);
               }
@@ -291,15 +382,33 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             } else {
-              if (has_res && c + 2 < BN / 32) {
+              if (has_res && c + 2 < BNT / 32) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 2) * 32) + j);
               }
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
               if (valid) {
-                for (int sp = 0; sp < p.splits; ++sp) {
-                  const float* wr = p.ws + (static_cast<size_t>(sp) * p.M + m) * p.N + n0;
+                // two K slices per round trip (16 independent 16-byte loads in flight); summed in slice order either way
+                const size_t slice = static_cast<size_t>(p.M) * p.N;
+                const float* wr = p.ws + static_cast<size_t>(m) * p.N + n0;
+                int sp = 0;
+                for (; sp + 1 < p.splits; sp += 2, wr += 2 * slice) {
+                  float4 ta[8], tb[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    ta[j] = __ldcg(reinterpret_cast<const float4*>(wr + 4 * j));
+                    tb[j] = __ldcg(reinterpret_cast<const float4*>(wr + slice + 4 * j));
+                  }
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    v[4 * j] = (v[4 * j] + ta[j].x) + tb[j].x;
+                    v[4 * j + 1] = (v[4 * j + 1] + ta[j].y) + tb[j].y;
+                    v[4 * j + 2] = (v[4 * j + 2] + ta[j].z) + tb[j].z;
+                    v[4 * j + 3] = (v[4 * j + 3] + ta[j].w) + tb[j].w;
+                  }
+                }
+                if (sp < p.splits) {
 #pragma unroll
                   for (int j = 0; j < 32; j += 4) {
                     const float4 t4 = __ldcg(reinterpret_cast<const float4*>(wr + j));
@@ -351,16 +460,16 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           }
         }
       } else {
-        // GEGLU: tile columns [0,BN/2) hold the value projection, [BN/2,BN) the gate projection of the same
+        // GEGLU: tile columns [0,BNT/2) hold the value projection, [BNT/2,BNT) the gate projection of the same
         // output columns (weights are packed that way by the engine).  attention.py:329-333 (erf GELU).
 #pragma unroll 1
-        for (int c = half; c < BN / 64; c += 2) {
+        for (int c = half; c < BNT / 64; c += 2) {
           uint32_t rv[32], rg[32];
           tmem_ld_32x32b_x32(taddr + c * 32, rv);
-          tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, rg);
+          tmem_ld_32x32b_x32(taddr + BNT / 2 + c * 32, rg);
           tmem_ld_wait();
-          const int nv = n_blk * BN + c * 32;
-          const int ng = nv + BN / 2;
+          const int nv = n_blk * BNT + c * 32;
+          const int ng = nv + BNT / 2;
           float o[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -369,7 +478,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             o[j] = vv * gelu_erf(gg);
           }
           if (valid) {
-            uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldc + n_blk * (BN / 2) + c * 32);
+            uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldc + n_blk * (BNT / 2) + c * 32);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u;
@@ -389,6 +498,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           if (PAIR) mbar_arrive_cluster(&tempty[as], 0); else mbar_arrive(&tempty[as]);
         }
       }
+    }
+    if (prof) {
+      p.prof[blockIdx.x * 8 + 5] = clock64() - ep_t0;
+      p.prof[blockIdx.x * 8 + 6] = ep_wait;
     }
   }
 
@@ -452,49 +565,69 @@ int encode_tensor_map_f16(CUtensorMap* m, const void* base, int rank, const uint
 
 namespace {
 
-template <int BN>
+template <int BN, int NSUB>
 int launch_t(const GemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg<BN, false>::SMEM));
-    PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg<BN, true>::SMEM));
+    PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, NSUB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<BN, NSUB, false>::SMEM));
+    if (NSUB == 1)
+      PNP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<BN, 1, true>::SMEM));
     attr_set = true;
   }
-  if (plan.cluster == 2)
-    PNP_CUDA(launch_kc(gemm_tcgen05_kernel<BN, true>, dim3(plan.grid), dim3(384), Cfg<BN, true>::SMEM, stream, 2, plan.p));
+  if (plan.cluster == 2 && NSUB == 1)
+    PNP_CUDA(launch_kc(gemm_tcgen05_kernel<BN, 1, true>, dim3(plan.grid), dim3(384), Cfg<BN, 1, true>::SMEM, stream, 2, plan.p));
   else
-    PNP_CUDA(launch_k(gemm_tcgen05_kernel<BN, false>, dim3(plan.grid), dim3(384), Cfg<BN, false>::SMEM, stream, plan.p));
+    PNP_CUDA(launch_k(gemm_tcgen05_kernel<BN, NSUB, false>, dim3(plan.grid), dim3(384), Cfg<BN, NSUB, false>::SMEM, stream,
+                      plan.p));
   return 0;
 }
 
 }  // namespace
 
-// Cost model (cycles) behind the tile-shape / split-K choice.  Measured on B200 (profiles/r1_per_op_*.md): most GEMMs of
-// this UNet are bound by L2->SM operand traffic (~5 KB/cycle chip-wide), not by the tensor pipe, so the model weighs
-//   tensor   : waves * k_blocks * max(2*BN, 128+BN)        (4 MMAs of 128xBNx16 vs shared-memory feed, per 64-wide K block)
-//   L2       : tiles * k_blocks * (16 KB + BN*128 B) / 5000
-//   epilogue : waves * (BN/32) * 700  (+ the split-K round trip through the fp32 workspace)
-static long gemm_cost(int M, int N, int num_kb, int bn, int splits, int num_sms, bool cl2 = false) {
+// Cost model (cycles) behind the tile-shape / split-K choice, calibrated with the in-kernel cycle counters
+// (PNP_GEMM_PROF, profiles/README.md).  Per CTA and 64-wide K block the slowest of
+//   tensor pipe   : 4 K-steps x nsub MMAs; an MMA of N columns takes N/2 cycles, but back-to-back MMAs into the SAME
+//                   accumulator issue no faster than ~120 cycles apart, so a lone accumulator costs max(N/2, 120) per step
+//   TMA producer  : ~220 cycles of serial issue latency per K block (wait, expect_tx, 1 + nsub copies)
+//   operand bytes : (16 KB + tile columns x 128 B) at the ~64 B/cycle one SM pulls from L2
+// plus the chip-wide L2 limit, the epilogue (~700 cycles per 32-column chunk pair) and, for split-K, the round trip of
+// the fp32 partials.
+static long gemm_cost(int M, int N, int num_kb, int bn, int nsub, int splits, int num_sms, bool pair = false) {
+  const long bnt = static_cast<long>(bn) * nsub;
   const long m_tiles = (M + BM - 1) / BM;
-  const long tiles = m_tiles * (N / bn);
+  const long tiles = m_tiles * (N / bnt);
   const long kb_per = (num_kb + splits - 1) / splits;
   const long ctas = tiles * splits;
   const long waves = (ctas + num_sms - 1) / num_sms;
-  // per CTA and 64-wide K block: tensor pipe, shared-memory feed, and the ~64 B/cycle one SM can pull from L2
-  const long stage_l2 = 16384L + (cl2 ? bn * 64L : bn * 128L);  // a pair stages half of the weight tile per SM
-  const long per_kb = std::max<long>(std::max(2 * bn, 128 + (cl2 ? bn / 2 : bn)), stage_l2 / 64);
+  // measured MMA-warp cycles per K block: ~480 for one accumulator whatever its width (dependent MMAs ~120 cycles apart),
+  // 537 for N=256, 800 for two accumulators of 160 (100 per MMA: shared-memory operand bandwidth)
+  const long mma = nsub > 1 ? 4 * nsub * std::max<long>(bn * 5 / 8, 60) : std::max<long>(2 * bn + 25, 480);
+  const long stage_l2 = 16384L + (pair ? bnt * 64L : bnt * 128L);
+  const long per_kb = std::max<long>(std::max<long>(mma, 300 + 40 * (nsub - 1)), stage_l2 / 64);
   const long tensor = waves * kb_per * per_kb;
   const long l2 = tiles * num_kb * stage_l2 / 5000;
-  long epi = waves * (bn / 32) * 700;
-  if (splits > 1) epi += waves * (bn / 32) * 300 + (bn / 32) * 200L * splits + 2000;
+  // epilogue: ~1800 cycles per 64 columns (two warps per lane quarter, 32 columns each); hidden behind the next tile's
+  // MMAs when TMEM holds two accumulator sets; split-K adds the fp32 round trip, paid by the last-arriving CTA
+  const long chunks = (bnt + 63) / 64;
+  long epi = chunks * 1800;
+  if (2 * bnt > 512 && waves > 1) epi += (waves - 1) * chunks * 1800;
+  if (splits > 1) epi += waves * chunks * 1500 + chunks * 2500L * splits + 6000;
   return std::max(tensor, l2) + epi + 4000;
 }
 
-static bool g_cluster_ok = true;
+static bool g_cluster_ok = false;  // pair mode (cta_group::2) is opt-in: PNP_GEMM_CLUSTER=1
 bool cluster_allowed() { return g_cluster_ok; }
 void set_cluster_allowed(bool on) { g_cluster_ok = on; }
+
+long gemm_model_cost(int M, int N, int num_kb, bool geglu, int bnt, int splits, int num_sms) {
+  int bn = 0, sp = 0;
+  gemm_choose(M, N, num_kb, geglu, num_sms, bnt, splits, &bn, &sp);
+  if (bn != bnt || sp != splits) return -1;
+  const int nsub = bnt == 320 ? 2 : 1;
+  return gemm_cost(M, N, num_kb, bnt / nsub, nsub, splits, num_sms, false);
+}
 
 int gemm_choose_bn(int M, int N, bool geglu, int num_sms) {
   int bn = 0, sp = 0;
@@ -502,29 +635,30 @@ int gemm_choose_bn(int M, int N, bool geglu, int num_sms) {
   return bn;
 }
 
+// bn_out encodes the tile: 64/128/160/256 = one accumulator of that width, 320 = two accumulators of 160
 void gemm_choose(int M, int N, int num_kb, bool geglu, int num_sms, int bn_force, int split_force, int* bn_out,
                  int* splits_out) {
-  const int cands[4] = {256, 160, 128, 64};
+  const int cands[5][2] = {{160, 2}, {256, 1}, {160, 1}, {128, 1}, {64, 1}};
   long best = -1;
   *bn_out = 0;
   *splits_out = 1;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
-    if (bn_force > 0 && bn != bn_force) continue;
-    if (N % bn != 0) continue;
-    if (geglu && bn != 256 && bn != 128) continue;
-    const long tiles = static_cast<long>((M + BM - 1) / BM) * (N / bn);
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i][0], nsub = cands[i][1], bnt = bn * nsub;
+    if (bn_force > 0 && bnt != bn_force) continue;
+    if (N % bnt != 0) continue;
+    if (geglu && bnt != 256 && bnt != 128) continue;
+    const long tiles = static_cast<long>((M + BM - 1) / BM) * (N / bnt);
     for (int sp = 1; sp <= 16; ++sp) {
       if (split_force > 0 && sp != split_force) continue;
       if (sp > 1 && (geglu || tiles > kGemmMaxCounters || num_kb / sp < 4)) continue;
       // a split must not leave an empty K range
       const int kb_per = (num_kb + sp - 1) / sp;
       if ((sp - 1) * kb_per >= num_kb) continue;
-      const bool cl2 = cluster_allowed() && ((M + BM - 1) / BM) % 2 == 0;
-      const long c = gemm_cost(M, N, num_kb, bn, sp, num_sms, cl2);
+      const bool pair = cluster_allowed() && nsub == 1 && ((M + BM - 1) / BM) % 2 == 0;
+      const long c = gemm_cost(M, N, num_kb, bn, nsub, sp, num_sms, pair);
       if (best < 0 || c < best) {
         best = c;
-        *bn_out = bn;
+        *bn_out = bnt;
         *splits_out = sp;
       }
     }
@@ -552,8 +686,11 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   gemm_choose(M, N, Ktot / BK, geglu, num_sms, bn_force, split_force, &bn, &splits);
   if (bn == 0 && split_force > 1) gemm_choose(M, N, Ktot / BK, geglu, num_sms, bn_force, 0, &bn, &splits);
   PNP_CHECK(bn != 0, "gemm: no valid tile shape for this N");
-  PNP_CHECK(bn == 256 || bn == 160 || bn == 128 || bn == 64, "gemm: unsupported BN");
+  PNP_CHECK(bn == 320 || bn == 256 || bn == 160 || bn == 128 || bn == 64, "gemm: unsupported BN");
   PNP_CHECK(N % bn == 0, "gemm: N must be a multiple of the column tile");
+  const int bnt = bn;  // columns of the CTA tile
+  const int nsub = bn == 320 ? 2 : 1;
+  bn = bnt / nsub;     // N of one MMA = rows of one weight box
   PNP_CHECK(!geglu || bn == 256 || bn == 128, "gemm: GEGLU epilogue needs BN 128/256");
   PNP_CHECK(ep.out != nullptr && ep.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0,
             "gemm: output alignment");
@@ -612,7 +749,7 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   p.M = M;
   p.N = N;
   p.m_tiles = (M + BM - 1) / BM;
-  p.n_tiles = N / bn;
+  p.n_tiles = N / bnt;
   p.bias = ep.bias;
   p.temb_table = ep.temb_table;
   p.t_index = ep.t_index;
@@ -628,10 +765,11 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   const int tiles = p.m_tiles * p.n_tiles;
   plan->bn = bn;
+  plan->nsub = nsub;
   plan->grid = std::min(tiles * p.splits, num_sms);
   // pair mode (cta_group::2: two vertically adjacent M tiles, each SM stages half of the weight tile) whenever it applies
   plan->cluster = 1;
-  if (cluster_allowed() && p.m_tiles % 2 == 0) {
+  if (cluster_allowed() && nsub == 1 && p.m_tiles % 2 == 0) {
     plan->cluster = 2;
     const int pairs = tiles / 2 * p.splits;
     plan->grid = 2 * std::min(pairs, num_sms / 2);
@@ -657,11 +795,12 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     set_last_error("gemm_launch: split-K plan without workspace");
     return -2;
   }
-  switch (plan.bn) {
-    case 256: return launch_t<256>(plan, stream);
-    case 160: return launch_t<160>(plan, stream);
-    case 128: return launch_t<128>(plan, stream);
-    case 64: return launch_t<64>(plan, stream);
+  switch (plan.bn * plan.nsub) {
+    case 320: return launch_t<160, 2>(plan, stream);
+    case 256: return launch_t<256, 1>(plan, stream);
+    case 160: return launch_t<160, 1>(plan, stream);
+    case 128: return launch_t<128, 1>(plan, stream);
+    case 64: return launch_t<64, 1>(plan, stream);
   }
   set_last_error("gemm_launch: bad plan");
   return -2;

@@ -238,8 +238,12 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
 // (mean, M2), the CTAs exchange those 64 floats through distributed shared memory, and every CTA then normalises its
 // own pixels (second read is an L2 hit).  Replaces stats + atomics/last-block + apply: the dependent chain is
 // load -> block reduce -> cluster barrier -> load -> store, with no global round trip for the statistics.
-__global__ void gn_cluster_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
-                                  int tx_n, int rows_y, int vpt, float eps, const float* __restrict__ gamma,
+// 512 threads with 8 (VPT=1) or 4 (VPT=2) 16-byte loads in flight each: one SM sustains bytes-in-flight / L2 latency, and
+// with only 16 CTAs per image the first version (256 threads x 4 loads) ran at 10 GB/s per SM.
+constexpr int GNC_THREADS = 512;
+template <int VPT, int U>
+__global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                  int tx_n, int rows_y, float eps, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, int do_silu, __half* __restrict__ out) {
   extern __shared__ float sm[];  // [rows_y][2*C] reduction scratch, then scale[C] | shift[C]
   __shared__ __align__(8) float part[GN_GROUPS * 2];
@@ -255,23 +259,22 @@ __global__ void gn_cluster_kernel(const __half* __restrict__ x0, int C0, const _
   const size_t row0 = static_cast<size_t>(b) * HW + static_cast<size_t>(rank) * ppc;
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
   const int cpg = C / GN_GROUPS;
-  float s[GN_MAX_VPT][8], ss[GN_MAX_VPT][8];
+  float s[VPT][8], ss[VPT][8];
 #pragma unroll
-  for (int i = 0; i < GN_MAX_VPT; ++i)
+  for (int i = 0; i < VPT; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[i][e] = ss[i][e] = 0.f;
   if (ty < rows_y) {
-    constexpr int U = 4;
     for (int pix0 = ty; pix0 < ppc; pix0 += U * rows_y) {
-      uint4 u[U][GN_MAX_VPT];
+      uint4 u[U][VPT];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const int pix = pix0 + j * rows_y;
         const size_t row = row0 + pix;
 #pragma unroll
-        for (int i = 0; i < GN_MAX_VPT; ++i) {
+        for (int i = 0; i < VPT; ++i) {
           u[j][i] = make_uint4(0, 0, 0, 0);
-          if (i < vpt && pix < ppc) {
+          if (pix < ppc) {
             const int v = tx + i * tx_n;
             u[j][i] = (v < nvec0) ? __ldg(reinterpret_cast<const uint4*>(x0 + row * C0 + v * 8))
                                   : __ldg(reinterpret_cast<const uint4*>(x1 + row * C1 + (v - nvec0) * 8));
@@ -281,8 +284,8 @@ __global__ void gn_cluster_kernel(const __half* __restrict__ x0, int C0, const _
 #pragma unroll
       for (int j = 0; j < U; ++j) {
 #pragma unroll
-        for (int i = 0; i < GN_MAX_VPT; ++i) {
-          if (i < vpt) {
+        for (int i = 0; i < VPT; ++i) {
+          {
             float f[8];
             unpack8(u[j][i], f);
 #pragma unroll
@@ -296,8 +299,8 @@ __global__ void gn_cluster_kernel(const __half* __restrict__ x0, int C0, const _
     }
     float* mine = sm + static_cast<size_t>(ty) * 2 * C;
 #pragma unroll
-    for (int i = 0; i < GN_MAX_VPT; ++i) {
-      if (i < vpt) {
+    for (int i = 0; i < VPT; ++i) {
+      {
         const int v = tx + i * tx_n;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -308,11 +311,11 @@ __global__ void gn_cluster_kernel(const __half* __restrict__ x0, int C0, const _
     }
   }
   // affine parameters are fetched while the reduction runs (their latency must not sit behind the cluster barrier)
-  constexpr int CPT = 10;  // C <= 2560 (checked by the launcher) -> at most 10 channels per thread
+  constexpr int CPT = 5;  // C <= 2560 (checked by the launcher) -> at most 5 channels per thread
   float gam[CPT], bet[CPT];
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
-    const int c = threadIdx.x + i * 256;
+    const int c = threadIdx.x + i * GNC_THREADS;
     gam[i] = c < C ? __ldg(gamma + c) : 0.f;
     bet[i] = c < C ? __ldg(beta + c) : 0.f;
   }
@@ -373,7 +376,7 @@ __global__ void gn_cluster_kernel(const __half* __restrict__ x0, int C0, const _
   float* shift = sm + C;
 #pragma unroll
   for (int i = 0; i < CPT; ++i) {
-    const int c = threadIdx.x + i * 256;
+    const int c = threadIdx.x + i * GNC_THREADS;
     if (c < C) {
       const int g = c / cpg;
       const float sc = gstat[g * 2 + 1] * gam[i];
@@ -384,7 +387,6 @@ __global__ void gn_cluster_kernel(const __half* __restrict__ x0, int C0, const _
   __syncthreads();
   {
     const int total = ppc * nvec;
-    constexpr int U = 4;
     for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
       uint4 u[U];
       int pixs[U], vs[U];
@@ -665,15 +667,19 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   if (cluster_cs < 0) {
     cluster_cs = 0;
     const char* e = getenv("PNP_GN_CLUSTER");
-    const int want = e ? atoi(e) : 16;
+    // measured on B200 (profiles/README.md, session 13): 1.31 ms per B=4 UNet call for the cluster kernel vs 1.19 ms for the
+    // statistics + apply pair (16 CTAs per image cannot keep enough loads in flight) -> opt-in only
+    const int want = e ? atoi(e) : 0;
     if (want >= 2) {
-      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<1, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<2, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       for (int cs = want; cs >= 2 && !cluster_cs; cs >>= 1) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cs, 1);
-        cfg.blockDim = dim3(256);
-        cfg.dynamicSmemBytes = 64 * 1024;
+        cfg.blockDim = dim3(GNC_THREADS);
+        cfg.dynamicSmemBytes = 96 * 1024;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = cs;
@@ -682,19 +688,27 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
         cfg.attrs = at;
         cfg.numAttrs = 1;
         int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_kernel, &cfg) == cudaSuccess && nclusters >= 4)
+        if (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_kernel<1, 8>, &cfg) == cudaSuccess && nclusters >= 4)
           cluster_cs = cs;
         else
           (void)cudaGetLastError();
       }
     }
   }
-  if (cluster_cs && C <= 2560 && sm1 <= 64 * 1024) {
+  if (cluster_cs && C <= 2560) {
     int cs = cluster_cs;
     while (cs > 1 && (HW % cs != 0 || HW / cs < 1)) cs >>= 1;
     if (cs >= 2) {
-      PNP_CUDA(launch_kc(gn_cluster_kernel, dim3(cs, B), dim3(256), sm1 > 2 * C * sizeof(float) ? sm1 : 2 * C * sizeof(float),
-                         s, cs, x0, C0, x1, C1, HW, tx_n, rows_y, vpt, eps, gamma, beta, do_silu ? 1 : 0, out));
+      const int ppcc = HW / cs;
+      int ry = GNC_THREADS / tx_n;  // pixel rows of threads; no more than there are pixels, and the scratch must fit
+      ry = std::max(1, std::min(ry, std::min(ppcc, static_cast<int>((96 * 1024) / (2 * C * sizeof(float))))));
+      const size_t smc = static_cast<size_t>(ry) * 2 * C * sizeof(float);
+      if (vpt == 1)
+        PNP_CUDA(launch_kc(gn_cluster_kernel<1, 8>, dim3(cs, B), dim3(GNC_THREADS), smc, s, cs, x0, C0, x1, C1, HW, tx_n, ry,
+                           eps, gamma, beta, do_silu ? 1 : 0, out));
+      else
+        PNP_CUDA(launch_kc(gn_cluster_kernel<2, 4>, dim3(cs, B), dim3(GNC_THREADS), smc, s, cs, x0, C0, x1, C1, HW, tx_n, ry,
+                           eps, gamma, beta, do_silu ? 1 : 0, out));
       return 0;
     }
   }

@@ -113,11 +113,16 @@ struct alignas(64) GemmParams {
   float* ws;
   int* counters;
   volatile unsigned int* dbg;
+  // optional per-CTA cycle counters [grid][8]: MMA thread (total, wait full, wait tempty), producer (total, wait empty),
+  // epilogue thread 128 (total, wait tfull); null in production
+  long long* prof;
+  int exp;  // experiments (PNP_GEMM_EXP, test entry points only): 1 = no TMA copies, 2 = no MMAs
 };
 
 struct GemmPlan {
   GemmParams p;
-  int bn = 0;
+  int bn = 0;    // N of one MMA
+  int nsub = 1;  // accumulators per CTA tile (tile = 128 x nsub*bn)
   int cluster = 1;
   int grid = 0;
   size_t smem = 0;
@@ -151,6 +156,8 @@ void gemm_choose(int M, int N, int num_kb, bool geglu, int num_sms, int bn_force
 size_t gemm_ws_floats(const GemmPlan& plan);
 void gemm_set_workspace(GemmPlan* plan, float* ws, int* counters);
 constexpr int kGemmMaxCounters = 4096;
+// modelled cycles of one launch (tile = bnt columns: 64/128/160/256, or 320 = two accumulators of 160); < 0 = invalid
+long gemm_model_cost(int M, int N, int num_kb, bool geglu, int bnt, int splits, int num_sms);
 
 // ------------------------------------------------------------------ normalisation kernels (norm.cu)
 // GroupNorm(32 groups) [+SiLU] over NHWC fp16; optional second source = channel concat (skip connection).

@@ -21,10 +21,10 @@ def _mk(shape, dev, seed, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).to(torch.float16).to(dev)
 
 
-@pytest.mark.parametrize("bn", [64, 128, 160, 256])
+@pytest.mark.parametrize("bn", [64, 128, 160, 256, 320])
 @pytest.mark.parametrize("M,K", [(128, 64), (256, 320), (308, 768), (1024, 1280)])
 def test_linear_plain(cuda, bn, M, K):
-    N = {64: 192, 128: 384, 160: 320, 256: 512}[bn]
+    N = {64: 192, 128: 384, 160: 320, 256: 512, 320: 640}[bn]  # 320 = two interleaved accumulators of 160 columns
     a = _mk((M, K), cuda, 1)
     w = _mk((N, K), cuda, 2, K ** -0.5)
     out = G.gemm(a, w, bn=bn)
@@ -105,6 +105,21 @@ def test_conv3x3_fused_shortcut_over_concat(cuda):
     cat = torch.cat([a, b], dim=-1).permute(0, 3, 1, 2).float()
     ref = (F.conv2d(hmid.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1) + F.conv2d(cat, ws.float()))
     assert G.rel_l2(out, ref.permute(0, 2, 3, 1)) < 1e-3
+
+
+@pytest.mark.parametrize("split", [1, 3])
+def test_conv3x3_two_accumulators_320(cuda, split):
+    """128 x 320 tiles = two interleaved accumulators of 160 columns (one accumulator set in TMEM: a CTA that gets a second
+    tile must wait for its own epilogue), with bias, residual and split-K."""
+    B, H, C, N = 2, 64, 64, 1280  # 64 x 4 = 256 tiles (x splits) on 148 CTAs
+    x = _mk((B, H, H, C), cuda, 40)
+    w = _mk((N, C, 3, 3), cuda, 41, (9 * C) ** -0.5)
+    bias = torch.randn(N, device=cuda) * 0.1
+    r = _mk((B, H, H, N), cuda, 42)
+    out = G.conv3x3(x, G.pack_conv3(w), bias=bias, residual=r, bn=320, split=split)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1) + r.float()
+    assert G.rel_l2(out, ref) < 1e-3
+    assert torch.equal(out, G.conv3x3(x, G.pack_conv3(w), bias=bias, residual=r, bn=320, split=split))
 
 
 @pytest.mark.parametrize("split", [0, 2, 5, 9])

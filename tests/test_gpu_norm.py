@@ -39,17 +39,17 @@ def test_groupnorm(cuda, B, HW, C0, C1, silu):
     assert G.rel_l2(out, ref) < 6e-4
 
 
-def test_groupnorm_two_kernel_path(cuda):
-    """The default is the single-launch cluster kernel; PNP_GN_CLUSTER=0 selects the statistics + apply pair, which must
-    stay correct (it is the fallback when a 16- or 8-CTA cluster cannot be co-scheduled).  The choice is made once per
-    process, hence the subprocess."""
+def test_groupnorm_cluster_kernel_path(cuda):
+    """The default is the statistics + apply pair; PNP_GN_CLUSTER=16 selects the single-launch cluster kernel (statistics
+    exchanged through distributed shared memory), which is slower on B200 but must stay correct.  The choice is made once
+    per process, hence the subprocess."""
     import os
     import subprocess
     import sys
 
-    env = dict(os.environ, PNP_GN_CLUSTER="0")
+    env = dict(os.environ, PNP_GN_CLUSTER="16")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
-                        "test_groupnorm and not two_kernel"], env=env, capture_output=True, text=True, timeout=600,
+                        "test_groupnorm and not cluster_kernel"], env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "7 passed" in r.stdout, r.stdout[-500:]

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for f in gemm attention; do
+  timeout 900 python -m pytest tests/test_gpu_$f.py -m gpu -q -x -s --timeout 600 -p no:cacheprovider > gpurun_out/test_$f.log 2>&1
+  echo "exit code $?" >> gpurun_out/test_$f.log
+done
+grep -E "passed|failed|rel-L2|Error|error" gpurun_out/test_*.log | cut -c1-300
+timeout 600 python tools/prof_gemm.py > gpurun_out/prof_gemm.log 2>&1
+grep "gemm prof\|====" gpurun_out/prof_gemm.log | awk 'NR%2==0 || /====/' | cut -c1-330
+timeout 300 python tools/run_attn_once.py 2>&1 | tail -2
+PNP_ATTN_CLUSTER=1 timeout 300 python tools/run_attn_once.py 2>&1 | tail -1
+PNP_GEMM_CLUSTER=0 timeout 600 python tools/time_unet.py 20 1,4 2>&1 | tail -2
+PNP_GEMM_CLUSTER=1 timeout 600 python tools/time_unet.py 20 1,4 2>&1 | tail -2
