@@ -49,11 +49,15 @@ constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 2048 + 1024;  // barriers, row-max exchange [4][128], alignment slack
 constexpr int TMEM_COLS = 512;
 constexpr int COL_S = 0;    // two S accumulators of 128 columns
-constexpr int COL_O = 256;  // O: 48 columns
+constexpr int COL_O = 256;  // O: four partial accumulators of 48 columns at a stride of 64 (group x K-step parity)
+constexpr int O_STRIDE = 64;
 
-__device__ __forceinline__ uint32_t ex2_pair(float a, float b) {
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
-  uint32_t x = *reinterpret_cast<uint32_t*>(&h), y;
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
+  uint32_t y;
   asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
@@ -229,7 +233,11 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
             for (int k = 0; k < 8; ++k) {  // 128 keys = 8 K=16 steps over two 64-key swizzle atoms
               const uint64_t adesc = umma_desc_sw128_kmajor(p_addr + (k >> 2) * P_ATOM) + 2u * (k & 3);
               const uint64_t bdesc = umma_desc_sw128_kmajor(v_addr + (k >> 2) * VT_ATOM) + 2u * (k & 3);
-              umma_f16_ss(tmem_base + COL_O, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+              // MMAs into the same accumulator issue ~120 cycles apart (measured in the GEMM); one O accumulator made
+              // all 8 x T PV MMAs of a CTA one dependent chain that also delayed the next S tile queued behind it.
+              // Four partial accumulators (tile parity x K-step parity) are summed in the epilogue.
+              umma_f16_ss(tmem_base + COL_O + (pb * 2 + (k & 1)) * O_STRIDE, adesc, bdesc, idesc_pv,
+                          (j > 1 || k > 1) ? 1u : 0u);
             }
             umma_commit(&p_empty[pb]);
             if (CL2) umma_commit_mc(&v_empty[vs], 0x3); else umma_commit(&v_empty[vs]);
@@ -292,21 +300,29 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         mbar_wait(&s_full[g], su[0] & 1, p.dbg, 32);
         tc_fence_after();
         uint8_t* prow = smem + OFF_P + g * P_BYTES + cg * P_ATOM + row * 128;
+        // both halves of the scores are pulled out of TMEM and packed to fp16 pairs FIRST, so that the accumulator goes
+        // back to the MMA warp ~200 cycles into the tile (the next S tile of this group is issued that much earlier)
+        uint32_t xh[32];
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(s_addr + hf * 32, r);
           tmem_ld_wait();
-          if (hf == 1) {  // both halves are in registers: hand the accumulator back
+          if (hf == 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[g]);
           }
           if (attempt == 0) smax = fmaxf(smax, max32(r));
-          uint32_t ph[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            ph[i] = ex2_pair(fmaf(__uint_as_float(r[2 * i]), p.sl2, -off), fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -off));
+            xh[hf * 16 + i] = pack_h2(fmaf(__uint_as_float(r[2 * i]), p.sl2, -off), fmaf(__uint_as_float(r[2 * i + 1]), p.sl2, -off));
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t ph[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ph[i] = ex2_h2(xh[hf * 16 + i]);
           if (hf == 0) mbar_wait(&p_empty[g], (pu[0] & 1) ^ 1u, p.dbg, 33);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -324,31 +340,40 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
       tc_fence_after();
       const int part = g * 2 + cg;  // 0,1: output columns [part*16, +16); 2: columns 32..39; 3: idle
       if (part < 3) {
-        uint32_t hi[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + 32, hi);
+        // O = sum of the partial accumulators (tiles of group 1 exist only when T > 1); column 40 = softmax denominator
+        const int nacc = T > 1 ? 4 : 2;
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0.f;
+        for (int a = 0; a < nacc; ++a) {
+          uint32_t th[16], tl[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + a * O_STRIDE + 32, th);
+          if (part < 2) tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + a * O_STRIDE + part * 16, tl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            hi[i] += __uint_as_float(th[i]);
+            if (part < 2) lo[i] += __uint_as_float(tl[i]);
+          }
+        }
         __half* orow = p.o + (static_cast<size_t>(b) * p.N + qt * QT + row) * p.ldo + h * D;
-        auto pack8 = [](const uint32_t* v, float inv) {
+        auto pack8 = [](const float* v, float inv) {
           uint4 u;
-          __half2 t0 = __floats2half2_rn(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-          __half2 t1 = __floats2half2_rn(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-          __half2 t2 = __floats2half2_rn(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-          __half2 t3 = __floats2half2_rn(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+          __half2 t0 = __floats2half2_rn(v[0] * inv, v[1] * inv);
+          __half2 t1 = __floats2half2_rn(v[2] * inv, v[3] * inv);
+          __half2 t2 = __floats2half2_rn(v[4] * inv, v[5] * inv);
+          __half2 t3 = __floats2half2_rn(v[6] * inv, v[7] * inv);
           u.x = *reinterpret_cast<uint32_t*>(&t0);
           u.y = *reinterpret_cast<uint32_t*>(&t1);
           u.z = *reinterpret_cast<uint32_t*>(&t2);
           u.w = *reinterpret_cast<uint32_t*>(&t3);
           return u;
         };
+        const float inv = 1.0f / hi[8];
         if (part < 2) {
-          uint32_t lo[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + part * 16, lo);
-          tmem_ld_wait();
-          const float inv = 1.0f / __uint_as_float(hi[8]);
           *reinterpret_cast<uint4*>(orow + part * 16) = pack8(lo, inv);
           *reinterpret_cast<uint4*>(orow + part * 16 + 8) = pack8(lo + 8, inv);
         } else {
-          tmem_ld_wait();
-          const float inv = 1.0f / __uint_as_float(hi[8]);
           *reinterpret_cast<uint4*>(orow + 32) = pack8(hi, inv);
         }
       }
@@ -451,7 +476,9 @@ int self_attention_tc_plan(SelfAttnTcParams* p, const __half* qkv, int ld, __hal
   p->k_row = k_row;
   p->v_row = v_row;
   p->dbg = debug_words_device();
-  p->cluster = ((N / QT) % 2 == 0) ? 2 : 1;
+  // cluster of 2 (K / V^T tiles multicast to two query tiles) is opt-in: measured 9.25 ms vs 9.16 ms per B=4 UNet call
+  // without it once the issue loops were fixed (TMA multicast does not pay below cluster size 8 on this part)
+  p->cluster = 1;
   if (const char* ev = getenv("PNP_ATTN_CLUSTER")) p->cluster = (atoi(ev) == 2 && (N / QT) % 2 == 0) ? 2 : 1;
   return 0;
 }

@@ -664,12 +664,15 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   (void)threads;
   // single-launch cluster kernel (one cluster of 16 or 8 CTAs per image) when the device can co-schedule it
   static int cluster_cs = -1;
+  static int cluster_force_all = 0;
   if (cluster_cs < 0) {
     cluster_cs = 0;
     const char* e = getenv("PNP_GN_CLUSTER");
-    // measured on B200 (profiles/README.md, session 13): 1.31 ms per B=4 UNet call for the cluster kernel vs 1.19 ms for the
-    // statistics + apply pair (16 CTAs per image cannot keep enough loads in flight) -> opt-in only
-    const int want = e ? atoi(e) : 0;
+    // measured on B200 (profiles/README.md): the cluster kernel wins on the small tensors (8x8: 10.5 vs 14.9 us, 16x16:
+    // 11-15 vs 14-17 us) and loses on the large ones (64x64: 31 vs 23 us: 16 CTAs per image cannot keep enough loads in
+    // flight), so by default it takes HW <= 256 only.  PNP_GN_CLUSTER=0 never, =8/16 always (tests).
+    const int want = e ? atoi(e) : 16;
+    cluster_force_all = e != nullptr && want >= 2;
     if (want >= 2) {
       PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<1, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -695,7 +698,7 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
       }
     }
   }
-  if (cluster_cs && C <= 2560) {
+  if (cluster_cs && C <= 2560 && (cluster_force_all || HW <= 256)) {
     int cs = cluster_cs;
     while (cs > 1 && (HW % cs != 0 || HW / cs < 1)) cs >>= 1;
     if (cs >= 2) {

@@ -160,6 +160,20 @@ def test_self_attention_tcgen05_d40(cuda, N, B):
     assert err < 2e-3
 
 
+def test_self_attention_tcgen05_cluster_multicast(cuda, monkeypatch):
+    """Opt-in variant: two query tiles of one (batch, head) form a cluster and share the key / value tiles through TMA
+    multicast (PNP_ATTN_CLUSTER=2, read when the plan is made)."""
+    monkeypatch.setenv("PNP_ATTN_CLUSTER", "2")
+    lib = _lib.load()
+    B, N, d = 2, 1024, 40
+    qkv = _mk((B, N, 3 * H * d), cuda, 55, 1.1)
+    out = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    ident = list(range(B))
+    assert G.rel_l2(out, _self_ref(qkv, d, ident, ident, ident)) < 2e-3
+
+
 def test_self_attention_tcgen05_row_indirection(cuda):
     lib = _lib.load()
     B, N, d = 4, 1024, 40

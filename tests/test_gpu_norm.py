@@ -40,19 +40,21 @@ def test_groupnorm(cuda, B, HW, C0, C1, silu):
 
 
 def test_groupnorm_cluster_kernel_path(cuda):
-    """The default is the statistics + apply pair; PNP_GN_CLUSTER=16 selects the single-launch cluster kernel (statistics
-    exchanged through distributed shared memory), which is slower on B200 but must stay correct.  The choice is made once
-    per process, hence the subprocess."""
+    """By default the single-launch cluster kernel (statistics exchanged through distributed shared memory) takes the small
+    tensors (HW <= 256) and the statistics + apply pair the large ones; PNP_GN_CLUSTER=16 forces the cluster kernel for
+    every shape, PNP_GN_CLUSTER=0 the pair.  Both must be correct everywhere.  The choice is made once per process, hence
+    the subprocesses."""
     import os
     import subprocess
     import sys
 
-    env = dict(os.environ, PNP_GN_CLUSTER="16")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
-                        "test_groupnorm and not cluster_kernel"], env=env, capture_output=True, text=True, timeout=600,
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "7 passed" in r.stdout, r.stdout[-500:]
+    for mode in ("16", "0"):
+        env = dict(os.environ, PNP_GN_CLUSTER=mode)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
+                            "test_groupnorm and not cluster_kernel"], env=env, capture_output=True, text=True, timeout=600,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "7 passed" in r.stdout, r.stdout[-500:]
 
 
 @pytest.mark.parametrize("rows,Cc", [(4096, 320), (1000, 640), (77, 1280)])
