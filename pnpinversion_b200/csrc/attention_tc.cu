@@ -3,20 +3,26 @@
 //   O = softmax(Q K^T / sqrt(d)) V      per (batch row, head), N = 4096 (any multiple of 128), d = 40
 //
 // One CTA = 128 queries of one (b, h); keys stream through in tiles of 128.  The exact schedule is two passes over the keys
-// (below); the kernel first tries an optimistic single pass whose softmax offset comes from the first key tile and falls
-// back to the two-pass schedule only if a probability would overflow fp16 (see the attempt loop).  Two passes, both on the
-// tensor core, so that no accumulator ever has to be rescaled:
-//   pass A : S = Q K^T (tcgen05.mma, 128x128x48 per tile, fp32 in TMEM) -> row maxima
-//   pass B : S again (recomputing it costs 192 tensor cycles per tile, far cheaper than a rescale round trip through
-//            TMEM), P = 2^((S - max) * scale * log2 e) on packed fp16 pairs (MUFU.EX2.F16x2), written 128B-swizzled to
-//            shared memory as the A operand of O += P V^T' (tcgen05.mma 128x48x128 per tile).
-// V is consumed as V^T (keys contiguous = K-major B operand) from a [B][H][41][N] buffer written by a small transpose
-// kernel; row 40 of that buffer is all ones, so column 40 of O is the softmax denominator, accumulated in fp32 by the
-// same MMAs from exactly the fp16 probabilities that multiply V.  Zero padding of the head dimension (40 -> 64 columns
-// of the 128-byte swizzle atom) and of the V^T rows (41 -> 48) is TMA out-of-bounds fill: no padded copies exist.
+// (pass A: S = Q K^T -> row maxima; pass B: S again, P = 2^((S - max) * scale * log2 e), O += P V); the kernel first tries an
+// optimistic single pass whose softmax offset comes from the first key tile and falls back to two passes only if a
+// probability would overflow fp16 (see the attempt loop).  Nothing is ever rescaled.
 //
-// Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..19 softmax
-// (four warps per TMEM lane quarter, 32 keys each).  All hand-offs are mbarriers; every wait is bounded (mbar_wait).
+// Both MMAs take their A operand from TENSOR MEMORY, not from shared memory (measured with the in-kernel cycle counters:
+// in SS mode every M=128 MMA first streams its 128 A rows out of shared memory, ~130 cycles per MMA whatever N is, and the
+// 11 MMAs per key tile kept the issuing warp busy 78 % of the kernel):
+//   Q   : 128 rows x 48 (40 + zero padding) fp16, copied once from global memory into 24 TMEM columns by four warps;
+//   P   : the softmax warps write the packed fp16 probabilities straight from registers into TMEM (tcgen05.st), two
+//         tiles of 64 columns - no shared-memory round trip, no proxy fence;
+//   K   : B operand of S = Q K^T, TMA tile of 128 keys x 64 (zero filled past 40), 128-byte swizzle;
+//   V^T : B operand of O += P V, from a [B][H][41][N] buffer written by a small transpose kernel; row 40 of that buffer is
+//         all ones, so column 40 of O is the softmax denominator, accumulated in fp32 by the same MMAs from exactly the
+//         fp16 probabilities that multiply V.  Rows 41..47 are TMA out-of-bounds zero fill.
+// TMEM map: S 2 x 128 fp32 columns | O 48 | P 2 x 64 | Q 24.
+//
+// Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer (whole warp in the loop, elected lane issues), warp 2
+// TMEM allocator, warps 4..19 softmax in two groups of 8 that work on alternate key tiles (two warps per TMEM lane
+// quarter, 64 keys each), so that one group's conversions overlap the other group's exponentials on the MUFU.
+// All hand-offs are mbarriers; every wait is bounded (mbar_wait).
 //
 // Controllers (same semantics as attention.cu): per-batch-row source indirection for Q / K / V.
 // Reference algebra: models/p2p/attention_control.py:34-45 (sim = q k^T * scale; softmax; attn @ v).
@@ -34,23 +40,20 @@ namespace {
 constexpr int D = 40;
 constexpr int QT = 128;  // queries per CTA
 constexpr int KT = 128;  // keys per tile
-constexpr int Q_BYTES = QT * 128;        // 128 rows x 64 halves
 constexpr int K_BYTES = KT * 128;
 constexpr int VT_ROWS = 48;              // 40 d + ones row + zero rows
 constexpr int VT_ATOM = VT_ROWS * 128;   // 64 keys x 48 rows
 constexpr int VT_BYTES = 2 * VT_ATOM;    // 128 keys
-constexpr int P_ATOM = QT * 128;         // 128 rows x 64 keys
-constexpr int P_BYTES = 2 * P_ATOM;
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + Q_BYTES;            // 2 stages
+constexpr int OFF_K = 0;                          // 2 stages
 constexpr int OFF_VT = OFF_K + 2 * K_BYTES;       // 2 stages
-constexpr int OFF_P = OFF_VT + 2 * VT_BYTES;      // 2 stages
-constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+constexpr int OFF_BAR = OFF_VT + 2 * VT_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 2048 + 1024;  // barriers, row-max exchange [4][128], alignment slack
+// TMEM map (512 columns): the A operands of BOTH MMAs live here, not in shared memory (see umma_f16_ts)
 constexpr int TMEM_COLS = 512;
-constexpr int COL_S = 0;    // two S accumulators of 128 columns
-constexpr int COL_O = 256;  // O: four partial accumulators of 48 columns at a stride of 64 (group x K-step parity)
-constexpr int O_STRIDE = 64;
+constexpr int COL_S = 0;    // two S accumulators of 128 fp32 columns
+constexpr int COL_O = 256;  // O accumulator: 48 fp32 columns
+constexpr int COL_P = 320;  // two probability tiles, 128 keys as 64 columns of packed fp16 pairs each
+constexpr int COL_Q = 448;  // the query tile: 48 (40 + zero padding) head-dim values as 24 columns of packed fp16 pairs
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
   }
   const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
+    mbar_init(q_full, 4);  // the four warps that copy the query rows into TMEM
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], CL2 ? 2 : 1);  // with a cluster both CTAs' MMAs must release a stage: the peer writes into it
@@ -131,6 +134,18 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
   // exponent; if any exceeds 15 (|P| would pass 2^15) the whole CTA (and its cluster peer) repeats with the full
   // two-pass schedule (attempt 1: pass A over all tiles).  Reading S from TMEM costs ~1000 cycles per 128x128 tile
   // (TMEM read bandwidth), as much as the exponentials, so skipping pass A nearly halves the kernel.
+  const bool prof = p.prof != nullptr;
+  long long pw[4] = {0, 0, 0, 0};  // accumulated wait cycles of this thread's role (meaning depends on the role)
+  const long long prof_t0 = prof ? clock64() : 0;
+  auto twait = [&](uint64_t* bar, uint32_t parity, uint32_t tag, int slot) {
+    if (prof) {
+      const long long t = clock64();
+      mbar_wait(bar, parity, p.dbg, tag);
+      pw[slot] += clock64() - t;
+    } else {
+      mbar_wait(bar, parity, p.dbg, tag);
+    }
+  };
   int kc = 0, vc = 0;       // K / V^T ring counters (producer and MMA issuer each advance their own copy)
   int su[2] = {0, 0};       // uses so far of S accumulator b (MMA issuer: both; a softmax warp: su[0] = its group's buffer)
   int pu[2] = {0, 0};       // uses so far of probability buffer b (same convention)
@@ -141,19 +156,11 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         // -------------------------------------------------------------- TMA producer
         // (whole warp in the loop, one elected lane issues: inside `if (lane == 0)` every UTMALDG / UTCHMMA / UTCBAR is
         // wrapped in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop, ~100 cycles of serial latency per instruction)
-        const int bq = p.q_row ? p.q_row[b] : b;
         const int bk = p.k_row ? p.k_row[b] : b;
         const int bv = p.v_row ? p.v_row[b] : b;
-        if (attempt == 0) {
-          if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, Q_BYTES);
-            tma_load_4d(smem + OFF_Q, &p.map_qk, q_full, 0, h, 0, bq * p.N + qt * QT);
-          }
-          __syncwarp();
-        }
         auto load_k = [&](int j) {
           const int ks = kc & 1;
-          mbar_wait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u, p.dbg, 11);
+          twait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u, 11, 0);
           if (elect_one()) {
             mbar_arrive_expect_tx(&k_full[ks], K_BYTES);
             if (CL2) {  // this CTA fetches half of the key tile and multicasts it to both CTAs of the cluster
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         };
         auto load_v = [&](int j) {
           const int vs = vc & 1;
-          mbar_wait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u, p.dbg, 12);
+          twait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u, 12, 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&v_full[vs], VT_BYTES);
             if (CL2) {
@@ -195,18 +202,16 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         // -------------------------------------------------------------- MMA issuer (whole warp, elected lane issues)
         constexpr uint32_t idesc_qk = umma_idesc_f16(QT, KT);
         constexpr uint32_t idesc_pv = umma_idesc_f16(QT, VT_ROWS);
-        const uint32_t q_addr = smem_u32(smem + OFF_Q);
         auto issue_qk = [&](int buf) {  // S tile into accumulator `buf` (pass-B tile j lives in buffer j & 1)
           const int ks = kc & 1;
-          mbar_wait(&k_full[ks], (kc >> 1) & 1, p.dbg, 21);
-          mbar_wait(&s_empty[buf], (su[buf] & 1) ^ 1u, p.dbg, 22);
+          twait(&k_full[ks], (kc >> 1) & 1, 21, 0);
+          twait(&s_empty[buf], (su[buf] & 1) ^ 1u, 22, 1);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128_kmajor(q_addr);
           const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + OFF_K + ks * K_BYTES));
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k)  // head dim 40 -> 48 = three K=16 steps (columns 40..63 are TMA zero fill)
-              umma_f16_ss(tmem_base + COL_S + buf * KT, adesc + 2u * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
+            for (int k = 0; k < 3; ++k)  // head dim 40 -> 48 = three K=16 steps (key columns 40..63 are TMA zero fill)
+              umma_f16_ts(tmem_base + COL_S + buf * KT, tmem_base + COL_Q + 8 * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
             if (CL2) umma_commit_mc(&k_empty[ks], 0x3); else umma_commit(&k_empty[ks]);
             umma_commit(&s_full[buf]);
           }
@@ -214,7 +219,10 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           ++kc;
           ++su[buf];
         };
-        if (attempt == 0) mbar_wait(q_full, 0, p.dbg, 20);
+        if (attempt == 0) {
+          mbar_wait(q_full, 0, p.dbg, 20);
+          tc_fence_after();
+        }
         for (int j = 0; j < TA; ++j) issue_qk(j & 1);  // pass A
         issue_qk(0);                                    // pass B, tiles 0 and 1
         if (T > 1) issue_qk(1);
@@ -223,21 +231,15 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           // each group always has its next tile waiting, and the two groups run half a tile apart
           if (j + 2 < T) issue_qk(j & 1);
           const int pb = j & 1, vs = vc & 1;
-          mbar_wait(&p_full[pb], pu[pb] & 1, p.dbg, 23);
-          mbar_wait(&v_full[vs], (vc >> 1) & 1, p.dbg, 24);
+          twait(&p_full[pb], pu[pb] & 1, 23, 2);
+          twait(&v_full[vs], (vc >> 1) & 1, 24, 3);
           tc_fence_after();
-          const uint32_t p_addr = smem_u32(smem + OFF_P + pb * P_BYTES);
           const uint32_t v_addr = smem_u32(smem + OFF_VT + vs * VT_BYTES);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {  // 128 keys = 8 K=16 steps over two 64-key swizzle atoms
-              const uint64_t adesc = umma_desc_sw128_kmajor(p_addr + (k >> 2) * P_ATOM) + 2u * (k & 3);
+            for (int k = 0; k < 8; ++k) {  // 128 keys = 8 K=16 steps: 8 TMEM columns of P, two 64-key swizzle atoms of V^T
               const uint64_t bdesc = umma_desc_sw128_kmajor(v_addr + (k >> 2) * VT_ATOM) + 2u * (k & 3);
-              // MMAs into the same accumulator issue ~120 cycles apart (measured in the GEMM); one O accumulator made
-              // all 8 x T PV MMAs of a CTA one dependent chain that also delayed the next S tile queued behind it.
-              // Four partial accumulators (tile parity x K-step parity) are summed in the epilogue.
-              umma_f16_ss(tmem_base + COL_O + (pb * 2 + (k & 1)) * O_STRIDE, adesc, bdesc, idesc_pv,
-                          (j > 1 || k > 1) ? 1u : 0u);
+              umma_f16_ts(tmem_base + COL_O, tmem_base + COL_P + pb * 64 + 8 * k, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&p_empty[pb]);
             if (CL2) umma_commit_mc(&v_empty[vs], 0x3); else umma_commit(&v_empty[vs]);
@@ -273,6 +275,25 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         }
         return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       };
+      if (attempt == 0 && warp < 8) {
+        // query rows -> TMEM (A operand of every S MMA of this CTA): lane = row, 20 words of data + 4 of zero padding
+        const int bq = p.q_row ? p.q_row[b] : b;
+        const uint4* qsrc = reinterpret_cast<const uint4*>(p.q_src + (static_cast<size_t>(bq) * p.N + qt * QT + row) * p.ld + h * D);
+        uint32_t qa[16], qb[8];
+        uint4 t[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t[i] = __ldg(qsrc + i);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { qa[4 * i] = t[i].x; qa[4 * i + 1] = t[i].y; qa[4 * i + 2] = t[i].z; qa[4 * i + 3] = t[i].w; }
+        qb[0] = t[4].x; qb[1] = t[4].y; qb[2] = t[4].z; qb[3] = t[4].w;
+        qb[4] = qb[5] = qb[6] = qb[7] = 0u;
+        tmem_st_32x32b_x16(tmem_base + lane_off + COL_Q, qa);
+        tmem_st_32x32b_x8(tmem_base + lane_off + COL_Q + 16, qb);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(q_full);
+      }
       // pass A: row maxima of the raw scores (first tile only in the optimistic attempt)
       float mx = -INFINITY;
       for (int j = g; j < TA; j += 2, ++su[0]) {
@@ -297,9 +318,9 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
       float smax = -INFINITY;  // largest raw score seen in pass B (overflow check of the optimistic attempt)
       // pass B: probabilities -> shared memory (A operand of the PV MMA)
       for (int j = g; j < T; j += 2, ++su[0], ++pu[0]) {
-        mbar_wait(&s_full[g], su[0] & 1, p.dbg, 32);
+        twait(&s_full[g], su[0] & 1, 32, 0);
         tc_fence_after();
-        uint8_t* prow = smem + OFF_P + g * P_BYTES + cg * P_ATOM + row * 128;
+        const uint32_t p_addr = tmem_base + lane_off + COL_P + g * 64 + cg * 32;  // this warp's 64 keys = 32 packed columns
         // both halves of the scores are pulled out of TMEM and packed to fp16 pairs FIRST, so that the accumulator goes
         // back to the MMA warp ~200 cycles into the tile (the next S tile of this group is issued that much earlier)
         uint32_t xh[32];
@@ -323,32 +344,29 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           uint32_t ph[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) ph[i] = ex2_h2(xh[hf * 16 + i]);
-          if (hf == 0) mbar_wait(&p_empty[g], (pu[0] & 1) ^ 1u, p.dbg, 33);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int chunk = (hf * 4 + i) ^ (row & 7);  // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
-            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-          }
+          if (hf == 0) twait(&p_empty[g], (pu[0] & 1) ^ 1u, 33, 1);
+          tmem_st_32x32b_x16(p_addr + hf * 16, ph);  // A operand of the P V MMA, straight from registers
         }
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
       }
       if (attempt == 0 && fmaf(smax, p.sl2, -off) > 15.0f) *ovf_flag = 1;
       // epilogue: O / l  (column 40 of O is the row sum of the probabilities)
-      mbar_wait(o_full, attempt & 1, p.dbg, 34);
+      twait(o_full, attempt & 1, 34, 2);
       tc_fence_after();
       const int part = g * 2 + cg;  // 0,1: output columns [part*16, +16); 2: columns 32..39; 3: idle
       if (part < 3) {
         // O = sum of the partial accumulators (tiles of group 1 exist only when T > 1); column 40 = softmax denominator
-        const int nacc = T > 1 ? 4 : 2;
+        const int nacc = 1;
         float hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0.f;
         for (int a = 0; a < nacc; ++a) {
           uint32_t th[16], tl[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + a * O_STRIDE + 32, th);
-          if (part < 2) tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + a * O_STRIDE + part * 16, tl);
+          tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + a * 64 + 32, th);
+          if (part < 2) tmem_ld_32x32b_x16(tmem_base + lane_off + COL_O + a * 64 + part * 16, tl);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -393,6 +411,15 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
     tc_fence_after();
   }
 
+  if (prof && lane == 0) {
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    long long* o = p.prof + static_cast<size_t>(cta) * 16;
+    const long long tot = clock64() - prof_t0;
+    if (warp == 1) { o[0] = tot; o[1] = pw[0]; o[2] = pw[1]; o[3] = pw[2]; o[4] = pw[3]; }
+    if (warp == 0) { o[5] = tot; o[6] = pw[0]; o[7] = pw[1]; }
+    if (warp == 4) { o[8] = tot; o[9] = pw[0]; o[10] = pw[1]; o[11] = pw[2]; }
+    if (warp == 12) { o[12] = tot; o[13] = pw[0]; o[14] = pw[1]; o[15] = pw[2]; }
+  }
   tc_fence_before();
   __syncthreads();
   if (CL2) cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
@@ -464,6 +491,7 @@ int self_attention_tc_plan(SelfAttnTcParams* p, const __half* qkv, int ld, __hal
     int rc = encode_tensor_map_f16(&p->map_vt, vt, 4, dims, strides, box);
     if (rc) return rc;
   }
+  p->q_src = qkv;
   p->v_src = qkv + 2 * 8 * D;
   p->ld = ld;
   p->vt = vt;

@@ -1479,6 +1479,34 @@ int pnp_test_self_attention_tc(const uint16_t* qkv_dev, int B, int N, const int3
                                 320, B, N, q_row_dev, k_row_dev, v_row_dev);
   if (!rc) rc = self_attention_tc_launch(tp, as_stream(stream));
   cudaError_t e2 = cudaStreamSynchronize(as_stream(stream));
+  if (!rc && e2 == cudaSuccess && getenv("PNP_ATTN_PROF") != nullptr) {
+    const int ncta = (N / 128) * 8 * B;
+    long long* prof = nullptr;
+    cudaMalloc(reinterpret_cast<void**>(&prof), static_cast<size_t>(ncta) * 16 * sizeof(long long));
+    cudaMemset(prof, 0, static_cast<size_t>(ncta) * 16 * sizeof(long long));
+    tp.prof = prof;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, as_stream(stream));
+    self_attention_tc_launch(tp, as_stream(stream));
+    cudaEventRecord(e1, as_stream(stream));
+    cudaStreamSynchronize(as_stream(stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> hp(static_cast<size_t>(ncta) * 16);
+    cudaMemcpy(hp.data(), prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double a[16] = {0};
+    for (int c = 0; c < ncta; ++c)
+      for (int j = 0; j < 16; ++j) a[j] += static_cast<double>(hp[static_cast<size_t>(c) * 16 + j]) / ncta;
+    fprintf(stderr,
+            "[attn prof] B=%d N=%d cluster=%d  %.1f us (transpose + attention) | mma: total %.0f, wait k_full %.0f, s_empty %.0f, "
+            "p_full %.0f, v_full %.0f | producer: total %.0f, wait k_empty %.0f, v_empty %.0f | softmax g0: total %.0f, wait "
+            "s_full %.0f, p_empty %.0f, o_full %.0f | softmax g1: total %.0f, wait s_full %.0f, p_empty %.0f, o_full %.0f\n",
+            B, N, tp.cluster, ms * 1000.0, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12],
+            a[13], a[14], a[15]);
+    cudaFree(prof);
+  }
   cudaFree(vt);
   if (!rc && e2 != cudaSuccess) {
     const unsigned int* dw = debug_words_host();

@@ -55,6 +55,7 @@ struct alignas(64) SelfAttnTcParams {
   CUtensorMap map_vt;  // V^T scratch [B][8][41][N] (row 40 = ones)
   CUtensorMap map_k64;  // same view as map_qk with a 64-row box (cluster-of-2 multicast: each CTA loads half a K tile)
   int cluster;          // 1 or 2
+  const __half* q_src;  // Q part of the fused activation (rows are copied into TMEM by the kernel)
   const __half* v_src;  // V part of the fused activation (transpose source)
   int ld;
   __half* vt;
@@ -66,6 +67,9 @@ struct alignas(64) SelfAttnTcParams {
   const int* k_row;
   const int* v_row;
   volatile unsigned int* dbg;
+  // optional cycle counters [CTA][16] (null in production): MMA warp total / wait k_full / s_empty / p_full / v_full,
+  // producer total / wait k_empty / v_empty, softmax warp 4 (group 0) and 12 (group 1): total / wait s_full / p_empty
+  long long* prof;
 };
 size_t self_attention_tc_vt_elems(int B, int N);
 int self_attention_tc_init_vt(__half* vt, int B, int N, cudaStream_t s);
