@@ -88,12 +88,21 @@ class StoreController:
     def __call__(self, attn, is_cross, place):
         h = attn.shape[0]
         attn[h // 2:] = self.forward(attn[h // 2:], is_cross, place)
+        self._layer_done()
+        return attn
+
+    def passthrough(self, is_cross, place):
+        """Bookkeeping of `__call__` for a layer whose maps this controller neither stores nor edits (self-attention
+        with more than 32^2 queries): lets the UNet restatement skip materialising the map."""
+        assert not is_cross
+        self._layer_done()
+
+    def _layer_done(self):
         self.cur_att_layer += 1
         if self.cur_att_layer == self.num_att_layers:
             self.cur_att_layer = 0
             self.cur_step += 1
             self.between_steps()
-        return attn
 
     def between_steps(self):
         if not self.attention_store:

@@ -80,11 +80,24 @@ class UNetRef:
 
         q, k, v = split(q), split(k), split(v)
         scale = (q.shape[-1]) ** -0.5
-        sim = torch.einsum("bid,bjd->bij", q, k) * scale
-        attn = sim.softmax(dim=-1)
-        if hook is not None:
-            attn = hook(attn, is_cross, place)
-        out = torch.einsum("bij,bjd->bid", attn, v)
+        n = q.shape[1]
+        lazy = hook is None or (not is_cross and n > 32 ** 2 and hasattr(hook, "passthrough"))
+        if not is_cross and n > 32 ** 2 and lazy:
+            # 64x64 self-attention: the [b*8, 4096, 4096] fp64 probability tensor (1 GB per image) is never materialised.
+            # Row-wise softmax makes query chunks independent, and both restated controllers are the identity on maps
+            # with more than 32^2 queries (attention_control.py:223,291) - they only need their layer bookkeeping.
+            if hook is not None:
+                hook.passthrough(is_cross, place)
+            out = torch.empty_like(q)
+            for i0 in range(0, n, 512):
+                sim = torch.einsum("bid,bjd->bij", q[:, i0:i0 + 512], k) * scale
+                out[:, i0:i0 + 512] = torch.einsum("bij,bjd->bid", sim.softmax(dim=-1), v)
+        else:
+            sim = torch.einsum("bid,bjd->bij", q, k) * scale
+            attn = sim.softmax(dim=-1)
+            if hook is not None:
+                attn = hook(attn, is_cross, place)
+            out = torch.einsum("bij,bjd->bid", attn, v)
         b8, n, d = out.shape
         out = out.reshape(b8 // HEADS, HEADS, n, d).permute(0, 2, 1, 3).reshape(b8 // HEADS, n, d * HEADS)
         return self._lin(out, name + ".to_out.0")
