@@ -60,15 +60,25 @@ struct Cfg {
 //   gelu(x) = x * (x >= 0 ? 1 - q : q),  q = (poly * exp(-z^2)) / 2
 // 14 FP instructions + MUFU.RCP + MUFU.EX2 instead of erff()'s two polynomial branches (the GEGLU epilogue was the
 // bottleneck of the FF1 GEMMs: 51 us for 26.8 GFLOP).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // one MUFU.RCP (2 ulp); __frcp_rn adds a Newton step + fix-up
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
   poly = fmaf(t, poly, 0.5f * 1.421413741f);
   poly = fmaf(t, poly, 0.5f * -0.284496736f);
   poly = fmaf(t, poly, 0.5f * 0.254829592f);
   poly *= t;
-  const float q = poly * exp2f(z * z * -1.4426950408889634f);
+  const float q = poly * ex2_approx(z * z * -1.4426950408889634f);
   return x * (x >= 0.f ? 1.0f - q : q);
 }
 
