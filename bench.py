@@ -4,10 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            # this repo (libpnpinv.so, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
 
-A "step" is one whole image: `P2PEditor("directinversion+p2p")` on one synthetic 4x64x64 latent with the cat prompt
-pair, i.e. the faithful 650 UNet sample-forwards (50 x B1 inversion + 3 x 50 x B4) + 200 fused epilogues
-(BASELINE.md section 2).  Weak scaling: every rank edits its own K images (image-parallel, SURVEY.md section 8e);
-NCCL only broadcasts the inputs and gathers the output latents.
+A "step" is one batch of `--lanes` whole images per GPU (default 3), each through `P2PEditor("directinversion+p2p")` on
+its own synthetic 4x64x64 latent with the cat prompt pair, i.e. the faithful 650 UNet sample-forwards per image
+(50 x B1 inversion + 3 x 50 x B4) + 200 fused epilogues.  The images of a step are in flight
+concurrently on one GPU (parallel.EditLanes: one CUDA stream, engine handle and host thread per lane) because one image's
+chain of ~330 short kernels per UNet call cannot keep the chip busy (measured on B200: 0.70 / 0.85 / 0.88 images/s with
+1 / 2 / 3 lanes).  Weak scaling: every rank edits its own K batches (image-parallel); NCCL only
+broadcasts the inputs and gathers the output latents.
 """
 import argparse
 import ctypes as C
@@ -146,6 +149,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3,
+                    help="images in flight per GPU (each on its own CUDA stream and engine handle, parallel.EditLanes)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,17 +173,29 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+    from pnpinversion_b200.parallel import EditLanes
+
     sd = synth.synth_unet_state_dict(0)
-    model = FusedModel(sd, device=str(dev), max_batch=4, tokenizer=synth.FakeTokenizer(),
+
+    def make_editor():
+        m = FusedModel(sd, device=str(dev), max_batch=4, tokenizer=synth.FakeTokenizer(),
                        text_encoder=synth.SynthTextEncoder())
-    editor = P2PEditor(["directinversion+p2p"], dev, num_ddim_steps=50, model=model)
+        return P2PEditor(["directinversion+p2p"], dev, num_ddim_steps=50, model=m)
+
+    L = max(1, args.lanes)
+    lanes = EditLanes(make_editor, L, dev)
+    model = lanes.editors[0].ldm_stable
     src, tgt = synth.CAT_PROMPTS
 
-    def edit(z):
+    def edit_on(editor, z):
         return editor("directinversion+p2p", image_path=z, prompt_src=src, prompt_tar=tgt, guidance_scale=7.5,
                       cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
 
-    total = args.warmup + args.steps
+    def edit_step(zs):
+        """One bench step = L images, one per lane, through the public editor call."""
+        return lanes.run([(lambda ed, z=z: edit_on(ed, z)) for z in zs])
+
+    total = (args.warmup + args.steps) * L
     # inputs: rank 0 draws the seeded latents for everybody and broadcasts them (the image-parallel scatter)
     z_all = torch.empty(world, total, 1, 4, 64, 64, device=dev)
     if rank == 0:
@@ -189,12 +206,16 @@ def main():
         dist.broadcast(z_all, src=0)
     z_dev = z_all[rank]
 
-    # ---------------- warm-up
-    for i in range(args.warmup):
-        edit(z_dev[i])
+    # ---------------- warm-up: the first image of every lane alone (plans, GEMM autotuning, graphs), then concurrently
+    for ln in range(L):
+        edit_on(lanes.editors[ln], z_dev[ln])
+        torch.cuda.synchronize()
+    for i in range(1, args.warmup):
+        edit_step([z_dev[i * L + ln] for ln in range(L)])
     torch.cuda.synchronize()
     lib = _lib.load()
-    l0 = model.unet.kernel_launches()
+    l0 = sum(ed.ldm_stable.unet.kernel_launches() for ed in lanes.editors)
+    first = args.warmup * L
 
     # ---------------- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
@@ -206,7 +227,7 @@ def main():
     e0.record()
     outs = []
     for i in range(args.steps):
-        outs.append(edit(z_dev[args.warmup + i]).latents)
+        outs.extend(r.latents for r in edit_step([z_dev[first + i * L + ln] for ln in range(L)]))
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -218,11 +239,11 @@ def main():
         gathered = [torch.empty_like(torch.stack(outs)) for _ in range(world)]
         dist.all_gather(gathered, torch.stack(outs))  # the image-parallel gather of the edited latents
     ms = float(ms.item())
-    launches = model.unet.kernel_launches() - l0
-    value = world * args.steps / (ms / 1000.0)
+    launches = sum(ed.ldm_stable.unet.kernel_launches() for ed in lanes.editors) - l0
+    value = world * args.steps * L / (ms / 1000.0)
 
     # ---------------- timed region 2: end to end through the public API with HOST buffers
-    z_host = [z_dev[args.warmup + i].cpu().pin_memory() for i in range(args.steps)]
+    z_host = [z_dev[first + i].cpu().pin_memory() for i in range(args.steps * L)]
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -231,8 +252,8 @@ def main():
     t0.record()
     host_results = []
     for i in range(args.steps):
-        res = edit(z_host[i])                      # H2D of the latent + context embeddings inside
-        host_results.append(res.latents.cpu())     # D2H of the result latents
+        # H2D of the latent + context embeddings and D2H of the result latents happen inside each lane's job
+        host_results.extend(lanes.run([(lambda ed, z=z: edit_on(ed, z).latents.cpu()) for z in z_host[i * L:(i + 1) * L]]))
     t1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -240,10 +261,10 @@ def main():
     ms2 = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if dist is not None:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / (float(ms2.item()) / 1000.0)
+    e2e_value = world * args.steps * L / (float(ms2.item()) / 1000.0)
     ctx_bytes = 4 * 77 * 768 * 4
-    h2d = 4 * 64 * 64 * 4 + 3 * ctx_bytes  # latent + the three context uploads (invert, reconstruct, edit)
-    d2h = 2 * 4 * 64 * 64 * 4
+    h2d = L * (4 * 64 * 64 * 4 + 3 * ctx_bytes)  # per image: latent + the three context uploads (invert, reconstruct, edit)
+    d2h = L * 2 * 4 * 64 * 64 * 4
 
     if rank != 0:
         if dist is not None:
@@ -313,11 +334,13 @@ def main():
         "metric": "images_per_sec_512x512_50step_invert_edit", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "directinversion+p2p 50 steps, 1 image per step (UNet B=1 inversion, B=4 offset/"
-                               "reconstruct/edit), faithful 650 UNet forwards, SD-1.x random-init UNet, cat prompts",
-                   "images_per_step_per_gpu": 1, "parallelism": f"image-parallel x{world}",
+        "config": {"workload": f"directinversion+p2p 50 steps, {L} image(s) per step and GPU, one per lane (UNet B=1 "
+                               "inversion, B=4 offset/reconstruct/edit per image), faithful 650 UNet forwards per image, "
+                               "SD-1.x random-init UNet, cat prompts",
+                   "images_per_step_per_gpu": L, "lanes_per_gpu": L,
+                   "parallelism": f"image-parallel x{world} GPUs x {L} concurrent lanes (CUDA streams) per GPU",
                    "l2": "each step streams 1.72 GB of fp16 weights per UNet call (> 126 MB L2), no flush needed",
-                   "accumulate": "fp32", "unet_step_ms_b4": ms / args.steps / (N_B4_CALLS + N_B1_CALLS * 0.4)},
+                   "accumulate": "fp32"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),

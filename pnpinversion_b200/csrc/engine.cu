@@ -4,6 +4,7 @@
 // (models/edict/my_diffusers/models/unet_2d_condition.py:189-273, unet_blocks.py, resnet.py:331-365,
 // attention.py:140-151,186-200,250-288,329-333, embeddings.py:21-80); see DESIGN.md for the kernel map.
 #include <algorithm>
+#include <mutex>
 #include <array>
 #include <cmath>
 #include <cstdio>
@@ -289,6 +290,11 @@ constexpr size_t kStoreFloats = static_cast<size_t>(kStoreLayers) * 2 * PNP_MAX_
 
 using namespace pnp;
 
+// shape key (device, M, N, K, taps, sources, residual, linear) -> (tile columns, K splits).  Process-wide, so that every
+// engine handle on a device (parallel.EditLanes keeps several) runs the same tiles and hence the same arithmetic.
+static std::map<std::array<int, 8>, std::pair<int, int>> g_gemm_tuned;
+static std::mutex g_gemm_tuned_mu;
+
 struct pnp_engine {
   int device = 0, num_sms = 148, max_batch = 4;
   bool finalized = false;
@@ -317,8 +323,7 @@ struct pnp_engine {
   // private stream: graphs cannot be captured on the legacy default stream the caller may hand us
   cudaStream_t es = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  // GEMM tile autotuning (plan build time): shape key -> (tile columns, K splits); scratch for the timed trial launches
-  std::map<std::array<int, 7>, std::pair<int, int>> gemm_tuned;
+  // GEMM tile autotuning (plan build time): scratch for the timed trial launches (the choices live in g_gemm_tuned)
   float* tune_ws = nullptr;
   int* tune_counters = nullptr;
   static constexpr size_t kTuneWsFloats = 24u << 20;  // 96 MB
@@ -584,12 +589,15 @@ struct PlanBuilder {
   void tune(const ASource* srcs, int nsrc, int taps, bool linear, int b, int h, int w, const __half* wt, int n, int ktot,
             const GemmEpilogue& ep, int* bnt_out, int* splits_out) {
     const int M = b * h * w, num_kb = ktot / 64;
-    const std::array<int, 7> key = {M, n, ktot, taps, nsrc, ep.residual != nullptr ? 1 : 0, linear ? 1 : 0};
-    auto it = e->gemm_tuned.find(key);
-    if (it != e->gemm_tuned.end()) {
-      *bnt_out = it->second.first;
-      *splits_out = it->second.second;
-      return;
+    const std::array<int, 8> key = {e->device, M, n, ktot, taps, nsrc, ep.residual != nullptr ? 1 : 0, linear ? 1 : 0};
+    {
+      std::lock_guard<std::mutex> lk(g_gemm_tuned_mu);
+      auto it = g_gemm_tuned.find(key);
+      if (it != g_gemm_tuned.end()) {
+        *bnt_out = it->second.first;
+        *splits_out = it->second.second;
+        return;
+      }
     }
     struct Cand { long cost; int bnt, sp; };
     std::vector<Cand> cands;
@@ -643,7 +651,10 @@ struct PlanBuilder {
     }
     *bnt_out = cands[best].bnt;
     *splits_out = cands[best].sp;
-    e->gemm_tuned[key] = {cands[best].bnt, cands[best].sp};
+    {
+      std::lock_guard<std::mutex> lk(g_gemm_tuned_mu);
+      g_gemm_tuned[key] = {cands[best].bnt, cands[best].sp};
+    }
   }
 
   void gemm(std::vector<std::function<int(cudaStream_t)>>& ops, const ASource* srcs, int nsrc, int taps, bool linear,

@@ -53,3 +53,55 @@ def gather_items(local: torch.Tensor, n_items: int, dist=None) -> torch.Tensor:
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad)
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+class EditLanes:
+    """Several images in flight on ONE GPU.
+
+    One image's 650 UNet calls are a serial chain of ~330 short kernels each: between two kernels of a chain the SMs idle
+    for the launch latency, and the B=1 inversion third of the chain cannot fill the chip at all.  A second, independent
+    image on its own CUDA stream (own engine handle = own activation arena, CUDA graph and controller state; the weights
+    are replicated, 1.7 GB per lane) fills those bubbles.  Each lane is driven by its own host thread (the C ABI calls
+    release the GIL) under its own `torch.cuda.Stream`; results come back in job order, and the caller's current stream
+    waits for every lane before `run` returns, so ordinary stream semantics hold for the caller.
+
+    `make_editor()` must build a fresh model + editor pair (e.g. `P2PEditor([...], device, model=FusedModel(...))`).
+    """
+
+    def __init__(self, make_editor, lanes: int = 2, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.editors = [make_editor() for _ in range(max(1, lanes))]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.editors]
+
+    def __len__(self):
+        return len(self.editors)
+
+    def run(self, jobs):
+        """jobs: callables `job(editor) -> result`; job i runs on lane i % lanes, jobs of one lane in order."""
+        import threading
+
+        n = len(self.editors)
+        results = [None] * len(jobs)
+        errors = []
+        caller = torch.cuda.current_stream(self.device)
+
+        def worker(lane):
+            try:
+                torch.cuda.set_device(self.device)
+                self.streams[lane].wait_stream(caller)  # inputs produced on the caller's stream are visible
+                with torch.cuda.stream(self.streams[lane]):
+                    for i in range(lane, len(jobs), n):
+                        results[i] = jobs[i](self.editors[lane])
+            except BaseException as e:  # surfaced in the caller's thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(lane,)) for lane in range(min(n, len(jobs)))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for s in self.streams:
+            caller.wait_stream(s)
+        if errors:
+            raise errors[0]
+        return results

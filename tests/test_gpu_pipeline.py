@@ -55,3 +55,31 @@ def test_directinversion_p2p_4_steps_matches_reference(cuda):
     # and the edit differs from the reconstruction (the controller did something)
     assert G.rel_l2(res.latents[1].cpu(), res.reconstruct_latent[1].cpu()) > 1e-2
     model.unet.close()
+
+
+def test_two_concurrent_lanes_reproduce_the_sequential_results(cuda):
+    """parallel.EditLanes: two images in flight on one GPU (own stream, engine handle and host thread each) must give
+    exactly what the same editor calls give one after the other - the lanes share weights' values, tile choices
+    (process-wide autotune cache) and nothing else."""
+    from pnpinversion_b200.parallel import EditLanes
+
+    src, tgt = synth.CAT_PROMPTS
+
+    def make():
+        return P2PEditor(["directinversion+p2p"], "cuda:0", num_ddim_steps=4,
+                         model=FusedModel.synthetic(device="cuda:0", max_batch=4))
+
+    def job(z):
+        return lambda ed: ed("directinversion+p2p", image_path=z, prompt_src=src, prompt_tar=tgt, guidance_scale=7.5,
+                             cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=(("cat",), ("cat",)),
+                             eq_params={"words": ("watercolor",), "values": (2,)}).latents
+
+    lanes = EditLanes(make, 2, "cuda:0")
+    zs = [synth.synth_latent(i) for i in range(4)]
+    seq = [job(z)(lanes.editors[0]) for z in zs]
+    torch.cuda.synchronize()
+    par = lanes.run([job(z) for z in zs])
+    torch.cuda.synchronize()
+    for a, b in zip(seq, par):
+        assert torch.isfinite(b).all()
+        assert torch.equal(a, b)
