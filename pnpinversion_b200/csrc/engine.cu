@@ -983,7 +983,7 @@ static int leave(pnp_engine* h, cudaStream_t caller) {
 extern "C" {
 
 const char* pnp_last_error(void) { return get_last_error(); }
-const char* pnp_version(void) { return "pnpinv-b200 0.1 (sm_100a, tcgen05 GEMM/conv, mma.sync attention)"; }
+const char* pnp_version(void) { return "pnpinv-b200 0.1 (sm_100a, tcgen05 GEMM/conv + attention, TMA, CUDA graphs)"; }
 
 int pnp_create(int device_ordinal, int max_batch, pnp_engine** out) {
   PNP_CHECK(out != nullptr, "pnp_create: out is null");

@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       const bool has_res = p.residual != nullptr && valid && !p.geglu;
       const __half* res_row = has_res ? p.residual + static_cast<size_t>(m) * p.ldr + n_blk * BNT : nullptr;
       if (has_res && half < BNT / 32) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rcur[j] = __ldg(reinterpret_cast<const uint4*>(res_row + half * 32) + j);
+        ldg256_nc(res_row + half * 32, rcur[0], rcur[1]);
+        ldg256_nc(res_row + half * 32 + 16, rcur[2], rcur[3]);
       }
       if (prof) {
         const long long t = clock64();
@@ -400,16 +400,16 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
               uint32_t r[32];
               tmem_ld_32x32b_x32(taddr + c * 32, r);
               if (has_res && c + 2 < BNT / 32) {  // prefetch the next chunk's residual under the TMEM load
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 2) * 32) + j);
+                ldg256_nc(res_row + (c + 2) * 32, rnext[0], rnext[1]);
+                ldg256_nc(res_row + (c + 2) * 32 + 16, rnext[2], rnext[3]);
               }
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             } else {
               if (has_res && c + 2 < BNT / 32) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rnext[j] = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 2) * 32) + j);
+                ldg256_nc(res_row + (c + 2) * 32, rnext[0], rnext[1]);
+                ldg256_nc(res_row + (c + 2) * 32 + 16, rnext[2], rnext[3]);
               }
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -471,16 +471,17 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
               }
-              uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldc + n0);
+              __half* op = p.out + static_cast<size_t>(m) * p.ldc + n0;
+              uint4 u[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack_half2(v[j * 8 + 0], v[j * 8 + 1]);
-                u.y = pack_half2(v[j * 8 + 2], v[j * 8 + 3]);
-                u.z = pack_half2(v[j * 8 + 4], v[j * 8 + 5]);
-                u.w = pack_half2(v[j * 8 + 6], v[j * 8 + 7]);
-                op[j] = u;
+                u[j].x = pack_half2(v[j * 8 + 0], v[j * 8 + 1]);
+                u[j].y = pack_half2(v[j * 8 + 2], v[j * 8 + 3]);
+                u[j].z = pack_half2(v[j * 8 + 4], v[j * 8 + 5]);
+                u[j].w = pack_half2(v[j * 8 + 6], v[j * 8 + 7]);
               }
+              stg256(op, u[0], u[1]);
+              stg256(op + 16, u[2], u[3]);
             }
           }
         }
@@ -506,16 +507,17 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             o[j + 3] = (__uint_as_float(rv[j + 3]) + bv.w) * gelu_erf(__uint_as_float(rg[j + 3]) + bg.w);
           }
           if (valid) {
-            uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldc + n_blk * (BNT / 2) + c * 32);
+            __half* op = p.out + static_cast<size_t>(m) * p.ldc + n_blk * (BNT / 2) + c * 32;
+            uint4 u[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack_half2(o[j * 8 + 0], o[j * 8 + 1]);
-              u.y = pack_half2(o[j * 8 + 2], o[j * 8 + 3]);
-              u.z = pack_half2(o[j * 8 + 4], o[j * 8 + 5]);
-              u.w = pack_half2(o[j * 8 + 6], o[j * 8 + 7]);
-              op[j] = u;
+              u[j].x = pack_half2(o[j * 8 + 0], o[j * 8 + 1]);
+              u[j].y = pack_half2(o[j * 8 + 2], o[j * 8 + 3]);
+              u[j].z = pack_half2(o[j * 8 + 4], o[j * 8 + 5]);
+              u[j].w = pack_half2(o[j * 8 + 6], o[j * 8 + 7]);
             }
+            stg256(op, u[0], u[1]);
+            stg256(op + 16, u[2], u[3]);
           }
         }
       }
@@ -720,10 +722,11 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   const int nsub = bn == 320 ? 2 : 1;
   bn = bnt / nsub;     // N of one MMA = rows of one weight box
   PNP_CHECK(!geglu || bn == 256 || bn == 128, "gemm: GEGLU epilogue needs BN 128/256");
-  PNP_CHECK(ep.out != nullptr && ep.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0,
-            "gemm: output alignment");
-  PNP_CHECK(ep.residual == nullptr || (ep.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0),
-            "gemm: residual alignment");
+  // the epilogue moves 32 bytes per lane and instruction (256-bit global accesses)
+  PNP_CHECK(ep.out != nullptr && ep.ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 31) == 0,
+            "gemm: output alignment (32 bytes, ldc % 16 == 0)");
+  PNP_CHECK(ep.residual == nullptr || (ep.ldr % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 31) == 0),
+            "gemm: residual alignment (32 bytes, ldr % 16 == 0)");
   PNP_CHECK(!geglu || ep.bias != nullptr, "gemm: GEGLU needs a bias");
 
   // A maps.  Box = 128 consecutive pixels x 64 channels.
