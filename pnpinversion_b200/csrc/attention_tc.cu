@@ -44,9 +44,10 @@ constexpr int K_BYTES = KT * 128;
 constexpr int VT_ROWS = 48;              // 40 d + ones row + zero rows
 constexpr int VT_ATOM = VT_ROWS * 128;   // 64 keys x 48 rows
 constexpr int VT_BYTES = 2 * VT_ATOM;    // 128 keys
-constexpr int OFF_K = 0;                          // 2 stages
-constexpr int OFF_VT = OFF_K + 2 * K_BYTES;       // 2 stages
-constexpr int OFF_BAR = OFF_VT + 2 * VT_BYTES;
+constexpr int NS = 3;  // K and V^T ring depth: with 2 the MMA warp waited 14 % of the kernel for the tiles (PNP_ATTN_PROF)
+constexpr int OFF_K = 0;
+constexpr int OFF_VT = OFF_K + NS * K_BYTES;
+constexpr int OFF_BAR = OFF_VT + NS * VT_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 2048 + 1024;  // barriers, row-max exchange [4][128], alignment slack
 // TMEM map (512 columns): the A operands of BOTH MMAs live here, not in shared memory (see umma_f16_ts)
 constexpr int TMEM_COLS = 512;
@@ -81,17 +82,18 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 7;
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_empty = bars + 11;
-  uint64_t* p_full = bars + 13;
-  uint64_t* p_empty = bars + 15;
-  uint64_t* o_full = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  volatile int* ovf_flag = reinterpret_cast<volatile int*>(bars + 19);
+  uint64_t* k_full = bars + 1;              // [NS]
+  uint64_t* k_empty = k_full + NS;          // [NS]
+  uint64_t* v_full = k_empty + NS;          // [NS]
+  uint64_t* v_empty = v_full + NS;          // [NS]
+  uint64_t* s_full = v_empty + NS;          // [2]
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* o_full = p_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  volatile int* ovf_flag = reinterpret_cast<volatile int*>(o_full + 2);
+  static_assert((1 + 4 * NS + 8 + 3) * 8 <= 256, "barrier block");
   float* rowmax_x = reinterpret_cast<float*>(smem + OFF_BAR + 256);  // [4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,11 +108,13 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
   const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 4);  // the four warps that copy the query rows into TMEM
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], CL2 ? 2 : 1);  // with a cluster both CTAs' MMAs must release a stage: the peer writes into it
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], CL2 ? 2 : 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 8);  // one arrival per warp of the softmax group that owns this buffer
       mbar_init(&p_full[i], 8);
@@ -159,8 +163,8 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         const int bk = p.k_row ? p.k_row[b] : b;
         const int bv = p.v_row ? p.v_row[b] : b;
         auto load_k = [&](int j) {
-          const int ks = kc & 1;
-          twait(&k_empty[ks], ((kc >> 1) & 1) ^ 1u, 11, 0);
+          const int ks = kc % NS;
+          twait(&k_empty[ks], ((kc / NS) & 1) ^ 1u, 11, 0);
           if (elect_one()) {
             mbar_arrive_expect_tx(&k_full[ks], K_BYTES);
             if (CL2) {  // this CTA fetches half of the key tile and multicasts it to both CTAs of the cluster
@@ -174,8 +178,8 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           ++kc;
         };
         auto load_v = [&](int j) {
-          const int vs = vc & 1;
-          twait(&v_empty[vs], ((vc >> 1) & 1) ^ 1u, 12, 1);
+          const int vs = vc % NS;
+          twait(&v_empty[vs], ((vc / NS) & 1) ^ 1u, 12, 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&v_full[vs], VT_BYTES);
             if (CL2) {
@@ -203,8 +207,8 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         constexpr uint32_t idesc_qk = umma_idesc_f16(QT, KT);
         constexpr uint32_t idesc_pv = umma_idesc_f16(QT, VT_ROWS);
         auto issue_qk = [&](int buf) {  // S tile into accumulator `buf` (pass-B tile j lives in buffer j & 1)
-          const int ks = kc & 1;
-          twait(&k_full[ks], (kc >> 1) & 1, 21, 0);
+          const int ks = kc % NS;
+          twait(&k_full[ks], (kc / NS) & 1, 21, 0);
           twait(&s_empty[buf], (su[buf] & 1) ^ 1u, 22, 1);
           tc_fence_after();
           const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + OFF_K + ks * K_BYTES));
@@ -230,9 +234,9 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           // S(j+2) goes into the buffer S(j) came from as soon as its softmax group has pulled S(j) into registers:
           // each group always has its next tile waiting, and the two groups run half a tile apart
           if (j + 2 < T) issue_qk(j & 1);
-          const int pb = j & 1, vs = vc & 1;
+          const int pb = j & 1, vs = vc % NS;
           twait(&p_full[pb], pu[pb] & 1, 23, 2);
-          twait(&v_full[vs], (vc >> 1) & 1, 24, 3);
+          twait(&v_full[vs], (vc / NS) & 1, 24, 3);
           tc_fence_after();
           const uint32_t v_addr = smem_u32(smem + OFF_VT + vs * VT_BYTES);
           if (elect_one()) {

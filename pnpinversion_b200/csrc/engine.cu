@@ -540,8 +540,15 @@ static int finalize(pnp_engine* e) {
     e->conv_in_w = upload_f32(e, p);
   }
   e->conv_in_b = up_vec(e, "conv_in.bias");
-  e->conv_out_w = upload_f16(e, pack_conv3(*find_param(e, "conv_out.weight"), 4, 320, nullptr, 0));  // [co][tap][c]
-  e->conv_out_b = up_vec(e, "conv_out.bias");
+  {
+    // conv_out (320 -> 4) runs on the tensor-core GEMM as one zero-padded 64-column tile: [64][9*320] fp16, bias [64]
+    std::vector<__half> w4 = pack_conv3(*find_param(e, "conv_out.weight"), 4, 320, nullptr, 0);  // [co][tap][c]
+    w4.resize(static_cast<size_t>(64) * 2880, __float2half(0.f));
+    e->conv_out_w = upload_f16(e, w4);
+    std::vector<float> b4 = to_f32(*find_param(e, "conv_out.bias"));
+    b4.resize(64, 0.f);
+    e->conv_out_b = upload_f32(e, b4);
+  }
   e->norm_out_g = up_vec(e, "conv_norm_out.weight");
   e->norm_out_b = up_vec(e, "conv_norm_out.bias");
   PNP_CHECK(e->norm_out_b != nullptr, "upload failed");
@@ -583,7 +590,7 @@ struct PlanBuilder {
     pl->kernels_per_forward += kernels;
   }
 
-  // Tile shape and K split of one GEMM: the cost model ranks the candidates, the best few are TIMED on the device with
+  // Tile shape and K split of one GEMM: the cost model ranks the candidates, the best dozen are TIMED on the device with
   // the real operands (plan build happens once per batch size, outside any capture), the fastest wins and is remembered
   // per shape so that equal layers get equal numerics.  PNP_GEMM_AUTOTUNE=0 keeps the model's first choice.
   void tune(const ASource* srcs, int nsrc, int taps, bool linear, int b, int h, int w, const __half* wt, int n, int ktot,
@@ -623,7 +630,7 @@ struct PlanBuilder {
         e->allocs.push_back(e->tune_counters);
       }
       // at most one candidate per (tile, split) among the model's best 8, and always the un-split version of each tile
-      const size_t ntry = std::min<size_t>(cands.size(), 8);
+      const size_t ntry = std::min<size_t>(cands.size(), 12);
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0);
       cudaEventCreate(&e1);
@@ -927,8 +934,12 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
   // ---- out
   pb.groupnorm(h, 320, nullptr, 0, 4096, e->norm_out_g, e->norm_out_b, 1e-5f, true, NRM);
   {
-    const __half* wo = e->conv_out_w; const float* bo = e->conv_out_b; float* o = pl->eps_out;
-    pb.op(5, 2.0 * B * 4096 * 4 * 2880, 1, [=](cudaStream_t s) { return conv_out_launch(NRM, B, 64, 64, 320, wo, bo, o, s); });
+    GemmEpilogue ep;
+    ep.bias = e->conv_out_b;
+    ep.out_f32_nchw4 = pl->eps_out;
+    ASource s{NRM, 320, 320};
+    pb.gemm(pl->ops, &s, 1, 9, false, B, 64, 64, e->conv_out_w, 64, 9 * 320, ep);
+    if (!pb.rc) pl->info.back().flops = 2.0 * B * 4096 * 4 * 2880;  // algorithmic: 4 output channels, not the padded 64
   }
   (void)H1;
   if (pb.rc) return pb.rc;

@@ -364,10 +364,12 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              __stcg(reinterpret_cast<float4*>(wrow + c * 32 + j),
-                     make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                 __uint_as_float(r[j + 3])));
+            for (int j = 0; j < 32; j += 8)
+              stg256_cg(wrow + c * 32 + j,
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                    __uint_as_float(r[j + 3])),
+                        make_float4(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]), __uint_as_float(r[j + 6]),
+                                    __uint_as_float(r[j + 7])));
           }
         }
         tc_fence_before();
@@ -421,9 +423,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 for (; sp + 1 < p.splits; sp += 2, wr += 2 * slice) {
                   float4 ta[8], tb[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    ta[j] = __ldcg(reinterpret_cast<const float4*>(wr + 4 * j));
-                    tb[j] = __ldcg(reinterpret_cast<const float4*>(wr + slice + 4 * j));
+                  for (int j = 0; j < 8; j += 2) {
+                    ldg256_cg(wr + 4 * j, ta[j], ta[j + 1]);
+                    ldg256_cg(wr + slice + 4 * j, tb[j], tb[j + 1]);
                   }
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
@@ -435,9 +437,11 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 }
                 if (sp < p.splits) {
 #pragma unroll
-                  for (int j = 0; j < 32; j += 4) {
-                    const float4 t4 = __ldcg(reinterpret_cast<const float4*>(wr + j));
+                  for (int j = 0; j < 32; j += 8) {
+                    float4 t4, t5;
+                    ldg256_cg(wr + j, t4, t5);
                     v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+                    v[j + 4] += t5.x; v[j + 5] += t5.y; v[j + 6] += t5.z; v[j + 7] += t5.w;
                   }
                 }
               }
@@ -456,7 +460,15 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
               }
             }
-            if (valid) {
+            if (p.out32 != nullptr) {
+              // conv_out: the first four columns go out as fp32 NCHW, one image plane per column (coalesced over pixels)
+              if (valid && c == 0) {
+                const int bimg = m / p.HW, pix = m - bimg * p.HW;
+                float* o32 = p.out32 + static_cast<size_t>(bimg) * 4 * p.HW + pix;
+#pragma unroll
+                for (int co = 0; co < 4; ++co) o32[static_cast<size_t>(co) * p.HW] = v[co];
+              }
+            } else if (valid) {
               if (has_res) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -723,8 +735,11 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   bn = bnt / nsub;     // N of one MMA = rows of one weight box
   PNP_CHECK(!geglu || bn == 256 || bn == 128, "gemm: GEGLU epilogue needs BN 128/256");
   // the epilogue moves 32 bytes per lane and instruction (256-bit global accesses)
-  PNP_CHECK(ep.out != nullptr && ep.ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 31) == 0,
+  PNP_CHECK(ep.out_f32_nchw4 != nullptr ||
+                (ep.out != nullptr && ep.ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 31) == 0),
             "gemm: output alignment (32 bytes, ldc % 16 == 0)");
+  PNP_CHECK(ep.out_f32_nchw4 == nullptr || (!linear && !geglu && ep.residual == nullptr),
+            "gemm: the fp32 NCHW output is for a plain convolution");
   PNP_CHECK(ep.residual == nullptr || (ep.ldr % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 31) == 0),
             "gemm: residual alignment (32 bytes, ldr % 16 == 0)");
   PNP_CHECK(!geglu || ep.bias != nullptr, "gemm: GEGLU needs a bias");
@@ -788,6 +803,7 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   p.residual = ep.residual;
   p.ldr = ep.ldr;
   p.out = ep.out;
+  p.out32 = ep.out_f32_nchw4;
   p.ldc = ep.ldc;
   p.geglu = geglu ? 1 : 0;
   p.dbg = debug_words_device();

@@ -550,81 +550,62 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, int B, int H, int 
 // ------------------------------------------------------------------ conv_in: NCHW fp32 (4 ch) -> NHWC fp16 (320 ch)
 constexpr int CIN_K = 36;
 constexpr int CIN_CO = 320;
-__global__ void conv_in_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w,
-                               const float* __restrict__ bias, __half* __restrict__ out) {
+// One thread = 8 output channels x 8 consecutive pixels of an image row.  The [k][co] weights live in shared memory and
+// every weight vector fetched serves 8 pixels (the first version fetched 2 x 16 bytes of weights per pixel and tap:
+// 3 GB of shared-memory reads per B=4 call, 60 us); the 3 x 10 input window of a channel is read once per row of taps.
+constexpr int CIN_PX = 8;
+__global__ void __launch_bounds__(240) conv_in_kernel(const float* __restrict__ x, int B, int H, int W,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      __half* __restrict__ out) {
   __shared__ __align__(16) float ws[CIN_K * CIN_CO];  // [k][co], k = ci*9 + tap
   for (int i = threadIdx.x; i < CIN_K * CIN_CO; i += blockDim.x) ws[i] = w[i];  // prepacked [k][co]
   __syncthreads();
   pdl_sync();  // the weights are constants: staged before waiting for the predecessor
   const int nvec = CIN_CO / 8;  // 40
-  const int ppb = blockDim.x / nvec;
-  const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
-  if (pl >= ppb) return;
-  const size_t npix = static_cast<size_t>(B) * H * W;
-  for (size_t pix = static_cast<size_t>(blockIdx.x) * ppb + pl; pix < npix; pix += static_cast<size_t>(gridDim.x) * ppb) {
-    const int xx = pix % W;
-    const int yy = (pix / W) % H;
-    const int b = pix / (static_cast<size_t>(W) * H);
-    float acc[8];
+  const int gpb = blockDim.x / nvec;  // pixel groups per CTA
+  const int v = threadIdx.x % nvec, gl = threadIdx.x / nvec;
+  const int gpr = W / CIN_PX;  // groups per image row
+  const size_t ngroups = static_cast<size_t>(B) * H * gpr;
+  float bs[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = bias[v * 8 + e];
+  for (int e = 0; e < 8; ++e) bs[e] = bias[v * 8 + e];
+  for (size_t grp = static_cast<size_t>(blockIdx.x) * gpb + gl; grp < ngroups; grp += static_cast<size_t>(gridDim.x) * gpb) {
+    const int x0 = static_cast<int>(grp % gpr) * CIN_PX;
+    const int yy = static_cast<int>((grp / gpr) % H);
+    const int b = static_cast<int>(grp / (static_cast<size_t>(gpr) * H));
+    float acc[CIN_PX][8];
+#pragma unroll
+    for (int j = 0; j < CIN_PX; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[j][e] = bs[e];
     for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int yi = yy + tap / 3 - 1, xi = xx + tap % 3 - 1;
-        float a = 0.f;
-        if (yi >= 0 && yi < H && xi >= 0 && xi < W) a = x[((static_cast<size_t>(b) * 4 + ci) * H + yi) * W + xi];
-        const float4 w0 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * CIN_CO + v * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * CIN_CO + v * 8 + 4);
-        acc[0] += a * w0.x; acc[1] += a * w0.y; acc[2] += a * w0.z; acc[3] += a * w0.w;
-        acc[4] += a * w1.x; acc[5] += a * w1.y; acc[6] += a * w1.z; acc[7] += a * w1.w;
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yi = yy + dy - 1;
+        float xin[CIN_PX + 2];
+        const float* row = x + ((static_cast<size_t>(b) * 4 + ci) * H + yi) * W;
+#pragma unroll
+        for (int j = 0; j < CIN_PX + 2; ++j) {
+          const int xi = x0 + j - 1;
+          xin[j] = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(row + xi) : 0.f;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float* wp = ws + (ci * 9 + dy * 3 + dx) * CIN_CO + v * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+          for (int j = 0; j < CIN_PX; ++j) {
+            const float a = xin[j + dx];
+            acc[j][0] += a * w0.x; acc[j][1] += a * w0.y; acc[j][2] += a * w0.z; acc[j][3] += a * w0.w;
+            acc[j][4] += a * w1.x; acc[j][5] += a * w1.y; acc[j][6] += a * w1.z; acc[j][7] += a * w1.w;
+          }
+        }
       }
     }
-    *reinterpret_cast<uint4*>(out + pix * CIN_CO + v * 8) = pack8(acc);
-  }
-}
-
-// ------------------------------------------------------------------ conv_out: NHWC fp16 (320 ch, already GN+SiLU) -> NCHW fp32 (4 ch)
-__global__ void conv_out_kernel(const __half* __restrict__ x, int B, int H, int W, int C, const __half* __restrict__ w,
-                                const float* __restrict__ bias, float* __restrict__ out) {
-  extern __shared__ __half wsh[];  // [co][tap][c]
-  const int K = 9 * C;
-  for (int i = threadIdx.x; i < 4 * K; i += blockDim.x) wsh[i] = w[i];  // prepacked fp16 [co][tap][c]
-  __syncthreads();
-  pdl_sync();
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const int nvec = C >> 3;
-  const size_t npix = static_cast<size_t>(B) * H * W;
-  for (size_t pix = static_cast<size_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); pix < npix;
-       pix += static_cast<size_t>(gridDim.x) * wpb) {
-    const int xx = pix % W;
-    const int yy = (pix / W) % H;
-    const int b = pix / (static_cast<size_t>(W) * H);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = lane; i < 9 * nvec; i += 32) {
-      const int tap = i / nvec, v = i % nvec;
-      const int yi = yy + tap / 3 - 1, xi = xx + tap % 3 - 1;
-      if (yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + yi) * W + xi) * C + v * 8), f);
+    const size_t pix0 = (static_cast<size_t>(b) * H + yy) * W + x0;
 #pragma unroll
-      for (int co = 0; co < 4; ++co) {
-        float g[8];
-        unpack8(*reinterpret_cast<const uint4*>(wsh + co * K + tap * C + v * 8), g);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[co] += f[e] * g[e];
-      }
-    }
-#pragma unroll
-    for (int co = 0; co < 4; ++co) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
-    }
-    if (lane < 4) {
-      const float val = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + bias[lane];
-      out[((static_cast<size_t>(b) * 4 + lane) * H + yy) * W + xx] = val;
-    }
+    for (int j = 0; j < CIN_PX; ++j) *reinterpret_cast<uint4*>(out + (pix0 + j) * CIN_CO + v * 8) = pack8(acc[j]);
   }
 }
 
@@ -770,20 +751,11 @@ int im2col_s2_launch(const __half* x, int B, int H, int W, int C, __half* out, c
 
 int conv_in_launch(const float* x_nchw, int B, int H, int W, const float* w, const float* bias, __half* out,
                    cudaStream_t s) {
-  const int threads = 240;  // 40 channel-octets x 6 pixels
-  const size_t npix = static_cast<size_t>(B) * H * W;
-  const int blocks = static_cast<int>(std::min<size_t>((npix + 5) / 6, 148 * 2));
+  const int threads = 240;  // 40 channel-octets x 6 groups of 8 pixels
+  PNP_CHECK(W % CIN_PX == 0, "conv_in: W must be a multiple of 8");
+  const size_t ngroups = static_cast<size_t>(B) * H * W / CIN_PX;
+  const int blocks = static_cast<int>(std::min<size_t>((ngroups + 5) / 6, 148 * 2));
   PNP_CUDA(launch_k(conv_in_kernel, dim3(blocks), dim3(threads), 0, s, x_nchw, B, H, W, w, bias, out));
-  return 0;
-}
-
-int conv_out_launch(const __half* x, int B, int H, int W, int C, const __half* w, const float* bias, float* out_nchw,
-                    cudaStream_t s) {
-  PNP_CHECK(C % 8 == 0, "conv_out: C");
-  const size_t sm = static_cast<size_t>(4) * 9 * C * sizeof(__half);
-  const size_t npix = static_cast<size_t>(B) * H * W;
-  const int blocks = static_cast<int>(std::min<size_t>((npix + 7) / 8, 148 * 4));
-  PNP_CUDA(launch_k(conv_out_kernel, dim3(blocks), dim3(256), sm, s, x, B, H, W, C, w, bias, out_nchw));
   return 0;
 }
 

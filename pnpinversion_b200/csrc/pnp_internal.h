@@ -116,6 +116,7 @@ struct alignas(64) GemmParams {
   // optional per-CTA cycle counters [grid][8]: MMA thread (total, wait full, wait tempty), producer (total, wait empty),
   // epilogue thread 128 (total, wait tfull); null in production
   long long* prof;
+  float* out32;  // GemmEpilogue::out_f32_nchw4
   int exp;  // experiments (PNP_GEMM_EXP, test entry points only): 1 = no TMA copies, 2 = no MMAs
 };
 
@@ -138,6 +139,9 @@ struct GemmEpilogue {
   __half* out = nullptr;
   int ldc = 0;
   bool geglu = false;
+  // conv_out: instead of the fp16 NHWC tile, columns 0..3 are written as fp32 NCHW [B,4,H,W] (the UNet's eps output);
+  // the weight matrix is zero-padded to one 64-column tile
+  float* out_f32_nchw4 = nullptr;
 };
 
 // fp16 tiled tensor map with 128-byte swizzle and zero out-of-bounds fill (rank 2..4); strides in bytes for dims 1..
@@ -171,8 +175,6 @@ int upsample2x_launch(const __half* x, int B, int H, int W, int C, __half* out, 
 int im2col_s2_launch(const __half* x, int B, int H, int W, int C, __half* out, cudaStream_t s);
 int conv_in_launch(const float* x_nchw, int B, int H, int W, const float* w, const float* bias, __half* out,
                    cudaStream_t s);
-int conv_out_launch(const __half* x, int B, int H, int W, int C, const __half* w, const float* bias, float* out_nchw,
-                    cudaStream_t s);
 int concat_launch(const __half* x0, int C0, const __half* x1, int C1, int rows, __half* out, cudaStream_t s);
 
 }  // namespace pnp

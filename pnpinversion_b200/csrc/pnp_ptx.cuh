@@ -265,6 +265,19 @@ __device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) 
                : "memory");
 }
 
+// L2-only variants for data exchanged between CTAs of one kernel (split-K partials)
+__device__ __forceinline__ void ldg256_cg(const void* p, float4& a, float4& b) {
+  asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void stg256_cg(void* p, const float4& a, const float4& b) {
+  asm volatile("st.global.cg.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+               "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = TMEM lane base+i)
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
