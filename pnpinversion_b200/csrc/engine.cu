@@ -689,7 +689,8 @@ struct PlanBuilder {
                  bool silu, __half* out) {
     pnp_engine* en = e;
     const int Bn = B;
-    op(1, 0.0, 2, [=](cudaStream_t s) { return groupnorm_launch(x0, c0, x1, c1, Bn, hw, g, b, eps, silu, out, en->gn_partials, s); });
+    op(1, 0.0, groupnorm_kernel_count(c0 + c1, hw),
+       [=](cudaStream_t s) { return groupnorm_launch(x0, c0, x1, c1, Bn, hw, g, b, eps, silu, out, en->gn_partials, s); });
   }
   void layernorm(const __half* x, int rows, int c, const float* g, const float* b, __half* out) {
     op(2, 0.0, 1, [=](cudaStream_t s) { return layernorm_launch(x, rows, c, g, b, 1e-5f, out, s); });
@@ -1243,7 +1244,7 @@ int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, 
       cudaGraphDestroy(g);
     }
   }
-  // groupnorm = 2 kernels per op; count them
+  // every op contributes the kernels it really launches (GroupNorm: 1 or 2, self-attention with its V transpose: 2, ...)
   h->launches += pl->kernels_per_forward;
   PNP_CUDA(cudaMemcpyAsync(eps_out_dev, pl->eps_out, bytes, cudaMemcpyDeviceToDevice, s));
   return leave(h, caller);

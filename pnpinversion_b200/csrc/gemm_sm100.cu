@@ -2,15 +2,20 @@
 //
 //   D[M,N] = A[M,K] . Wt[N,K]^T   fp16 operands, fp32 accumulation in TMEM, fused epilogue.
 //
-// One persistent CTA per SM, 384 threads, warp-specialised:
-//   warp 0 (lane 0)  TMA producer: per 64-wide K block one 4-D box of the NHWC activation (128 pixels x 64 channels,
-//                    shifted by the 3x3 tap, hardware zero fill = the conv padding) and one 2-D box of the weights,
-//                    both landing 128B-swizzled in a STAGES-deep shared-memory ring guarded by full/empty mbarriers.
-//   warp 1 (lane 0)  MMA issuer: 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of two TMEM accumulators,
-//                    tcgen05.commit releases the stage / publishes the accumulator.
+// One persistent CTA per SM, 384 threads, warp-specialised (each role loop runs on a converged warp, one elected lane
+// issues):
+//   warp 0           TMA producer: per 64-wide K block one 4-D box of the NHWC activation (128 pixels x 64 channels,
+//                    shifted by the 3x3 tap, hardware zero fill = the conv padding) and one 2-D box per accumulator of
+//                    the weights, all landing 128B-swizzled in a STAGES-deep shared-memory ring (full/empty mbarriers).
+//   warp 1           MMA issuer: 4 x NSUB tcgen05.mma (M=128, N=BN, K=16) per stage into NSUB interleaved TMEM
+//                    accumulators; tcgen05.commit releases the stage / publishes the accumulators.
 //   warp 2           TMEM allocator.
-//   warps 4..11      epilogue (two warps per TMEM lane quarter): tcgen05.ld 32 lanes x 32 columns, + bias + time-embedding + residual (or GEGLU),
-//                    fp16 pack, 16-byte global stores; overlaps the next tile's MMAs (double-buffered accumulator).
+//   warps 4..11      epilogue (two warps per TMEM lane quarter): tcgen05.ld 32 lanes x 32 columns, + bias + time
+//                    embedding + residual (or GEGLU, or the fp32 NCHW planes of conv_out), fp16 pack, 256-bit global
+//                    stores; overlaps the next tile's MMAs when TMEM holds two accumulator sets.
+// Tile shapes: 128 x {64,128,160,256} with one accumulator, 128 x 320 as two accumulators of 160 (NSUB = 2), and an
+// opt-in pair mode (PAIR: two CTAs of a cluster, tcgen05.mma.cta_group::2, 256 x BN).  Split-K over the K blocks with a
+// deterministic last-arrival reduction.  Optional in-kernel role cycle counters (GemmParams::prof).
 //
 // This is the only place the library does dense contractions: ResnetBlock2D convs (reference arithmetic:
 // models/edict/my_diffusers/models/resnet.py:331-365), 1x1 proj_in/out, attention projections and the GEGLU

@@ -616,6 +616,62 @@ size_t groupnorm_partials_floats(int B, int HW) {
   return static_cast<size_t>(B) * (HW / ppc) * GN_GROUPS * 2;
 }
 
+// Cluster size of the single-launch GroupNorm kernel this device can co-schedule (0 = unavailable / disabled) and whether it
+// is forced for every shape.  Decided once per process.
+static int gn_cluster_config(int* force_all) {
+  static int cluster_cs = -1;
+  static int cluster_force_all = 0;
+  if (cluster_cs < 0) {
+    cluster_cs = 0;
+    const char* e = getenv("PNP_GN_CLUSTER");
+    // measured on B200 (profiles/README.md): the cluster kernel wins on the small tensors (8x8: 10.5 vs 14.9 us, 16x16:
+    // 11-15 vs 14-17 us) and loses on the large ones (64x64: 31 vs 23 us: 16 CTAs per image cannot keep enough loads in
+    // flight), so by default it takes HW <= 256 only.  PNP_GN_CLUSTER=0 never, =8/16 always (tests).
+    const int want = e ? atoi(e) : 16;
+    cluster_force_all = e != nullptr && want >= 2;
+    if (want >= 2) {
+      bool ok = true;
+      ok &= cudaFuncSetAttribute(gn_cluster_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(gn_cluster_kernel<1, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(gn_cluster_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(gn_cluster_kernel<2, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+      if (!ok) (void)cudaGetLastError();  // no cluster kernel on this device: the two-kernel path serves every shape
+      for (int cs = want; ok && cs >= 2 && !cluster_cs; cs >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs, 1);
+        cfg.blockDim = dim3(GNC_THREADS);
+        cfg.dynamicSmemBytes = 96 * 1024;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_kernel<1, 8>, &cfg) == cudaSuccess && nclusters >= 4)
+          cluster_cs = cs;
+        else
+          (void)cudaGetLastError();
+      }
+    }
+  }
+  *force_all = cluster_force_all;
+  return cluster_cs;
+}
+
+// cluster size the launcher will use for this shape, 0 = two-kernel path
+static int gn_cluster_for(int C, int HW) {
+  int force_all = 0;
+  const int cluster_cs = gn_cluster_config(&force_all);
+  if (!(cluster_cs && C <= 2560 && (force_all || HW <= 256))) return 0;
+  int cs = cluster_cs;
+  while (cs > 1 && (HW % cs != 0 || HW / cs < 1)) cs >>= 1;
+  return cs >= 2 ? cs : 0;
+}
+
+int groupnorm_kernel_count(int C, int HW) { return gn_cluster_for(C, HW) ? 1 : 2; }
+
 int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, int HW, const float* gamma,
                      const float* beta, float eps, bool do_silu, __half* out, float* partials, cudaStream_t s) {
   const int C = C0 + C1;
@@ -644,57 +700,18 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   PNP_CHECK(B <= 64, "groupnorm: batch");
   (void)threads;
   // single-launch cluster kernel (one cluster of 16 or 8 CTAs per image) when the device can co-schedule it
-  static int cluster_cs = -1;
-  static int cluster_force_all = 0;
-  if (cluster_cs < 0) {
-    cluster_cs = 0;
-    const char* e = getenv("PNP_GN_CLUSTER");
-    // measured on B200 (profiles/README.md): the cluster kernel wins on the small tensors (8x8: 10.5 vs 14.9 us, 16x16:
-    // 11-15 vs 14-17 us) and loses on the large ones (64x64: 31 vs 23 us: 16 CTAs per image cannot keep enough loads in
-    // flight), so by default it takes HW <= 256 only.  PNP_GN_CLUSTER=0 never, =8/16 always (tests).
-    const int want = e ? atoi(e) : 16;
-    cluster_force_all = e != nullptr && want >= 2;
-    if (want >= 2) {
-      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<1, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      PNP_CUDA(cudaFuncSetAttribute(gn_cluster_kernel<2, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      for (int cs = want; cs >= 2 && !cluster_cs; cs >>= 1) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(cs, 1);
-        cfg.blockDim = dim3(GNC_THREADS);
-        cfg.dynamicSmemBytes = 96 * 1024;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = cs;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_kernel<1, 8>, &cfg) == cudaSuccess && nclusters >= 4)
-          cluster_cs = cs;
-        else
-          (void)cudaGetLastError();
-      }
-    }
-  }
-  if (cluster_cs && C <= 2560 && (cluster_force_all || HW <= 256)) {
-    int cs = cluster_cs;
-    while (cs > 1 && (HW % cs != 0 || HW / cs < 1)) cs >>= 1;
-    if (cs >= 2) {
-      const int ppcc = HW / cs;
-      int ry = GNC_THREADS / tx_n;  // pixel rows of threads; no more than there are pixels, and the scratch must fit
-      ry = std::max(1, std::min(ry, std::min(ppcc, static_cast<int>((96 * 1024) / (2 * C * sizeof(float))))));
-      const size_t smc = static_cast<size_t>(ry) * 2 * C * sizeof(float);
-      if (vpt == 1)
-        PNP_CUDA(launch_kc(gn_cluster_kernel<1, 8>, dim3(cs, B), dim3(GNC_THREADS), smc, s, cs, x0, C0, x1, C1, HW, tx_n, ry,
-                           eps, gamma, beta, do_silu ? 1 : 0, out));
-      else
-        PNP_CUDA(launch_kc(gn_cluster_kernel<2, 4>, dim3(cs, B), dim3(GNC_THREADS), smc, s, cs, x0, C0, x1, C1, HW, tx_n, ry,
-                           eps, gamma, beta, do_silu ? 1 : 0, out));
-      return 0;
-    }
+  if (const int cs = gn_cluster_for(C, HW)) {
+    const int ppcc = HW / cs;
+    int ry = GNC_THREADS / tx_n;  // pixel rows of threads; no more than there are pixels, and the scratch must fit
+    ry = std::max(1, std::min(ry, std::min(ppcc, static_cast<int>((96 * 1024) / (2 * C * sizeof(float))))));
+    const size_t smc = static_cast<size_t>(ry) * 2 * C * sizeof(float);
+    if (vpt == 1)
+      PNP_CUDA(launch_kc(gn_cluster_kernel<1, 8>, dim3(cs, B), dim3(GNC_THREADS), smc, s, cs, x0, C0, x1, C1, HW, tx_n, ry,
+                         eps, gamma, beta, do_silu ? 1 : 0, out));
+    else
+      PNP_CUDA(launch_kc(gn_cluster_kernel<2, 4>, dim3(cs, B), dim3(GNC_THREADS), smc, s, cs, x0, C0, x1, C1, HW, tx_n, ry,
+                         eps, gamma, beta, do_silu ? 1 : 0, out));
+    return 0;
   }
   PNP_CUDA(launch_k(gn_stats_kernel, dim3(nslices, B), dim3(256), sm1, s, x0, C0, x1, C1, HW, ppc, tx_n, rows_y, vpt, parts,
                     eps, mean_rstd, counters));

@@ -91,7 +91,7 @@ struct ASource {
 struct alignas(64) GemmParams {
   CUtensorMap map_a[3];
   CUtensorMap map_b;
-  CUtensorMap map_b_half;  // box of BN/2 weight rows (cluster-of-2 multicast)
+  CUtensorMap map_b_half;  // box of BN/2 weight rows (pair mode: each CTA of the pair stages half of the weight tile)
   int taps0, chunks0, chunks1, chunks2;
   int num_kb;
   int linear;
@@ -168,6 +168,7 @@ long gemm_model_cost(int M, int N, int num_kb, bool geglu, int bnt, int splits, 
 int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, int HW, const float* gamma,
                      const float* beta, float eps, bool silu, __half* out, float* partials, cudaStream_t s);
 size_t groupnorm_partials_floats(int B, int HW);
+int groupnorm_kernel_count(int C, int HW);      // 1 = cluster kernel, 2 = statistics + apply (what groupnorm_launch will launch)
 size_t groupnorm_workspace_floats(int B, int HW);  // partials + mean/rstd + per-batch counters (zero-initialised)
 int layernorm_launch(const __half* x, int rows, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t s);
