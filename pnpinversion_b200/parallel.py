@@ -69,27 +69,35 @@ class EditLanes:
     """
 
     def __init__(self, make_editor, lanes: int = 2, device=None):
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
         self.editors = [make_editor() for _ in range(max(1, lanes))]
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.editors]
+        # a non-CUDA device keeps the lane / thread / ordering logic testable on a CPU-only machine (no streams)
+        self.streams = ([torch.cuda.Stream(device=self.device) for _ in self.editors]
+                        if self.device.type == "cuda" else [None] * len(self.editors))
 
     def __len__(self):
         return len(self.editors)
 
     def run(self, jobs):
         """jobs: callables `job(editor) -> result`; job i runs on lane i % lanes, jobs of one lane in order."""
+        import contextlib
         import threading
 
         n = len(self.editors)
+        jobs = list(jobs)
         results = [None] * len(jobs)
         errors = []
-        caller = torch.cuda.current_stream(self.device)
+        cuda = self.device.type == "cuda"
+        caller = torch.cuda.current_stream(self.device) if cuda else None
 
         def worker(lane):
             try:
-                torch.cuda.set_device(self.device)
-                self.streams[lane].wait_stream(caller)  # inputs produced on the caller's stream are visible
-                with torch.cuda.stream(self.streams[lane]):
+                if cuda:
+                    torch.cuda.set_device(self.device)
+                    self.streams[lane].wait_stream(caller)  # inputs produced on the caller's stream are visible
+                with (torch.cuda.stream(self.streams[lane]) if cuda else contextlib.nullcontext()):
                     for i in range(lane, len(jobs), n):
                         results[i] = jobs[i](self.editors[lane])
             except BaseException as e:  # surfaced in the caller's thread
@@ -100,8 +108,9 @@ class EditLanes:
             t.start()
         for t in threads:
             t.join()
-        for s in self.streams:
-            caller.wait_stream(s)
+        if cuda:
+            for s in self.streams:
+                caller.wait_stream(s)
         if errors:
             raise errors[0]
         return results

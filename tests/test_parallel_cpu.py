@@ -62,3 +62,44 @@ def test_two_rank_gloo_scatter_edit_gather(n_items):
     g = torch.Generator().manual_seed(0)
     ref = torch.randn(n_items, 4, 8, 8, generator=g) * 2.0 + 1.0
     assert torch.equal(full, ref)
+
+
+def test_edit_lanes_assign_jobs_round_robin_keep_order_and_propagate_errors():
+    """Host logic of parallel.EditLanes on a CPU device (no CUDA streams): job i runs on lane i % lanes, the jobs of one
+    lane run in order on that lane's editor, results come back in job order, an exception in a lane reaches the caller."""
+    import threading
+
+    import pytest
+
+    from pnpinversion_b200.parallel import EditLanes
+
+    made = []
+
+    class FakeEditor:
+        def __init__(self):
+            self.idx = len(made)
+            self.seen = []
+            self.threads = set()
+            made.append(self)
+
+    lanes = EditLanes(FakeEditor, lanes=3, device="cpu")
+    assert len(lanes) == 3 and [e.idx for e in lanes.editors] == [0, 1, 2]
+
+    def job(i):
+        def run(ed):
+            ed.seen.append(i)
+            ed.threads.add(threading.get_ident())
+            return (ed.idx, i * i)
+        return run
+
+    out = lanes.run([job(i) for i in range(8)])
+    assert out == [(i % 3, i * i) for i in range(8)]
+    assert [e.seen for e in lanes.editors] == [[0, 3, 6], [1, 4, 7], [2, 5]]
+    assert all(len(e.threads) == 1 for e in lanes.editors)  # the jobs of a lane share one host thread
+    assert lanes.run([]) == []
+
+    def boom(ed):
+        raise ValueError("lane failure")
+
+    with pytest.raises(ValueError, match="lane failure"):
+        lanes.run([job(0), boom, job(2)])
