@@ -8,7 +8,7 @@ A "step" is one batch of `--lanes` whole images per GPU (default 3), each throug
 its own synthetic 4x64x64 latent with the cat prompt pair, i.e. the faithful 650 UNet sample-forwards per image
 (50 x B1 inversion + 3 x 50 x B4) + 200 fused epilogues.  The images of a step are in flight
 concurrently on one GPU (parallel.EditLanes: one CUDA stream, engine handle and host thread per lane) because one image's
-chain of ~330 short kernels per UNet call cannot keep the chip busy (measured on B200: 0.70 / 0.85 / 0.88 images/s with
+chain of ~360 short kernels per UNet call cannot keep the chip busy (measured on B200: 0.70 / 0.85 / 0.88 images/s with
 1 / 2 / 3 lanes).  Weak scaling: every rank edits its own K batches (image-parallel); NCCL only
 broadcasts the inputs and gathers the output latents.
 """

@@ -58,7 +58,7 @@ def gather_items(local: torch.Tensor, n_items: int, dist=None) -> torch.Tensor:
 class EditLanes:
     """Several images in flight on ONE GPU.
 
-    One image's 650 UNet calls are a serial chain of ~330 short kernels each: between two kernels of a chain the SMs idle
+    One image's 650 UNet calls are a serial chain of ~360 short kernels each: between two kernels of a chain the SMs idle
     for the launch latency, and the B=1 inversion third of the chain cannot fill the chip at all.  A second, independent
     image on its own CUDA stream (own engine handle = own activation arena, CUDA graph and controller state; the weights
     are replicated, 1.7 GB per lane) fills those bubbles.  Each lane is driven by its own host thread (the C ABI calls
