@@ -3,10 +3,13 @@
 the mixing layers (:854-859, :931-936), the leapfrog order (:862-880) and the attention reuse of its P2P mode
 (:250-297: attn1 replaced wholesale, attn2 = P*(1-mask) + P_saved[..., indices]*mask), driving oracle/unet_ref.py.
 
-PARITY UNPINNED for this file: edict_functions.py loads CLIP/UNet/VAE from the hub at import time and moves them to
-'cuda' (:36-53), so it cannot be executed in the build container and the reference ships no fixtures for it; the
-restatement is checked only through EDICT's defining property (reverse followed by forward reproduces the input) and
-line-by-line review against the cited lines.  Only tests/ may import this module.
+PARITY PINNED: tests/golden/edict_2steps.npz holds outputs of the reference's own `coupled_stablediffusion`, run
+UNMODIFIED in the build container (oracle/ref_shim.load_reference_edict compiles the file's function definitions and
+supplies the module globals - the vendored fp64 UNet with the synthetic weights, a CLIP stand-in, the whitespace
+tokenizer - because the module itself downloads its models from the hub and moves them to 'cuda' at import time, :36-53;
+generator: `python -m oracle.make_golden edict`).  tests/test_oracle_cpu.py replays the recorded UNet calls through
+`coupled` (same call order, inputs and resulting latents to 1e-6) and checks the attention save / reuse hook on a full-size
+forward pair against the recorded predictions (1e-6).  Only tests/ may import this module.
 """
 from __future__ import annotations
 

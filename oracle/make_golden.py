@@ -6,6 +6,8 @@ Run in the build container only (the GPU box has no /root/reference):
     python -m oracle.make_golden tables        # integer/0-1 host tables  (seconds)
     python -m oracle.make_golden unet          # single UNet forwards, fp64 vendored UNet (minutes)
     python -m oracle.make_golden pipeline 3    # directinversion+p2p, 3 DDIM steps, full-size UNet (~10 min)
+    python -m oracle.make_golden masactrl      # one B=4 forward through the reference's MutualSelfAttentionControl
+    python -m oracle.make_golden edict         # EDICT: 2 coupled steps of inversion + 2 of P2P generation (~5 min)
 
 What runs is the reference's own `DirectInversion.invert`, `direct_inversion_p2p_guidance_forward`,
 `AttentionStore / AttentionRefine / AttentionReweight / LocalBlend`, `register_attention_control`,
@@ -213,6 +215,72 @@ def gen_masactrl():
     print("masactrl_forward.npz written")
 
 
+def gen_edict():
+    """The reference's own `coupled_stablediffusion` (models/edict/edict_functions.py:707-956): deterministic noising of a
+    latent pair over the last two of 50 timesteps (init_image_strength 0.04 -> t = 0, 20), then generation from that pair
+    with the Prompt-to-Prompt attention reuse (prompt_edit given).  Every UNet call is recorded (timestep, which text
+    embedding, checksum of the input latent, the predicted noise) so that the CPU restatement can be replayed against the
+    exact call sequence without running a UNet, and pinned on single calls where it does."""
+    model = build_model()
+    tok, te = model.tokenizer, model.text_encoder
+    src, tgt = synth.CAT_PROMPTS
+
+    class Tok:  # CLIPTokenizer call surface used by edict_functions.py:818-838
+        model_max_length = tok.model_max_length
+
+        def __call__(self, text, padding="max_length", max_length=77, truncation=True, return_tensors="pt",
+                     return_overflowing_tokens=True):
+            return tok(text, padding=padding, max_length=max_length, truncation=truncation, return_tensors=return_tensors)
+
+    embs, keep = {}, []
+
+    class Clip:  # clip(ids).last_hidden_state
+        def __call__(self, ids):
+            e = te(ids)[0]
+            keep.append(e)  # keeps id(e) unique for the lifetime of the run
+            embs[id(e)] = self.n  # 0 = null prompt, 1 = prompt, 2 = prompt_edit (order of edict_functions.py:818-838)
+            self.n += 1
+            return types.SimpleNamespace(last_hidden_state=e)
+
+    clip = Clip()
+    clip.n = 0
+
+    calls = []
+
+    class Recorder:  # the `unet` global of the reference functions
+        in_channels = model.unet.in_channels
+
+        def named_modules(self):
+            return model.unet.named_modules()
+
+        def __call__(self, x, t, encoder_hidden_states=None):
+            out = model.unet(x, t, encoder_hidden_states=encoder_hidden_states)
+            calls.append(dict(t=int(t), ctx=embs[id(encoder_hidden_states)], s=float(x.sum()), a=float(x.abs().sum()),
+                              eps=out.sample.detach().clone()))
+            return out
+
+    ns = ref_shim.load_reference_edict(Recorder(), clip, Tok(), "cpu")
+    z = synth.synth_latent(6).double()
+    t0 = time.time()
+    lat = ns["coupled_stablediffusion"](src, reverse=True, init_image=[z, z.clone()], init_image_strength=0.04, steps=50,
+                                        mix_weight=0.93, guidance_scale=3.0)
+    n_rev = len(calls)
+    print(f"reverse pass: {n_rev} UNet calls, {time.time() - t0:.0f}s", flush=True)
+    clip.n = 0  # the generation pass encodes null prompt, prompt, prompt_edit again
+    out = ns["coupled_stablediffusion"](src, tgt, fixed_starting_latent=lat, init_image_strength=0.04, steps=50,
+                                        mix_weight=0.93, guidance_scale=3.0, return_latents=True)
+    print(f"forward P2P pass: {len(calls) - n_rev} UNet calls, {time.time() - t0:.0f}s", flush=True)
+    attn2 = next(m for n, m in model.unet.named_modules() if type(m).__name__ == "CrossAttention" and "attn2" in n)
+    np.savez_compressed(
+        os.path.join(GOLD, "edict_2steps.npz"), z=z.numpy().astype(np.float32),
+        lat=torch.stack(lat).numpy(), out=torch.stack(out).numpy(), n_reverse_calls=np.int64(n_rev),
+        call_t=np.array([c["t"] for c in calls], np.int64), call_ctx=np.array([c["ctx"] for c in calls], np.int64),
+        call_in_sum=np.array([c["s"] for c in calls], np.float64), call_in_abs=np.array([c["a"] for c in calls], np.float64),
+        call_eps=torch.cat([c["eps"] for c in calls]).numpy().astype(np.float32),
+        edit_mask=attn2.last_attn_slice_mask.numpy(), edit_indices=attn2.last_attn_slice_indices.numpy())
+    print("wrote edict_2steps.npz:", [(c["t"], c["ctx"]) for c in calls])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
@@ -225,3 +293,5 @@ if __name__ == "__main__":
         gen_pipeline(int(sys.argv[2]))
     elif what == "masactrl":
         gen_masactrl()
+    elif what == "edict":
+        gen_edict()

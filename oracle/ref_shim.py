@@ -99,3 +99,35 @@ def load_reference_p2p():
     ns.seq_aligner = importlib.import_module("models.p2p.seq_aligner")
     ns.utils = importlib.import_module("utils.utils")
     return ns
+
+
+def load_reference_edict(unet, clip, clip_tokenizer, device="cpu"):
+    """The reference's EDICT functions (models/edict/edict_functions.py) as a dict of callables, UNMODIFIED.
+
+    The module cannot be imported: at import time it downloads CLIP / the SD UNet / the VAE from the hub and moves them to
+    'cuda' (:36-53), and its functions find `unet`, `clip`, `clip_tokenizer`, `device` as module globals.  So the file is
+    parsed, only its top-level `def`s are compiled - from the reference's own source text, nothing is copied into this
+    repository - and they are executed in a namespace whose globals are the objects passed in (the vendored fp64 UNet
+    with synthetic weights, a CLIP stand-in, the whitespace tokenizer).  `coupled_stablediffusion`, `forward_step`,
+    `reverse_step`, `init_attention_*`, `use_last_*` / `save_last_*` then run exactly as written.
+    """
+    import ast
+    import math
+    import random
+    from difflib import SequenceMatcher
+
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from PIL import Image
+    from tqdm.auto import tqdm
+
+    md = load_my_diffusers()
+    path = os.path.join(REF, "models", "edict", "edict_functions.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    tree.body = [n for n in tree.body if isinstance(n, ast.FunctionDef)]
+    ns = dict(torch=torch, np=np, F=F, math=math, random=random, Image=Image, tqdm=tqdm, SequenceMatcher=SequenceMatcher,
+              DDIMScheduler=md.DDIMScheduler, unet=unet, clip=clip, clip_tokenizer=clip_tokenizer, device=device, vae=None)
+    exec(compile(tree, path, "exec"), ns)
+    return ns

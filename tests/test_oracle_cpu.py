@@ -86,3 +86,85 @@ def test_oracle_pipeline_matches_reference_pipeline_small():
     assert _rel(recon[0], x_stars[0]) < 1e-6 and _rel(edit[0], x_stars[0]) < 1e-6
     # offset_calculate feeds both prompt rows the same latents but different cond contexts -> different losses
     assert not torch.equal(nl[:, 0], nl[:, 1])
+
+
+# ---------------------------------------------------------------------------------------------------- EDICT (row a15)
+EDICT_GOLD = os.path.join(GOLD, "edict_2steps.npz")
+
+
+def _edict_embeddings():
+    tok, te = synth.FakeTokenizer(), synth.SynthTextEncoder(dtype=torch.float64)
+    src, tgt = synth.CAT_PROMPTS
+    return [te(tok(s).input_ids)[0] for s in ("", src, tgt)], tok
+
+
+def test_oracle_edict_loop_replays_the_reference_call_sequence():
+    """tests/golden/edict_2steps.npz was produced by the reference's own `coupled_stablediffusion`
+    (models/edict/edict_functions.py:707-956, run unmodified through oracle/ref_shim.load_reference_edict): two coupled
+    steps of deterministic noising, then two of Prompt-to-Prompt generation, every UNet call recorded.  Driving the
+    restatement with a 'UNet' that replays the recorded predictions checks - without running a UNet - that it makes the
+    same calls in the same order (timestep, text embedding, input latent: un-mixing, leapfrog order) and lands on the same
+    latents (forward_step / reverse_step / mixing layers)."""
+    from oracle import edict_ref
+
+    g = np.load(EDICT_GOLD)
+    (emb_u, emb_c, emb_e), _ = _edict_embeddings()
+    kind = {id(emb_u): 0, id(emb_c): 1, id(emb_e): 2}
+    eps = torch.from_numpy(g["call_eps"]).double()
+    pos = [0]
+
+    def replay(x, t, ctx, hook):
+        i = pos[0]
+        pos[0] += 1
+        assert int(t) == int(g["call_t"][i]) and kind[id(ctx)] == int(g["call_ctx"][i]), (i, int(t), kind[id(ctx)])
+        assert abs(float(x.sum()) - float(g["call_in_sum"][i])) <= 1e-5 * float(g["call_in_abs"][i]), i
+        assert abs(float(x.abs().sum()) - float(g["call_in_abs"][i])) <= 1e-5 * float(g["call_in_abs"][i]), i
+        return eps[i:i + 1]
+
+    ac, ts = p2p_ref.alphas_cumprod("float64"), p2p_ref.timesteps(50)
+    z = torch.from_numpy(g["z"]).double()
+    lat = edict_ref.coupled(replay, ac, ac[0], ts, [z, z.clone()], emb_u, emb_c, guidance=3.0, steps=50, t_limit=48,
+                            reverse=True)
+    assert pos[0] == int(g["n_reverse_calls"]) == 8
+    for i in range(2):
+        assert _rel(lat[i], torch.from_numpy(g["lat"][i])) < 1e-6  # call_eps is stored as float32
+    mask, idx = torch.from_numpy(g["edit_mask"]).double(), torch.from_numpy(g["edit_indices"])
+    out = edict_ref.coupled(replay, ac, ac[0], ts, [torch.from_numpy(g["lat"][i]) for i in range(2)], emb_u, emb_c, emb_e,
+                            mask, idx, guidance=3.0, steps=50, t_limit=48, reverse=False)
+    assert pos[0] == len(g["call_t"]) == 20
+    for i in range(2):
+        assert _rel(out[i], torch.from_numpy(g["out"][i])) < 1e-6
+
+
+def test_edict_attention_edit_tables_match_the_reference():
+    """`init_attention_edit` (edict_functions.py:225-247) as left on the reference's CrossAttention modules."""
+    from pnpinversion_b200 import edict
+
+    g = np.load(EDICT_GOLD)
+    tok = synth.FakeTokenizer()
+    src, tgt = synth.CAT_PROMPTS
+    mask, idx = edict.attention_edit_tables(tok(src).input_ids[0].tolist(), tok(tgt).input_ids[0].tolist())
+    assert torch.equal(mask, torch.from_numpy(g["edit_mask"]).to(mask.dtype))
+    assert torch.equal(idx, torch.from_numpy(g["edit_indices"]))
+
+
+@pytest.mark.slow
+def test_oracle_edict_attention_reuse_matches_the_reference(ref_unet):
+    """First generation sub-step of the fixture (t = 20, input = the second latent of the noised pair): the conditional
+    pass saves every attention map, the edited pass reuses them (self-attention wholesale, cross-attention through mask /
+    indices) - edict_functions.py:250-297, 893-917.  Two full-size fp64 UNet forwards of the restatement."""
+    from oracle import edict_ref
+
+    g = np.load(EDICT_GOLD)
+    (emb_u, emb_c, emb_e), _ = _edict_embeddings()
+    n = int(g["n_reverse_calls"])
+    assert [int(g["call_ctx"][n + k]) for k in range(3)] == [0, 1, 2] and int(g["call_t"][n]) == 20
+    x = torch.from_numpy(g["lat"][1])
+    assert abs(float(x.sum()) - float(g["call_in_sum"][n])) <= 1e-9 * float(g["call_in_abs"][n])
+    hook = edict_ref._Reuse(torch.from_numpy(g["edit_mask"]).double(), torch.from_numpy(g["edit_indices"]))
+    hook.mode = "save"
+    e_c = ref_unet(x, 20, emb_c, hook)
+    hook.mode = "use"
+    e_e = ref_unet(x, 20, emb_e, hook)
+    assert _rel(e_c, torch.from_numpy(g["call_eps"][n + 1:n + 2])) < 1e-6
+    assert _rel(e_e, torch.from_numpy(g["call_eps"][n + 2:n + 3])) < 1e-6
