@@ -147,6 +147,16 @@ class FusedModel:
 
     @classmethod
     def from_state_dict_file(cls, path: str, **kw):
-        """Loads a diffusers-format UNet state_dict (`unet/diffusion_pytorch_model.bin` of an SD-1.x checkpoint)."""
-        sd = torch.load(path, map_location="cpu")
-        return cls(sd, **kw)
+        """Loads a diffusers-format UNet state_dict: a `.safetensors` / `.bin` file, the `unet/` directory or the whole
+        pipeline directory of an SD-1.x checkpoint; validated against the architecture table (checkpoint.py)."""
+        from .checkpoint import load_unet_state_dict
+
+        return cls(load_unet_state_dict(path), **kw)
+
+    @classmethod
+    def from_pretrained(cls, path: str, **kw):
+        """Local-directory counterpart of `StableDiffusionPipeline.from_pretrained` (models/p2p_editor.py:23-25): UNet into
+        the fused engine, CLIP tokenizer / text encoder from the same directory when present."""
+        from .checkpoint import load_fused_model
+
+        return load_fused_model(path, **kw)
