@@ -8,6 +8,7 @@ Run in the build container only (the GPU box has no /root/reference):
     python -m oracle.make_golden pipeline 3    # directinversion+p2p, 3 DDIM steps, full-size UNet (~10 min)
     python -m oracle.make_golden masactrl      # one B=4 forward through the reference's MutualSelfAttentionControl
     python -m oracle.make_golden edict         # EDICT: 2 coupled steps of inversion + 2 of P2P generation (~5 min)
+    python -m oracle.make_golden vae           # vendored AutoencoderKL: encode a 64x64 image, decode an 8x8 latent
 
 What runs is the reference's own `DirectInversion.invert`, `direct_inversion_p2p_guidance_forward`,
 `AttentionStore / AttentionRefine / AttentionReweight / LocalBlend`, `register_attention_control`,
@@ -281,6 +282,30 @@ def gen_edict():
     print("wrote edict_2steps.npz:", [(c["t"], c["ctx"]) for c in calls])
 
 
+def gen_vae():
+    """The vendored AutoencoderKL (models/edict/my_diffusers/models/vae.py:480-557, SD-1.x configuration, fp64) on the
+    synthetic VAE weights: posterior moments of a seeded 64x64 image and the decode of a seeded 8x8 latent - the two calls
+    of utils/utils.py:58-80 at a size that keeps the fixture small (the network is fully convolutional apart from the
+    single-head attention of the mid blocks, whose token count changes with the size but not its arithmetic)."""
+    md = ref_shim.load_my_diffusers()
+    vae = md.AutoencoderKL(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4,
+                           up_block_types=("UpDecoderBlock2D",) * 4, block_out_channels=(128, 256, 512, 512),
+                           layers_per_block=2, act_fn="silu", latent_channels=4, sample_size=512)
+    sd = synth.synth_vae_state_dict(0)
+    vae.load_state_dict({k: v.double() for k, v in sd.items()})
+    vae = vae.double().eval()
+    g = torch.Generator().manual_seed(4242)
+    img = (torch.rand(1, 3, 64, 64, generator=g) * 2 - 1).double()
+    z = torch.randn(1, 4, 8, 8, generator=g).double()
+    dist = vae.encode(img).latent_dist
+    dec = vae.decode(z).sample
+    np.savez_compressed(os.path.join(GOLD, "vae_small.npz"), img=img.numpy().astype(np.float32),
+                        z=z.numpy().astype(np.float32), mean=dist.mean.numpy(), logvar=dist.logvar.numpy(),
+                        dec=dec.numpy())
+    print("wrote vae_small.npz: mean", tuple(dist.mean.shape), "dec", tuple(dec.shape),
+          "mean rms %.3f dec rms %.3f" % (float(dist.mean.pow(2).mean().sqrt()), float(dec.pow(2).mean().sqrt())))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
@@ -295,3 +320,5 @@ if __name__ == "__main__":
         gen_masactrl()
     elif what == "edict":
         gen_edict()
+    elif what == "vae":
+        gen_vae()

@@ -65,7 +65,9 @@ def load_my_diffusers():
     _mkpkg(_PKG + ".schedulers", os.path.join(_MD, "schedulers"))
     _load(_PKG + ".schedulers.scheduling_utils", os.path.join(_MD, "schedulers", "scheduling_utils.py"))
     sched = _load(_PKG + ".schedulers.scheduling_ddim", os.path.join(_MD, "schedulers", "scheduling_ddim.py"))
+    vae = _load(f"{_PKG}.models.vae", os.path.join(_MD, "models", "vae.py"))
     _loaded.update(
+        AutoencoderKL=vae.AutoencoderKL,
         UNet2DConditionModel=mods["unet_2d_condition"].UNet2DConditionModel,
         CrossAttention=mods["attention"].CrossAttention,
         DDIMScheduler=sched.DDIMScheduler,

@@ -113,3 +113,67 @@ def transformer_order(latent_hw: int = 64):
             order.append((f"up_blocks.{i}.attentions.{j}", "up", list(reversed(BLOCK_OUT))[i], hw * hw))
         hw *= 2
     return order
+
+
+# ---------------------------------------------------------------------------------------------------- AutoencoderKL
+# SD-1.x VAE ("next"): `models/edict/my_diffusers/models/vae.py:54-131,133-210,480-557`,
+# blocks `unet_blocks.py` (DownEncoderBlock2D / UpDecoderBlock2D / UNetMidBlock2D), `attention.py:9-93` (AttentionBlock).
+VAE_BLOCK_OUT = (128, 256, 512, 512)
+VAE_LAYERS_PER_BLOCK = 2
+VAE_LATENT_C = 4
+
+
+def _vae_resnet(specs: List[Spec], p: str, cin: int, cout: int) -> None:
+    specs += [
+        (f"{p}.norm1.weight", (cin,)), (f"{p}.norm1.bias", (cin,)),
+        (f"{p}.conv1.weight", (cout, cin, 3, 3)), (f"{p}.conv1.bias", (cout,)),
+        (f"{p}.norm2.weight", (cout,)), (f"{p}.norm2.bias", (cout,)),
+        (f"{p}.conv2.weight", (cout, cout, 3, 3)), (f"{p}.conv2.bias", (cout,)),
+    ]
+    if cin != cout:
+        specs += [(f"{p}.conv_shortcut.weight", (cout, cin, 1, 1)), (f"{p}.conv_shortcut.bias", (cout,))]
+
+
+def _vae_mid(specs: List[Spec], p: str, c: int) -> None:
+    a = f"{p}.attentions.0"
+    specs += [(f"{a}.group_norm.weight", (c,)), (f"{a}.group_norm.bias", (c,))]
+    for n in ("query", "key", "value", "proj_attn"):
+        specs += [(f"{a}.{n}.weight", (c, c)), (f"{a}.{n}.bias", (c,))]
+    _vae_resnet(specs, f"{p}.resnets.0", c, c)
+    _vae_resnet(specs, f"{p}.resnets.1", c, c)
+
+
+def vae_param_specs() -> List[Spec]:
+    """(name, shape) of the 248 AutoencoderKL parameters (83.65 M values); names as in a diffusers SD-1.x `vae/` state dict."""
+    bo = VAE_BLOCK_OUT
+    s: List[Spec] = []
+    # encoder (vae.py:54-131)
+    s += [("encoder.conv_in.weight", (bo[0], 3, 3, 3)), ("encoder.conv_in.bias", (bo[0],))]
+    cout = bo[0]
+    for i in range(len(bo)):
+        cin, cout = cout, bo[i]
+        for j in range(VAE_LAYERS_PER_BLOCK):
+            _vae_resnet(s, f"encoder.down_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout)
+        if i != len(bo) - 1:
+            s += [(f"encoder.down_blocks.{i}.downsamplers.0.conv.weight", (cout, cout, 3, 3)),
+                  (f"encoder.down_blocks.{i}.downsamplers.0.conv.bias", (cout,))]
+    _vae_mid(s, "encoder.mid_block", bo[-1])
+    s += [("encoder.conv_norm_out.weight", (bo[-1],)), ("encoder.conv_norm_out.bias", (bo[-1],)),
+          ("encoder.conv_out.weight", (2 * VAE_LATENT_C, bo[-1], 3, 3)), ("encoder.conv_out.bias", (2 * VAE_LATENT_C,))]
+    # decoder (vae.py:133-210)
+    s += [("decoder.conv_in.weight", (bo[-1], VAE_LATENT_C, 3, 3)), ("decoder.conv_in.bias", (bo[-1],))]
+    _vae_mid(s, "decoder.mid_block", bo[-1])
+    rev = list(reversed(bo))
+    cout = rev[0]
+    for i in range(len(rev)):
+        cin, cout = cout, rev[i]
+        for j in range(VAE_LAYERS_PER_BLOCK + 1):
+            _vae_resnet(s, f"decoder.up_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout)
+        if i != len(rev) - 1:
+            s += [(f"decoder.up_blocks.{i}.upsamplers.0.conv.weight", (cout, cout, 3, 3)),
+                  (f"decoder.up_blocks.{i}.upsamplers.0.conv.bias", (cout,))]
+    s += [("decoder.conv_norm_out.weight", (bo[0],)), ("decoder.conv_norm_out.bias", (bo[0],)),
+          ("decoder.conv_out.weight", (3, bo[0], 3, 3)), ("decoder.conv_out.bias", (3,))]
+    s += [("quant_conv.weight", (2 * VAE_LATENT_C, 2 * VAE_LATENT_C, 1, 1)), ("quant_conv.bias", (2 * VAE_LATENT_C,)),
+          ("post_quant_conv.weight", (VAE_LATENT_C, VAE_LATENT_C, 1, 1)), ("post_quant_conv.bias", (VAE_LATENT_C,))]
+    return s

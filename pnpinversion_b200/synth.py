@@ -52,6 +52,29 @@ def synth_unet_state_dict(seed: int = 0, dtype=torch.float16) -> Dict[str, torch
     return out
 
 
+def synth_vae_state_dict(seed: int = 0, dtype=torch.float16) -> Dict[str, torch.Tensor]:
+    """Seeded stand-in for the SD-1.x VAE weights (same recipe as the UNet: U(-b,b) with b = 2/sqrt(fan_in), norms near
+    identity, small biases).  Used by the VAE oracle / fixtures."""
+    from .arch import vae_param_specs
+
+    out: Dict[str, torch.Tensor] = {}
+    for idx, (name, shape) in enumerate(vae_param_specs()):
+        g = torch.Generator().manual_seed(900_001 + seed * 1_000_003 + idx)
+        if "norm" in name:
+            t = torch.randn(shape, generator=g) * 0.1
+            if name.endswith("weight"):
+                t = t + 1.0
+        elif name.endswith("bias"):
+            t = torch.randn(shape, generator=g) * 0.05
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            t = (torch.rand(shape, generator=g) * 2.0 - 1.0) * (2.0 / math.sqrt(fan_in))
+        out[name] = t.to(dtype)
+    return out
+
+
 class FakeTokenizer:
     """Whitespace tokenizer with the CLIP tokenizer's call surface (what the reference touches:
     `__call__(..., padding="max_length", max_length=77, truncation=True, return_tensors="pt").input_ids`,

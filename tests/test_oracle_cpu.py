@@ -168,3 +168,27 @@ def test_oracle_edict_attention_reuse_matches_the_reference(ref_unet):
     e_e = ref_unet(x, 20, emb_e, hook)
     assert _rel(e_c, torch.from_numpy(g["call_eps"][n + 1:n + 2])) < 1e-6
     assert _rel(e_e, torch.from_numpy(g["call_eps"][n + 2:n + 3])) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------- VAE (row a16, next)
+def test_oracle_vae_matches_the_reference_autoencoder():
+    """oracle/vae_ref.py against the vendored AutoencoderKL (tests/golden/vae_small.npz, oracle/make_golden.py vae): the
+    posterior moments of `image2latent` and the `latent2image` decode (utils/utils.py:58-80).  The CUDA VAE is a 'next' row
+    (SURVEY.md section 8f); this pins the gate it will have to pass."""
+    from oracle import vae_ref
+
+    g = np.load(os.path.join(GOLD, "vae_small.npz"))
+    torch.set_grad_enabled(False)
+    vae = vae_ref.VaeRef(synth.synth_vae_state_dict(0))
+    mean, logvar = vae.encode_moments(torch.from_numpy(g["img"]).double())
+    assert _rel(mean, torch.from_numpy(g["mean"])) < 1e-9 and _rel(logvar, torch.from_numpy(g["logvar"])) < 1e-9
+    assert _rel(vae.decode(torch.from_numpy(g["z"]).double()), torch.from_numpy(g["dec"])) < 1e-9
+
+
+def test_vae_parameter_table_has_the_reference_layout():
+    from pnpinversion_b200 import arch
+
+    specs = arch.vae_param_specs()
+    assert len(specs) == 248 and sum(int(np.prod(s)) for _, s in specs) == 83_653_863  # SURVEY.md: 83.65 M parameters
+    sd = synth.synth_vae_state_dict(0)
+    assert list(sd) == [k for k, _ in specs] and all(tuple(sd[k].shape) == s for k, s in specs)
