@@ -1,0 +1,69 @@
+"""Differential test of the host tables against the REFERENCE's own functions on random prompts (row a11: bit-exact).
+
+Runs only where the reference tree is mounted (the build container); on a machine without /root/reference (the GPU box)
+the module is skipped - the committed fixtures of tests/test_host_tables.py cover that case.  The reference functions are
+imported unmodified through oracle/ref_shim.py: models/p2p/seq_aligner.py (get_refinement_mapper :121-128,
+get_replacement_mapper :189-195), utils/utils.py (get_word_inds :84-102, get_time_words_attention_alpha :117-135),
+models/p2p/attention_control.py (get_equalizer :84-92)."""
+import random
+
+import pytest
+import torch
+
+from oracle import ref_shim
+from pnpinversion_b200 import ptp_utils, seq_aligner, synth
+from pnpinversion_b200.attention_control import get_equalizer
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted")
+
+VOCAB = ("a the cat dog sitting standing on under table chair with green blue eyes photo of house hill red snowy night "
+         "round square cake orange frosting wooden plate two birds branch colorful man riding horse quick brown fox jumps "
+         "over lazy watercolor painting").split()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_shim.load_reference_p2p()
+
+
+def _edit(rng, words):
+    """A target prompt derived from the source by word replacements / insertions / deletions."""
+    out = list(words)
+    for _ in range(rng.randint(0, 3)):
+        op = rng.choice(("replace", "insert", "delete"))
+        if op == "replace" and out:
+            out[rng.randrange(len(out))] = rng.choice(VOCAB)
+        elif op == "insert":
+            out.insert(rng.randrange(len(out) + 1), rng.choice(VOCAB))
+        elif op == "delete" and len(out) > 1:
+            del out[rng.randrange(len(out))]
+    return out
+
+
+def test_refinement_and_replacement_mappers_word_indices_gates_and_equalizer(ref):
+    rng = random.Random(20240923)
+    tok = synth.FakeTokenizer()
+    n_replace = 0
+    for _ in range(120):
+        src_w = [rng.choice(VOCAB) for _ in range(rng.randint(1, 14))]
+        tgt_w = _edit(rng, src_w)
+        prompts = [" ".join(src_w), " ".join(tgt_w)]
+        m, a = seq_aligner.get_refinement_mapper(prompts, tok)
+        rm, ra = ref.seq_aligner.get_refinement_mapper(prompts, tok)
+        assert torch.equal(m, rm) and torch.equal(a, ra), prompts
+        if len(src_w) == len(tgt_w):  # the Replace controller requires equal word counts (seq_aligner.py:155-157)
+            assert torch.equal(seq_aligner.get_replacement_mapper(prompts, tok), ref.seq_aligner.get_replacement_mapper(prompts, tok))
+            n_replace += 1
+        for text, words in ((prompts[0], src_w), (prompts[1], tgt_w)):
+            w = rng.choice(words)
+            assert seq_aligner.get_word_inds(text, w, tok).tolist() == ref.utils.get_word_inds(text, w, tok).tolist()
+            i = rng.randrange(len(words))
+            assert seq_aligner.get_word_inds(text, i, tok).tolist() == ref.utils.get_word_inds(text, i, tok).tolist()
+        steps = rng.choice((50, 20, 4))
+        cross = rng.choice((0.4, 0.8, {"default_": 0.4}, {"default_": 1.0, tgt_w[0]: (0.0, 0.5)}))
+        mine = ptp_utils.get_time_words_attention_alpha(prompts, steps, cross, tok)
+        theirs = ref.utils.get_time_words_attention_alpha(prompts, steps, cross, tok)
+        assert torch.equal(mine, theirs), (prompts, steps, cross)
+        w = rng.choice(tgt_w)
+        assert torch.equal(get_equalizer(prompts[1], (w,), (2.0,), tok), ref.attention_control.get_equalizer(prompts[1], (w,), (2.0,), tok))
+    assert n_replace >= 10
