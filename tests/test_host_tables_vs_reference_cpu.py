@@ -67,3 +67,32 @@ def test_refinement_and_replacement_mappers_word_indices_gates_and_equalizer(ref
         w = rng.choice(tgt_w)
         assert torch.equal(get_equalizer(prompts[1], (w,), (2.0,), tok), ref.attention_control.get_equalizer(prompts[1], (w,), (2.0,), tok))
     assert n_replace >= 10
+
+
+@pytest.mark.parametrize("table", ["float32", "float64"])
+def test_step_coefficients_reproduce_the_reference_ddim_steps_bit_for_bit(ref, table):
+    """`DirectInversion.next_step` / `prev_step` (models/p2p/inversion.py:247-270) on random latents against the expression
+    the fused epilogue kernel evaluates from `scheduler.step_coefficients` (same operation order, fp32): equal bits, for the
+    fp32 table of diffusers >= 0.10 (P2P / MasaCtrl paths) and the fp64 table of the vendored scheduler."""
+    import types
+
+    from oracle import p2p_ref
+    from pnpinversion_b200.scheduler import step_coefficients
+
+    ac = p2p_ref.alphas_cumprod(table)
+    inv = object.__new__(ref.inversion.DirectInversion)
+    sched = types.SimpleNamespace(alphas_cumprod=ac, final_alpha_cumprod=ac[0],
+                                  config=types.SimpleNamespace(num_train_timesteps=1000), num_inference_steps=50)
+    inv.model = types.SimpleNamespace(scheduler=sched)  # `scheduler` is a property over model.scheduler
+    g = torch.Generator().manual_seed(7)
+    for t in p2p_ref.timesteps(50).tolist():
+        x = torch.randn(1, 4, 64, 64, generator=g)
+        eps = torch.randn(1, 4, 64, 64, generator=g)
+        # inverse step: from min(t - 20, 999) (final alpha below 0) to t
+        c = step_coefficients(ac, ac[0], min(t - 20, 999), t)
+        mine = c[2] * ((x - c[1] * eps) / c[0]) + c[3] * eps
+        assert torch.equal(mine, inv.next_step(eps, t, x).to(torch.float32)), ("next", t)
+        # forward step: from t to t - 20
+        c = step_coefficients(ac, ac[0], t, t - 20)
+        mine = c[2] * ((x - c[1] * eps) / c[0]) + c[3] * eps
+        assert torch.equal(mine, inv.prev_step(eps, t, x)[0].to(torch.float32)), ("prev", t)
