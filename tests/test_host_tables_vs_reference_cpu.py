@@ -96,3 +96,50 @@ def test_step_coefficients_reproduce_the_reference_ddim_steps_bit_for_bit(ref, t
         c = step_coefficients(ac, ac[0], t, t - 20)
         mine = c[2] * ((x - c[1] * eps) / c[0]) + c[3] * eps
         assert torch.equal(mine, inv.prev_step(eps, t, x)[0].to(torch.float32)), ("prev", t)
+
+
+def test_restated_controllers_track_the_reference_controllers_over_many_steps(ref):
+    """oracle/p2p_ref.EditController (the gate of the GPU controller tests) against the reference's own
+    AttentionRefine + AttentionReweight + LocalBlend (attention_control.py:95-147,214-363) on random attention maps: the
+    same synthetic list of 'layers' is pushed through both for more steps than the schedule has, crossing the cross-replace
+    window, the self-replace window and the LocalBlend start; edited maps, accumulated stores and blended latents must
+    agree at every step."""
+    import types
+
+    from oracle import p2p_ref
+    from oracle.make_golden import make_controller_cpu
+
+    n_steps = 10
+    prompts = list(synth.CAT_PROMPTS)
+    tok = synth.FakeTokenizer()
+    model = types.SimpleNamespace(tokenizer=tok)
+    rc = make_controller_cpu(ref, model, prompts, n_steps, cross=0.4, self_=0.6, blend_word=(("cat",), ("cat",)),
+                             eq_params={"words": ("watercolor",), "values": (2,)})
+    mapper, alphas = seq_aligner.get_refinement_mapper(prompts, tok)
+    ca = ptp_utils.get_time_words_attention_alpha(prompts, n_steps, {"default_": 0.4}, tok).double()
+    eq = get_equalizer(prompts[1], ("watercolor",), (2,), tok).double()
+    blend = torch.zeros(2, 1, 1, 1, 1, 77, dtype=torch.float64)
+    for i, p in enumerate(prompts):
+        blend[i, ..., seq_aligner.get_word_inds(p, "cat", tok)] = 1
+    oc = p2p_ref.EditController(n_steps, ca, 0.6, mapper, alphas.double(), eq, blend)
+    # (place, is_cross, queries): four stored down-cross and three up-cross maps of 16x16 queries (what LocalBlend reads),
+    # self-attention at a replaced size, at the 32x32 limit and beyond it, one unstored cross map
+    layers = [("down", True, 256), ("down", True, 256), ("down", False, 256), ("down", True, 256), ("down", True, 256),
+              ("mid", True, 64), ("mid", False, 64), ("up", True, 256), ("up", False, 1024), ("up", True, 256),
+              ("up", True, 256), ("up", False, 1156), ("up", True, 1156)]
+    rc.num_att_layers = oc.num_att_layers = len(layers)
+    g = torch.Generator().manual_seed(11)
+    for step in range(n_steps + 1):
+        for place, is_cross, hw in layers:
+            k = 77 if is_cross else hw
+            a = torch.softmax(torch.randn(8, hw, k, generator=g, dtype=torch.float64) * 2.0, dim=-1)  # B=4 x 2 heads
+            out_r = rc(a.clone(), is_cross, place)
+            out_o = oc(a.clone(), is_cross, place)
+            assert torch.allclose(out_r, out_o, rtol=0, atol=1e-14), (step, place, is_cross, hw)
+        assert rc.cur_step == oc.cur_step == step + 1
+        for key in rc.attention_store:
+            assert len(rc.attention_store[key]) == len(oc.attention_store[key]), key
+            for mr, mo in zip(rc.attention_store[key], oc.attention_store[key]):
+                assert torch.allclose(mr, mo, rtol=0, atol=1e-12), (step, key)
+        x = torch.randn(2, 4, 64, 64, generator=g, dtype=torch.float64)
+        assert torch.equal(rc.step_callback(x.clone()), oc.step_callback(x.clone())), step
