@@ -143,3 +143,52 @@ def test_restated_controllers_track_the_reference_controllers_over_many_steps(re
                 assert torch.allclose(mr, mo, rtol=0, atol=1e-12), (step, key)
         x = torch.randn(2, 4, 64, 64, generator=g, dtype=torch.float64)
         assert torch.equal(rc.step_callback(x.clone()), oc.step_callback(x.clone())), step
+
+
+def test_masactrl_descriptor_means_what_the_reference_editor_computes():
+    """`pnpinversion_b200.masactrl.MutualSelfAttentionControl` lowers the reference editor (models/masactrl/masactrl.py:14-72,
+    masactrl_utils.py:13-36) to a K/V source-row descriptor for the fused self-attention kernels.  Here the reference class
+    itself runs on random q, k, v for every attention layer of several UNet calls, and the descriptor - interpreted the way
+    the kernels interpret it (rows of transformer blocks [lo, hi) read keys / values of their source row) - must give the
+    same outputs, including the step and layer gating."""
+    import importlib
+    import sys
+
+    if ref_shim.REF not in sys.path:
+        sys.path.insert(0, ref_shim.REF)
+    ref_masa = importlib.import_module("models.masactrl.masactrl")
+    from pnpinversion_b200 import masactrl as mine_mod
+
+    H, n, d, B = 8, 12, 8, 4
+    scale = d ** -0.5
+    r_ed = ref_masa.MutualSelfAttentionControl(start_step=2, start_layer=10, total_steps=6)
+    r_ed.num_att_layers = 32
+    m_ed = mine_mod.MutualSelfAttentionControl(2, 10, total_steps=6)
+    g = torch.Generator().manual_seed(3)
+    hits = 0
+    for step in range(6):
+        desc = m_ed.descriptor(B)
+        for layer in range(32):
+            block, is_cross = layer // 2, layer % 2 == 1
+            nk = 5 if is_cross else n
+            q = torch.randn(B * H, n, d, generator=g, dtype=torch.float64)
+            k = torch.randn(B * H, nk, d, generator=g, dtype=torch.float64)
+            v = torch.randn(B * H, nk, d, generator=g, dtype=torch.float64)
+            sim = torch.einsum("bid,bjd->bij", q, k) * scale
+            attn = sim.softmax(-1)
+            out_ref = r_ed(q, k, v, sim, attn, is_cross, "up", H, scale=scale)
+            # the descriptor as the kernels read it
+            rows_k = rows_v = list(range(B))
+            active = desc is not None and not is_cross and desc.self_layer_lo <= block < desc.self_layer_hi
+            if active and n <= desc.self_max_tokens:
+                rows_k, rows_v = [desc.self_k_row[r] for r in range(B)], [desc.self_v_row[r] for r in range(B)]
+                hits += 1
+            qb, kb, vb = (t.reshape(B, H, -1, d) for t in (q, k, v))
+            outs = []
+            for r in range(B):
+                p = (torch.einsum("hid,hjd->hij", qb[r], kb[rows_k[r]]) * scale).softmax(-1)
+                outs.append(torch.einsum("hij,hjd->hid", p, vb[rows_v[r]]).permute(1, 0, 2).reshape(-1, H * d))
+            assert torch.allclose(torch.stack(outs), out_ref, rtol=0, atol=1e-12), (step, layer)
+        m_ed.after_unet_call()
+        assert m_ed.cur_step == r_ed.cur_step == step + 1
+    assert hits == 4 * 6  # steps 2..5 x transformer blocks 10..15
