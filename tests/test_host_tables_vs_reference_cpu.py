@@ -192,3 +192,26 @@ def test_masactrl_descriptor_means_what_the_reference_editor_computes():
         m_ed.after_unet_call()
         assert m_ed.cur_step == r_ed.cur_step == step + 1
     assert hits == 4 * 6  # steps 2..5 x transformer blocks 10..15
+
+
+def test_edict_step_coefficients_against_the_reference_forward_and_reverse_steps():
+    """`pnpinversion_b200.edict.step_coeffs` folds EDICT's forward_step / reverse_step (edict_functions.py:621-684, with the
+    float `prev_timestep` and alpha interpolation of get_alpha_and_beta :599-617) into the four coefficients of the fused
+    epilogue; the reference's own two functions (compiled from its source by oracle/ref_shim.load_reference_edict) on the
+    vendored fp64 scheduler give the same latents."""
+    from pnpinversion_b200 import edict
+
+    md = ref_shim.load_my_diffusers()
+    ns = ref_shim.load_reference_edict(unet=None, clip=None, clip_tokenizer=None, device="cpu")
+    sched = md.DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
+                             clip_sample=False, set_alpha_to_one=False)
+    sched.set_timesteps(50)
+    g = torch.Generator().manual_seed(5)
+    for t in sched.timesteps:
+        x = torch.randn(1, 4, 64, 64, generator=g, dtype=torch.float64)
+        e = torch.randn(1, 4, 64, 64, generator=g, dtype=torch.float64)
+        for reverse, fn in ((False, ns["forward_step"]), (True, ns["reverse_step"])):
+            c = edict.step_coeffs(sched, int(t), 20, reverse)
+            mine = c[2] * ((x - c[1] * e) / c[0]) + c[3] * e
+            theirs = fn(sched, e, t, x)
+            assert float((mine - theirs).abs().max()) <= 1e-12 * float(theirs.abs().max()), (int(t), reverse)
