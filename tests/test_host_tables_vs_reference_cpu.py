@@ -215,3 +215,62 @@ def test_edict_step_coefficients_against_the_reference_forward_and_reverse_steps
             mine = c[2] * ((x - c[1] * e) / c[0]) + c[3] * e
             theirs = fn(sched, e, t, x)
             assert float((mine - theirs).abs().max()) <= 1e-12 * float(theirs.abs().max()), (int(t), reverse)
+
+
+@pytest.mark.parametrize("kind", ["refine+reweight", "replace"])
+def test_p2p_descriptor_means_what_the_reference_controllers_compute(ref, kind):
+    """The product controllers (pnpinversion_b200/attention_control.py) lower AttentionRefine / AttentionReweight /
+    AttentionReplace to a `pnp_attn_ctrl` descriptor per UNet call.  For every step of a schedule, random attention maps go
+    through the REFERENCE controllers (attention_control.py:251-363), and the descriptor - interpreted the way the
+    attention kernels interpret it - must produce the same edited maps: cross-attention gather(mapper) / alphas /
+    equalizer / per-step word gates, self-attention replacement inside its step window and size limit."""
+    import types
+
+    from pnpinversion_b200 import attention_control as prod
+
+    n_steps, heads, B = 10, 2, 4
+    tok = synth.FakeTokenizer()
+    pipe = types.SimpleNamespace(tokenizer=tok)
+    ac = ref.attention_control
+    if kind == "replace":
+        prompts = ["a cat sitting on a table with a green eyes", "a dog sitting on a table with a green eyes"]
+        rc = ac.AttentionReplace(prompts, n_steps, cross_replace_steps={"default_": 0.4}, self_replace_steps=0.6,
+                                 local_blend=None, tokenizer=tok, device="cpu")
+        rc.mapper = rc.mapper.double()  # the maps below are float64; the 0/1 matrix is exact in either type
+        pc = prod.make_controller(pipe, prompts, True, {"default_": 0.4}, 0.6, None, None, num_ddim_steps=n_steps)
+    else:
+        prompts = list(synth.CAT_PROMPTS)
+        from oracle.make_golden import make_controller_cpu
+
+        rc = make_controller_cpu(ref, pipe, prompts, n_steps, cross=0.4, self_=0.6, blend_word=None,
+                                 eq_params={"words": ("watercolor",), "values": (2,)})
+        pc = prod.make_controller(pipe, prompts, False, {"default_": 0.4}, 0.6, None,
+                                  {"words": ("watercolor",), "values": (2,)}, num_ddim_steps=n_steps)
+    layers = [(0, True, 256), (0, False, 256), (5, True, 64), (5, False, 1024), (9, False, 1156), (15, True, 1156)]
+    rc.num_att_layers = len(layers)
+    g = torch.Generator().manual_seed(17)
+    edited_cross = edited_self = 0
+    for step in range(n_steps + 1):
+        d = pc.descriptor(B)
+        for block, is_cross, hw in layers:
+            k = 77 if is_cross else hw
+            p = torch.softmax(torch.randn(B, heads, hw, k, generator=g, dtype=torch.float64) * 2.0, dim=-1)
+            out_ref = rc(p.reshape(B * heads, hw, k).clone(), is_cross, "up").reshape(B, heads, hw, k)
+            mine = p.clone()
+            for r in range(B):
+                if is_cross and d is not None and d.cross_base_row[r] >= 0:
+                    s, slot = d.cross_base_row[r], d.cross_slot[r]
+                    mp = torch.tensor(list(d.mapper[slot]), dtype=torch.long)
+                    al, eq, ca = (torch.tensor(list(t[slot]), dtype=torch.float64) for t in (d.alphas, d.equalizer, d.cross_alpha))
+                    new = (p[s][..., mp] * al + p[r] * (1 - al)) * eq
+                    mine[r] = new * ca + (1 - ca) * p[r]
+                    edited_cross += 1
+                elif (not is_cross) and d is not None and d.self_layer_lo <= block < d.self_layer_hi and \
+                        hw <= d.self_max_tokens and d.self_q_row[r] != r:
+                    assert d.self_q_row[r] == d.self_k_row[r]  # probabilities of the source row, own values
+                    mine[r] = p[d.self_q_row[r]]
+                    edited_self += 1
+            assert torch.allclose(mine, out_ref, rtol=0, atol=1e-14), (step, block, is_cross, hw)
+        pc.after_unet_call()
+        assert pc.cur_step == rc.cur_step == step + 1
+    assert edited_cross == 3 * (n_steps + 1) and edited_self == 2 * int(n_steps * 0.6)
