@@ -274,3 +274,21 @@ def test_p2p_descriptor_means_what_the_reference_controllers_compute(ref, kind):
         pc.after_unet_call()
         assert pc.cur_step == rc.cur_step == step + 1
     assert edited_cross == 3 * (n_steps + 1) and edited_self == 2 * int(n_steps * 0.6)
+
+
+def test_local_blend_host_parameters_match_the_reference(ref):
+    """LocalBlend.__init__ (attention_control.py:123-147): token selection `alpha_layers`, `start_blend`, thresholds."""
+    from pnpinversion_b200 import attention_control as prod
+
+    rng = random.Random(99)
+    tok = synth.FakeTokenizer()
+    for _ in range(40):
+        src_w = [rng.choice(VOCAB) for _ in range(rng.randint(2, 12))]
+        tgt_w = _edit(rng, src_w)
+        prompts = [" ".join(src_w), " ".join(tgt_w)]
+        words = ((rng.choice(src_w),), (rng.choice(tgt_w),))
+        steps = rng.choice((50, 20, 7))
+        r = ref.attention_control.LocalBlend(prompts, words, tokenizer=tok, device="cpu", num_ddim_steps=steps)
+        m = prod.LocalBlend(prompts, words, tokenizer=tok, num_ddim_steps=steps)
+        assert torch.equal(m.alpha_layers, r.alpha_layers.reshape(2, -1).to(m.alpha_layers.dtype)), prompts
+        assert m.start_blend == r.start_blend and tuple(m.th) == tuple(r.th) and m.counter == r.counter == 0
