@@ -5,6 +5,7 @@ The reference builds its pipeline with `StableDiffusionPipeline.from_pretrained(
 installed, so this module reads the files of such a checkpoint directly:
 
   <dir>/unet/diffusion_pytorch_model.safetensors | .bin     the 686 UNet tensors (diffusers key names)
+  <file>.safetensors | .ckpt (CompVis / LDM single file)     same tensors under model.diffusion_model.* (converted)
   <dir>/tokenizer/, <dir>/text_encoder/                     CLIP, through `transformers` (local files only)
 
 and hands the UNet state dict to `FusedModel` (which repacks it for the kernels).  Everything is validated against the
@@ -57,14 +58,71 @@ def check_unet_state_dict(sd: Dict[str, torch.Tensor]) -> Tuple[List[str], List[
     return missing, unexpected, bad
 
 
+_LDM_PREFIX = "model.diffusion_model."
+_LDM_RESNET = {"in_layers.0": "norm1", "in_layers.2": "conv1", "emb_layers.1": "time_emb_proj", "out_layers.0": "norm2",
+               "out_layers.3": "conv2", "skip_connection": "conv_shortcut"}
+
+
+def ldm_to_diffusers_unet(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Original CompVis / LDM single-file checkpoints (`v1-5-pruned-emaonly.safetensors`, `sd-v1-4.ckpt`: UNet keys under
+    `model.diffusion_model.`) -> diffusers key names.  SD-1.x layout: `input_blocks.0` = conv_in, `input_blocks.{1..11}` =
+    three entries per resolution (resnet [+ transformer]) x2 then a stride-2 conv (`op`), `middle_block.{0,1,2}`,
+    `output_blocks.{0..11}` = (resnet [+ transformer] [+ upsample conv]) three per resolution, `time_embed.{0,2}`,
+    `out.{0,2}`.  Tensors are passed through untouched (the 1x1 proj_in / proj_out convolutions keep their 4-D shape in
+    SD-1.x); anything that is not a UNet tensor (VAE, CLIP, EMA bookkeeping) is dropped."""
+    def resnet(dst, rest):
+        for a, b in _LDM_RESNET.items():
+            if rest.startswith(a + "."):
+                return f"{dst}.{b}.{rest[len(a) + 1:]}"
+        raise ValueError(f"unexpected resnet tensor {rest!r}")
+
+    out: Dict[str, torch.Tensor] = {}
+    for key, t in sd.items():
+        if not key.startswith(_LDM_PREFIX):
+            continue
+        k = key[len(_LDM_PREFIX):]
+        p = k.split(".")
+        if p[0] == "time_embed":
+            new = f"time_embedding.linear_{1 if p[1] == '0' else 2}.{p[2]}"
+        elif p[0] == "out":
+            new = f"{'conv_norm_out' if p[1] == '0' else 'conv_out'}.{p[2]}"
+        elif p[0] == "input_blocks":
+            i, sub, rest = int(p[1]), p[2], ".".join(p[3:])
+            if i == 0:
+                new = f"conv_in.{rest}"
+            else:
+                b, l = (i - 1) // 3, (i - 1) % 3
+                if rest.startswith("op."):
+                    new = f"down_blocks.{b}.downsamplers.0.conv.{rest[3:]}"
+                elif sub == "0":
+                    new = resnet(f"down_blocks.{b}.resnets.{l}", rest)
+                else:
+                    new = f"down_blocks.{b}.attentions.{l}.{rest}"
+        elif p[0] == "middle_block":
+            sub, rest = p[1], ".".join(p[2:])
+            new = f"mid_block.attentions.0.{rest}" if sub == "1" else resnet(f"mid_block.resnets.{0 if sub == '0' else 1}", rest)
+        elif p[0] == "output_blocks":
+            i, sub, rest = int(p[1]), p[2], ".".join(p[3:])
+            b, l = i // 3, i % 3
+            if rest.startswith("conv."):  # the upsampler: entry 1 of a block without attention, entry 2 otherwise
+                new = f"up_blocks.{b}.upsamplers.0.{rest}"
+            elif sub == "0":
+                new = resnet(f"up_blocks.{b}.resnets.{l}", rest)
+            else:
+                new = f"up_blocks.{b}.attentions.{l}.{rest}"
+        else:
+            raise ValueError(f"unexpected UNet tensor {key!r}")
+        out[new] = t
+    return out
+
+
 def load_unet_state_dict(path: str, strict: bool = True) -> Dict[str, torch.Tensor]:
-    """The 686 tensors of an SD-1.x diffusers UNet, validated.  Original CompVis `.ckpt` files (keys starting with
-    `model.diffusion_model.`) use the LDM naming and are rejected with an explicit message - convert them with diffusers'
-    `convert_original_stable_diffusion_to_diffusers.py` first."""
-    f = find_unet_file(path)
+    """The 686 tensors of an SD-1.x UNet, validated: diffusers layout as is, original CompVis / LDM single-file
+    checkpoints (keys under `model.diffusion_model.`) through `ldm_to_diffusers_unet`."""
+    f = path if os.path.isfile(path) else find_unet_file(path)
     sd = read_state_dict(f)
-    if any(k.startswith("model.diffusion_model.") for k in sd):
-        raise NotImplementedError(f"{f}: original LDM checkpoint layout; a diffusers-format UNet state dict is required")
+    if any(k.startswith(_LDM_PREFIX) for k in sd):
+        sd = ldm_to_diffusers_unet(sd)
     missing, unexpected, bad = check_unet_state_dict(sd)
     if missing or bad or (strict and unexpected):
         def head(xs):

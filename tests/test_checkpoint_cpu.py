@@ -50,10 +50,62 @@ def test_validation_reports_missing_unexpected_and_misshaped_tensors(tmp_path):
     save_file(_tiny_sd(), f)
     with pytest.raises(ValueError, match=r"680 missing"):
         checkpoint.load_unet_state_dict(f)
-    save_file({"model.diffusion_model.input_blocks.0.0.weight": torch.zeros(1)}, f)
-    with pytest.raises(NotImplementedError, match="LDM"):
-        checkpoint.load_unet_state_dict(f)
 
 
 def test_text_components_are_optional(tmp_path):
     assert checkpoint.load_text_components(str(tmp_path)) == (None, None)
+
+
+def _to_ldm(name):
+    """diffusers -> original CompVis / LDM key (the inverse of checkpoint.ldm_to_diffusers_unet), SD-1.x layout."""
+    inv = {v: k for k, v in checkpoint._LDM_RESNET.items()}
+    p = name.split(".")
+
+    def res(prefix, rest):
+        head, _, tail = rest.partition(".")
+        return f"{prefix}.{inv[head]}.{tail}"
+
+    if p[0] == "time_embedding":
+        return f"time_embed.{0 if p[1] == 'linear_1' else 2}.{p[2]}"
+    if p[0] in ("conv_in", "conv_norm_out", "conv_out"):
+        return {"conv_in": "input_blocks.0.0", "conv_norm_out": "out.0", "conv_out": "out.2"}[p[0]] + "." + p[1]
+    if p[0] == "down_blocks":
+        b = int(p[1])
+        if p[2] == "resnets":
+            return res(f"input_blocks.{1 + 3 * b + int(p[3])}.0", ".".join(p[4:]))
+        if p[2] == "attentions":
+            return f"input_blocks.{1 + 3 * b + int(p[3])}.1." + ".".join(p[4:])
+        return f"input_blocks.{3 * (b + 1)}.0.op." + ".".join(p[5:])
+    if p[0] == "mid_block":
+        if p[1] == "attentions":
+            return "middle_block.1." + ".".join(p[3:])
+        return res(f"middle_block.{0 if p[2] == '0' else 2}", ".".join(p[3:]))
+    b = int(p[1])
+    if p[2] == "resnets":
+        return res(f"output_blocks.{3 * b + int(p[3])}.0", ".".join(p[4:]))
+    if p[2] == "attentions":
+        return f"output_blocks.{3 * b + int(p[3])}.1." + ".".join(p[4:])
+    return f"output_blocks.{3 * b + 2}.{1 if b == 0 else 2}." + ".".join(p[4:])
+
+
+def test_original_ldm_single_file_layout_is_converted(tmp_path):
+    """`model.diffusion_model.*` keys of a CompVis checkpoint map onto exactly the 686 diffusers names with the right shapes;
+    VAE / CLIP / other tensors of the single file are ignored.  Spot checks of well-known key pairs guard the inverse
+    mapping used to build the input."""
+    specs = arch.unet_param_specs()
+    assert _to_ldm("down_blocks.0.attentions.1.transformer_blocks.0.attn2.to_k.weight") == \
+        "input_blocks.2.1.transformer_blocks.0.attn2.to_k.weight"
+    assert _to_ldm("down_blocks.1.downsamplers.0.conv.weight") == "input_blocks.6.0.op.weight"
+    assert _to_ldm("up_blocks.0.upsamplers.0.conv.bias") == "output_blocks.2.1.conv.bias"
+    assert _to_ldm("up_blocks.2.upsamplers.0.conv.bias") == "output_blocks.8.2.conv.bias"
+    assert _to_ldm("up_blocks.3.resnets.2.conv_shortcut.weight") == "output_blocks.11.0.skip_connection.weight"
+    assert _to_ldm("mid_block.resnets.1.time_emb_proj.bias") == "middle_block.2.emb_layers.1.bias"
+    assert _to_ldm("time_embedding.linear_2.weight") == "time_embed.2.weight"
+    ldm = {"model.diffusion_model." + _to_ldm(k): torch.empty(shape, device="meta") for k, shape in specs}
+    assert len(ldm) == 686  # the inverse mapping is injective
+    ldm["first_stage_model.decoder.conv_in.weight"] = torch.empty((1,), device="meta")
+    ldm["cond_stage_model.transformer.text_model.embeddings.position_ids"] = torch.empty((1, 77), device="meta")
+    back = checkpoint.ldm_to_diffusers_unet(ldm)
+    assert checkpoint.check_unet_state_dict(back) == ([], [], [])
+    with pytest.raises(ValueError):
+        checkpoint.ldm_to_diffusers_unet({"model.diffusion_model.label_emb.0.0.weight": torch.empty((1,), device="meta")})
