@@ -29,6 +29,11 @@ typedef struct pnp_engine pnp_engine;
 /* ---- lifecycle ---------------------------------------------------------------------------------------------- */
 /* replaces StableDiffusionPipeline.from_pretrained(...).to(device) for the UNet part, models/p2p_editor.py:23-24 */
 int pnp_create(int device_ordinal, int max_batch, pnp_engine** out);
+/* a second handle on the same GPU that SHARES the parent's read-only parameter buffers and time-embedding table (1.72 GB)
+ * and owns only its activation arenas, CUDA graphs, controller state and stream: several images in flight per GPU
+ * without replicating the weights.  The parent must be finalized, must have seen pnp_set_timesteps, and must outlive
+ * the clone. */
+int pnp_clone(pnp_engine* parent, int max_batch, pnp_engine** out);
 void pnp_destroy(pnp_engine* h);
 const char* pnp_last_error(void);
 const char* pnp_version(void);
@@ -71,6 +76,12 @@ typedef struct pnp_attn_ctrl {
   float alphas[PNP_MAX_SLOTS][PNP_TOKENS];
   float equalizer[PNP_MAX_SLOTS][PNP_TOKENS];
   float cross_alpha[PNP_MAX_SLOTS][PNP_TOKENS];
+  /* AttentionReplace with unequal token spans (models/p2p/seq_aligner.py:152-185, applied by the einsum of
+   * attention_control.py:303-304): column w of the 77x77 mapper is `map_weight` on the map_count[w] consecutive source
+   * tokens starting at mapper[w], so P_src[:, mapper] above generalises to
+   *   map_weight[w] * sum_{k < map_count[w]} P_src[:, mapper[w] + k]          (identity: count 1, weight 1). */
+  int32_t map_count[PNP_MAX_SLOTS][PNP_TOKENS];
+  float map_weight[PNP_MAX_SLOTS][PNP_TOKENS];
   /* AttentionStore for LocalBlend: rows with store_slot[r] >= 0 accumulate their (post-injection) 16x16 cross maps of
    * the five layers down_cross[2:4] + up_cross[:3] into slot store_slot[r]. */
   int32_t store_slot[PNP_MAX_BATCH];
@@ -101,6 +112,9 @@ typedef struct pnp_step_args {
   const float* target_dev; /* offset mode: [target_rows,16384], or NULL */
   int32_t target_rows;
   float* loss_out_dev;     /* offset mode: [n,16384] */
+  float loss_scale;        /* offset mode: loss = (target - x_new) * loss_scale; 1 = DirectInversion.offset_calculate,
+                              `scale` of offset_calculate_not_full (inversion.py:478-492), 0 on the skipped steps of
+                              offset_calculate_skip_step (:501-519) */
   const float* noise_loss_dev; /* rectification: [n,16384], or NULL */
   uint32_t add_mask;       /* bit r: add noise_loss row r */
 } pnp_step_args;
@@ -111,12 +125,69 @@ int pnp_step_epilogue(pnp_engine* h, const pnp_step_args* a, void* stream);
  * entries of alpha_layers per prompt (<= 8 each). mask_out_dev: optional [2,4096] floats. */
 int pnp_local_blend(pnp_engine* h, float* x_dev, const int32_t* nwords2_host, const int32_t* words2x8_host,
                     const float* alpha2x8_host, float threshold, float* mask_out_dev, void* stream);
+/* the same for several (source, target) latent pairs of one batch in ONE launch, with the `substruct_words` branch
+ * (attention_control.py:116-118): mask = pooled-mask(words, th_pool) & ~unpooled-mask(sub_words, th_sub). */
+typedef struct pnp_blend_desc {
+  int32_t src_row, tgt_row;   /* latent rows of the pair inside x_dev */
+  int32_t src_slot, tgt_slot; /* store slots the two branches accumulated into (pnp_attn_ctrl.store_slot) */
+  int32_t nwords[2];          /* [source prompt, target prompt] */
+  int32_t words[2][8];
+  float alpha[2][8];
+  int32_t nsub[2];            /* substruct words (0 = none) */
+  int32_t sub_words[2][8];
+  float sub_alpha[2][8];
+  float th_pool, th_sub;      /* LocalBlend.th[0], th[1] */
+} pnp_blend_desc;
+#define PNP_MAX_BLEND 8
+int pnp_local_blend_batch(pnp_engine* h, float* x_dev, int n_rows, const pnp_blend_desc* descs_host, int n_desc,
+                          float* mask_out_dev /* optional [n_desc][2][4096] */, void* stream);
+
+/* ---- whole step loops behind the boundary (pnp_invert / pnp_offset / pnp_edit) ---------- */
+/* One call enqueues `n_steps` x { UNet forward ; fused step epilogue [; LocalBlend] } on the stream: no per-step host
+ * tensor op, no intermediate copy (the epilogue reads the UNet's output buffer in place).  Latent rows are
+ * PROMPT-MAJOR for L images with P prompts each: row = p * L + image; the UNet batch of the guided modes is
+ * [unconditional rows | conditional rows] like `torch.cat([latents] * 2)` (p2p_guidance_forward.py:108).
+ *   PNP_LOOP_INVERT  replaces DirectInversion.ddim_loop (models/p2p/inversion.py:308-319; with guidance != 0 the
+ *                    CFG variant ddim_with_guidance_scale_loop :349-363): step i runs the UNet at t_host[i] and the
+ *                    inverse step with coef_host[i]; traj_dev receives the n_steps+1 latents (x_stars).
+ *   PNP_LOOP_OFFSET  replaces DirectInversion.offset_calculate (:375-391): target of step i = traj_dev[n_steps-i-1]
+ *                    (row r uses image r % images), loss_dev[i] = (target - rec) * loss_scale_host[i], x = rec + loss.
+ *   PNP_LOOP_FORWARD replaces direct_inversion_p2p_guidance_forward (models/p2p/p2p_guidance_forward.py:135-173) and,
+ *                    with loss_dev == NULL, p2p_guidance_forward (:21-62): CFG + scheduler.step + rectification of the
+ *                    rows in add_mask with loss_dev[i], controller descriptor ctrl_host[i], LocalBlend after step i
+ *                    once i + 1 > blend_start. */
+#define PNP_LOOP_INVERT 0
+#define PNP_LOOP_OFFSET 1
+#define PNP_LOOP_FORWARD 2
+typedef struct pnp_loop_args {
+  int32_t mode, n_steps;
+  int32_t rows;                /* latent rows n (UNet batch n for INVERT without guidance, else 2n) */
+  int32_t images;              /* L */
+  const int32_t* t_host;       /* [n_steps] timestep of each step's UNet call */
+  const float* coef_host;      /* [n_steps][4]: sqrt_a_from, sqrt_1m_a_from, sqrt_a_to, sqrt_1m_a_to */
+  float guidance;
+  const float* ctx_dev;        /* [UNet batch,77,768] fp32 */
+  float* x_dev;                /* [rows,16384] start latents in, final latents out */
+  float* traj_dev;             /* INVERT: out [n_steps+1][rows][16384]; OFFSET: in [n_steps+1][images][16384] */
+  float* loss_dev;             /* OFFSET: out [n_steps][rows][16384]; FORWARD: in, or NULL (no rectification) */
+  const float* loss_scale_host;/* OFFSET: [n_steps], or NULL (= 1) */
+  uint32_t add_mask;           /* FORWARD: rows that receive loss_dev */
+  const pnp_attn_ctrl* ctrl_host; /* FORWARD: [n_steps] descriptors, or NULL */
+  const pnp_blend_desc* blend_host; /* FORWARD: [n_blend] or NULL */
+  int32_t n_blend, blend_start;
+} pnp_loop_args;
+int pnp_run_loop(pnp_engine* h, const pnp_loop_args* a, void* stream);
+
 /* replaces the EDICT mixing layers on the coupled latent pair, in place (models/edict/edict_functions.py:854-859 when
  * reverse != 0, :931-936 otherwise); x_dev, y_dev: [n_rows,16384] */
 int pnp_edict_mix(pnp_engine* h, float* x_dev, float* y_dev, int n_rows, float mix_weight, int reverse, void* stream);
 int pnp_store_reset(pnp_engine* h, void* stream);          /* AttentionStore.reset() */
 /* debug/inspection: copy the accumulated maps [5][2*PNP_MAX_SLOTS... see DESIGN.md] */
 int pnp_store_read(pnp_engine* h, float* out_dev, int64_t max_floats, void* stream);
+
+/* sizeof() of the boundary structs as this library was compiled (0 pnp_attn_ctrl, 1 pnp_step_args, 2 pnp_blend_desc,
+ * 3 pnp_loop_args): lets a binding verify its mirror of the layouts at load time. */
+int pnp_struct_size(int which);
 
 /* ---- instrumentation ----------------------------------------------------------------------------------------- */
 /* runs one UNet forward eagerly with a CUDA event pair around every op of the plan (on the engine's stream);

@@ -182,6 +182,55 @@ def gen_pipeline(n_steps: int):
     print("pipeline fixture written")
 
 
+def gen_pipeline_full(n_steps: int = 50):
+    """BASELINE config 2 at its true length: the reference's own DirectInversion.invert +
+    direct_inversion_p2p_guidance_forward (AttentionStore pass, then Refine+Reweight+LocalBlend) over `n_steps` DDIM
+    steps on the vendored fp64 UNet = 13 * n_steps sample-forwards (hours of CPU at 50).  Checkpoints after each phase
+    under gpurun_out/ (scratch) so a lost session does not lose the run; the committed fixture keeps every x_star, every
+    fifth noise_loss, and the two final latent pairs.  Also config 1: a 20-step ddim_loop of the same latent."""
+    ref = ref_shim.load_reference_p2p()
+    model = build_model()
+    prompts = list(synth.CAT_PROMPTS)
+    z0 = synth.synth_latent(0).double()
+    scratch = os.path.join(os.path.dirname(GOLD), "..", "gpurun_out")
+    os.makedirs(scratch, exist_ok=True)
+    t0 = time.time()
+    # config 1: 20-step inversion only (inversion.py:308-319 through invert's first half)
+    inv20 = ref.inversion.DirectInversion(model=model, num_ddim_steps=20)
+    model.scheduler.set_timesteps(20)
+    inv20.init_prompt(prompts)  # ddim_loop uses cond_embeddings[[0]] = the source prompt (inversion.py:309-311)
+    ref.attention_control.register_attention_control(model, None)
+    x20 = inv20.ddim_loop(z0)
+    np.savez_compressed(os.path.join(GOLD, "inversion_20steps.npz"), x_stars=torch.cat(x20).float().numpy())
+    print("config-1 20-step inversion done", time.time() - t0, flush=True)
+    inv = ref.inversion.DirectInversion(model=model, num_ddim_steps=n_steps)
+    model.scheduler.set_timesteps(n_steps)
+    _, _, x_stars, noise_loss = inv.invert(image_gt=z0, prompt=prompts, guidance_scale=7.5)
+    print("invert done", time.time() - t0, flush=True)
+    np.savez_compressed(os.path.join(scratch, f"pipeline_{n_steps}_partial_invert.npz"),
+                        x_stars=torch.cat(x_stars).numpy(), noise_loss=torch.stack(noise_loss).numpy())
+    x_t = x_stars[-1]
+    ctrl = ref.attention_control.AttentionStore()
+    recon, _ = ref.p2p_guidance_forward.direct_inversion_p2p_guidance_forward(
+        model=model, prompt=prompts, controller=ctrl, noise_loss_list=noise_loss, latent=x_t,
+        num_inference_steps=n_steps, guidance_scale=7.5, generator=None)
+    print("recon done", time.time() - t0, flush=True)
+    np.savez_compressed(os.path.join(scratch, f"pipeline_{n_steps}_partial_recon.npz"), recon=recon.numpy())
+    ctrl = make_controller_cpu(ref, model, prompts, n_steps, blend_word=(("cat",), ("cat",)),
+                               eq_params={"words": ("watercolor",), "values": (2,)})
+    edit, _ = ref.p2p_guidance_forward.direct_inversion_p2p_guidance_forward(
+        model=model, prompt=prompts, controller=ctrl, noise_loss_list=noise_loss, latent=x_t,
+        num_inference_steps=n_steps, guidance_scale=7.5, generator=None)
+    print("edit done", time.time() - t0, flush=True)
+    keep = sorted(set(list(range(0, n_steps, 5)) + [n_steps - 1]))
+    np.savez_compressed(
+        os.path.join(GOLD, f"pipeline_{n_steps}steps.npz"),
+        x_stars=torch.cat(x_stars).float().numpy(), noise_loss_idx=np.array(keep, np.int64),
+        noise_loss=torch.stack([noise_loss[i] for i in keep]).float().numpy(),
+        recon=recon.float().numpy(), edit=edit.float().numpy())
+    print("pipeline fixture written", flush=True)
+
+
 def gen_masactrl():
     """One B=4 UNet forward with the reference's own MutualSelfAttentionControl (models/masactrl/masactrl.py:14-72)
     registered through its own regiter_attention_editor_diffusers (masactrl_utils.py:79-144) on the vendored UNet.
@@ -316,6 +365,8 @@ if __name__ == "__main__":
         gen_unet()
     elif what == "pipeline":
         gen_pipeline(int(sys.argv[2]))
+    elif what == "pipeline_full":
+        gen_pipeline_full(int(sys.argv[2]) if len(sys.argv) > 2 else 50)
     elif what == "masactrl":
         gen_masactrl()
     elif what == "edict":

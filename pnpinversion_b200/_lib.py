@@ -37,6 +37,8 @@ class AttnCtrl(C.Structure):
         ("alphas", (C.c_float * PNP_TOKENS) * PNP_MAX_SLOTS),
         ("equalizer", (C.c_float * PNP_TOKENS) * PNP_MAX_SLOTS),
         ("cross_alpha", (C.c_float * PNP_TOKENS) * PNP_MAX_SLOTS),
+        ("map_count", (C.c_int32 * PNP_TOKENS) * PNP_MAX_SLOTS),
+        ("map_weight", (C.c_float * PNP_TOKENS) * PNP_MAX_SLOTS),
         ("store_slot", C.c_int32 * PNP_MAX_BATCH),
     ]
 
@@ -58,8 +60,52 @@ class StepArgs(C.Structure):
         ("target_dev", C.c_void_p),
         ("target_rows", C.c_int32),
         ("loss_out_dev", C.c_void_p),
+        ("loss_scale", C.c_float),
         ("noise_loss_dev", C.c_void_p),
         ("add_mask", C.c_uint32),
+    ]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        if "loss_scale" not in kw:
+            self.loss_scale = 1.0
+
+
+class BlendDesc(C.Structure):
+    """Mirror of `pnp_blend_desc`."""
+
+    _fields_ = [
+        ("src_row", C.c_int32), ("tgt_row", C.c_int32), ("src_slot", C.c_int32), ("tgt_slot", C.c_int32),
+        ("nwords", C.c_int32 * 2),
+        ("words", (C.c_int32 * 8) * 2),
+        ("alpha", (C.c_float * 8) * 2),
+        ("nsub", C.c_int32 * 2),
+        ("sub_words", (C.c_int32 * 8) * 2),
+        ("sub_alpha", (C.c_float * 8) * 2),
+        ("th_pool", C.c_float), ("th_sub", C.c_float),
+    ]
+
+
+PNP_LOOP_INVERT, PNP_LOOP_OFFSET, PNP_LOOP_FORWARD = 0, 1, 2
+
+
+class LoopArgs(C.Structure):
+    """Mirror of `pnp_loop_args`."""
+
+    _fields_ = [
+        ("mode", C.c_int32), ("n_steps", C.c_int32), ("rows", C.c_int32), ("images", C.c_int32),
+        ("t_host", C.POINTER(C.c_int32)),
+        ("coef_host", C.POINTER(C.c_float)),
+        ("guidance", C.c_float),
+        ("ctx_dev", C.c_void_p),
+        ("x_dev", C.c_void_p),
+        ("traj_dev", C.c_void_p),
+        ("loss_dev", C.c_void_p),
+        ("loss_scale_host", C.POINTER(C.c_float)),
+        ("add_mask", C.c_uint32),
+        ("ctrl_host", C.POINTER(AttnCtrl)),
+        ("blend_host", C.POINTER(BlendDesc)),
+        ("n_blend", C.c_int32), ("blend_start", C.c_int32),
     ]
 
 
@@ -69,6 +115,7 @@ _lib: Optional[C.CDLL] = None
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "pnp_create": (_i, [_i, _i, C.POINTER(_vp)]),
+    "pnp_clone": (_i, [_vp, _i, C.POINTER(_vp)]),
     "pnp_destroy": (None, [_vp]),
     "pnp_last_error": (C.c_char_p, []),
     "pnp_version": (C.c_char_p, []),
@@ -82,10 +129,13 @@ SIGNATURES = {
     "pnp_unet_forward": (_i, [_vp, _vp, _i, _i, C.POINTER(AttnCtrl), _vp, _vp]),
     "pnp_step_epilogue": (_i, [_vp, C.POINTER(StepArgs), _vp]),
     "pnp_local_blend": (_i, [_vp, _vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_f), _f, _vp, _vp]),
+    "pnp_local_blend_batch": (_i, [_vp, _vp, _i, C.POINTER(BlendDesc), _i, _vp, _vp]),
+    "pnp_run_loop": (_i, [_vp, C.POINTER(LoopArgs), _vp]),
     "pnp_edict_mix": (_i, [_vp, _vp, _vp, _i, _f, _i, _vp]),
     "pnp_store_reset": (_i, [_vp, _vp]),
     "pnp_store_read": (_i, [_vp, _vp, _i64, _vp]),
     "pnp_unet_profile": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(C.c_int32), C.POINTER(C.c_double), _i, C.POINTER(_i)]),
+    "pnp_struct_size": (_i, [_i]),
     "pnp_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
     "pnp_set_use_graph": (_i, [_vp, _i]),
     "pnp_test_gemm": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -119,6 +169,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    for which, cls in enumerate((AttnCtrl, StepArgs, BlendDesc, LoopArgs)):
+        if lib.pnp_struct_size(which) != C.sizeof(cls):
+            raise PnpError(f"ABI mismatch: {cls.__name__} is {C.sizeof(cls)} bytes here, "
+                           f"{lib.pnp_struct_size(which)} in {_LIB_PATH} (rebuild with `make`)")
     _lib = lib
     return lib
 

@@ -44,27 +44,57 @@ def get_equalizer(text, word_select, values, tokenizer=None):
     return equalizer
 
 
+def _words_of(alpha_row):
+    nz = torch.nonzero(alpha_row).flatten().tolist()
+    if len(nz) > 8:
+        raise NotImplementedError("at most 8 blend tokens per prompt")
+    return nz
+
+
 class LocalBlend:
-    """attention_control.py:95-147.  Works on the maps accumulated by the cross-attention kernel (store slots 0,1)."""
+    """attention_control.py:95-147.  Works on the maps accumulated by the cross-attention kernel (store slots of the
+    source / target row, 0 and 1 unless a batched loop places the pair elsewhere)."""
 
     def __init__(self, prompts, words, substruct_words=None, start_blend=0.2, th=(.3, .3), tokenizer=None, device="cuda",
                  num_ddim_steps=50):
         if len(prompts) != 2:
             raise NotImplementedError("LocalBlend is implemented for one (source, target) prompt pair")
-        if substruct_words is not None:
-            raise NotImplementedError("substruct_words is not used on the PnP-inversion path")
-        alpha_layers = torch.zeros(len(prompts), MAX_NUM_WORDS)
-        for i, (prompt, words_) in enumerate(zip(prompts, words)):
-            if isinstance(words_, str):
-                words_ = [words_]
-            for word in words_:
-                alpha_layers[i, get_word_inds(prompt, word, tokenizer)] = 1
-        self.alpha_layers = alpha_layers
+        self.alpha_layers = self._layers(prompts, words, tokenizer)
+        self.substruct_layers = None if substruct_words is None else self._layers(prompts, substruct_words, tokenizer)
         self.start_blend = int(start_blend * num_ddim_steps)
         self.counter = 0
         self.th = th
         self._engine = None
         self.last_mask = None
+
+    @staticmethod
+    def _layers(prompts, words, tokenizer):
+        layers = torch.zeros(len(prompts), MAX_NUM_WORDS)
+        for i, (prompt, words_) in enumerate(zip(prompts, words)):
+            if isinstance(words_, str):
+                words_ = [words_]
+            for word in words_:
+                layers[i, get_word_inds(prompt, word, tokenizer)] = 1
+        return layers
+
+    def blend_desc(self, src_row=0, tgt_row=1, src_slot=0, tgt_slot=1) -> "_lib.BlendDesc":
+        """The `pnp_blend_desc` of this pair (attention_control.py:97-121 incl. the substruct branch :116-118)."""
+        d = _lib.BlendDesc()
+        d.src_row, d.tgt_row, d.src_slot, d.tgt_slot = src_row, tgt_row, src_slot, tgt_slot
+        d.th_pool, d.th_sub = float(self.th[0]), float(self.th[1])
+        for p in range(2):
+            nz = _words_of(self.alpha_layers[p])
+            d.nwords[p] = len(nz)
+            for j, w in enumerate(nz):
+                d.words[p][j] = w
+                d.alpha[p][j] = float(self.alpha_layers[p, w])
+            if self.substruct_layers is not None:
+                nz = _words_of(self.substruct_layers[p])
+                d.nsub[p] = len(nz)
+                for j, w in enumerate(nz):
+                    d.sub_words[p][j] = w
+                    d.sub_alpha[p][j] = float(self.substruct_layers[p, w])
+        return d
 
     def __call__(self, x_t, attention_store=None):
         self.counter += 1
@@ -74,19 +104,9 @@ class LocalBlend:
             if not (x_t.is_cuda and x_t.dtype == torch.float32 and x_t.shape[0] == 2):
                 raise _lib.PnpError("LocalBlend expects CUDA float32 latents of shape (2,4,64,64)")
             x_t = x_t.contiguous()
-            nwords = (C.c_int32 * 2)()
-            words = (C.c_int32 * 16)()
-            alpha = (C.c_float * 16)()
-            for p in range(2):
-                nz = torch.nonzero(self.alpha_layers[p]).flatten().tolist()
-                if len(nz) > 8:
-                    raise NotImplementedError("at most 8 blend tokens per prompt")
-                nwords[p] = len(nz)
-                for j, w in enumerate(nz):
-                    words[p * 8 + j] = w
-                    alpha[p * 8 + j] = float(self.alpha_layers[p, w])
-            _lib.check(_lib.load().pnp_local_blend(self._engine, C.c_void_p(x_t.data_ptr()), nwords, words, alpha,
-                                                   float(self.th[0]), None, _lib.current_stream_ptr()))
+            d = self.blend_desc()
+            _lib.check(_lib.load().pnp_local_blend_batch(self._engine, C.c_void_p(x_t.data_ptr()), 2, C.byref(d), 1, None,
+                                                         _lib.current_stream_ptr()))
         return x_t
 
 
@@ -228,22 +248,37 @@ def _set_row(arr, values):
 
 
 class AttentionReplace(AttentionControlEdit):
-    """attention_control.py:301-314: P_src @ mapper.  Lowered to a gather when every target token takes its
-    probability from exactly one source token (the word-swap case); fractional splits are not implemented."""
+    """attention_control.py:301-314: `einsum('hpw,bwn->bhpn', attn_base, mapper)`.  Every column of the replacement
+    mapper (seq_aligner.py:152-185) is zero, a single 1 (token kept or swapped for a word of equal token count), or the
+    uniform weight 1/len(target span) on the CONSECUTIVE tokens of the replaced source word (unequal token counts), so the
+    einsum is lowered to `weight * sum of count consecutive source probabilities` per target token."""
 
     def __init__(self, prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend=None, tokenizer=None,
                  device="cuda"):
         super().__init__(prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend, tokenizer, device)
         self.mapper = seq_aligner.get_replacement_mapper(prompts, tokenizer)  # (n-1,77,77)
-        self._gather = []
-        for m in self.mapper:
-            cols_ok = ((m == 0) | (m == 1)).all() and (m.sum(0) == 1).all()
-            if not bool(cols_ok):
-                raise NotImplementedError("AttentionReplace with fractional token splits is not implemented")
-            self._gather.append(m.argmax(0).tolist())
+        self._spans = [self._columns(m) for m in self.mapper]
+
+    @staticmethod
+    def _columns(m):
+        """(start, count, weight) per target token; raises if a column is not a uniform consecutive run."""
+        start, count, weight = [], [], []
+        for n in range(m.shape[1]):
+            rows = torch.nonzero(m[:, n]).flatten().tolist()
+            if not rows:
+                start.append(0), count.append(1), weight.append(0.0)
+                continue
+            vals = m[rows, n]
+            if rows != list(range(rows[0], rows[0] + len(rows))) or not bool((vals == vals[0]).all()):
+                raise NotImplementedError("replacement mapper column is not a uniform run of consecutive source tokens")
+            start.append(rows[0]), count.append(len(rows)), weight.append(float(vals[0]))
+        return start, count, weight
 
     def _fill_tables(self, c, slot):
-        _set_row(c.mapper[slot], self._gather[slot])
+        start, count, weight = self._spans[slot]
+        _set_row(c.mapper[slot], start)
+        _set_row(c.map_count[slot], count)
+        _set_row(c.map_weight[slot], weight)
         _set_row(c.alphas[slot], [1.0] * MAX_NUM_WORDS)
         _set_row(c.equalizer[slot], [1.0] * MAX_NUM_WORDS)
 

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnParams p
   uint8_t* sQs = sV + KT;   // source-row Q (edited rows only)
   uint8_t* sKs = sQs + QT;  // source-row K
   float* sP = reinterpret_cast<float*>(sKs + KT);  // [4 warps][16][XK]
-  float* sTab = sP + 4 * 16 * XK;                  // alphas[80], eq[80], ca[80], then int mapper[80]
+  float* sTab = sP + 4 * 16 * XK;                  // alphas[80], eq[80], ca[80], int mapper[80], int count[80], weight[80]
   pdl_sync();
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -366,6 +366,8 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnParams p
       sTab[XK + i] = ok ? p.equalizer[slot * 77 + i] : 0.f;
       sTab[2 * XK + i] = ok ? p.cross_alpha[slot * 77 + i] : 0.f;
       reinterpret_cast<int*>(sTab + 3 * XK)[i] = ok ? p.mapper[slot * 77 + i] : 0;
+      reinterpret_cast<int*>(sTab + 4 * XK)[i] = (ok && p.map_count != nullptr) ? p.map_count[slot * 77 + i] : 1;
+      sTab[5 * XK + i] = (ok && p.map_weight != nullptr) ? p.map_weight[slot * 77 + i] : 1.f;
     }
   }
   cp_async_commit();
@@ -401,6 +403,8 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnParams p
     const float* eq = sTab + XK;
     const float* ca = sTab + 2 * XK;
     const int* mp = reinterpret_cast<const int*>(sTab + 3 * XK);
+    const int* mcnt = reinterpret_cast<const int*>(sTab + 4 * XK);
+    const float* mw = sTab + 5 * XK;
 #pragma unroll
     for (int nt = 0; nt < XNT; ++nt) {
 #pragma unroll
@@ -411,7 +415,12 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnParams p
           const float pt = s[nt][e];
           int mc = mp[c];
           if (mc < 0) mc += p.nk;  // torch negative index: -1 -> last column (seq_aligner.py:96,116)
-          const float ps = myP[r * XK + mc];
+          // AttentionReplace with unequal spans: weight * sum of `count` consecutive source tokens
+          // (seq_aligner.py:168-174); count 1 / weight 1 is the plain gather of Refine and of equal-length Replace
+          float ps = myP[r * XK + mc];
+          const int cnt = mcnt[c];
+          for (int k2 = 1; k2 < cnt; ++k2) ps += myP[r * XK + min(mc + k2, XK - 1)];
+          ps *= mw[c];
           float nw = ps * al[c] + pt * (1.f - al[c]);
           nw = nw * eq[c];
           s[nt][e] = nw * ca[c] + (1.f - ca[c]) * pt;
@@ -459,7 +468,7 @@ template <int D>
 size_t self_smem() { return 5 * 64 * Geo<D>::PITCH; }
 template <int D>
 size_t cross_smem() {
-  return 2 * 64 * Geo<D>::PITCH + 3 * XK * Geo<D>::PITCH + 4 * 16 * XK * sizeof(float) + 4 * XK * sizeof(float);
+  return 2 * 64 * Geo<D>::PITCH + 3 * XK * Geo<D>::PITCH + 4 * 16 * XK * sizeof(float) + 6 * XK * sizeof(float);
 }
 
 template <int D>

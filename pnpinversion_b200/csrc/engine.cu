@@ -255,6 +255,8 @@ struct DevCtrl {  // device-resident controller state for one forward
   float alphas[PNP_MAX_SLOTS][PNP_TOKENS];
   float equalizer[PNP_MAX_SLOTS][PNP_TOKENS];
   float cross_alpha[PNP_MAX_SLOTS][PNP_TOKENS];
+  int map_count[PNP_MAX_SLOTS][PNP_TOKENS];
+  float map_weight[PNP_MAX_SLOTS][PNP_TOKENS];
   int t_index;
 };
 
@@ -297,6 +299,7 @@ static std::mutex g_gemm_tuned_mu;
 
 struct pnp_engine {
   int device = 0, num_sms = 148, max_batch = 4;
+  pnp_engine* parent = nullptr;  // pnp_clone: parameter buffers and the time-embedding table belong to the parent
   bool finalized = false;
   bool use_graph = true;
   int64_t launches = 0;
@@ -380,6 +383,19 @@ static std::vector<__half> pack_conv3(const std::vector<__half>& w, int cout, in
     if (sc) memcpy(row + static_cast<size_t>(9) * cin, sc->data() + static_cast<size_t>(co) * sc_cin, sc_cin * sizeof(__half));
   }
   return p;
+}
+
+// per-handle mutable state (a clone has its own): controller tables, AttentionStore maps, GroupNorm workspace
+static int alloc_state(pnp_engine* e) {
+  e->d_ctrl = e->dalloc<DevCtrl>(1);
+  PNP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ctrl_ring), sizeof(DevCtrl) * kRing, cudaHostAllocDefault));
+  e->store = e->dalloc<float>(kStoreFloats);
+  PNP_CHECK(e->d_ctrl && e->store, "alloc failed");
+  PNP_CUDA(cudaMemset(e->store, 0, kStoreFloats * sizeof(float)));
+  e->gn_partials = e->dalloc<float>(groupnorm_workspace_floats(PNP_MAX_BATCH, 4096) + 4096);
+  PNP_CHECK(e->gn_partials != nullptr, "alloc failed");
+  PNP_CUDA(cudaMemset(e->gn_partials, 0, (groupnorm_workspace_floats(PNP_MAX_BATCH, 4096) + 4096) * sizeof(float)));
+  return 0;
 }
 
 static int finalize(pnp_engine* e) {
@@ -553,14 +569,8 @@ static int finalize(pnp_engine* e) {
   e->norm_out_b = up_vec(e, "conv_norm_out.bias");
   PNP_CHECK(e->norm_out_b != nullptr, "upload failed");
   e->host.clear();
-  e->d_ctrl = e->dalloc<DevCtrl>(1);
-  PNP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ctrl_ring), sizeof(DevCtrl) * kRing, cudaHostAllocDefault));
-  e->store = e->dalloc<float>(kStoreFloats);
-  PNP_CHECK(e->d_ctrl && e->store, "alloc failed");
-  PNP_CUDA(cudaMemset(e->store, 0, kStoreFloats * sizeof(float)));
-  e->gn_partials = e->dalloc<float>(groupnorm_workspace_floats(PNP_MAX_BATCH, 4096) + 4096);
-  PNP_CHECK(e->gn_partials != nullptr, "alloc failed");
-  PNP_CUDA(cudaMemset(e->gn_partials, 0, (groupnorm_workspace_floats(PNP_MAX_BATCH, 4096) + 4096) * sizeof(float)));
+  int rc = alloc_state(e);
+  if (rc) return rc;
   e->temb_table = e->dalloc<float>(static_cast<size_t>(kMaxTimesteps) * e->temb_total);
   PNP_CHECK(e->temb_table != nullptr, "alloc failed");
   e->finalized = true;
@@ -833,6 +843,7 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
       cp.base_row = e->d_ctrl->cross_base; cp.edit_slot = e->d_ctrl->cross_slot;
       cp.mapper = &e->d_ctrl->mapper[0][0]; cp.alphas = &e->d_ctrl->alphas[0][0];
       cp.equalizer = &e->d_ctrl->equalizer[0][0]; cp.cross_alpha = &e->d_ctrl->cross_alpha[0][0];
+      cp.map_count = &e->d_ctrl->map_count[0][0]; cp.map_weight = &e->d_ctrl->map_weight[0][0];
       // the five 16x16 cross layers LocalBlend reads: down_cross[2:4] + up_cross[:3] = transformer blocks 4,5,7,8,9
       int store_layer = -1;
       if (layer == 4) store_layer = 0; else if (layer == 5) store_layer = 1;
@@ -992,6 +1003,24 @@ static int leave(pnp_engine* h, cudaStream_t caller) {
   return 0;
 }
 
+// every exit path after enter() re-joins the caller's stream with the engine stream (also the error paths)
+struct StreamScope {
+  pnp_engine* h;
+  cudaStream_t caller;
+  ~StreamScope() { leave(h, caller); }
+};
+
+static int init_handle_common(pnp_engine* e) {
+  debug_words_device();
+  if (const char* ev = getenv("PNP_PDL")) set_pdl_enabled(atoi(ev) != 0);
+  if (const char* ev = getenv("PNP_TC_ATTN")) g_tc_attn = atoi(ev) != 0;
+  if (const char* ev = getenv("PNP_GEMM_CLUSTER")) set_cluster_allowed(atoi(ev) != 0);
+  PNP_CUDA(cudaStreamCreateWithFlags(&e->es, cudaStreamNonBlocking));
+  PNP_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+  PNP_CUDA(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+  return 0;
+}
+
 extern "C" {
 
 const char* pnp_last_error(void) { return get_last_error(); }
@@ -1021,13 +1050,41 @@ int pnp_create(int device_ordinal, int max_batch, pnp_engine** out) {
   e->device = device_ordinal;
   e->num_sms = prop.multiProcessorCount;
   e->max_batch = max_batch;
-  debug_words_device();
-  if (const char* ev = getenv("PNP_PDL")) set_pdl_enabled(atoi(ev) != 0);
-  if (const char* ev = getenv("PNP_TC_ATTN")) g_tc_attn = atoi(ev) != 0;
-  if (const char* ev = getenv("PNP_GEMM_CLUSTER")) set_cluster_allowed(atoi(ev) != 0);
-  PNP_CUDA(cudaStreamCreateWithFlags(&e->es, cudaStreamNonBlocking));
-  PNP_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
-  PNP_CUDA(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+  int rc = init_handle_common(e);
+  if (rc) { delete e; return rc; }
+  *out = e;
+  return 0;
+}
+
+int pnp_clone(pnp_engine* parent, int max_batch, pnp_engine** out) {
+  PNP_CHECK(out != nullptr, "pnp_clone: out is null");
+  *out = nullptr;
+  PNP_CHECK(parent != nullptr && parent->finalized && parent->parent == nullptr,
+            "pnp_clone: the parent must be a finalized, non-cloned handle");
+  PNP_CHECK(parent->n_t > 0, "pnp_clone: call pnp_set_timesteps on the parent first (the table is shared)");
+  PNP_CHECK(max_batch >= 1 && max_batch <= PNP_MAX_BATCH, "pnp_clone: max_batch out of range");
+  PNP_CUDA(cudaSetDevice(parent->device));
+  auto* e = new pnp_engine();
+  e->device = parent->device;
+  e->num_sms = parent->num_sms;
+  e->max_batch = max_batch;
+  e->parent = parent;
+  // read-only parameter tables: the structs hold device pointers owned by the parent
+  e->resnets = parent->resnets;
+  e->xf = parent->xf;
+  for (int i = 0; i < 3; ++i) { e->down[i] = parent->down[i]; e->up[i] = parent->up[i]; }
+  e->conv_in_w = parent->conv_in_w; e->conv_in_b = parent->conv_in_b;
+  e->conv_out_w = parent->conv_out_w; e->conv_out_b = parent->conv_out_b;
+  e->norm_out_g = parent->norm_out_g; e->norm_out_b = parent->norm_out_b;
+  e->te1 = parent->te1; e->te2 = parent->te2; e->temb_proj = parent->temb_proj;
+  e->te1_b = parent->te1_b; e->te2_b = parent->te2_b; e->temb_proj_b = parent->temb_proj_b;
+  e->temb_total = parent->temb_total;
+  e->temb_table = parent->temb_table;
+  e->n_t = parent->n_t;
+  int rc = init_handle_common(e);
+  if (!rc) rc = alloc_state(e);
+  if (rc) { pnp_destroy(e); return rc; }
+  e->finalized = true;
   *out = e;
   return 0;
 }
@@ -1084,6 +1141,7 @@ int pnp_finalize_params(pnp_engine* h) {
 int pnp_set_timesteps(pnp_engine* h, const int64_t* ts, int n, void* stream) {
   PNP_CHECK(h && h->finalized, "pnp_set_timesteps: engine not ready");
   PNP_CHECK(ts != nullptr && n >= 1 && n <= kMaxTimesteps, "pnp_set_timesteps: 1..1000 timesteps");
+  PNP_CHECK(h->parent == nullptr, "pnp_set_timesteps: a clone shares its parent's table; set it on the parent");
   cudaStream_t s = as_stream(stream);
   // sinusoidal embedding on the host in double, [cos | sin] order (flip_sin_to_cos=True, freq_shift=0):
   // my_diffusers/models/embeddings.py:40-55
@@ -1118,6 +1176,20 @@ int pnp_set_timesteps(pnp_engine* h, const int64_t* ts, int n, void* stream) {
   return 0;
 }
 
+// context K/V of the 16 cross-attention layers for one batch, on the engine stream
+static int set_context_on(pnp_engine* h, Plan* pl, const float* ctx_dev, int batch, cudaStream_t s) {
+  const size_t n = static_cast<size_t>(batch) * 77 * kCrossDim;
+  f32_to_f16_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 2048)), 256, 0, s>>>(ctx_dev, pl->ctx16, n);
+  PNP_CUDA(cudaGetLastError());
+  for (auto& f : pl->ctx_ops) {
+    int rc = f(s);
+    if (rc) return rc;
+  }
+  h->launches += 1 + static_cast<int64_t>(pl->ctx_ops.size());
+  h->ctx_batch = batch;
+  return 0;
+}
+
 int pnp_set_context(pnp_engine* h, const float* ctx_dev, int batch, void* stream) {
   PNP_CHECK(h && h->finalized, "pnp_set_context: engine not ready");
   PNP_CHECK(ctx_dev != nullptr, "pnp_set_context: null context");
@@ -1127,19 +1199,8 @@ int pnp_set_context(pnp_engine* h, const float* ctx_dev, int batch, void* stream
   cudaStream_t caller = as_stream(stream);
   rc = enter(h, caller);
   if (rc) return rc;
-  cudaStream_t s = h->es;
-  const size_t n = static_cast<size_t>(batch) * 77 * kCrossDim;
-  f32_to_f16_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 2048)), 256, 0, s>>>(ctx_dev, pl->ctx16, n);
-  PNP_CUDA(cudaGetLastError());
-  for (auto& f : pl->ctx_ops) {
-    rc = f(s);
-    if (rc) return rc;
-  }
-  rc = leave(h, caller);
-  if (rc) return rc;
-  h->launches += 1 + static_cast<int64_t>(pl->ctx_ops.size());
-  h->ctx_batch = batch;
-  return 0;
+  StreamScope scope{h, caller};
+  return set_context_on(h, pl, ctx_dev, batch, h->es);
 }
 
 void pnp_attn_ctrl_init(pnp_attn_ctrl* c) {
@@ -1160,6 +1221,8 @@ void pnp_attn_ctrl_init(pnp_attn_ctrl* c) {
       c->alphas[s][i] = 1.f;
       c->equalizer[s][i] = 1.f;
       c->cross_alpha[s][i] = 0.f;
+      c->map_count[s][i] = 1;
+      c->map_weight[s][i] = 1.f;
     }
 }
 
@@ -1196,28 +1259,19 @@ static int push_ctrl(pnp_engine* h, int batch, int t_index, const pnp_attn_ctrl*
   memcpy(hc->alphas, c->alphas, sizeof hc->alphas);
   memcpy(hc->equalizer, c->equalizer, sizeof hc->equalizer);
   memcpy(hc->cross_alpha, c->cross_alpha, sizeof hc->cross_alpha);
+  memcpy(hc->map_count, c->map_count, sizeof hc->map_count);
+  memcpy(hc->map_weight, c->map_weight, sizeof hc->map_weight);
+  for (int sl = 0; sl < PNP_MAX_SLOTS; ++sl)
+    for (int w = 0; w < PNP_TOKENS; ++w)
+      PNP_CHECK(c->map_count[sl][w] >= 0 && c->map_count[sl][w] <= PNP_TOKENS, "controller: map_count out of range");
   hc->t_index = t_index;
   PNP_CUDA(cudaMemcpyAsync(h->d_ctrl, hc, sizeof(DevCtrl), cudaMemcpyHostToDevice, s));
   return 0;
 }
 
-int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, const pnp_attn_ctrl* ctrl_host,
-                     float* eps_out_dev, void* stream) {
-  PNP_CHECK(h && h->finalized, "pnp_unet_forward: engine not ready");
-  PNP_CHECK(x_dev && eps_out_dev, "pnp_unet_forward: null tensor");
-  PNP_CHECK(t_index >= 0 && t_index < h->n_t, "pnp_unet_forward: t_index outside the list given to pnp_set_timesteps");
-  PNP_CHECK(h->ctx_batch == batch, "pnp_unet_forward: pnp_set_context was not called for this batch size");
-  Plan* pl = nullptr;
-  int rc = get_plan(h, batch, &pl);
-  if (rc) return rc;
-  cudaStream_t caller = as_stream(stream);
-  rc = enter(h, caller);
-  if (rc) return rc;
-  cudaStream_t s = h->es;
-  rc = push_ctrl(h, batch, t_index, ctrl_host, s);
-  if (rc) return rc;
-  const size_t bytes = static_cast<size_t>(batch) * PNP_LATENT_ELEMS * sizeof(float);
-  PNP_CUDA(cudaMemcpyAsync(pl->x_in, x_dev, bytes, cudaMemcpyDeviceToDevice, s));
+// runs the plan on stream s: pl->x_in holds the input, pl->eps_out receives the prediction
+static int run_plan(pnp_engine* h, Plan* pl, cudaStream_t s) {
+  int rc = 0;
   if (h->use_graph && pl->graph != nullptr) {
     PNP_CUDA(cudaGraphLaunch(pl->graph, s));
   } else {
@@ -1240,14 +1294,166 @@ int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, 
         }
       }
       PNP_CUDA(cudaStreamEndCapture(s, &g));
-      PNP_CUDA(cudaGraphInstantiate(&pl->graph, g, 0));
+      cudaError_t ie = cudaGraphInstantiate(&pl->graph, g, 0);
       cudaGraphDestroy(g);
+      if (ie != cudaSuccess) {
+        pl->graph = nullptr;
+        set_last_error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ie));
+        return -1;
+      }
     }
   }
   // every op contributes the kernels it really launches (GroupNorm: 1 or 2, self-attention with its V transpose: 2, ...)
   h->launches += pl->kernels_per_forward;
+  return 0;
+}
+
+int pnp_unet_forward(pnp_engine* h, const float* x_dev, int batch, int t_index, const pnp_attn_ctrl* ctrl_host,
+                     float* eps_out_dev, void* stream) {
+  PNP_CHECK(h && h->finalized, "pnp_unet_forward: engine not ready");
+  PNP_CHECK(x_dev && eps_out_dev, "pnp_unet_forward: null tensor");
+  PNP_CHECK(t_index >= 0 && t_index < h->n_t, "pnp_unet_forward: t_index outside the list given to pnp_set_timesteps");
+  PNP_CHECK(h->ctx_batch == batch, "pnp_unet_forward: pnp_set_context was not called for this batch size");
+  Plan* pl = nullptr;
+  int rc = get_plan(h, batch, &pl);
+  if (rc) return rc;
+  cudaStream_t caller = as_stream(stream);
+  rc = enter(h, caller);
+  if (rc) return rc;
+  StreamScope scope{h, caller};
+  cudaStream_t s = h->es;
+  rc = push_ctrl(h, batch, t_index, ctrl_host, s);
+  if (rc) return rc;
+  const size_t bytes = static_cast<size_t>(batch) * PNP_LATENT_ELEMS * sizeof(float);
+  PNP_CUDA(cudaMemcpyAsync(pl->x_in, x_dev, bytes, cudaMemcpyDeviceToDevice, s));
+  rc = run_plan(h, pl, s);
+  if (rc) return rc;
   PNP_CUDA(cudaMemcpyAsync(eps_out_dev, pl->eps_out, bytes, cudaMemcpyDeviceToDevice, s));
-  return leave(h, caller);
+  return 0;
+}
+
+static void fill_blend_item(LocalBlendItem* it, const pnp_blend_desc* d) {
+  it->src_row = d->src_row; it->tgt_row = d->tgt_row; it->src_slot = d->src_slot; it->tgt_slot = d->tgt_slot;
+  for (int i = 0; i < 2; ++i) {
+    it->nwords[i] = d->nwords[i];
+    it->nsub[i] = d->nsub[i];
+    for (int j = 0; j < 8; ++j) {
+      it->words[i][j] = d->words[i][j]; it->alpha[i][j] = d->alpha[i][j];
+      it->sub_words[i][j] = d->sub_words[i][j]; it->sub_alpha[i][j] = d->sub_alpha[i][j];
+    }
+  }
+  it->th_pool = d->th_pool; it->th_sub = d->th_sub;
+}
+
+static int blend_params(pnp_engine* h, LocalBlendParams* p, float* x_dev, int n_rows, const pnp_blend_desc* descs, int n_desc,
+                        float* mask_out_dev) {
+  PNP_CHECK(descs != nullptr && n_desc >= 1 && n_desc <= PNP_MAX_BLEND, "local blend: 1..8 latent pairs");
+  p->store = h->store;
+  p->layer_stride = static_cast<long long>(2) * PNP_MAX_SLOTS * 8 * 256 * 77;
+  p->slot_stride = 8LL * 256 * 77;
+  p->x = x_dev;
+  p->mask_out = mask_out_dev;
+  p->n_items = n_desc;
+  for (int i = 0; i < n_desc; ++i) {
+    const pnp_blend_desc* d = &descs[i];
+    PNP_CHECK(d->src_row >= 0 && d->src_row < n_rows && d->tgt_row >= 0 && d->tgt_row < n_rows, "local blend: latent row");
+    PNP_CHECK(d->src_slot >= 0 && d->src_slot < 2 * PNP_MAX_SLOTS && d->tgt_slot >= 0 && d->tgt_slot < 2 * PNP_MAX_SLOTS,
+              "local blend: store slot");
+    for (int pr = 0; pr < 2; ++pr) {
+      PNP_CHECK(d->nwords[pr] >= 0 && d->nwords[pr] <= 8 && d->nsub[pr] >= 0 && d->nsub[pr] <= 8,
+                "local blend: at most 8 (substruct) words per prompt");
+      for (int j = 0; j < 8; ++j) {
+        PNP_CHECK(j >= d->nwords[pr] || (d->words[pr][j] >= 0 && d->words[pr][j] < PNP_TOKENS), "local blend: word index");
+        PNP_CHECK(j >= d->nsub[pr] || (d->sub_words[pr][j] >= 0 && d->sub_words[pr][j] < PNP_TOKENS),
+                  "local blend: substruct word index");
+      }
+    }
+    fill_blend_item(&p->items[i], d);
+  }
+  return 0;
+}
+
+int pnp_run_loop(pnp_engine* h, const pnp_loop_args* a, void* stream) {
+  PNP_CHECK(h && h->finalized && a, "pnp_run_loop: engine not ready");
+  PNP_CHECK(a->mode == PNP_LOOP_INVERT || a->mode == PNP_LOOP_OFFSET || a->mode == PNP_LOOP_FORWARD, "pnp_run_loop: mode");
+  PNP_CHECK(a->n_steps >= 1 && a->n_steps <= kMaxTimesteps && a->t_host && a->coef_host, "pnp_run_loop: schedule");
+  PNP_CHECK(a->rows >= 1 && a->x_dev != nullptr && a->ctx_dev != nullptr, "pnp_run_loop: latents / context");
+  const int n = a->rows;
+  const bool cfg = a->mode != PNP_LOOP_INVERT || a->guidance != 0.f;
+  const int B = cfg ? 2 * n : n;
+  PNP_CHECK(B <= h->max_batch && B <= PNP_MAX_BATCH, "pnp_run_loop: UNet batch exceeds max_batch of this handle");
+  if (a->mode == PNP_LOOP_INVERT) PNP_CHECK(a->traj_dev != nullptr, "pnp_run_loop: INVERT needs traj_dev");
+  if (a->mode == PNP_LOOP_OFFSET)
+    PNP_CHECK(a->traj_dev != nullptr && a->loss_dev != nullptr && a->images >= 1 && n % a->images == 0,
+              "pnp_run_loop: OFFSET needs traj_dev, loss_dev and rows % images == 0");
+  for (int i = 0; i < a->n_steps; ++i)
+    PNP_CHECK(a->t_host[i] >= 0 && a->t_host[i] < h->n_t, "pnp_run_loop: timestep outside the pnp_set_timesteps table");
+  LocalBlendParams lb;
+  const bool blend = a->mode == PNP_LOOP_FORWARD && a->blend_host != nullptr && a->n_blend > 0;
+  if (blend) {
+    int rc = blend_params(h, &lb, a->x_dev, n, a->blend_host, a->n_blend, nullptr);
+    if (rc) return rc;
+  }
+  Plan* pl = nullptr;
+  int rc = get_plan(h, B, &pl);
+  if (rc) return rc;
+  cudaStream_t caller = as_stream(stream);
+  rc = enter(h, caller);
+  if (rc) return rc;
+  StreamScope scope{h, caller};
+  cudaStream_t s = h->es;
+  rc = set_context_on(h, pl, a->ctx_dev, B, s);
+  if (rc) return rc;
+  const size_t lat_rows = static_cast<size_t>(n) * PNP_LATENT_ELEMS;
+  const size_t row_bytes = lat_rows * sizeof(float);
+  if (a->mode == PNP_LOOP_INVERT) PNP_CUDA(cudaMemcpyAsync(a->traj_dev, a->x_dev, row_bytes, cudaMemcpyDeviceToDevice, s));
+  for (int i = 0; i < a->n_steps; ++i) {
+    const pnp_attn_ctrl* ctrl = (a->mode == PNP_LOOP_FORWARD && a->ctrl_host != nullptr) ? &a->ctrl_host[i] : nullptr;
+    rc = push_ctrl(h, B, a->t_host[i], ctrl, s);
+    if (rc) return rc;
+    const float* x_cur = a->mode == PNP_LOOP_INVERT ? a->traj_dev + static_cast<size_t>(i) * lat_rows : a->x_dev;
+    PNP_CUDA(cudaMemcpyAsync(pl->x_in, x_cur, row_bytes, cudaMemcpyDeviceToDevice, s));
+    if (cfg) PNP_CUDA(cudaMemcpyAsync(pl->x_in + lat_rows, x_cur, row_bytes, cudaMemcpyDeviceToDevice, s));
+    rc = run_plan(h, pl, s);
+    if (rc) return rc;
+    StepParams p;
+    memset(&p, 0, sizeof p);
+    p.x = x_cur;
+    p.eps_u = cfg ? pl->eps_out : nullptr;
+    p.eps_c = cfg ? pl->eps_out + lat_rows : pl->eps_out;
+    p.n = n;
+    p.guidance = a->guidance;
+    p.sqrt_a_from = a->coef_host[4 * i + 0]; p.sqrt_1m_a_from = a->coef_host[4 * i + 1];
+    p.sqrt_a_to = a->coef_host[4 * i + 2]; p.sqrt_1m_a_to = a->coef_host[4 * i + 3];
+    p.loss_scale = 1.0f;
+    if (a->mode == PNP_LOOP_INVERT) {
+      p.x_out = a->traj_dev + static_cast<size_t>(i + 1) * lat_rows;
+    } else if (a->mode == PNP_LOOP_OFFSET) {
+      p.x_out = a->x_dev;
+      p.target = a->traj_dev + static_cast<size_t>(a->n_steps - i - 1) * a->images * PNP_LATENT_ELEMS;
+      p.target_rows = a->images;
+      p.loss_out = a->loss_dev + static_cast<size_t>(i) * lat_rows;
+      if (a->loss_scale_host != nullptr) p.loss_scale = a->loss_scale_host[i];
+    } else {
+      p.x_out = a->x_dev;
+      if (a->loss_dev != nullptr) {
+        p.noise_loss = a->loss_dev + static_cast<size_t>(i) * lat_rows;
+        p.add_mask = a->add_mask;
+      }
+    }
+    rc = step_epilogue_launch(p, s);
+    if (rc) return rc;
+    h->launches += 1;
+    if (blend && i + 1 > a->blend_start) {
+      rc = local_blend_launch(lb, s);
+      if (rc) return rc;
+      h->launches += 1;
+    }
+  }
+  if (a->mode == PNP_LOOP_INVERT)
+    PNP_CUDA(cudaMemcpyAsync(a->x_dev, a->traj_dev + static_cast<size_t>(a->n_steps) * lat_rows, row_bytes,
+                             cudaMemcpyDeviceToDevice, s));
+  return 0;
 }
 
 int pnp_unet_profile(pnp_engine* h, int batch, int t_index, int reps, float* ms_out, int32_t* kind_out,
@@ -1300,6 +1506,7 @@ int pnp_step_epilogue(pnp_engine* h, const pnp_step_args* a, void* stream) {
   p.sqrt_a_from = a->sqrt_a_from; p.sqrt_1m_a_from = a->sqrt_1m_a_from;
   p.sqrt_a_to = a->sqrt_a_to; p.sqrt_1m_a_to = a->sqrt_1m_a_to;
   p.target = a->target_dev; p.target_rows = a->target_rows; p.loss_out = a->loss_out_dev;
+  p.loss_scale = a->loss_scale;
   p.noise_loss = a->noise_loss_dev; p.add_mask = a->add_mask;
   h->launches += 1;
   return step_epilogue_launch(p, as_stream(stream));
@@ -1308,23 +1515,28 @@ int pnp_step_epilogue(pnp_engine* h, const pnp_step_args* a, void* stream) {
 int pnp_local_blend(pnp_engine* h, float* x_dev, const int32_t* nwords2, const int32_t* words2x8,
                     const float* alpha2x8, float threshold, float* mask_out_dev, void* stream) {
   PNP_CHECK(h && h->finalized && x_dev && nwords2 && words2x8 && alpha2x8, "pnp_local_blend: null argument");
-  LocalBlendParams p;
-  // slots 0 (source prompt) and 1 (target prompt) of each of the five layers
-  p.store = h->store;
-  p.layer_stride = static_cast<long long>(2) * PNP_MAX_SLOTS * 8 * 256 * 77;
-  p.slot_stride = 8LL * 256 * 77;
+  // rows 0 / 1 of x_dev, slots 0 (source prompt) and 1 (target prompt) of each of the five layers
+  pnp_blend_desc d;
+  memset(&d, 0, sizeof d);
+  d.src_row = 0; d.tgt_row = 1; d.src_slot = 0; d.tgt_slot = 1;
+  d.th_pool = d.th_sub = threshold;
   for (int i = 0; i < 2; ++i) {
-    p.nwords[i] = nwords2[i];
     PNP_CHECK(nwords2[i] >= 0 && nwords2[i] <= 8, "pnp_local_blend: at most 8 blend words per prompt");
+    d.nwords[i] = nwords2[i];
     for (int j = 0; j < 8; ++j) {
-      p.words[i][j] = words2x8[i * 8 + j];
-      p.alpha[i][j] = alpha2x8[i * 8 + j];
-      PNP_CHECK(j >= nwords2[i] || (p.words[i][j] >= 0 && p.words[i][j] < PNP_TOKENS), "pnp_local_blend: word index");
+      d.words[i][j] = words2x8[i * 8 + j];
+      d.alpha[i][j] = alpha2x8[i * 8 + j];
     }
   }
-  p.threshold = threshold;
-  p.x = x_dev;
-  p.mask_out = mask_out_dev;
+  return pnp_local_blend_batch(h, x_dev, 2, &d, 1, mask_out_dev, stream);
+}
+
+int pnp_local_blend_batch(pnp_engine* h, float* x_dev, int n_rows, const pnp_blend_desc* descs_host, int n_desc,
+                          float* mask_out_dev, void* stream) {
+  PNP_CHECK(h && h->finalized && x_dev, "pnp_local_blend_batch: null argument");
+  LocalBlendParams p;
+  int rc = blend_params(h, &p, x_dev, n_rows, descs_host, n_desc, mask_out_dev);
+  if (rc) return rc;
   h->launches += 1;
   return local_blend_launch(p, as_stream(stream));
 }
@@ -1346,6 +1558,16 @@ int pnp_store_read(pnp_engine* h, float* out_dev, int64_t max_floats, void* stre
   const size_t n = std::min<size_t>(static_cast<size_t>(max_floats), kStoreFloats);
   PNP_CUDA(cudaMemcpyAsync(out_dev, h->store, n * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
   return 0;
+}
+
+int pnp_struct_size(int which) {
+  switch (which) {
+    case 0: return static_cast<int>(sizeof(pnp_attn_ctrl));
+    case 1: return static_cast<int>(sizeof(pnp_step_args));
+    case 2: return static_cast<int>(sizeof(pnp_blend_desc));
+    case 3: return static_cast<int>(sizeof(pnp_loop_args));
+  }
+  return -1;
 }
 
 int pnp_kernel_launches(pnp_engine* h, int64_t* out) {
@@ -1551,6 +1773,8 @@ int pnp_test_cross_attention(const uint16_t* q_dev, const uint16_t* kv_dev, int 
     int base[PNP_MAX_BATCH], slot[PNP_MAX_BATCH], sslot[PNP_MAX_BATCH];
     int mapper[PNP_MAX_SLOTS][PNP_TOKENS];
     float alphas[PNP_MAX_SLOTS][PNP_TOKENS], eq[PNP_MAX_SLOTS][PNP_TOKENS], ca[PNP_MAX_SLOTS][PNP_TOKENS];
+    int mcount[PNP_MAX_SLOTS][PNP_TOKENS];
+    float mweight[PNP_MAX_SLOTS][PNP_TOKENS];
   };
   Tab* d_tab = nullptr;
   CrossAttnParams cp;
@@ -1564,11 +1788,14 @@ int pnp_test_cross_attention(const uint16_t* q_dev, const uint16_t* kv_dev, int 
     memcpy(t.alphas, c->alphas, sizeof t.alphas);
     memcpy(t.eq, c->equalizer, sizeof t.eq);
     memcpy(t.ca, c->cross_alpha, sizeof t.ca);
+    memcpy(t.mcount, c->map_count, sizeof t.mcount);
+    memcpy(t.mweight, c->map_weight, sizeof t.mweight);
     PNP_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_tab), sizeof(Tab)));
     PNP_CUDA(cudaMemcpy(d_tab, &t, sizeof(Tab), cudaMemcpyHostToDevice));
     cp.base_row = d_tab->base; cp.edit_slot = d_tab->slot; cp.store_slot = d_tab->sslot;
     cp.mapper = &d_tab->mapper[0][0]; cp.alphas = &d_tab->alphas[0][0];
     cp.equalizer = &d_tab->eq[0][0]; cp.cross_alpha = &d_tab->ca[0][0];
+    cp.map_count = &d_tab->mcount[0][0]; cp.map_weight = &d_tab->mweight[0][0];
     cp.store = store_dev;
   }
   cp.q = reinterpret_cast<const __half*>(q_dev); cp.ldq = ch;

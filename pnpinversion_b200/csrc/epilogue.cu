@@ -37,6 +37,8 @@ __global__ void step_epilogue_kernel(const StepParams p) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         l[k] = __fsub_rn(t[k], o[k]);
+        // ablations: `loss * scale` (inversion.py:489), zeros on skipped steps (:514-517); scale 1 multiplies exactly
+        if (p.loss_scale != 1.0f) l[k] = __fmul_rn(l[k], p.loss_scale);
         o[k] = __fadd_rn(o[k], l[k]);
       }
       reinterpret_cast<float4*>(p.loss_out)[i] = make_float4(l[0], l[1], l[2], l[3]);
@@ -52,61 +54,85 @@ __global__ void step_epilogue_kernel(const StepParams p) {
   }
 }
 
-// attention_control.py:97-121.  One CTA, thread = one 16x16 position.
+// attention_control.py:97-121.  One CTA per (source, target) latent pair, thread = one 16x16 position.
+//   get_mask(maps, alpha, use_pool): (maps * alpha).sum(-1).mean(1) [-> 3x3 max pool] -> nearest x4 -> / max -> > th
+//   mask = get_mask(words, pool) ; if substruct: mask &= ~get_mask(sub_words, no pool) ; mask = mask[:1] + mask
 __global__ void __launch_bounds__(256) local_blend_kernel(const LocalBlendParams p) {
   __shared__ float m[2][256];
   __shared__ float mp[2][256];
   __shared__ float red[2][8];
   __shared__ unsigned char mk[2][256];
+  __shared__ unsigned char sk[2][256];
+  const LocalBlendItem& it = p.items[blockIdx.x];
   const int pos = threadIdx.x;
-  for (int pr = 0; pr < 2; ++pr) {
-    float acc = 0.f;
-    for (int lh = 0; lh < 40; ++lh) {
-      const int layer = lh / 8, h = lh % 8;
-      const float* row = p.store + layer * p.layer_stride + pr * p.slot_stride + (static_cast<size_t>(h) * 256 + pos) * 77;
-      float s = 0.f;
-      for (int w = 0; w < p.nwords[pr]; ++w) s += row[p.words[pr][w]] * p.alpha[pr][w];
-      acc += s;
-    }
-    m[pr][pos] = acc / 40.f;
-  }
-  __syncthreads();
+  const int slot_of[2] = {it.src_slot, it.tgt_slot};
   const int y = pos / 16, x = pos % 16;
-  for (int pr = 0; pr < 2; ++pr) {
-    float v = -INFINITY;
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int yy = y + dy, xx = x + dx;
-        if (yy >= 0 && yy < 16 && xx >= 0 && xx < 16) v = fmaxf(v, m[pr][yy * 16 + xx]);
+  for (int pass = 0; pass < 2; ++pass) {  // 0: blend words (pooled), 1: substruct words (not pooled)
+    const bool sub = pass == 1;
+    if (sub && it.nsub[0] == 0 && it.nsub[1] == 0) {
+      sk[0][pos] = sk[1][pos] = 0;
+      break;
+    }
+    for (int pr = 0; pr < 2; ++pr) {
+      const int nw = sub ? it.nsub[pr] : it.nwords[pr];
+      float acc = 0.f;
+      for (int lh = 0; lh < 40; ++lh) {
+        const int layer = lh / 8, h = lh % 8;
+        const float* row =
+            p.store + layer * p.layer_stride + slot_of[pr] * p.slot_stride + (static_cast<size_t>(h) * 256 + pos) * 77;
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w)
+          s += sub ? row[it.sub_words[pr][w]] * it.sub_alpha[pr][w] : row[it.words[pr][w]] * it.alpha[pr][w];
+        acc += s;
       }
-    mp[pr][pos] = v;
-    float w = v;
+      m[pr][pos] = acc / 40.f;
+    }
+    __syncthreads();
+    for (int pr = 0; pr < 2; ++pr) {
+      float v;
+      if (!sub) {
+        v = -INFINITY;
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            if (yy >= 0 && yy < 16 && xx >= 0 && xx < 16) v = fmaxf(v, m[pr][yy * 16 + xx]);
+          }
+      } else {
+        v = m[pr][pos];
+      }
+      mp[pr][pos] = v;
+      float w = v;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
-    if ((pos & 31) == 0) red[pr][pos >> 5] = w;
+      for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+      if ((pos & 31) == 0) red[pr][pos >> 5] = w;
+    }
+    __syncthreads();
+    for (int pr = 0; pr < 2; ++pr) {
+      float mx = red[pr][0];
+      for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[pr][i]);
+      const unsigned char bit = (mp[pr][pos] / mx) > (sub ? it.th_sub : it.th_pool) ? 1 : 0;
+      if (sub) sk[pr][pos] = bit; else mk[pr][pos] = bit;
+    }
+    __syncthreads();
   }
   __syncthreads();
-  for (int pr = 0; pr < 2; ++pr) {
-    float mx = red[pr][0];
-    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[pr][i]);
-    mk[pr][pos] = (mp[pr][pos] / mx) > p.threshold ? 1 : 0;
-  }
-  __syncthreads();
-  // mask = mask[:1] + mask ; x_t = x_t[:1] + mask * (x_t - x_t[:1])
+  // mask = mask[:1] + mask (both the blend and the substruct mask) ; x_t = x_t[:1] + mask * (x_t - x_t[:1])
+  float* xs = p.x + static_cast<size_t>(it.src_row) * LAT;
+  float* xt = p.x + static_cast<size_t>(it.tgt_row) * LAT;
   for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
     const int yy = i / 64, xx = i % 64;
     const int cell = (yy / 4) * 16 + (xx / 4);
-    const float m0 = mk[0][cell] ? 1.f : 0.f;
-    const float m1 = (mk[0][cell] | mk[1][cell]) ? 1.f : 0.f;
+    const float m0 = (mk[0][cell] && !sk[0][cell]) ? 1.f : 0.f;
+    const float m1 = ((mk[0][cell] | mk[1][cell]) && !(sk[0][cell] | sk[1][cell])) ? 1.f : 0.f;
     if (p.mask_out != nullptr) {
-      p.mask_out[i] = m0;
-      p.mask_out[4096 + i] = m1;
+      p.mask_out[(static_cast<size_t>(blockIdx.x) * 2) * 4096 + i] = m0;
+      p.mask_out[(static_cast<size_t>(blockIdx.x) * 2 + 1) * 4096 + i] = m1;
     }
     for (int c = 0; c < 4; ++c) {
-      const float x0 = p.x[c * 4096 + i];
-      const float x1 = p.x[LAT + c * 4096 + i];
-      p.x[c * 4096 + i] = __fadd_rn(x0, __fmul_rn(m0, __fsub_rn(x0, x0)));
-      p.x[LAT + c * 4096 + i] = __fadd_rn(x0, __fmul_rn(m1, __fsub_rn(x1, x0)));
+      const float x0 = xs[c * 4096 + i];
+      const float x1 = xt[c * 4096 + i];
+      xs[c * 4096 + i] = __fadd_rn(x0, __fmul_rn(m0, __fsub_rn(x0, x0)));
+      xt[c * 4096 + i] = __fadd_rn(x0, __fmul_rn(m1, __fsub_rn(x1, x0)));
     }
   }
 }
@@ -151,8 +177,13 @@ int step_epilogue_launch(const StepParams& p, cudaStream_t s) {
 }
 
 int local_blend_launch(const LocalBlendParams& p, cudaStream_t s) {
-  PNP_CHECK(p.nwords[0] >= 0 && p.nwords[0] <= 8 && p.nwords[1] >= 0 && p.nwords[1] <= 8, "local blend: <= 8 words");
-  local_blend_kernel<<<1, 256, 0, s>>>(p);
+  PNP_CHECK(p.n_items >= 1 && p.n_items <= 8, "local blend: 1..8 latent pairs per launch");
+  for (int i = 0; i < p.n_items; ++i)
+    for (int pr = 0; pr < 2; ++pr)
+      PNP_CHECK(p.items[i].nwords[pr] >= 0 && p.items[i].nwords[pr] <= 8 && p.items[i].nsub[pr] >= 0 &&
+                    p.items[i].nsub[pr] <= 8,
+                "local blend: <= 8 words");
+  local_blend_kernel<<<p.n_items, 256, 0, s>>>(p);
   PNP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -43,6 +43,8 @@ struct CrossAttnParams {
   const float* alphas;       // [slots][77]
   const float* equalizer;    // [slots][77]
   const float* cross_alpha;  // [slots][77]  (row cur_step of cross_replace_alpha)
+  const int* map_count;      // [slots][77] source tokens summed per target token (null = 1), see pnp_attn_ctrl
+  const float* map_weight;   // [slots][77] weight of that sum (null = 1)
   float* store;
   const int* store_slot;
 };
@@ -98,22 +100,31 @@ struct StepParams {
   const float* target;      // OFFSET: [target_rows, 16384] latent the branch must land on (row r uses r % target_rows)
   int target_rows;
   float* loss_out;          // OFFSET: [n, 16384]
+  float loss_scale;         // OFFSET: loss = (target - x_new) * loss_scale (1 = the default method)
   const float* noise_loss;  // RECTIFY: [n, 16384]
   unsigned add_mask;        // RECTIFY: bit r set -> add noise_loss row r to x_new row r
 };
 int step_epilogue_launch(const StepParams& p, cudaStream_t s);
 int edict_mix_launch(float* x, float* y, int n_elems, float w, bool reverse, cudaStream_t s);
 
-// LocalBlend (attention_control.py:97-121): store = accumulated [layers*? ...] see epilogue.cu
-struct LocalBlendParams {
-  const float* store;  // [5 layers][slots][8 heads][256 queries][77] running sum over steps; slots 0,1 are read
-  long long layer_stride, slot_stride;  // floats
-  int nwords[2];       // words with alpha_layers != 0 per prompt
+// LocalBlend (attention_control.py:97-121), one CTA per (source, target) latent pair
+struct LocalBlendItem {
+  int src_row, tgt_row, src_slot, tgt_slot;
+  int nwords[2];  // words with alpha_layers != 0 per prompt
   int words[2][8];
   float alpha[2][8];
-  float threshold;
-  float* x;         // [2, 4, 64, 64] in/out (row 0 = source, row 1 = target)
-  float* mask_out;  // optional [2][64*64] inspection output (may be null)
+  int nsub[2];  // substruct words (attention_control.py:116-118)
+  int sub_words[2][8];
+  float sub_alpha[2][8];
+  float th_pool, th_sub;
+};
+struct LocalBlendParams {
+  const float* store;  // [5 layers][slots][8 heads][256 queries][77] running sum over steps
+  long long layer_stride, slot_stride;  // floats
+  float* x;         // [rows, 4, 64, 64] in/out
+  float* mask_out;  // optional [n_items][2][64*64] inspection output (may be null)
+  int n_items;
+  LocalBlendItem items[8];
 };
 int local_blend_launch(const LocalBlendParams& p, cudaStream_t s);
 

@@ -31,16 +31,33 @@ class FusedUNet:
 
     in_channels = 4
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", max_batch: int = 4):
+    def __init__(self, state_dict: Optional[Dict[str, torch.Tensor]], device="cuda:0", max_batch: int = 4,
+                 share_weights_with: "Optional[FusedUNet]" = None):
         self._lib = _lib.load()
         dev = torch.device(device)
         if dev.type != "cuda":
             raise _lib.PnpError("FusedUNet needs a CUDA device (sm_100a); there is no CPU fallback")
+        if dev.index is None:  # 'cuda' means the CURRENT device (torchrun ranks set it), not ordinal 0
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         self.max_batch = max_batch
+        self._ctx_ref = None
+        self._ctx_version = None
+        self._ctx_batch = None
+        self._controller = None
+        self.num_calls = 0
+        self._parent = share_weights_with
         h = C.c_void_p()
+        if share_weights_with is not None:
+            # a second handle on the same GPU sharing the read-only weights (pnp_clone): own arenas / graphs / stream
+            if share_weights_with.device != dev:
+                raise _lib.PnpError("share_weights_with: the parent engine lives on another device")
+            with torch.cuda.device(dev):
+                _lib.check(self._lib.pnp_clone(share_weights_with.handle, max_batch, C.byref(h)))
+            self._h = h
+            return
         with torch.cuda.device(dev):
-            _lib.check(self._lib.pnp_create(dev.index or 0, max_batch, C.byref(h)))
+            _lib.check(self._lib.pnp_create(dev.index, max_batch, C.byref(h)))
             self._h = h
             for name, shape in arch.unet_param_specs():
                 t = state_dict[name]
@@ -52,11 +69,6 @@ class FusedUNet:
             # time embeddings for every possible timestep value: t_index == t
             ts = (C.c_int64 * 1000)(*range(1000))
             _lib.check(self._lib.pnp_set_timesteps(h, ts, 1000, _lib.current_stream_ptr()))
-        self._ctx_ref = None
-        self._ctx_version = None
-        self._ctx_batch = None
-        self._controller = None
-        self.num_calls = 0
 
     # -- controller registration (models/p2p/attention_control.py:12-81 patches 32 CrossAttention.forward; here the
     #    controller is lowered to a pnp_attn_ctrl descriptor per call)
@@ -87,6 +99,8 @@ class FusedUNet:
         x = sample
         if not x.is_cuda:
             raise _lib.PnpError("FusedUNet: latents must be CUDA tensors (no CPU fallback)")
+        if x.device != self.device or (encoder_hidden_states.is_cuda and encoder_hidden_states.device != self.device):
+            raise _lib.PnpError(f"FusedUNet on {self.device}: latents / context live on {x.device}")
         x = x.detach().to(torch.float32).contiguous()
         B = x.shape[0]
         if tuple(x.shape[1:]) != (4, 64, 64):
@@ -127,13 +141,21 @@ class FusedModel:
     """The `ldm_stable` pipeline object of the reference editors (models/p2p_editor.py:23-25)."""
 
     def __init__(self, unet_state_dict, device="cuda:0", max_batch: int = 4, tokenizer=None, text_encoder=None, vae=None,
-                 table_dtype: str = "float32"):
-        self.device = torch.device(device)
-        self.unet = FusedUNet(unet_state_dict, device=device, max_batch=max_batch)
+                 table_dtype: str = "float32", share_weights_with: "Optional[FusedModel]" = None):
+        self.unet = FusedUNet(unet_state_dict, device=device, max_batch=max_batch,
+                              share_weights_with=None if share_weights_with is None else share_weights_with.unet)
+        self.device = self.unet.device
+        self.table_dtype = table_dtype
         self.scheduler = DDIMSchedulerDev(engine=self.unet.handle, table_dtype=table_dtype)
         self.tokenizer = tokenizer
         self.text_encoder = text_encoder
         self.vae = vae
+
+    def clone(self, max_batch: Optional[int] = None) -> "FusedModel":
+        """A second model handle on the same GPU that shares this one's weight buffers (lanes of parallel.EditLanes)."""
+        return FusedModel(None, device=str(self.device), max_batch=max_batch or self.unet.max_batch,
+                          tokenizer=self.tokenizer, text_encoder=self.text_encoder, vae=self.vae,
+                          table_dtype=self.table_dtype, share_weights_with=self)
 
     @classmethod
     def synthetic(cls, device="cuda:0", max_batch: int = 4, seed: int = 0, table_dtype: str = "float32"):

@@ -108,3 +108,102 @@ def p2p_guidance_forward(model, prompt, controller, num_inference_steps: int = 5
             context = context_default
         latents = p2p_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale)
     return latents, latent
+
+
+@torch.no_grad()
+def p2p_guidance_forward_single_branch(model, prompt, controller, num_inference_steps: int = 50, guidance_scale=7.5,
+                                       generator=None, latent=None, uncond_embeddings=None):
+    """p2p_guidance_forward.py:65-100: the optimised unconditional embedding replaces only the FIRST unconditional row."""
+    batch_size = len(prompt)
+    register_attention_control(model, controller)
+    context_default = _encode(model, prompt)
+    uncond_default, text_embeddings = context_default[:batch_size], context_default[batch_size:]
+    latent, latents = init_latent(latent, model, 512, 512, generator, batch_size)
+    latents = latents.to(torch.float32).contiguous()
+    model.scheduler.set_timesteps(num_inference_steps)
+    for i, t in enumerate(model.scheduler.timesteps):
+        context = torch.cat([torch.cat([uncond_embeddings[i].to(text_embeddings), uncond_default[1:]]),
+                             text_embeddings]).contiguous()
+        latents = p2p_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale)
+    return latents, latent
+
+
+def _dilate(image, kernel_size, stride=1, padding=0):
+    """proximal_guidance_forward.py:7-17."""
+    assert image.max() <= 1 and image.min() >= 0
+    return torch.nn.functional.max_pool2d(image, kernel_size, stride, padding)
+
+
+def proximal_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale, low_resource=False,
+                                     edit_stage=True, prox=None, quantile=0.7, image_enc=None, recon_lr=0.1,
+                                     recon_t=400, inversion_guidance=False, x_stars=None, i=0, dilate_mask=0):
+    """proximal_guidance_forward.py:20-93.  Without `prox` this is exactly the plain guided step (one UNet call + one
+    fused epilogue).  With prox = 'l0' / 'l1' the score difference is thresholded at its `quantile` (a sort: torch on the
+    device, off the headline path) and the DDIM step is fed the already-combined prediction; the optional reconstruction
+    term on the predicted x0 (scheduler_dev.py:61-70) is applied with the same scalar coefficients."""
+    if low_resource:
+        raise NotImplementedError("low_resource (two B=n UNet calls) is not on the hot path")
+    if not (edit_stage and prox is not None):
+        latents = direct_inversion_p2p_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale,
+                                                               None, add_offset=False)
+        return latents
+    n = latents.shape[0]
+    noise_pred = model.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context)["sample"]
+    noise_pred_uncond, noise_prediction_text = noise_pred[:n], noise_pred[n:]
+    tt = int(t)
+    ref_image, lr, recon_mask, mask_edit = None, 0.0, None, None
+    score_delta = noise_prediction_text - noise_pred_uncond
+    threshold = score_delta.abs().quantile(quantile) if quantile > 0 else -quantile
+    score_delta = score_delta - score_delta.clamp(-threshold, threshold)
+    if prox == "l1":
+        score_delta = torch.where(score_delta > 0, score_delta - threshold, score_delta)
+        score_delta = torch.where(score_delta < 0, score_delta + threshold, score_delta)
+    elif prox != "l0":
+        raise NotImplementedError
+    if (recon_t > 0 and tt < recon_t) or (recon_t < 0 and tt > -recon_t):
+        ref_image, lr = image_enc, recon_lr
+        mask_edit = (score_delta.abs() > threshold).float()
+        if dilate_mask > 0:
+            radius = int(dilate_mask)
+            mask_edit = _dilate(mask_edit.float(), kernel_size=2 * radius + 1, padding=radius)
+        recon_mask = 1 - mask_edit
+    noise_pred = (noise_pred_uncond + guidance_scale * score_delta).contiguous()
+    sched = model.scheduler
+    co = step_coefficients(sched.alphas_cumprod, sched.final_alpha_cumprod, tt,
+                           tt - sched.config.num_train_timesteps // sched.num_inference_steps)
+    if ref_image is not None and lr > 0.0:
+        a_t, b_t, a_p, b_p = co
+        x0 = (latents - b_t * noise_pred) / a_t
+        x0 = x0 - lr * (x0 - ref_image.expand_as(x0)) * recon_mask.expand_as(x0).float()
+        latents = a_p * x0 + b_p * noise_pred
+    else:
+        latents = fused_step(model.unet.handle, latents.contiguous(), noise_pred, co)
+    if (mask_edit is not None and inversion_guidance and (recon_t > 0 and tt < recon_t)) or (recon_t < 0 and tt > -recon_t):
+        recon_mask = 1 - mask_edit
+        latents = latents - recon_lr * (latents - x_stars[len(x_stars) - i - 2].expand_as(latents)) * recon_mask
+    return controller.step_callback(latents.contiguous())
+
+
+@torch.no_grad()
+def proximal_guidance_forward(model, prompt, controller, guidance_scale=7.5, generator=None, latent=None,
+                              uncond_embeddings=None, edit_stage=True, prox=None, quantile=0.7, image_enc=None,
+                              recon_lr=0.1, recon_t=400, inversion_guidance=False, x_stars=None, dilate_mask=None):
+    """proximal_guidance_forward.py:96-170 (note: like the reference it does not call scheduler.set_timesteps)."""
+    batch_size = len(prompt)
+    register_attention_control(model, controller)
+    context_default = _encode(model, prompt)
+    text_embeddings = context_default[batch_size:]
+    latent, latents = init_latent(latent, model, 512, 512, generator, batch_size)
+    latents = latents.to(torch.float32).contiguous()
+    for i, t in enumerate(model.scheduler.timesteps):
+        if uncond_embeddings is not None:
+            context = torch.cat([uncond_embeddings[i].to(text_embeddings).expand(*text_embeddings.shape),
+                                 text_embeddings]).contiguous()
+        else:
+            context = context_default
+        latents = proximal_guidance_diffusion_step(model, controller, latents, context, t, guidance_scale,
+                                                   edit_stage=edit_stage, prox=prox, quantile=quantile,
+                                                   image_enc=image_enc, recon_lr=recon_lr, recon_t=recon_t,
+                                                   inversion_guidance=inversion_guidance, x_stars=x_stars, i=i,
+                                                   dilate_mask=dilate_mask or 0)
+    return latents, latent

