@@ -4,13 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            # this repo (libpnpinv.so, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
 
-A "step" is one batch of `--lanes` whole images per GPU (default 3), each through `P2PEditor("directinversion+p2p")` on
+A "step" is `--lanes` x `--batch` whole images per GPU, each through `P2PEditor.edit_batch` ("directinversion+p2p") on
 its own synthetic 4x64x64 latent with the cat prompt pair, i.e. the faithful 650 UNet sample-forwards per image
-(50 x B1 inversion + 3 x 50 x B4) + 200 fused epilogues.  The images of a step are in flight
-concurrently on one GPU (parallel.EditLanes: one CUDA stream, engine handle and host thread per lane) because one image's
-chain of ~360 short kernels per UNet call cannot keep the chip busy (measured on B200: 0.70 / 0.85 / 0.88 images/s with
-1 / 2 / 3 lanes).  Weak scaling: every rank edits its own K batches (image-parallel); NCCL only
-broadcasts the inputs and gathers the output latents.
+(50 inversion + 3 x 50 x 4 offset / reconstruction / edit) + 200 fused epilogues.  `--batch L`
+images share every UNet call (batch L for the inversion, 4 L afterwards; the four 50-step loops run inside
+libpnpinv.so, `pnp_run_loop`); `--lanes N` such passes are in flight concurrently on one GPU (parallel.EditLanes: one
+CUDA stream, engine handle and host thread per lane, all lanes SHARING one copy of the weights through `pnp_clone`).
+`--batch 1 --lanes 1` is the single-image latency configuration (BASELINE config 2 as worded).  Weak scaling: every rank
+edits its own K steps (image-parallel); NCCL only broadcasts the inputs and gathers the outputs.
 """
 import argparse
 import ctypes as C
@@ -156,8 +157,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=3,
-                    help="images in flight per GPU (each on its own CUDA stream and engine handle, parallel.EditLanes)")
+    ap.add_argument("--batch", type=int, default=3, help="images that share every UNet call (UNet batch L / 4L)")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="passes in flight per GPU (own CUDA stream / engine handle / host thread, shared weights)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -183,23 +185,30 @@ def main():
     from pnpinversion_b200.parallel import EditLanes
 
     sd = synth.synth_unet_state_dict(0)
+    NB = max(1, args.batch)          # images per pass
+    NL = max(1, args.lanes)          # concurrent passes
+    L = NB * NL                      # images per step and GPU
+    parent = FusedModel(sd, device=str(dev), max_batch=4 * NB, tokenizer=synth.FakeTokenizer(),
+                        text_encoder=synth.SynthTextEncoder())
+    made = []
 
     def make_editor():
-        m = FusedModel(sd, device=str(dev), max_batch=4, tokenizer=synth.FakeTokenizer(),
-                       text_encoder=synth.SynthTextEncoder())
+        m = parent if not made else parent.clone()  # lanes share ONE copy of the weights (pnp_clone)
+        made.append(m)
         return P2PEditor(["directinversion+p2p"], dev, num_ddim_steps=50, model=m)
 
-    L = max(1, args.lanes)
-    lanes = EditLanes(make_editor, L, dev)
-    model = lanes.editors[0].ldm_stable
+    lanes = EditLanes(make_editor, NL, dev)
+    model = parent
     src, tgt = synth.CAT_PROMPTS
 
     def edit_on(editor, z):
-        return editor("directinversion+p2p", image_path=z, prompt_src=src, prompt_tar=tgt, guidance_scale=7.5,
-                      cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
+        """z: (NB,1,4,64,64) or (NB,4,64,64) latents of one pass -> BatchEditResult"""
+        zz = z.reshape(NB, 4, 64, 64).to(dev, non_blocking=True)
+        return editor.edit_batch(zz, [src] * NB, [tgt] * NB, guidance_scale=7.5, cross_replace_steps=0.4,
+                                 self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
 
     def edit_step(zs):
-        """One bench step = L images, one per lane, through the public editor call."""
+        """One bench step = NL passes of NB images, one pass per lane, through the public editor call."""
         return lanes.run([(lambda ed, z=z: edit_on(ed, z)) for z in zs])
 
     total = (args.warmup + args.steps) * L
@@ -213,16 +222,17 @@ def main():
         dist.broadcast(z_all, src=0)
     z_dev = z_all[rank]
 
-    # ---------------- warm-up: the first image of every lane alone (plans, GEMM autotuning, graphs), then concurrently
-    for ln in range(L):
-        edit_on(lanes.editors[ln], z_dev[ln])
+    # ---------------- warm-up: the first pass of every lane alone (plans, GEMM autotuning, graphs), then concurrently
+    z_pass = z_dev.reshape(-1, NB, 1, 4, 64, 64)  # [(warmup+steps) * NL passes][NB]
+    for ln in range(NL):
+        edit_on(lanes.editors[ln], z_pass[ln])
         torch.cuda.synchronize()
     for i in range(1, args.warmup):
-        edit_step([z_dev[i * L + ln] for ln in range(L)])
+        edit_step([z_pass[i * NL + ln] for ln in range(NL)])
     torch.cuda.synchronize()
     lib = _lib.load()
     l0 = sum(ed.ldm_stable.unet.kernel_launches() for ed in lanes.editors)
-    first = args.warmup * L
+    first = args.warmup * NL
 
     # ---------------- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
@@ -234,7 +244,7 @@ def main():
     e0.record()
     outs = []
     for i in range(args.steps):
-        outs.extend(r.latents for r in edit_step([z_dev[first + i * L + ln] for ln in range(L)]))
+        outs.extend(r.latents for r in edit_step([z_pass[first + i * NL + ln] for ln in range(NL)]))
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -250,7 +260,7 @@ def main():
     value = world * args.steps * L / (ms / 1000.0)
 
     # ---------------- timed region 2: end to end through the public API with HOST buffers
-    z_host = [z_dev[first + i].cpu().pin_memory() for i in range(args.steps * L)]
+    z_host = [z_pass[first + i].cpu().pin_memory() for i in range(args.steps * NL)]
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -259,8 +269,9 @@ def main():
     t0.record()
     host_results = []
     for i in range(args.steps):
-        # H2D of the latent + context embeddings and D2H of the result latents happen inside each lane's job
-        host_results.extend(lanes.run([(lambda ed, z=z: edit_on(ed, z).latents.cpu()) for z in z_host[i * L:(i + 1) * L]]))
+        # H2D of the latents + context embeddings and D2H of the result latents happen inside each lane's job
+        host_results.extend(lanes.run([(lambda ed, z=z: edit_on(ed, z).latents.cpu())
+                                       for z in z_host[i * NL:(i + 1) * NL]]))
     t1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -269,9 +280,10 @@ def main():
     if dist is not None:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps * L / (float(ms2.item()) / 1000.0)
-    ctx_bytes = 4 * 77 * 768 * 4
-    h2d = L * (4 * 64 * 64 * 4 + 3 * ctx_bytes)  # per image: latent + the three context uploads (invert, reconstruct, edit)
-    d2h = L * 2 * 4 * 64 * 64 * 4
+    # per pass: NB latents from pinned memory + the [4 NB,77,768] fp32 context rows (the synthetic text encoder runs on
+    # the host, its output is uploaded once per pass)
+    h2d = NL * (NB * 4 * 64 * 64 * 4 + 4 * NB * 77 * 768 * 4)
+    d2h = NL * 2 * NB * 4 * 64 * 64 * 4
 
     if rank != 0:
         if dist is not None:
@@ -291,7 +303,7 @@ def main():
     reps = 3
     per_op = None
     for _ in range(reps):
-        _lib.check(lib.pnp_unet_profile(model.unet.handle, 4, 501, 10, ms_op, kind, fl, maxops, C.byref(n)))
+        _lib.check(lib.pnp_unet_profile(model.unet.handle, 4 * NB, 501, 10, ms_op, kind, fl, maxops, C.byref(n)))
         if per_op is None:
             per_op = [[kind[i], fl[i], 0.0] for i in range(n.value)]
         for i in range(n.value):
@@ -310,23 +322,24 @@ def main():
     n_gemm = g[2] // reps
     achieved = g[1] / (g[0] * 1e-3) / 1e12 if g[0] > 0 else 0.0
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tcgen05_kernel<BN> (all GEMM / implicit-conv launches of one B=4 UNet call)",
-        "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-        "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step); burst {burst}",
+        "bound": "tensor",
+        "kernel": f"gemm_tcgen05_kernel<BN> (all GEMM / implicit-conv launches of one B={4 * NB} UNet call)",
+        "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+        "peak_source": f"{peak_src} bf16_tflops (burst: every op is timed alone, 10 launches back to back between two "
+                       f"CUDA events); sustained {sustained}",
+        "frac_of_sustained_peak": achieved / sustained,
         "launches_per_unet_call": n_gemm, "gflop_per_launch_avg": g[1] / max(n_gemm, 1) / 1e9,
         "avg_launch_us": 1000.0 * g[0] / max(n_gemm, 1), "share_of_unet_time": g[0] / tot_ms if tot_ms else None,
         "traffic": None,
-        "by_kernel_ms_per_b4_unet_call": {k: round(v[0], 4) for k, v in agg.items()},
-        "unet_b4_sum_of_kernels_ms": tot_ms,
+        "unet_batch": 4 * NB,
+        "by_kernel_ms_per_unet_call": {k: round(v[0], 4) for k, v in agg.items()},
+        "unet_sum_of_kernels_ms": tot_ms,
+        "unet_tflops_sum_of_kernels": 4 * NB * UNET_GFLOP / tot_ms / 1e3 if tot_ms else None,
         "whole_job_tflops": value * FWD_PER_IMAGE * UNET_GFLOP / 1e3,
         "whole_job_frac_of_sustained_peak": value * FWD_PER_IMAGE * UNET_GFLOP / 1e3 / (sustained * world),
     }
-    prof = os.path.join(ROOT, "profiles", "traffic_latest.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("gemm_dram_bytes_per_launch")
-        except Exception:
-            pass
+    # `traffic` stays null: DRAM bytes per launch come from an ncu capture, which cannot run inside a timed bench; the
+    # warm-cache captures of this build are under profiles/ (r2_*)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -341,11 +354,14 @@ def main():
         "metric": "images_per_sec_512x512_50step_invert_edit", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"directinversion+p2p 50 steps, {L} image(s) per step and GPU, one per lane (UNet B=1 "
-                               "inversion, B=4 offset/reconstruct/edit per image), faithful 650 UNet forwards per image, "
-                               "SD-1.x random-init UNet, cat prompts",
-                   "images_per_step_per_gpu": L, "lanes_per_gpu": L,
-                   "parallelism": f"image-parallel x{world} GPUs x {L} concurrent lanes (CUDA streams) per GPU",
+        "config": {"workload": f"directinversion+p2p 50 steps, {L} image(s) per step and GPU = {NL} concurrent pass(es) x "
+                               f"{NB} image(s) per pass (UNet batch {NB} for the inversion, {4 * NB} for the offset / "
+                               "reconstruction / edit loops), faithful 650 UNet forwards per image, SD-1.x random-init "
+                               "UNet, cat prompts, step loops inside libpnpinv.so (pnp_run_loop)",
+                   "images_per_step_per_gpu": L, "lanes_per_gpu": NL, "images_per_pass": NB,
+                   "weights": "one fp16 copy per GPU shared by all lanes (pnp_clone)",
+                   "parallelism": f"image-parallel x{world} GPUs x {NL} concurrent passes (CUDA streams) x {NB} images "
+                                  "per UNet call",
                    "l2": "each step streams 1.72 GB of fp16 weights per UNet call (> 126 MB L2), no flush needed",
                    "accumulate": "fp32"},
         "clocks": clocks,

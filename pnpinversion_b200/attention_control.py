@@ -210,10 +210,30 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
             x_t = self.local_blend(x_t, None)
         return x_t
 
-    # subclasses fill mapper / alphas / equalizer of one target slot
+    # subclasses fill mapper / alphas / equalizer of target `slot` of THIS controller into table slot `dst` of c
     @abc.abstractmethod
-    def _fill_tables(self, c: _lib.AttnCtrl, slot: int):
+    def _fill_tables(self, c: _lib.AttnCtrl, slot: int, dst: Optional[int] = None):
         raise NotImplementedError
+
+    def self_replace_on(self) -> bool:
+        return self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1]
+
+    def fill_pair(self, c: _lib.AttnCtrl, src_row: int, tgt_row: int, slot: int, dst: int, store_src=None,
+                  store_tgt=None):
+        """Writes the edit of target `slot` (UNet batch rows src_row -> tgt_row, conditional half) into descriptor c,
+        using table slot `dst`: attention_control.py:269-282 for the current step."""
+        gate = self.cross_replace_alpha[self.cur_step]  # (n-1,1,1,77)
+        c.cross_base_row[tgt_row] = src_row
+        c.cross_slot[tgt_row] = dst
+        self._fill_tables(c, slot, dst)
+        _set_row(c.cross_alpha[dst], gate[slot].reshape(-1).tolist())
+        if self.self_replace_on():
+            c.self_layer_lo, c.self_layer_hi, c.self_max_tokens = 0, 16, _SELF_REPLACE_MAX_TOKENS
+            c.self_q_row[tgt_row] = src_row
+            c.self_k_row[tgt_row] = src_row
+        if self._want_store and store_src is not None:
+            c.store_slot[src_row] = store_src
+            c.store_slot[tgt_row] = store_tgt
 
     def descriptor(self, batch):
         n = self.batch_size
@@ -221,30 +241,13 @@ class AttentionControlEdit(AttentionStore, abc.ABC):
             raise _lib.PnpError(f"controller built for {n} prompts expects a UNet batch of {2 * n}, got {batch}")
         c = _lib.new_ctrl()
         src = n  # first cond row; the controller only touches attn[h//2:] (attention_control.py:184)
-        gate = self.cross_replace_alpha[self.cur_step]  # (n-1,1,1,77)
-        self_on = self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1]
-        if self_on:
-            c.self_layer_lo, c.self_layer_hi, c.self_max_tokens = 0, 16, _SELF_REPLACE_MAX_TOKENS
         for i in range(1, n):
-            r, slot = n + i, i - 1
-            c.cross_base_row[r] = src
-            c.cross_slot[r] = slot
-            self._fill_tables(c, slot)
-            g = gate[slot].reshape(-1)
-            for w in range(MAX_NUM_WORDS):
-                c.cross_alpha[slot][w] = float(g[w])
-            if self_on:
-                c.self_q_row[r] = src
-                c.self_k_row[r] = src
-        if self._want_store:
-            c.store_slot[n] = 0
-            c.store_slot[n + 1] = 1
+            self.fill_pair(c, src, n + i, i - 1, i - 1, store_src=0 if i == 1 else None, store_tgt=1)
         return c
 
 
 def _set_row(arr, values):
-    for w in range(MAX_NUM_WORDS):
-        arr[w] = values[w]
+    arr[:] = list(values)[:MAX_NUM_WORDS]
 
 
 class AttentionReplace(AttentionControlEdit):
@@ -274,13 +277,14 @@ class AttentionReplace(AttentionControlEdit):
             start.append(rows[0]), count.append(len(rows)), weight.append(float(vals[0]))
         return start, count, weight
 
-    def _fill_tables(self, c, slot):
+    def _fill_tables(self, c, slot, dst=None):
+        dst = slot if dst is None else dst
         start, count, weight = self._spans[slot]
-        _set_row(c.mapper[slot], start)
-        _set_row(c.map_count[slot], count)
-        _set_row(c.map_weight[slot], weight)
-        _set_row(c.alphas[slot], [1.0] * MAX_NUM_WORDS)
-        _set_row(c.equalizer[slot], [1.0] * MAX_NUM_WORDS)
+        _set_row(c.mapper[dst], start)
+        _set_row(c.map_count[dst], count)
+        _set_row(c.map_weight[dst], weight)
+        _set_row(c.alphas[dst], [1.0] * MAX_NUM_WORDS)
+        _set_row(c.equalizer[dst], [1.0] * MAX_NUM_WORDS)
 
 
 class AttentionRefine(AttentionControlEdit):
@@ -292,10 +296,11 @@ class AttentionRefine(AttentionControlEdit):
         self.mapper, alphas = seq_aligner.get_refinement_mapper(prompts, tokenizer)
         self.alphas = alphas.reshape(alphas.shape[0], 1, 1, alphas.shape[1])
 
-    def _fill_tables(self, c, slot):
-        _set_row(c.mapper[slot], self.mapper[slot].tolist())
-        _set_row(c.alphas[slot], self.alphas[slot].reshape(-1).tolist())
-        _set_row(c.equalizer[slot], [1.0] * MAX_NUM_WORDS)
+    def _fill_tables(self, c, slot, dst=None):
+        dst = slot if dst is None else dst
+        _set_row(c.mapper[dst], self.mapper[slot].tolist())
+        _set_row(c.alphas[dst], self.alphas[slot].reshape(-1).tolist())
+        _set_row(c.equalizer[dst], [1.0] * MAX_NUM_WORDS)
 
 
 class AttentionReweight(AttentionControlEdit):
@@ -307,14 +312,15 @@ class AttentionReweight(AttentionControlEdit):
         self.equalizer = equalizer
         self.prev_controller = controller
 
-    def _fill_tables(self, c, slot):
+    def _fill_tables(self, c, slot, dst=None):
+        dst = slot if dst is None else dst
         if self.prev_controller is not None:
-            self.prev_controller._fill_tables(c, slot)
+            self.prev_controller._fill_tables(c, slot, dst)
         else:
-            _set_row(c.mapper[slot], list(range(MAX_NUM_WORDS)))
-            _set_row(c.alphas[slot], [1.0] * MAX_NUM_WORDS)
+            _set_row(c.mapper[dst], list(range(MAX_NUM_WORDS)))
+            _set_row(c.alphas[dst], [1.0] * MAX_NUM_WORDS)
         eq = self.equalizer[slot if self.equalizer.shape[0] > 1 else 0].reshape(-1).tolist()
-        _set_row(c.equalizer[slot], eq)
+        _set_row(c.equalizer[dst], eq)
 
 
 def make_controller(pipeline, prompts, is_replace_controller, cross_replace_steps, self_replace_steps, blend_words=None,

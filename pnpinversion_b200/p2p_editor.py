@@ -49,7 +49,7 @@ SUPPORTED_METHODS = (("ddim+p2p", "directinversion+p2p", "negative-prompt-invers
 
 
 class P2PEditor:
-    def __init__(self, method_list, device, num_ddim_steps=50, model=None) -> None:
+    def __init__(self, method_list, device, num_ddim_steps=50, model=None, fused_loops=None) -> None:
         self.device = device
         self.method_list = method_list
         self.num_ddim_steps = num_ddim_steps
@@ -64,6 +64,8 @@ class P2PEditor:
                      else FusedModel.synthetic(device=str(device)))
         self.ldm_stable = model
         self.ldm_stable.scheduler.set_timesteps(self.num_ddim_steps)
+        # the C-side step loops need the fused engine; a test double of the engine keeps the Python loops
+        self.fused_loops = hasattr(getattr(model, "unet", None), "handle") if fused_loops is None else bool(fused_loops)
 
     def __call__(self, edit_method, image_path, prompt_src, prompt_tar, guidance_scale=7.5, proximal=None,
                  quantile=0.7, use_reconstruction_guidance=False, recon_t=400, recon_lr=0.1, cross_replace_steps=0.4,
@@ -137,87 +139,133 @@ class P2PEditor:
                                self_replace_steps=self_replace_steps, blend_words=blend_word,
                                equilizer_params=eq_params, num_ddim_steps=self.num_ddim_steps, device=self.device)
 
-    def _direct(self, image_path, prompt_src, prompt_tar, invert, forward_guidance, cross_replace_steps,
-                self_replace_steps, blend_word, eq_params, is_replace_controller, add_target=False,
-                loss_transform=None):
+    def _direct(self, image_path, prompt_src, prompt_tar, forward_guidance, cross_replace_steps, self_replace_steps,
+                blend_word, eq_params, is_replace_controller, add_target=False, add_source=False,
+                inverse_guidance=None, scale=None, skip_step=None):
         """Shared body of the DirectInversion methods (p2p_editor.py:415-479 and its ablation copies :481-548,
-        :707-976): `invert(inversion, image_gt, prompts)` picks the inversion variant."""
+        :707-976).  With `fused_loops` (default) the four 50-step loops run inside libpnpinv.so (`pnp_run_loop`, through
+        batched.BatchedDirectInversionP2P with one image); otherwise through the Python loops that mirror the
+        reference's (inversion.py, p2p_guidance_forward.py) - bit-identical results (tests/test_gpu_batched.py)."""
         image_gt = self._load(image_path)
         prompts = [prompt_src, prompt_tar]
-        inversion = DirectInversion(model=self.ldm_stable, num_ddim_steps=self.num_ddim_steps)
-        _, _, x_stars, noise_loss_list = invert(inversion, image_gt, prompts)
+        n = self.num_ddim_steps
+        loss_scales = None
+        if scale is not None:
+            loss_scales = [float(scale)] * n
+        if skip_step is not None:
+            loss_scales = [1.0 if (i % skip_step) == 0 else 0.0 for i in range(n)]
+        if self.fused_loops:
+            from .batched import BatchedDirectInversionP2P
+            from .ptp_utils import image2latent
+
+            latent = image2latent(self.ldm_stable.vae, image_gt).to(self.ldm_stable.device, torch.float32)
+            res = BatchedDirectInversionP2P(self.ldm_stable, n).edit(
+                latent, [prompt_src], [prompt_tar], guidance_scale=forward_guidance,
+                cross_replace_steps=cross_replace_steps, self_replace_steps=self_replace_steps, blend_word=blend_word,
+                eq_params=eq_params, is_replace_controller=is_replace_controller, add_target=add_target,
+                add_source=add_source, inverse_guidance_scale=inverse_guidance, loss_scales=loss_scales,
+                device=self.device)
+            x_stars, noise_loss_list, reconstruct_latent, latents = res.image(0)
+            return self._panel(image_gt, prompt_src, prompt_tar, reconstruct_latent, latents, x_stars, noise_loss_list)
+        inversion = DirectInversion(model=self.ldm_stable, num_ddim_steps=n)
+        if inverse_guidance is not None:
+            out = inversion.invert_with_guidance_scale_vary_guidance(
+                image_gt=image_gt, prompt=prompts, inverse_guidance_scale=inverse_guidance,
+                forward_guidance_scale=forward_guidance)
+        elif scale is not None:
+            out = inversion.invert_not_full(image_gt=image_gt, prompt=prompts, guidance_scale=forward_guidance, scale=scale)
+        elif skip_step is not None:
+            out = inversion.invert_skip_step(image_gt=image_gt, prompt=prompts, guidance_scale=forward_guidance,
+                                             skip_step=skip_step)
+        else:
+            out = inversion.invert(image_gt=image_gt, prompt=prompts, guidance_scale=forward_guidance)
+        _, _, x_stars, noise_loss_list = out
         x_t = x_stars[-1]
-        fwd_losses = noise_loss_list if loss_transform is None else loss_transform(noise_loss_list)
-        fwd = direct_inversion_p2p_guidance_forward_add_target if add_target else direct_inversion_p2p_guidance_forward
+        fwd_losses = noise_loss_list
+        if add_source:  # p2p_editor.py:930-932
+            fwd_losses = [l[[0]].repeat(2, 1, 1, 1) for l in noise_loss_list]
+        both = add_target or add_source
+        fwd = direct_inversion_p2p_guidance_forward_add_target if both else direct_inversion_p2p_guidance_forward
         controller = AttentionStore()
         reconstruct_latent, x_t = fwd(model=self.ldm_stable, prompt=prompts, controller=controller,
-                                      noise_loss_list=fwd_losses, latent=x_t,
-                                      num_inference_steps=self.num_ddim_steps, guidance_scale=forward_guidance,
-                                      generator=None)
+                                      noise_loss_list=fwd_losses, latent=x_t, num_inference_steps=n,
+                                      guidance_scale=forward_guidance, generator=None)
         controller = self._controller(prompts, cross_replace_steps, self_replace_steps, blend_word, eq_params,
                                       is_replace_controller)
         latents, _ = fwd(model=self.ldm_stable, prompt=prompts, controller=controller, noise_loss_list=fwd_losses,
-                         latent=x_t, num_inference_steps=self.num_ddim_steps, guidance_scale=forward_guidance,
-                         generator=None)
+                         latent=x_t, num_inference_steps=n, guidance_scale=forward_guidance, generator=None)
         return self._panel(image_gt, prompt_src, prompt_tar, reconstruct_latent, latents, x_stars, noise_loss_list)
+
+    def edit_batch(self, images, prompts_src, prompts_tar, guidance_scale=7.5, cross_replace_steps=0.4,
+                   self_replace_steps=0.6, blend_word=None, eq_params=None, is_replace_controller=False,
+                   per_image_params=False):
+        """`directinversion+p2p` for L images in ONE pass (UNet batch L for the inversion, 4 L afterwards): `images` is
+        an (L,4,64,64) latent tensor or a list of L image paths / HWC uint8 arrays.  Returns batched.BatchEditResult
+        for latents, a list of L reference-format PIL strips for images."""
+        from .batched import BatchedDirectInversionP2P
+        from .ptp_utils import image2latent
+
+        is_latent = isinstance(images, torch.Tensor) and images.dim() == 4
+        if is_latent:
+            gts, lat = None, images
+        else:
+            gts = [load_512(im) for im in images]
+            lat = torch.cat([image2latent(self.ldm_stable.vae, g) for g in gts])
+        res = BatchedDirectInversionP2P(self.ldm_stable, self.num_ddim_steps).edit(
+            lat.to(self.ldm_stable.device, torch.float32), list(prompts_src), list(prompts_tar),
+            guidance_scale=guidance_scale, cross_replace_steps=cross_replace_steps,
+            self_replace_steps=self_replace_steps, blend_word=blend_word, eq_params=eq_params,
+            is_replace_controller=is_replace_controller, per_image_params=per_image_params, device=self.device)
+        if is_latent or self.ldm_stable.vae is None:
+            return res
+        out = []
+        for i, g in enumerate(gts):
+            x_stars, nl, rec, lat_i = res.image(i)
+            out.append(self._panel(g, prompts_src[i], prompts_tar[i], rec, lat_i, x_stars, nl))
+        return out
 
     def edit_image_directinversion(self, image_path, prompt_src, prompt_tar, guidance_scale=7.5,
                                    cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=None, eq_params=None,
                                    is_replace_controller=False, add_target=False):
-        return self._direct(image_path, prompt_src, prompt_tar,
-                            lambda inv, img, pr: inv.invert(image_gt=img, prompt=pr, guidance_scale=guidance_scale),
-                            guidance_scale, cross_replace_steps, self_replace_steps, blend_word, eq_params,
-                            is_replace_controller, add_target=add_target)
+        return self._direct(image_path, prompt_src, prompt_tar, guidance_scale, cross_replace_steps,
+                            self_replace_steps, blend_word, eq_params, is_replace_controller, add_target=add_target)
 
     def edit_image_directinversion_vary_guidance_scale(self, image_path, prompt_src, prompt_tar,
                                                        inverse_guidance_scale=1, forward_guidance_scale=7.5,
                                                        cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=None,
                                                        eq_params=None, is_replace_controller=False):
         """p2p_editor.py:481-548."""
-        return self._direct(image_path, prompt_src, prompt_tar,
-                            lambda inv, img, pr: inv.invert_with_guidance_scale_vary_guidance(
-                                image_gt=img, prompt=pr, inverse_guidance_scale=inverse_guidance_scale,
-                                forward_guidance_scale=forward_guidance_scale),
-                            forward_guidance_scale, cross_replace_steps, self_replace_steps, blend_word, eq_params,
-                            is_replace_controller)
+        return self._direct(image_path, prompt_src, prompt_tar, forward_guidance_scale, cross_replace_steps,
+                            self_replace_steps, blend_word, eq_params, is_replace_controller,
+                            inverse_guidance=inverse_guidance_scale)
 
     def edit_image_directinversion_not_full(self, image_path, prompt_src, prompt_tar, guidance_scale=7.5,
                                             cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=None,
                                             eq_params=None, is_replace_controller=False, scale=1.):
         """p2p_editor.py:707-773."""
-        return self._direct(image_path, prompt_src, prompt_tar,
-                            lambda inv, img, pr: inv.invert_not_full(image_gt=img, prompt=pr,
-                                                                     guidance_scale=guidance_scale, scale=scale),
-                            guidance_scale, cross_replace_steps, self_replace_steps, blend_word, eq_params,
-                            is_replace_controller)
+        return self._direct(image_path, prompt_src, prompt_tar, guidance_scale, cross_replace_steps,
+                            self_replace_steps, blend_word, eq_params, is_replace_controller, scale=scale)
 
     def edit_image_directinversion_skip_step(self, image_path, prompt_src, prompt_tar, skip_step, guidance_scale=7.5,
                                              cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=None,
                                              eq_params=None, is_replace_controller=False):
         """p2p_editor.py:775-840."""
-        return self._direct(image_path, prompt_src, prompt_tar,
-                            lambda inv, img, pr: inv.invert_skip_step(image_gt=img, prompt=pr,
-                                                                      guidance_scale=guidance_scale, skip_step=skip_step),
-                            guidance_scale, cross_replace_steps, self_replace_steps, blend_word, eq_params,
-                            is_replace_controller)
+        return self._direct(image_path, prompt_src, prompt_tar, guidance_scale, cross_replace_steps,
+                            self_replace_steps, blend_word, eq_params, is_replace_controller, skip_step=skip_step)
 
     def edit_image_directinversion_add_target(self, image_path, prompt_src, prompt_tar, guidance_scale=7.5,
                                               cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=None,
                                               eq_params=None, is_replace_controller=False):
         """p2p_editor.py:842-907: the offsets of both branches are added back."""
-        return self.edit_image_directinversion(image_path, prompt_src, prompt_tar, guidance_scale, cross_replace_steps,
-                                               self_replace_steps, blend_word, eq_params, is_replace_controller,
-                                               add_target=True)
+        return self._direct(image_path, prompt_src, prompt_tar, guidance_scale, cross_replace_steps,
+                            self_replace_steps, blend_word, eq_params, is_replace_controller, add_target=True)
 
     def edit_image_directinversion_add_source(self, image_path, prompt_src, prompt_tar, guidance_scale=7.5,
                                               cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=None,
                                               eq_params=None, is_replace_controller=False):
         """p2p_editor.py:909-976: the SOURCE branch's offset is added to both branches."""
-        return self._direct(image_path, prompt_src, prompt_tar,
-                            lambda inv, img, pr: inv.invert(image_gt=img, prompt=pr, guidance_scale=guidance_scale),
-                            guidance_scale, cross_replace_steps, self_replace_steps, blend_word, eq_params,
-                            is_replace_controller, add_target=True,
-                            loss_transform=lambda losses: [l[[0]].repeat(2, 1, 1, 1) for l in losses])
+        return self._direct(image_path, prompt_src, prompt_tar, guidance_scale, cross_replace_steps,
+                            self_replace_steps, blend_word, eq_params, is_replace_controller, add_source=True)
 
     def edit_image_ddim(self, image_path, prompt_src, prompt_tar, guidance_scale=7.5, cross_replace_steps=0.4,
                         self_replace_steps=0.6, blend_word=None, eq_params=None, is_replace_controller=False):

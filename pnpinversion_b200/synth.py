@@ -126,6 +126,24 @@ class FakeTokenizer:
         return o
 
 
+class PieceTokenizer(FakeTokenizer):
+    """Splits every word longer than 4 characters into 3-character pieces (a stand-in for CLIP's BPE splitting rare
+    words), so that swapped words can have different token counts: the fractional branch of the replacement mapper
+    (seq_aligner.py:168-174)."""
+
+    def encode(self, text):
+        ids = [self.BOS]
+        for w in text.split():
+            pieces = [w] if len(w) <= 4 else [w[i:i + 3] for i in range(0, len(w), 3)]
+            ids += [self._tok(p) for p in pieces]
+        return ids + [self.EOS]
+
+    def decode(self, ids):
+        if isinstance(ids, int):
+            ids = [ids]
+        return "".join(self._inv.get(int(i), "?") for i in ids)
+
+
 class SynthTextEncoder:
     """Seeded embedding-table "text encoder": token id + position -> N(0,1) row of 768 (fp16-rounded).
     Satisfies `model.text_encoder(ids)[0]` (models/p2p/inversion.py:296,305)."""

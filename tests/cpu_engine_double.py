@@ -9,13 +9,15 @@ import torch
 
 
 def cpu_fused_step(engine, x, eps_c, coeffs, eps_u=None, guidance=1.0, target=None, loss_out=None, noise_loss=None,
-                   add_mask=0, out=None):
+                   add_mask=0, out=None, loss_scale=1.0):
     c0, c1, c2, c3 = coeffs
     eps = eps_c if eps_u is None else eps_u + guidance * (eps_c - eps_u)
     x_new = c2 * ((x - c1 * eps) / c0) + c3 * eps
     if target is not None:  # OFFSET: loss = target - x_new ; x_new = x_new + loss (row r uses target row r % target_rows)
         tgt = target[[r % target.shape[0] for r in range(x.shape[0])]]
         loss = tgt - x_new
+        if loss_scale != 1.0:
+            loss = loss * loss_scale
         if loss_out is not None:
             loss_out.copy_(loss)
         x_new = x_new + loss

@@ -180,3 +180,150 @@ def test_edict_coupled_loop_follows_the_reference_for_40_plus_40_steps(monkeypat
     for i in range(2):
         assert rel(lat_m[i], lat_r[i]) < 2e-3, (i, rel(lat_m[i], lat_r[i]))
         assert rel(out_m[i], out_r[i]) < 2e-3, (i, rel(out_m[i], out_r[i]))
+
+
+def test_inversion_variants_follow_the_reference(monkeypatch):
+    """The guidance / ablation family of `models/p2p/inversion.py::DirectInversion`: CFG inversion
+    (`invert_with_guidance_scale_vary_guidance` :412-419 - the reference's two B=1 calls per step are the two rows of one
+    B=2 call here), the scaled offset (`invert_not_full` :478-499), the skipped offset (`invert_skip_step` :501-526), and
+    `NegativePromptInversion.invert` (:78-101, with and without the slerp interpolation) - over 50 steps on the fake UNet."""
+    from pnpinversion_b200 import inversion as my_inv
+    from pnpinversion_b200 import scheduler as my_sched_mod
+
+    for mod in (my_inv, my_sched_mod):
+        monkeypatch.setattr(mod, "fused_step", cpu_fused_step)
+    ref = ref_shim.load_reference_p2p()
+    prompts = list(synth.CAT_PROMPTS)
+    z = synth.synth_latent(5)
+    torch.set_grad_enabled(False)
+
+    def both(call_ref, call_mine):
+        ref_model, my_model = _models()
+        r = call_ref(ref.inversion.DirectInversion(model=ref_model, num_ddim_steps=50))
+        m = call_mine(my_inv.DirectInversion(model=my_model, num_ddim_steps=50))
+        return r, m, ref_model, my_model
+
+    # CFG inversion at 2.5, offsets at 7.5
+    r, m, rm, mm = both(lambda inv: inv.invert_with_guidance_scale_vary_guidance(z, prompts, 2.5, 7.5),
+                        lambda inv: inv.invert_with_guidance_scale_vary_guidance(z, prompts, 2.5, 7.5))
+    t_ref = [t for _, t in rm.unet.calls]
+    t_mine = [t for _, t in mm.unet.calls]
+    assert t_ref[0:100:2] == t_mine[:50] and t_ref[100:] == t_mine[50:]  # 2 x B=1 calls per step there, 1 x B=2 here
+    assert mm.unet.calls[0][0] == (2, 4, 64, 64)
+    for a, b in zip(r[2], m[2]):
+        assert torch.allclose(a, b, rtol=0, atol=2e-5)
+    for a, b in zip(r[3], m[3]):
+        assert torch.allclose(a, b, rtol=0, atol=5e-5)
+
+    # loss * 0.8 and loss on every 5th step only
+    for kw_name, kw in (("invert_not_full", dict(scale=0.8)), ("invert_skip_step", dict(skip_step=5))):
+        r, m, rm, mm = both(lambda inv: getattr(inv, kw_name)(image_gt=z, prompt=prompts, guidance_scale=7.5, **kw),
+                            lambda inv: getattr(inv, kw_name)(image_gt=z, prompt=prompts, guidance_scale=7.5, **kw))
+        assert rm.unet.calls == mm.unet.calls
+        for i, (a, b) in enumerate(zip(r[3], m[3])):
+            assert torch.allclose(a, b, rtol=0, atol=5e-6), (kw_name, i)
+        if kw_name == "invert_skip_step":
+            assert float(m[3][1].abs().max()) == 0.0 and float(m[3][5].abs().max()) > 0.0
+
+    # negative-prompt inversion
+    for interp in (0.0, 0.3):
+        ref_model, my_model = _models()
+        ri = ref.inversion.NegativePromptInversion(model=ref_model, num_ddim_steps=50).invert(z, prompts[0], npi_interp=interp)
+        mi = my_inv.NegativePromptInversion(model=my_model, num_ddim_steps=50).invert(z, prompts[0], npi_interp=interp)
+        assert ref_model.unet.calls == my_model.unet.calls and len(my_model.unet.calls) == 50
+        for a, b in zip(ri[2], mi[2]):
+            assert torch.equal(a, b)
+        assert len(ri[3]) == len(mi[3]) == 50 and torch.allclose(ri[3][0], mi[3][0].to(ri[3][0].dtype), rtol=0, atol=1e-6)
+
+
+def test_schedule_with_a_step_count_that_does_not_divide_1000(monkeypatch):
+    """30 steps: diffusers 0.10's `(arange(0, n) * (1000 // n)).round()[::-1]` gives 30 timesteps from 957 (the vendored
+    0.3.0 scheduler would give 31 from 990); inversion, offsets and the rectified forward pass run over exactly 30 steps
+    and the source branch still lands on the inverted latent."""
+    from pnpinversion_b200 import inversion as my_inv
+    from pnpinversion_b200 import p2p_guidance_forward as my_fwd
+    from pnpinversion_b200 import scheduler as my_sched_mod
+    from pnpinversion_b200.attention_control import EmptyControl
+
+    for mod in (my_inv, my_fwd, my_sched_mod):
+        monkeypatch.setattr(mod, "fused_step", cpu_fused_step)
+    _, my_model = _models()
+    my_model.scheduler.set_timesteps(30)
+    assert my_model.scheduler.timesteps.tolist() == [33 * i for i in range(29, -1, -1)]
+    prompts = list(synth.CAT_PROMPTS)
+    z = synth.synth_latent(2)
+    torch.set_grad_enabled(False)
+    _, _, xs, nl = my_inv.DirectInversion(model=my_model, num_ddim_steps=30).invert(image_gt=z, prompt=prompts,
+                                                                                   guidance_scale=7.5)
+    assert len(xs) == 31 and len(nl) == 30
+    lat, _ = my_fwd.direct_inversion_p2p_guidance_forward(model=my_model, prompt=prompts, controller=EmptyControl(),
+                                                          latent=xs[-1], noise_loss_list=nl, num_inference_steps=30,
+                                                          guidance_scale=7.5, generator=None)
+    assert [t for _, t in my_model.unet.calls[:30]] == [33 * i for i in range(30)]
+    assert float((lat[0] - xs[0][0]).abs().max()) < 1e-4
+
+
+def test_proximal_guidance_forward_follows_the_reference(monkeypatch):
+    """`proximal_guidance_forward` (models/p2p/proximal_guidance_forward.py:20-170) as the negative-prompt-inversion
+    methods call it (p2p_editor.py:350-410): reconstruction pass (prox None), edit pass with prox 'l0' / 'l1', with and
+    without the reconstruction guidance on the predicted x0 (scheduler_dev.py:61-70)."""
+    from pnpinversion_b200 import p2p_guidance_forward as my_fwd
+    from pnpinversion_b200 import scheduler as my_sched_mod
+    from pnpinversion_b200.attention_control import EmptyControl
+
+    for mod in (my_fwd, my_sched_mod):
+        monkeypatch.setattr(mod, "fused_step", cpu_fused_step)
+    import importlib
+    import sys
+    ref = ref_shim.load_reference_p2p()
+    ref_prox = importlib.import_module("models.p2p.proximal_guidance_forward")
+    # models/p2p/scheduler_dev.py subclasses `diffusers.DDIMScheduler` (0.10, absent here).  The harness offers it the
+    # vendored 0.3.0 scheduler under that name, with the one config field step() reads that 0.3.0 lacks; the
+    # reference's DDIMSchedulerDev.step (:10-121) itself runs unmodified.
+    md = ref_shim.load_my_diffusers()
+
+    class _Sched(md.DDIMScheduler):
+        @property
+        def config(self):
+            return types.SimpleNamespace(**dict(super().config), prediction_type="epsilon")
+
+    class _Out(dict):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.__dict__.update(kw)
+
+    if "diffusers" not in sys.modules:
+        d = types.ModuleType("diffusers")
+        d.__path__ = []
+        d.DDIMScheduler = _Sched
+        ds = types.ModuleType("diffusers.schedulers")
+        ds.__path__ = []
+        dd = types.ModuleType("diffusers.schedulers.scheduling_ddim")
+        dd.DDIMScheduler, dd.DDIMSchedulerOutput = _Sched, _Out
+        monkeypatch.setitem(sys.modules, "diffusers", d)
+        monkeypatch.setitem(sys.modules, "diffusers.schedulers", ds)
+        monkeypatch.setitem(sys.modules, "diffusers.schedulers.scheduling_ddim", dd)
+    sys.modules.pop("models.p2p.scheduler_dev", None)
+    ref_sd = importlib.import_module("models.p2p.scheduler_dev")
+    prompts = list(synth.CAT_PROMPTS)
+    torch.set_grad_enabled(False)
+    g = torch.Generator().manual_seed(33)
+    x_t = torch.randn(1, 4, 64, 64, generator=g)
+    enc = torch.randn(1, 4, 64, 64, generator=g)
+    x_stars = [torch.randn(1, 4, 64, 64, generator=g) for _ in range(51)]
+    te, tok = synth.SynthTextEncoder(), synth.FakeTokenizer()
+    uncond = [te(tok([prompts[0]]).input_ids)[0]] * 50
+    for prox, guided in ((None, False), ("l0", False), ("l1", True)):
+        ref_model, my_model = _models()
+        # the reference's proximal path needs scheduler.step(..., ref_image=, recon_lr=, recon_mask=): DDIMSchedulerDev
+        ref_model.scheduler = ref_sd.DDIMSchedulerDev(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                                      clip_sample=False, set_alpha_to_one=False)
+        ref_model.scheduler.set_timesteps(50)
+        kw = dict(guidance_scale=7.5, generator=None, uncond_embeddings=uncond, edit_stage=True, prox=prox, quantile=0.7,
+                  image_enc=enc if guided else None, recon_lr=0.1 if guided else 0, recon_t=400 if guided else 1000,
+                  x_stars=x_stars, dilate_mask=1)
+        a, _ = ref_prox.proximal_guidance_forward(model=ref_model, prompt=prompts,
+                                                  controller=ref.attention_control.EmptyControl(), latent=x_t, **kw)
+        b, _ = my_fwd.proximal_guidance_forward(model=my_model, prompt=prompts, controller=EmptyControl(), latent=x_t, **kw)
+        assert ref_model.unet.calls == my_model.unet.calls and len(my_model.unet.calls) == 50
+        assert torch.allclose(a, b, rtol=0, atol=1e-4), (prox, guided, float((a - b).abs().max()))

@@ -63,10 +63,18 @@ def test_schedule_tables(gold):
     sch = scheduler.DDIMSchedulerDev(table_dtype="float64")
     assert float(sch.final_alpha_cumprod) == s["final_alpha_cumprod"]
     assert [float(sch.alphas_cumprod[i]) for i in range(0, 1000, 100)] == s["alphas_cumprod_f64_every_100"]
-    for n in (50, 20, 3):
+    for n in (50, 20):  # divisors of 1000: the vendored 0.3.0 scheduler of the fixture and diffusers 0.10 agree
         sch.set_timesteps(n)
         assert sch.timesteps.dtype == torch.int64
         assert sch.timesteps.tolist() == s[f"timesteps_{n}"]
+    # non-divisors follow diffusers 0.10 (what DDIMSchedulerDev inherits, models/p2p/scheduler_dev.py:3-10):
+    # (arange(0, n) * (1000 // n)).round()[::-1] -> exactly n timesteps (the vendored 0.3.0 arange(0,1000,1000//n)
+    # of the fixture yields n + 1 for n = 3 or 30, which overruns noise_loss_list in the forward loops)
+    for n, first in ((3, 666), (30, 957), (75, 962), (7, 852)):
+        sch.set_timesteps(n)
+        ts = sch.timesteps.tolist()
+        assert len(ts) == n and ts[0] == first and ts[-1] == 0 and ts == sorted(ts, reverse=True)
+        assert ts == [(n - 1 - i) * (1000 // n) for i in range(n)]
     sch.set_timesteps(50)
     assert sch.timesteps.tolist() == list(range(980, -1, -20))
     # the float32 table (diffusers >= 0.10 way) agrees with the float64 one to fp32 precision

@@ -217,22 +217,7 @@ def test_edict_step_coefficients_against_the_reference_forward_and_reverse_steps
             assert float((mine - theirs).abs().max()) <= 1e-12 * float(theirs.abs().max()), (int(t), reverse)
 
 
-class PieceTokenizer(synth.FakeTokenizer):
-    """Splits every word longer than 4 characters into 3-character pieces (a stand-in for CLIP's BPE splitting rare
-    words), so that swapped words can have different token counts: the fractional branch of the replacement mapper
-    (seq_aligner.py:168-174)."""
-
-    def encode(self, text):
-        ids = [self.BOS]
-        for w in text.split():
-            pieces = [w] if len(w) <= 4 else [w[i:i + 3] for i in range(0, len(w), 3)]
-            ids += [self._tok(p) for p in pieces]
-        return ids + [self.EOS]
-
-    def decode(self, ids):
-        if isinstance(ids, int):
-            ids = [ids]
-        return "".join(self._inv.get(int(i), "?") for i in ids)
+PieceTokenizer = synth.PieceTokenizer
 
 
 def test_replacement_mapper_with_unequal_token_spans_matches_the_reference(ref):
