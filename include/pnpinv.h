@@ -198,6 +198,24 @@ int pnp_unet_profile(pnp_engine* h, int batch, int t_index, int reps, float* ms_
 int pnp_kernel_launches(pnp_engine* h, int64_t* out); /* kernels launched by this handle so far (graph nodes count) */
 int pnp_set_use_graph(pnp_engine* h, int enable);     /* capture each UNet forward into a CUDA graph (default on) */
 
+/* ---- the VAE around the loop ------------------------------------------------------- */
+/* replaces AutoencoderKL.encode / .decode as utils/utils.py:58-80 calls them (image2latent: encode(img).latent_dist.mean
+ * * 0.18215; latent2image: decode(z / 0.18215)); arithmetic spec my_diffusers/models/vae.py:54-210,480-557.  Parameters
+ * carry the names of a diffusers SD-1.x `vae/` state dict (248 tensors, fp16 values in PyTorch layouts).  The 0.18215
+ * scaling and the uint8 conversion stay with the caller, exactly where the reference has them. */
+typedef struct pnp_vae pnp_vae;
+int pnp_vae_create(int device_ordinal, pnp_vae** out);
+void pnp_vae_destroy(pnp_vae* h);
+int pnp_vae_load_param(pnp_vae* h, const char* name, const uint16_t* data_host, int64_t numel);
+int pnp_vae_finalize(pnp_vae* h);
+/* image_dev: [batch,3,H,W] fp32 in [-1,1] (H, W in {128,256,512}); moments_out_dev: [batch,8,H/8,W/8] fp32 = posterior
+ * mean (channels 0..3) and log-variance (4..7) after quant_conv */
+int pnp_vae_encode(pnp_vae* h, const float* image_dev, int batch, int img_h, int img_w, float* moments_out_dev,
+                   void* stream);
+/* z_dev: [batch,4,h,w] fp32 (already divided by 0.18215); image_out_dev: [batch,3,8h,8w] fp32 */
+int pnp_vae_decode(pnp_vae* h, const float* z_dev, int batch, int lat_h, int lat_w, float* image_out_dev, void* stream);
+int pnp_vae_kernel_launches(pnp_vae* h, int64_t* out);
+
 /* ---- stand-alone kernel entry points (used by tests/ and bench.py to measure single kernels) ------------------ */
 /* D[M,N] = A[M,K].W[N,K]^T (+bias)(+residual) ; mode 0 plain, 1 GEGLU (N = 2*out columns, weights pre-interleaved by
  * pnp_test_pack_geglu) ; conv3x3: A is NHWC [B,H,W,C], W packed (N, 9*C) tap-major */

@@ -138,6 +138,13 @@ SIGNATURES = {
     "pnp_struct_size": (_i, [_i]),
     "pnp_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
     "pnp_set_use_graph": (_i, [_vp, _i]),
+    "pnp_vae_create": (_i, [_i, C.POINTER(_vp)]),
+    "pnp_vae_destroy": (None, [_vp]),
+    "pnp_vae_load_param": (_i, [_vp, C.c_char_p, _vp, _i64]),
+    "pnp_vae_finalize": (_i, [_vp]),
+    "pnp_vae_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "pnp_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "pnp_vae_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
     "pnp_test_gemm": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "pnp_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "pnp_test_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp]),

@@ -151,14 +151,53 @@ def load_text_components(path: str, device="cpu", dtype=torch.float32):
     return tok, enc
 
 
+# diffusers >= 0.15 renamed the VAE attention projections; the engine takes the 0.3.0 .. 0.14 names of the reference's pins
+_VAE_ATTN_RENAMES = (("to_q.", "query."), ("to_k.", "key."), ("to_v.", "value."), ("to_out.0.", "proj_attn."))
+
+
+def load_vae_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """The 248 AutoencoderKL tensors of `<path>/vae/` (or a single VAE weight file), diffusers names, validated against
+    arch.vae_param_specs (linear attention weights may come as (C,C,1,1) convs)."""
+    if os.path.isdir(path):
+        d = os.path.join(path, "vae") if os.path.isdir(os.path.join(path, "vae")) else path
+        cands = [os.path.join(d, n) for n in ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin")]
+        f = next((c for c in cands if os.path.isfile(c)), None)
+        if f is None:
+            raise FileNotFoundError(f"no VAE weight file under {d}")
+    else:
+        f = path
+    sd = read_state_dict(f)
+    out = {}
+    for k, v in sd.items():
+        if ".attentions." in k:
+            for new, old in _VAE_ATTN_RENAMES:
+                k = k.replace("." + new, "." + old)
+        out[k] = v
+    res = {}
+    for name, shape in arch.vae_param_specs():
+        if name not in out:
+            raise ValueError(f"{f} is not an SD-1.x AutoencoderKL state dict: {name} missing")
+        t = out[name]
+        n = 1
+        for s_ in shape:
+            n *= s_
+        if t.numel() != n:
+            raise ValueError(f"{f}: {name} has shape {tuple(t.shape)}, expected {shape}")
+        res[name] = t.reshape(shape)
+    return res
+
+
 def load_fused_model(path: str, device="cuda:0", max_batch: int = 4, tokenizer=None, text_encoder=None, vae=None,
                      table_dtype: str = "float32", strict: bool = True):
-    """`StableDiffusionPipeline.from_pretrained(path)` for the fused path: UNet -> libpnpinv engine, CLIP from the same
-    directory when present.  The VAE is not built yet (section 8f): pass latents, or a `vae` object with the reference's
-    `encode(...)['latent_dist'].mean` / `decode(...)['sample']` surface (utils/utils.py:58-80)."""
+    """`StableDiffusionPipeline.from_pretrained(path)` for the fused path: UNet -> libpnpinv engine, VAE -> the fused VAE
+    (csrc/vae.cu) when `<path>/vae` exists, CLIP from the same directory when present."""
     from .model import FusedModel
 
     sd = load_unet_state_dict(path, strict=strict)
+    if vae is None and os.path.isdir(path) and os.path.isdir(os.path.join(path, "vae")):
+        from .vae import FusedVAE
+
+        vae = FusedVAE(load_vae_state_dict(path), device=device)
     if os.path.isdir(path) and (tokenizer is None or text_encoder is None):
         tok, enc = load_text_components(path, device=device)
         tokenizer = tokenizer if tokenizer is not None else tok

@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           x0 = p0; y0 = 0; b0 = 0;
         } else {
           b0 = p0 / p.HW;
-          y0 = (p0 - b0 * p.HW) / p.W;
-          x0 = 0;
+          const int rem = p0 - b0 * p.HW;
+          y0 = rem / p.W;
+          x0 = rem - y0 * p.W;  // 0 unless the image is wider than one tile (W = 256 / 512: the VAE levels)
         }
         // K-block cursor kept incrementally (segment, tap offsets, channel chunk): an integer division per K block put
         // a ~150-cycle dependent chain into this loop, which has nothing else to overlap it with
@@ -451,6 +452,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 }
               }
             }
+            if (p.out_scale != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+            }
             if (p.bias != nullptr) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -469,9 +474,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
               // conv_out: the first four columns go out as fp32 NCHW, one image plane per column (coalesced over pixels)
               if (valid && c == 0) {
                 const int bimg = m / p.HW, pix = m - bimg * p.HW;
-                float* o32 = p.out32 + static_cast<size_t>(bimg) * 4 * p.HW + pix;
+                float* o32 = p.out32 + static_cast<size_t>(bimg) * p.out32_ch * p.HW + pix;
 #pragma unroll
-                for (int co = 0; co < 4; ++co) o32[static_cast<size_t>(co) * p.HW] = v[co];
+                for (int co = 0; co < 8; ++co)
+                  if (co < p.out32_ch) o32[static_cast<size_t>(co) * p.HW] = v[co];
               }
             } else if (valid) {
               if (has_res) {
@@ -755,9 +761,11 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
     PNP_CHECK(B == 1 && H == 1, "gemm: linear mode takes M as W");
     box[0] = BK; box[1] = BM; box[2] = 1; box[3] = 1;
   } else {
-    PNP_CHECK(W <= 128 && 128 % W == 0, "gemm: conv mode needs W | 128");
-    const int rows = 128 / W;  // image rows per tile
-    if (rows <= H) {
+    PNP_CHECK((W <= 128 && 128 % W == 0) || W % 128 == 0, "gemm: conv mode needs W | 128 or 128 | W");
+    const int rows = 128 / W;  // image rows per tile (0: the image is wider than a tile)
+    if (rows == 0) {
+      box[0] = BK; box[1] = 128; box[2] = 1; box[3] = 1;
+    } else if (rows <= H) {
       PNP_CHECK(H % rows == 0, "gemm: conv tile rows must divide H");
       box[0] = BK; box[1] = W; box[2] = rows; box[3] = 1;
     } else {
@@ -809,6 +817,9 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   p.ldr = ep.ldr;
   p.out = ep.out;
   p.out32 = ep.out_f32_nchw4;
+  p.out32_ch = ep.out32_channels;
+  p.out_scale = ep.out_scale;
+  PNP_CHECK(ep.out32_channels >= 1 && ep.out32_channels <= 8, "gemm: 1..8 fp32 NCHW output planes");
   p.ldc = ep.ldc;
   p.geglu = geglu ? 1 : 0;
   p.dbg = debug_words_device();

@@ -117,6 +117,8 @@ struct alignas(64) GemmParams {
   // epilogue thread 128 (total, wait tfull); null in production
   long long* prof;
   float* out32;  // GemmEpilogue::out_f32_nchw4
+  int out32_ch;  // planes written there (first out32_ch columns of the tile)
+  float out_scale;  // accumulators are multiplied by this before bias / residual (1 = off)
   int exp;  // experiments (PNP_GEMM_EXP, test entry points only): 1 = no TMA copies, 2 = no MMAs
 };
 
@@ -142,6 +144,8 @@ struct GemmEpilogue {
   // conv_out: instead of the fp16 NHWC tile, columns 0..3 are written as fp32 NCHW [B,4,H,W] (the UNet's eps output);
   // the weight matrix is zero-padded to one 64-column tile
   float* out_f32_nchw4 = nullptr;
+  int out32_channels = 4;  // ... or the first 1..8 columns (VAE: 3 image planes, 8 posterior moments)
+  float out_scale = 1.0f;  // D = out_scale * (A . W^T) + bias ... (single-head VAE attention: 1/sqrt(C) on Q.K^T)
 };
 
 // fp16 tiled tensor map with 128-byte swizzle and zero out-of-bounds fill (rank 2..4); strides in bytes for dims 1..

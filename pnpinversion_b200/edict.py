@@ -42,27 +42,34 @@ def attention_edit_tables(tokens: Sequence[int], tokens_edit: Sequence[int]):
 
 
 class EdictP2PController:
-    """Batch rows [uncond, cond(source prompt), cond(edit prompt)] on one latent."""
+    """Batch rows [uncond x L | cond(source prompts) x L | cond(edit prompts) x L] on the L latents of one call (the
+    reference handles one image: L = 1; config 5 of BASELINE.json batches 8).  `masks` / `indices`: one (77,) table per
+    image, or a single table for L = 1."""
 
     def __init__(self, mask, indices, weights=None):
-        self.mask, self.indices = mask, indices
+        self.masks = list(mask) if isinstance(mask, (list, tuple)) else [mask]
+        self.indices = list(indices) if isinstance(indices, (list, tuple)) else [indices]
         self.weights = weights if weights is not None else torch.ones(MAX_TOKENS)
         self.num_att_layers = 32
+        if len(self.masks) > _lib.PNP_MAX_SLOTS:
+            raise _lib.PnpError(f"at most {_lib.PNP_MAX_SLOTS} images per EDICT batch")
 
     def descriptor(self, batch):
-        if batch != 3:
-            raise _lib.PnpError("EDICT P2P expects the batch [uncond, cond, cond_edit]")
+        L = len(self.masks)
+        if batch != 3 * L:
+            raise _lib.PnpError(f"EDICT P2P expects the batch [uncond, cond, cond_edit] x {L} images, got {batch}")
         c = _lib.new_ctrl()
         c.self_layer_lo, c.self_layer_hi, c.self_max_tokens = 0, 16, 1 << 30  # attn1 reused wholesale in every layer
-        c.self_q_row[2] = 1
-        c.self_k_row[2] = 1
-        c.cross_base_row[2] = 1
-        c.cross_slot[2] = 0
-        for w in range(MAX_TOKENS):
-            c.mapper[0][w] = int(self.indices[w])
-            c.alphas[0][w] = float(self.mask[w])
-            c.equalizer[0][w] = float(self.weights[w])
-            c.cross_alpha[0][w] = 1.0
+        for img in range(L):
+            src, tgt = L + img, 2 * L + img
+            c.self_q_row[tgt] = src
+            c.self_k_row[tgt] = src
+            c.cross_base_row[tgt] = src
+            c.cross_slot[tgt] = img
+            c.mapper[img][:] = [int(v) for v in self.indices[img]]
+            c.alphas[img][:] = [float(v) for v in self.masks[img]]
+            c.equalizer[img][:] = [float(v) for v in self.weights]
+            c.cross_alpha[img][:] = [1.0] * MAX_TOKENS
         return c
 
     def after_unet_call(self):
@@ -85,7 +92,8 @@ def step_coeffs(sched, t: int, ratio: int, reverse: bool):
     return (q, float((1 - a_t) ** 0.5), 1.0, float((1 - a_p) ** 0.5))
 
 
-def _embed(model, text: str):
+def _embed(model, text):
+    """text: one prompt or a list of L prompts -> (ids [L,77], embeddings [L,77,768])"""
     tok, enc = model.tokenizer, model.text_encoder
     ids = tok(text, padding="max_length", max_length=tok.model_max_length, truncation=True, return_tensors="pt")
     return ids, enc(ids.input_ids.to(model.device))[0].to(model.device, torch.float32)
@@ -96,7 +104,8 @@ def coupled_stablediffusion(model, prompt="", prompt_edit=None, null_prompt="", 
                             init_image=None, init_image_strength=1.0, reverse=False, fixed_starting_latent=None,
                             mix_weight=0.93, leapfrog_steps=True, run_baseline=False):
     """Returns the coupled latent pair [x, y] (the reference returns it for reverse=True / return_latents=True; the
-    VAE decode of the forward direction is outside this library)."""
+    VAE decode of the forward direction is outside this library).  `prompt` / `prompt_edit` may be lists of L prompts
+    with (L,4,64,64) latents: L images share every UNet call (BASELINE config 5: batch 8)."""
     if run_baseline:
         raise NotImplementedError("run_baseline=True is plain DDIM, covered by the P2P / MasaCtrl paths")
     dev = model.device
@@ -116,17 +125,22 @@ def coupled_stablediffusion(model, prompt="", prompt_edit=None, null_prompt="", 
     sched.set_timesteps(steps)
     ratio = sched.config.num_train_timesteps // steps
 
-    ids_c, emb_c = _embed(model, prompt)
-    _, emb_u = _embed(model, null_prompt)
+    L = pair[0].shape[0]
+    as_list = lambda p: list(p) if isinstance(p, (list, tuple)) else [p] * L
+    prompts = as_list(prompt)
+    if len(prompts) != L:
+        raise ValueError(f"{len(prompts)} prompts for {L} latents")
+    ids_c, emb_c = _embed(model, prompts)
+    _, emb_u = _embed(model, [null_prompt] * L)
     controller = None
     if prompt_edit is not None:
-        ids_e, emb_e = _embed(model, prompt_edit)
-        mask, indices = attention_edit_tables(ids_c.input_ids[0].tolist(), ids_e.input_ids[0].tolist())
-        controller = EdictP2PController(mask, indices)
+        ids_e, emb_e = _embed(model, as_list(prompt_edit))
+        tabs = [attention_edit_tables(ids_c.input_ids[i].tolist(), ids_e.input_ids[i].tolist()) for i in range(L)]
+        controller = EdictP2PController([m for m, _ in tabs], [ix for _, ix in tabs])
         context = torch.cat([emb_u, emb_c, emb_e]).contiguous()
     else:
         context = torch.cat([emb_u, emb_c]).contiguous()
-    nb = context.shape[0]
+    groups = context.shape[0] // L  # 2 = [uncond, cond], 3 = [uncond, cond, cond_edit]
     model.unet.set_controller(controller)
     lib, h = _lib.load(), model.unet.handle
 
@@ -145,11 +159,11 @@ def coupled_stablediffusion(model, prompt="", prompt_edit=None, null_prompt="", 
             else:
                 latent_i = (k + i % 2) % 2 if leapfrog_steps else k
             latent_j = (latent_i + 1) % 2
-            x_in = pair[latent_j].expand(nb, -1, -1, -1).contiguous()
+            x_in = torch.cat([pair[latent_j]] * groups).contiguous()
             eps = model.unet(x_in, tt, encoder_hidden_states=context)["sample"]
-            eps_c = eps[nb - 1:nb]  # cond (or cond_edit when P2P is on) -- edict_functions.py:913-915
+            eps_c = eps[(groups - 1) * L:]  # cond (or cond_edit when P2P is on) -- edict_functions.py:913-915
             co = step_coeffs(sched, tt, ratio, reverse)
-            pair[latent_i] = fused_step(h, pair[latent_i], eps_c.contiguous(), co, eps_u=eps[0:1].contiguous(),
+            pair[latent_i] = fused_step(h, pair[latent_i], eps_c.contiguous(), co, eps_u=eps[0:L].contiguous(),
                                         guidance=guidance_scale)
         if not reverse:
             _lib.check(lib.pnp_edict_mix(h, C.c_void_p(pair[0].data_ptr()), C.c_void_p(pair[1].data_ptr()),
@@ -173,7 +187,7 @@ def EDICT_editing(model, latent, base_prompt, edit_prompt, use_p2p=False, steps=
 def edit_image_edict_p2p(model, image_path, prompt_src, prompt_tar, use_p2p, steps=50):
     """run_editing_edict.py:32-61 on latents: returns (reconstruction pair, edit pair)."""
     if not (isinstance(image_path, torch.Tensor) and image_path.dim() == 4):
-        raise _lib.PnpError("pass the (1,4,64,64) image latent (the VAE is outside this library)")
+        raise _lib.PnpError("pass the (L,4,64,64) image latents (prompts: one string, or a list of L)")
     latents = coupled_stablediffusion(model, prompt_src, reverse=True, init_image=image_path, steps=steps)
     recon = coupled_stablediffusion(model, prompt_src, reverse=False, fixed_starting_latent=latents, steps=steps)
     edit = EDICT_editing(model, image_path, prompt_src, prompt_tar, use_p2p=use_p2p, steps=steps)

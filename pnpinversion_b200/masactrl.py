@@ -14,6 +14,7 @@ here `MutualSelfAttentionControl` lowers itself to the K/V source-row indirectio
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -56,8 +57,10 @@ class AttentionBase:
 class MutualSelfAttentionControl(AttentionBase):
     MODEL_TYPE = {"SD": 16, "SDXL": 70}
 
-    def __init__(self, start_step=4, start_layer=10, layer_idx=None, step_idx=None, total_steps=50, model_type="SD"):
+    def __init__(self, start_step=4, start_layer=10, layer_idx=None, step_idx=None, total_steps=50, model_type="SD",
+                 images=1):
         super().__init__()
+        self.images = images  # L images per call, rows prompt-major inside each CFG half (batched.py)
         if model_type != "SD":
             raise NotImplementedError("only the SD-1.x UNet (16 transformer blocks) is implemented")
         self.total_steps = total_steps
@@ -80,8 +83,11 @@ class MutualSelfAttentionControl(AttentionBase):
         c = _lib.new_ctrl()
         c.self_layer_lo, c.self_layer_hi = self._layers
         c.self_max_tokens = 1 << 30
+        if n % self.images:
+            raise _lib.PnpError(f"a CFG half of {n} rows does not hold {self.images} images")
         for r in range(batch):
-            src = 0 if r < n else n  # ku[:num_heads] / kc[:num_heads]: the first image of each CFG half
+            # ku[:num_heads] / kc[:num_heads]: the first prompt (= the source) of each CFG half, for the same image
+            src = (0 if r < n else n) + (r % n) % self.images
             c.self_k_row[r] = src
             c.self_v_row[r] = src
         return c
@@ -158,6 +164,14 @@ class MasaCtrlResult:
     latents: torch.Tensor         # (2,4,64,64): [reconstruction of the source, MasaCtrl edit]
 
 
+@dataclass
+class MasaCtrlBatchResult:
+    x_stars: torch.Tensor       # (n+1, L, 4,64,64)
+    noise_loss: torch.Tensor    # (n, 2L, 4,64,64) prompt-major
+    latents_fixed: torch.Tensor  # (L, 4,64,64)
+    latents: torch.Tensor       # (2L, 4,64,64): rows [0,L) reconstructions of the sources, [L,2L) MasaCtrl edits
+
+
 class MasaCtrlEditor:
     def __init__(self, method_list, device, num_ddim_steps=50, model=None) -> None:
         if model is None:
@@ -176,6 +190,38 @@ class MasaCtrlEditor:
             return self.edit_image_directinversion_MasaCtrl(image_path, prompt_src, prompt_tar, guidance_scale,
                                                             step=step, layper=layper)
         raise NotImplementedError(f"No edit method named {edit_method}")
+
+    def edit_batch(self, latents, prompts_tar, guidance_scale=7.5, step=4, layper=10):
+        """`directinversion+masactrl` (run_editing_masactrl.py:89-129) for L images per call - BASELINE config 4
+        (batch 4 -> UNet batch 16) - with every 50-step loop inside libpnpinv.so (`pnp_run_loop`): inversion (B = L),
+        offsets with prompts ["", target] (B = 4L), direct synthesis with the target prompt (B = 2L), MasaCtrl pass
+        (B = 4L) = 550 UNet sample-forwards per image.  Returns MasaCtrlBatchResult."""
+        from . import batched as bt
+
+        m, n = self.model, self.num_ddim_steps
+        L = latents.shape[0]
+        b = bt.BatchedDirectInversionP2P(m, n)
+        x_stars, noise_loss = b.invert(latents, [""] * L, list(prompts_tar), guidance_scale=guidance_scale)
+        ts, fwd_co = b._sched
+        x_T = x_stars[n]
+        ctx = b._ctx  # [uncond 2L | "" x L, target x L]
+        ctx_fixed = torch.cat([ctx[:L], ctx[3 * L:]]).contiguous()
+        fixed = x_T.clone().contiguous()
+        bt.run_loop(m, _lib.PNP_LOOP_FORWARD, n, L, L, ts, fwd_co, guidance_scale, ctx_fixed, fixed)
+        editor = MutualSelfAttentionControl(step, layper, total_steps=n, images=L)
+        ctrls = (_lib.AttnCtrl * n)()
+        lib = _lib.load()
+        for i in range(n):
+            d = editor.descriptor(4 * L)
+            if d is None:
+                lib.pnp_attn_ctrl_init(C.byref(ctrls[i]))
+            else:
+                ctrls[i] = d
+            editor.after_unet_call()
+        out = torch.cat([x_T] * 2).contiguous()
+        bt.run_loop(m, _lib.PNP_LOOP_FORWARD, n, 2 * L, L, ts, fwd_co, guidance_scale, ctx, out, loss=noise_loss,
+                    add_mask=(1 << L) - 1, ctrls=ctrls)
+        return MasaCtrlBatchResult(x_stars, noise_loss, fixed, out)
 
     def _latent(self, image_path):
         if isinstance(image_path, torch.Tensor) and image_path.dim() == 4:

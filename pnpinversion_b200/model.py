@@ -158,13 +158,19 @@ class FusedModel:
                           table_dtype=self.table_dtype, share_weights_with=self)
 
     @classmethod
-    def synthetic(cls, device="cuda:0", max_batch: int = 4, seed: int = 0, table_dtype: str = "float32"):
-        """Random-init SD-1.x UNet + fake tokenizer / text encoder (pnpinversion_b200/synth.py) -- the offline stand-in
-        for StableDiffusionPipeline.from_pretrained("CompVis/stable-diffusion-v1-4")."""
+    def synthetic(cls, device="cuda:0", max_batch: int = 4, seed: int = 0, table_dtype: str = "float32",
+                  with_vae: bool = False):
+        """Random-init SD-1.x UNet (+ VAE) + fake tokenizer / text encoder (pnpinversion_b200/synth.py) -- the offline
+        stand-in for StableDiffusionPipeline.from_pretrained("CompVis/stable-diffusion-v1-4")."""
         from . import synth
 
+        vae = None
+        if with_vae:
+            from .vae import FusedVAE
+
+            vae = FusedVAE(synth.synth_vae_state_dict(seed), device=device)
         return cls(synth.synth_unet_state_dict(seed), device=device, max_batch=max_batch,
-                   tokenizer=synth.FakeTokenizer(), text_encoder=synth.SynthTextEncoder(), vae=None,
+                   tokenizer=synth.FakeTokenizer(), text_encoder=synth.SynthTextEncoder(), vae=vae,
                    table_dtype=table_dtype)
 
     @classmethod
