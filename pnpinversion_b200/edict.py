@@ -192,3 +192,25 @@ def edit_image_edict_p2p(model, image_path, prompt_src, prompt_tar, use_p2p, ste
     recon = coupled_stablediffusion(model, prompt_src, reverse=False, fixed_starting_latent=latents, steps=steps)
     edit = EDICT_editing(model, image_path, prompt_src, prompt_tar, use_p2p=use_p2p, steps=steps)
     return recon, edit
+
+
+def edit_image_edict_p2p_strip(model, image_path, prompt_src, prompt_tar, use_p2p, steps=50):
+    """run_editing_edict.py:32-61 end to end: image file / HWC uint8 array -> the 2048x512 strip
+    [instruction | source | reconstruction | edit].  The reference draws the initial latent from the VAE posterior
+    (`latent_dist.sample()`, edict_functions.py:753) under the seed its caller set; so does this."""
+    import numpy as np
+    from PIL import Image
+
+    from .ptp_utils import latent2image, load_512, txt_draw
+
+    if model.vae is None:
+        raise _lib.PnpError("edit_image_edict_p2p_strip needs a VAE on the model handle")
+    image_gt = load_512(image_path)
+    img = torch.from_numpy(image_gt.astype(np.float32) / 255.0 * 2.0 - 1.0).permute(2, 0, 1).unsqueeze(0).to(model.device)
+    dist = model.vae.encode(img)["latent_dist"]
+    z = (dist.mean + torch.exp(0.5 * dist.logvar) * torch.randn(dist.mean.shape, device=model.device)) * 0.18215
+    recon, edit = edit_image_edict_p2p(model, z, prompt_src, prompt_tar, use_p2p, steps=steps)
+    rec_img = latent2image(model.vae, recon[0], rounding=True)[0]
+    edit_img = latent2image(model.vae, edit[0], rounding=True)[0]
+    instruct = txt_draw(f"source prompt: {prompt_src}\ntarget prompt: {prompt_tar}")
+    return Image.fromarray(np.concatenate((instruct, image_gt, rec_img, edit_img), axis=1))

@@ -185,11 +185,36 @@ class MasaCtrlEditor:
 
     def __call__(self, edit_method, image_path, prompt_src, prompt_tar, guidance_scale, step=4, layper=10):
         if edit_method == "ddim+masactrl":
-            return self.edit_image_ddim_MasaCtrl(image_path, prompt_src, prompt_tar, guidance_scale, step=step, layper=layper)
+            res = self.edit_image_ddim_MasaCtrl(image_path, prompt_src, prompt_tar, guidance_scale, step=step, layper=layper)
         elif edit_method == "directinversion+masactrl":
-            return self.edit_image_directinversion_MasaCtrl(image_path, prompt_src, prompt_tar, guidance_scale,
-                                                            step=step, layper=layper)
-        raise NotImplementedError(f"No edit method named {edit_method}")
+            res = self.edit_image_directinversion_MasaCtrl(image_path, prompt_src, prompt_tar, guidance_scale,
+                                                           step=step, layper=layper)
+        else:
+            raise NotImplementedError(f"No edit method named {edit_method}")
+        if isinstance(image_path, torch.Tensor) or self.model.vae is None:
+            return res  # latents in, latents out
+        return self._strip(load_512(image_path), prompt_src, prompt_tar, res.latents)
+
+    def _strip(self, image_gt, prompt_src, prompt_tar, latents2):
+        """run_editing_masactrl.py:121-129: [instruction | source | reconstruction (row 0) | MasaCtrl edit (row -1)]."""
+        import numpy as np
+        from PIL import Image
+
+        from .ptp_utils import latent2image, txt_draw
+
+        imgs = latent2image(self.model.vae, latents2)
+        instruct = txt_draw(f"source prompt: {prompt_src}\ntarget prompt: {prompt_tar}")
+        return Image.fromarray(np.concatenate((instruct, image_gt, imgs[0], imgs[-1]), axis=1))
+
+    def edit_batch_images(self, image_paths, prompts_src, prompts_tar, guidance_scale=7.5, step=4, layper=10):
+        """`directinversion+masactrl` for a list of images in one pass -> list of PIL strips."""
+        from .ptp_utils import image2latent
+
+        gts = [load_512(p) for p in image_paths]
+        lat = torch.cat([image2latent(self.model.vae, g) for g in gts]).to(self.model.device, torch.float32)
+        res = self.edit_batch(lat, list(prompts_tar), guidance_scale=guidance_scale, step=step, layper=layper)
+        L = len(gts)
+        return [self._strip(g, prompts_src[i], prompts_tar[i], res.latents[[i, L + i]]) for i, g in enumerate(gts)]
 
     def edit_batch(self, latents, prompts_tar, guidance_scale=7.5, step=4, layper=10):
         """`directinversion+masactrl` (run_editing_masactrl.py:89-129) for L images per call - BASELINE config 4

@@ -42,13 +42,14 @@ def init_latent(latent, model, height, width, generator, batch_size):
 
 
 @torch.no_grad()
-def latent2image(model, latents, return_type="np"):
+def latent2image(model, latents, return_type="np", rounding=False):
     latents = 1 / 0.18215 * latents.detach()
     image = model.decode(latents)["sample"]
     if return_type == "np":
         image = (image / 2 + 0.5).clamp(0, 1)
         image = image.cpu().permute(0, 2, 3, 1).numpy()
-        image = (image * 255).astype(np.uint8)  # truncation like the reference
+        # utils/utils.py:79 truncates; EDICT's prep_image_for_return rounds (edict_functions.py:698)
+        image = (image * 255).round().astype(np.uint8) if rounding else (image * 255).astype(np.uint8)
     return image
 
 
