@@ -127,6 +127,22 @@ def run_reference(args, rank, world):
     # the B=4 : B=1 ratio of that first measurement.  K = 3 steps ~ 2 minutes, K = 10 ~ 3-4 minutes.
     first = cpu_unet_times(sd, threads)
     ratio = first["b4"] / first["b1"]
+    # BASELINE config 1 timed IN FULL: the 20-step DDIM inversion of one latent through the
+    # oracle port's UNet and inverse step, 20 B=1 forwards
+    cfg1_s = None
+    if not args.no_config1:
+        from oracle import p2p_ref, unet_ref
+
+        ref = unet_ref.UNetRef(sd, dtype=torch.float32)
+        tok, te = synth.FakeTokenizer(), synth.SynthTextEncoder()
+        ctx1 = te(tok([synth.CAT_PROMPTS[0]]).input_ids)[0]
+        sch = p2p_ref.Schedule(20, "float32")
+        x = synth.synth_latent(0)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for t in [50 * i for i in range(20)]:
+                x = sch.next_step(ref(x, t, ctx1).float(), t, x)
+        cfg1_s = time.perf_counter() - t0
     vals = []
     t_all0 = time.perf_counter()
     for i in range(args.steps):
@@ -143,7 +159,8 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"per step: one B=1 fp32 UNet forward of oracle/unet_ref.py ({1000 * wall / max(args.steps, 1):.0f} ms); "
                                    f"B=4 forward measured once ({first['b4']:.1f} s = {ratio:.2f} x B=1); x150 / x50 "
-                                   "extrapolation to one image (650 UNet sample-forwards)"},
+                                   "extrapolation to one image (650 UNet sample-forwards)",
+                         "config1_20_step_inversion_s": cfg1_s},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -157,7 +174,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=3, help="images that share every UNet call (UNet batch L / 4L)")
+    ap.add_argument("--no-config1", action="store_true", help="reference arm: skip the full 20-step config-1 timing")
+    ap.add_argument("--workload", default="p2p", choices=["p2p", "masactrl", "edict"],
+                    help="p2p: directinversion+p2p (BASELINE configs 2/3, the headline); masactrl: directinversion+masactrl "
+                         "(config 4, default batch 4 -> UNet batch 16); edict: edict+p2p (config 5, default batch 8)")
+    ap.add_argument("--batch", type=int, default=0, help="images that share every UNet call (0 = the workload's default)")
     ap.add_argument("--lanes", type=int, default=2,
                     help="passes in flight per GPU (own CUDA stream / engine handle / host thread, shared weights)")
     args = ap.parse_args()
@@ -184,11 +205,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from pnpinversion_b200.parallel import EditLanes
 
+    WL = {"p2p": dict(batch=4, fwd=650, rows=4, name="directinversion+p2p",
+                      what="UNet batch L for the inversion, 4L for the offset / reconstruction / edit loops"),
+          "masactrl": dict(batch=4, fwd=550, rows=4, name="directinversion+masactrl",
+                           what="UNet batch L inversion, 4L offsets, 2L direct synthesis, 4L mutual self-attention pass"),
+          "edict": dict(batch=8, fwd=800, rows=3, name="edict+p2p",
+                        what="coupled pair: 2 x (50 + 50 + 40) steps at UNet batch 2L, 2 x 40 P2P steps at 3L")}[args.workload]
+    FWD = WL["fwd"]
     sd = synth.synth_unet_state_dict(0)
-    NB = max(1, args.batch)          # images per pass
+    NB = max(1, args.batch or WL["batch"])  # images per pass
     NL = max(1, args.lanes)          # concurrent passes
     L = NB * NL                      # images per step and GPU
-    parent = FusedModel(sd, device=str(dev), max_batch=4 * NB, tokenizer=synth.FakeTokenizer(),
+    parent = FusedModel(sd, device=str(dev), max_batch=WL["rows"] * NB, tokenizer=synth.FakeTokenizer(),
                         text_encoder=synth.SynthTextEncoder())
     made = []
 
@@ -201,11 +229,23 @@ def main():
     model = parent
     src, tgt = synth.CAT_PROMPTS
 
+    from types import SimpleNamespace
+
     def edit_on(editor, z):
-        """z: (NB,1,4,64,64) or (NB,4,64,64) latents of one pass -> BatchEditResult"""
+        """z: (NB,1,4,64,64) or (NB,4,64,64) latents of one pass -> object with .latents (the edited latents)"""
         zz = z.reshape(NB, 4, 64, 64).to(dev, non_blocking=True)
-        return editor.edit_batch(zz, [src] * NB, [tgt] * NB, guidance_scale=7.5, cross_replace_steps=0.4,
-                                 self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
+        if args.workload == "p2p":
+            return editor.edit_batch(zz, [src] * NB, [tgt] * NB, guidance_scale=7.5, cross_replace_steps=0.4,
+                                     self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
+        if args.workload == "masactrl":
+            from pnpinversion_b200.masactrl import MasaCtrlEditor
+
+            me = MasaCtrlEditor(["directinversion+masactrl"], dev, num_ddim_steps=50, model=editor.ldm_stable)
+            return me.edit_batch(zz, [tgt] * NB, guidance_scale=7.5, step=4, layper=10)
+        from pnpinversion_b200.edict import edit_image_edict_p2p
+
+        recon, edit = edit_image_edict_p2p(editor.ldm_stable, zz, [src] * NB, [tgt] * NB, use_p2p=True, steps=50)
+        return SimpleNamespace(latents=torch.cat([recon[0], edit[0]]))
 
     def edit_step(zs):
         """One bench step = NL passes of NB images, one pass per lane, through the public editor call."""
@@ -282,7 +322,8 @@ def main():
     e2e_value = world * args.steps * L / (float(ms2.item()) / 1000.0)
     # per pass: NB latents from pinned memory + the [4 NB,77,768] fp32 context rows (the synthetic text encoder runs on
     # the host, its output is uploaded once per pass)
-    h2d = NL * (NB * 4 * 64 * 64 * 4 + 4 * NB * 77 * 768 * 4)
+    ctx_rows = {"p2p": 4, "masactrl": 4, "edict": 9}[args.workload] * NB  # edict: 4 coupled passes encode 2+2+2+3 rows per image
+    h2d = NL * (NB * 4 * 64 * 64 * 4 + ctx_rows * 77 * 768 * 4)
     d2h = NL * 2 * NB * 4 * 64 * 64 * 4
 
     if rank != 0:
@@ -302,8 +343,14 @@ def main():
     agg = {k: [0.0, 0.0, 0] for k in kinds.values()}
     reps = 3
     per_op = None
+    PB = WL["rows"] * NB  # the UNet batch of the guided loops
+    if model.unet._ctx_batch != PB or True:
+        # pnp_unet_profile needs the context of that batch size installed on this handle
+        ctxp = torch.zeros(PB, 77, 768, device=dev)
+        _lib.check(lib.pnp_set_context(model.unet.handle, C.c_void_p(ctxp.data_ptr()), PB, _lib.current_stream_ptr()))
+        model.unet._ctx_ref = None
     for _ in range(reps):
-        _lib.check(lib.pnp_unet_profile(model.unet.handle, 4 * NB, 501, 10, ms_op, kind, fl, maxops, C.byref(n)))
+        _lib.check(lib.pnp_unet_profile(model.unet.handle, PB, 501, 10, ms_op, kind, fl, maxops, C.byref(n)))
         if per_op is None:
             per_op = [[kind[i], fl[i], 0.0] for i in range(n.value)]
         for i in range(n.value):
@@ -323,7 +370,7 @@ def main():
     achieved = g[1] / (g[0] * 1e-3) / 1e12 if g[0] > 0 else 0.0
     roofline = {
         "bound": "tensor",
-        "kernel": f"gemm_tcgen05_kernel<BN> (all GEMM / implicit-conv launches of one B={4 * NB} UNet call)",
+        "kernel": f"gemm_tcgen05_kernel<BN> (all GEMM / implicit-conv launches of one B={PB} UNet call)",
         "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
         "peak_source": f"{peak_src} bf16_tflops (burst: every op is timed alone, 10 launches back to back between two "
                        f"CUDA events); sustained {sustained}",
@@ -331,12 +378,12 @@ def main():
         "launches_per_unet_call": n_gemm, "gflop_per_launch_avg": g[1] / max(n_gemm, 1) / 1e9,
         "avg_launch_us": 1000.0 * g[0] / max(n_gemm, 1), "share_of_unet_time": g[0] / tot_ms if tot_ms else None,
         "traffic": None,
-        "unet_batch": 4 * NB,
+        "unet_batch": PB,
         "by_kernel_ms_per_unet_call": {k: round(v[0], 4) for k, v in agg.items()},
         "unet_sum_of_kernels_ms": tot_ms,
-        "unet_tflops_sum_of_kernels": 4 * NB * UNET_GFLOP / tot_ms / 1e3 if tot_ms else None,
-        "whole_job_tflops": value * FWD_PER_IMAGE * UNET_GFLOP / 1e3,
-        "whole_job_frac_of_sustained_peak": value * FWD_PER_IMAGE * UNET_GFLOP / 1e3 / (sustained * world),
+        "unet_tflops_sum_of_kernels": PB * UNET_GFLOP / tot_ms / 1e3 if tot_ms else None,
+        "whole_job_tflops": value * FWD * UNET_GFLOP / 1e3,
+        "whole_job_frac_of_sustained_peak": value * FWD * UNET_GFLOP / 1e3 / (sustained * world),
     }
     # `traffic` stays null: DRAM bytes per launch come from an ncu capture, which cannot run inside a timed bench; the
     # warm-cache captures of this build are under profiles/ (r2_*)
@@ -354,10 +401,10 @@ def main():
         "metric": "images_per_sec_512x512_50step_invert_edit", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"directinversion+p2p 50 steps, {L} image(s) per step and GPU = {NL} concurrent pass(es) x "
-                               f"{NB} image(s) per pass (UNet batch {NB} for the inversion, {4 * NB} for the offset / "
-                               "reconstruction / edit loops), faithful 650 UNet forwards per image, SD-1.x random-init "
-                               "UNet, cat prompts, step loops inside libpnpinv.so (pnp_run_loop)",
+        "config": {"workload": f"{WL['name']} 50 steps, {L} image(s) per step and GPU = {NL} concurrent pass(es) x "
+                               f"{NB} image(s) per pass ({WL['what']}), faithful {FWD} UNet sample-forwards per image, "
+                               "SD-1.x random-init UNet, cat prompts"
+                               + (", step loops inside libpnpinv.so (pnp_run_loop)" if args.workload != "edict" else ""),
                    "images_per_step_per_gpu": L, "lanes_per_gpu": NL, "images_per_pass": NB,
                    "weights": "one fp16 copy per GPU shared by all lanes (pnp_clone)",
                    "parallelism": f"image-parallel x{world} GPUs x {NL} concurrent passes (CUDA streams) x {NB} images "

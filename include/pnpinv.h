@@ -185,6 +185,10 @@ int pnp_store_reset(pnp_engine* h, void* stream);          /* AttentionStore.res
 /* debug/inspection: copy the accumulated maps [5][2*PNP_MAX_SLOTS... see DESIGN.md] */
 int pnp_store_read(pnp_engine* h, float* out_dev, int64_t max_floats, void* stream);
 
+/* inspection: the activations the last forward of this batch size left in skip tensor `which` (0..11: conv_in output,
+ * then every down-path block output; fp16 NHWC [batch, H, W, C]) - used by tools/diag_layers.py */
+int pnp_debug_read(pnp_engine* h, int batch, int which, uint16_t* out_dev, int64_t max_elems, int64_t* n_out, void* stream);
+
 /* sizeof() of the boundary structs as this library was compiled (0 pnp_attn_ctrl, 1 pnp_step_args, 2 pnp_blend_desc,
  * 3 pnp_loop_args): lets a binding verify its mirror of the layouts at load time. */
 int pnp_struct_size(int which);

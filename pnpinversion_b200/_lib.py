@@ -135,6 +135,7 @@ SIGNATURES = {
     "pnp_store_reset": (_i, [_vp, _vp]),
     "pnp_store_read": (_i, [_vp, _vp, _i64, _vp]),
     "pnp_unet_profile": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(C.c_int32), C.POINTER(C.c_double), _i, C.POINTER(_i)]),
+    "pnp_debug_read": (_i, [_vp, _i, _i, _vp, _i64, C.POINTER(_i64), _vp]),
     "pnp_struct_size": (_i, [_i]),
     "pnp_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
     "pnp_set_use_graph": (_i, [_vp, _i]),

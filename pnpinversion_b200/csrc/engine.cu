@@ -283,6 +283,7 @@ struct Plan {
   __half* ctxkv[16] = {nullptr};
   float* gemm_ws = nullptr;      // shared split-K workspace
   int* gemm_counters = nullptr;  // zero-initialised, self-resetting
+  std::vector<std::pair<const __half*, size_t>> dbg;  // inspection points: the 12 skip tensors (pnp_debug_read)
 };
 
 constexpr int kStoreLayers = 5;
@@ -743,6 +744,7 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
   __half* SK[12];
   for (int i = 0; i < 12; ++i) SK[i] = pb.buf(static_cast<size_t>(B) * skip_hw[i] * skip_hw[i] * skip_c[i]);
   if (pb.rc) return pb.rc;
+  for (int i = 0; i < 12; ++i) pl->dbg.push_back({SK[i], static_cast<size_t>(B) * skip_hw[i] * skip_hw[i] * skip_c[i]});
 
   // context K/V buffers and their projection plans
   pl->ctx16 = pb.buf(static_cast<size_t>(B) * 77 * kCrossDim);
@@ -1557,6 +1559,19 @@ int pnp_store_read(pnp_engine* h, float* out_dev, int64_t max_floats, void* stre
   PNP_CHECK(h && h->finalized && out_dev, "pnp_store_read: bad argument");
   const size_t n = std::min<size_t>(static_cast<size_t>(max_floats), kStoreFloats);
   PNP_CUDA(cudaMemcpyAsync(out_dev, h->store, n * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
+  return 0;
+}
+
+int pnp_debug_read(pnp_engine* h, int batch, int which, uint16_t* out_dev, int64_t max_elems, int64_t* n_out, void* stream) {
+  PNP_CHECK(h && h->finalized && out_dev && n_out, "pnp_debug_read: bad argument");
+  auto it = h->plans.find(batch);
+  PNP_CHECK(it != h->plans.end(), "pnp_debug_read: no plan for this batch size yet");
+  Plan* pl = it->second.get();
+  PNP_CHECK(which >= 0 && which < static_cast<int>(pl->dbg.size()), "pnp_debug_read: index");
+  const size_t n = std::min<size_t>(pl->dbg[which].second, static_cast<size_t>(max_elems));
+  PNP_CUDA(cudaStreamSynchronize(h->es));
+  PNP_CUDA(cudaMemcpyAsync(out_dev, pl->dbg[which].first, n * sizeof(uint16_t), cudaMemcpyDeviceToDevice, as_stream(stream)));
+  *n_out = static_cast<int64_t>(n);
   return 0;
 }
 

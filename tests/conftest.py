@@ -27,4 +27,9 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.fail("this test is marked gpu and needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(0)
+    # the fp32 references of the kernel tests are computed by PyTorch on the GPU: keep them true fp32 (cuDNN / cuBLAS
+    # would otherwise be free to use TF32, 10 mantissa bits - no better than the fp16 operands under test)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
     return torch.device("cuda:0")

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def model(cuda):
-    m = FusedModel.synthetic(device="cuda:0", max_batch=4, table_dtype="float64")
+    m = FusedModel.synthetic(device="cuda:0", max_batch=6, table_dtype="float64")
     yield m
     m.unet.close()
 
@@ -116,3 +116,22 @@ def test_two_coupled_steps_with_p2p_match_the_oracle(model):
     errs = [G.rel_l2(lat[i].cpu(), lat_ref[i]) for i in range(2)] + [G.rel_l2(out[i].cpu(), out_ref[i]) for i in range(2)]
     print("EDICT vs oracle (reverse pair, forward-P2P pair):", errs)
     assert max(errs) < 5e-2
+
+
+def test_edict_image_batch_matches_single_images(model):
+    """BASELINE config 5 in small: two images per coupled pass (UNet batch 4 / 6) against one image at a time."""
+    src, tgt = synth.CAT_PROMPTS
+    srcs, tgts = [src, "a photo of a house on a hill"], [tgt, "a photo of a red house on a hill"]
+    zs = torch.cat([synth.synth_latent(6), synth.synth_latent(7)]).cuda()
+    kw = dict(steps=50, init_image_strength=0.06, guidance_scale=3.0)  # the last three timesteps
+    lat = edict.coupled_stablediffusion(model, srcs, reverse=True, init_image=zs, **kw)
+    out = edict.coupled_stablediffusion(model, srcs, tgts, fixed_starting_latent=lat, **kw)
+    torch.cuda.synchronize()
+    assert out[0].shape == (2, 4, 64, 64)
+    for i in range(2):
+        lat1 = edict.coupled_stablediffusion(model, srcs[i], reverse=True, init_image=zs[i:i + 1], **kw)
+        out1 = edict.coupled_stablediffusion(model, srcs[i], tgts[i], fixed_starting_latent=lat1, **kw)
+        torch.cuda.synchronize()
+        e = [G.rel_l2(out[k][i:i + 1], out1[k]) for k in range(2)]
+        print(f"edict image {i}: batched vs single pair rel-L2 {e}")
+        assert max(e) < 3e-2

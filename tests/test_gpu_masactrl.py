@@ -19,7 +19,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "masactrl_forward.npz")
 
 @pytest.fixture(scope="module")
 def model(cuda):
-    m = FusedModel.synthetic(device="cuda:0", max_batch=4)
+    m = FusedModel.synthetic(device="cuda:0", max_batch=8)
     yield m
     m.unet.close()
 
@@ -71,3 +71,23 @@ def test_directinversion_masactrl_loop_invariants(model):
     assert G.rel_l2(res.latents[1].cpu(), res.latents_fixed[0].cpu()) > 1e-3
     with pytest.raises(NotImplementedError):
         editor("no-such-method", z0, "", "x", 7.5)
+
+
+def test_masactrl_image_batch_through_the_c_loops_matches_single_images(model):
+    """BASELINE config 4 in small: two images per pass (UNet batch 2 / 8 / 4 / 8, loops inside pnp_run_loop) against the
+    single-image Python-loop editor; source rows prompt-major, every image's queries attend to ITS source's keys/values."""
+    editor = MasaCtrlEditor(["directinversion+masactrl"], "cuda:0", num_ddim_steps=6, model=model)
+    zs = torch.cat([synth.synth_latent(3), synth.synth_latent(4)]).cuda()
+    tars = [synth.CAT_PROMPTS[1], "a photo of a red house on a snowy hill at night"]
+    res = editor.edit_batch(zs, tars, guidance_scale=7.5, step=2, layper=10)
+    torch.cuda.synchronize()
+    assert res.latents.shape == (4, 4, 64, 64) and torch.isfinite(res.latents).all()
+    for i in range(2):
+        one = editor("directinversion+masactrl", zs[i:i + 1], "", tars[i], guidance_scale=7.5, step=2, layper=10)
+        torch.cuda.synchronize()
+        assert (res.latents[i] - zs[i]).abs().max() < 2e-5  # rectified source branch = the inverted latent
+        e_fixed = G.rel_l2(res.latents_fixed[i], one.latents_fixed[0])
+        e_edit = G.rel_l2(res.latents[2 + i], one.latents[1])
+        print(f"masactrl image {i}: batched vs single: fixed {e_fixed:.2e} edit {e_edit:.2e}")
+        assert e_fixed < 8e-2 and e_edit < 8e-2  # CFG 7.5 on rounding-level differences of two tilings, 6 steps
+    assert G.rel_l2(res.latents[2], res.latents[3]) > 1e-2
