@@ -179,7 +179,7 @@ def main():
                     help="p2p: directinversion+p2p (BASELINE configs 2/3, the headline); masactrl: directinversion+masactrl "
                          "(config 4, default batch 4 -> UNet batch 16); edict: edict+p2p (config 5, default batch 8)")
     ap.add_argument("--batch", type=int, default=0, help="images that share every UNet call (0 = the workload's default)")
-    ap.add_argument("--lanes", type=int, default=2,
+    ap.add_argument("--lanes", type=int, default=1,
                     help="passes in flight per GPU (own CUDA stream / engine handle / host thread, shared weights)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -205,7 +205,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from pnpinversion_b200.parallel import EditLanes
 
-    WL = {"p2p": dict(batch=4, fwd=650, rows=4, name="directinversion+p2p",
+    WL = {"p2p": dict(batch=8, fwd=650, rows=4, name="directinversion+p2p",
                       what="UNet batch L for the inversion, 4L for the offset / reconstruction / edit loops"),
           "masactrl": dict(batch=4, fwd=550, rows=4, name="directinversion+masactrl",
                            what="UNet batch L inversion, 4L offsets, 2L direct synthesis, 4L mutual self-attention pass"),
@@ -381,7 +381,7 @@ def main():
         "unet_batch": PB,
         "by_kernel_ms_per_unet_call": {k: round(v[0], 4) for k, v in agg.items()},
         "unet_sum_of_kernels_ms": tot_ms,
-        "unet_tflops_sum_of_kernels": PB * UNET_GFLOP / tot_ms / 1e3 if tot_ms else None,
+        "unet_tflops_sum_of_kernels": PB * UNET_GFLOP / tot_ms if tot_ms else None,
         "whole_job_tflops": value * FWD * UNET_GFLOP / 1e3,
         "whole_job_frac_of_sustained_peak": value * FWD * UNET_GFLOP / 1e3 / (sustained * world),
     }

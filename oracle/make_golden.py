@@ -265,6 +265,71 @@ def gen_masactrl():
     print("masactrl_forward.npz written")
 
 
+def gen_masactrl_pipeline(n_steps: int = 3):
+    """`directinversion+masactrl` end to end with the reference's own loops (run_editing_masactrl.py:89-129):
+    DirectInversion.invert with prompts ["", target] (models/p2p/inversion.py), then MasaCtrlPipeline.__call__
+    (models/masactrl/diffuser_utils.py:90-193) twice - direct synthesis with the target prompt, and the mutual
+    self-attention pass with the rectification of :183-184 - on the vendored fp64 UNet.  MasaCtrlPipeline subclasses the
+    absent diffusers StableDiffusionPipeline, so its methods are compiled from the reference's source text (nothing is
+    copied into this repository) and bound to a harness object carrying unet / scheduler / tokenizer / text_encoder; the
+    harness's latent2image returns the latents themselves (the VAE is a separate fixture)."""
+    import ast
+    import importlib
+    import sys as _sys
+
+    from tqdm import tqdm
+
+    ref = ref_shim.load_reference_p2p()
+    if ref_shim.REF not in _sys.path:
+        _sys.path.insert(0, ref_shim.REF)
+    masactrl = importlib.import_module("models.masactrl.masactrl")
+    mutils = importlib.import_module("models.masactrl.masactrl_utils")
+    model = build_model()
+    md = ref_shim.load_my_diffusers()
+    path = os.path.join(ref_shim.REF, "models", "masactrl", "diffuser_utils.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "MasaCtrlPipeline")
+    funcs = ast.Module(body=[n for n in cls.body if isinstance(n, ast.FunctionDef)], type_ignores=[])
+    ns = dict(torch=torch, np=np, tqdm=tqdm)
+    exec(compile(funcs, path, "exec"), ns)
+
+    class Harness:
+        next_step, step, invert = ns["next_step"], ns["step"], ns["invert"]
+        __call__ = ns["__call__"]
+
+        def latent2image(self, latents, return_type="pt"):
+            return latents
+
+    pipe = Harness()
+    pipe.unet, pipe.scheduler, pipe.tokenizer, pipe.text_encoder = model.unet, model.scheduler, model.tokenizer, model.text_encoder
+    tgt = synth.CAT_PROMPTS[1]
+    prompts = ["", tgt]
+    z0 = synth.synth_latent(3).double()
+    t0 = time.time()
+    model.scheduler.set_timesteps(n_steps)
+    inv = ref.inversion.DirectInversion(model=model, num_ddim_steps=n_steps)
+    _, _, x_stars, noise_loss = inv.invert(image_gt=z0, prompt=prompts, guidance_scale=7.5)
+    print("invert done", time.time() - t0, flush=True)
+    x_t = x_stars[-1]
+    md.CrossAttention.__name__ = "Attention"  # masactrl_utils.py:129 matches the diffusers >= 0.15 class name
+    try:
+        mutils.regiter_attention_editor_diffusers(model, mutils.AttentionBase())
+        fixed = pipe([tgt], latents=x_t, num_inference_steps=n_steps, guidance_scale=7.5, noise_loss_list=None)
+        print("direct synthesis done", time.time() - t0, flush=True)
+        editor = masactrl.MutualSelfAttentionControl(1, 10, total_steps=n_steps)
+        mutils.regiter_attention_editor_diffusers(model, editor)
+        out = pipe(prompts, latents=x_t.expand(2, -1, -1, -1), num_inference_steps=n_steps, guidance_scale=7.5,
+                   noise_loss_list=noise_loss)
+        print("masactrl pass done", time.time() - t0, flush=True)
+    finally:
+        md.CrossAttention.__name__ = "CrossAttention"
+    np.savez_compressed(os.path.join(GOLD, f"masactrl_pipeline_{n_steps}steps.npz"),
+                        x_stars=torch.cat(x_stars).float().numpy(), noise_loss=torch.stack(noise_loss).float().numpy(),
+                        fixed=fixed.float().numpy(), out=out.float().numpy())
+    print("masactrl pipeline fixture written")
+
+
 def gen_edict():
     """The reference's own `coupled_stablediffusion` (models/edict/edict_functions.py:707-956): deterministic noising of a
     latent pair over the last two of 50 timesteps (init_image_strength 0.04 -> t = 0, 20), then generation from that pair
@@ -367,6 +432,8 @@ if __name__ == "__main__":
         gen_pipeline(int(sys.argv[2]))
     elif what == "pipeline_full":
         gen_pipeline_full(int(sys.argv[2]) if len(sys.argv) > 2 else 50)
+    elif what == "masactrl_pipeline":
+        gen_masactrl_pipeline(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
     elif what == "masactrl":
         gen_masactrl()
     elif what == "edict":

@@ -140,10 +140,15 @@ def main():
     configs["fp32_streams + split all GEMM A operands + fp32 probs"] = {
         c: ("split" if c in ("gn_out", "ln_out", "attn_out", "geglu_out") else "fp16")
         for c in CLASSES if c not in ("stream", "inner_stream", "h1", "probs")}
+    configs["everything split: fp32 streams, hi/lo GEMM and attention operands (gn_out, ln_out, attn_out, geglu_out, qkv), fp32 probs"] = {
+        c: "split" for c in ("gn_out", "ln_out", "attn_out", "geglu_out", "qkv")}
     if args.configs:
         want = args.configs.split(",")
         configs = {k: v for k, v in configs.items() if k == "exact" or any(w in k for w in want)}
     res, ref = {}, None
+    outp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), args.out)
+    if args.configs and os.path.exists(outp):
+        res = json.load(open(outp)).get("results", {})
     with torch.no_grad():
         for name, rnd in configs.items():
             t0 = time.time()
