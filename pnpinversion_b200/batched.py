@@ -105,7 +105,7 @@ class BatchedDirectInversionP2P:
 
     # -- the four loops ------------------------------------------------------------------------------------------
     def invert(self, latents: torch.Tensor, prompts_src: Sequence[str], prompts_tar: Sequence[str], guidance_scale=7.5,
-               inverse_guidance_scale=None, loss_scales=None):
+               inverse_guidance_scale=None, loss_scales=None, source_rows_only=False):
         """DirectInversion.invert for L images: (x_stars (n+1,L,..), noise_loss (n,2L,..)); `inverse_guidance_scale`
         not None is invert_with_guidance_scale_vary_guidance (inversion.py:412-419), `loss_scales` the not_full /
         skip_step ablations (:478-526)."""
@@ -128,11 +128,22 @@ class BatchedDirectInversionP2P:
         else:
             ctx_inv, g_inv = torch.cat([uncond[:L], cond[:L]]).contiguous(), float(inverse_guidance_scale)
         run_loop(m, _lib.PNP_LOOP_INVERT, n, L, L, inv_t, inv_co, g_inv, ctx_inv, z, traj=x_stars)
+        self._sched = (ts, fwd_co)
+        if source_rows_only:
+            # the default method rectifies the SOURCE rows only (p2p_guidance_forward.py:113-114 reads noise_loss[:1]):
+            # their offsets do not depend on the target rows of the batch, so the offset pass can run on the L source
+            # prompts alone (UNet batch 2L instead of 4L); the target rows of noise_loss are returned as zeros
+            noise_src = torch.empty((n, L, 4, 64, 64), device=m.device, dtype=torch.float32)
+            ctx_src = torch.cat([uncond[:L], cond[:L]]).contiguous()
+            cur = x_stars[n].clone().contiguous()
+            run_loop(m, _lib.PNP_LOOP_OFFSET, n, L, L, ts, fwd_co, guidance_scale, ctx_src, cur, traj=x_stars,
+                     loss=noise_src, loss_scales=loss_scales)
+            noise_loss = torch.cat([noise_src, torch.zeros_like(noise_src)], dim=1).contiguous()
+            return x_stars, noise_loss
         noise_loss = torch.empty((n, 2 * L, 4, 64, 64), device=m.device, dtype=torch.float32)
         cur = torch.cat([x_stars[n]] * 2).contiguous()
         run_loop(m, _lib.PNP_LOOP_OFFSET, n, 2 * L, L, ts, fwd_co, guidance_scale, self._ctx, cur, traj=x_stars,
                  loss=noise_loss, loss_scales=loss_scales)
-        self._sched = (ts, fwd_co)
         return x_stars, noise_loss
 
     def forward(self, x_T: torch.Tensor, noise_loss: Optional[torch.Tensor], guidance_scale=7.5,
@@ -178,9 +189,17 @@ class BatchedDirectInversionP2P:
     def edit(self, latents, prompts_src, prompts_tar, guidance_scale=7.5, cross_replace_steps=0.4,
              self_replace_steps=0.6, blend_word=None, eq_params=None, is_replace_controller=False, add_target=False,
              inverse_guidance_scale=None, forward_guidance_scale=None, loss_scales=None, add_source=False,
-             per_image_params=False, device="cuda") -> BatchEditResult:
+             per_image_params=False, device="cuda", minimal=False) -> BatchEditResult:
         """`blend_word` / `eq_params` apply to every image, or are lists with one entry per image when
-        `per_image_params` is set."""
+        `per_image_params` is set.
+
+        `minimal=True` ("minimal-350"): the work the default method's OUTPUT does not depend on is
+        skipped - the reconstruction pass (the editor decodes only its source row, which the rectification pins to
+        x_stars[0] = the inverted latent, tests assert 2e-5) and the target rows of the offset pass (never read by
+        `latents[:1] + noise_loss[:1]`): 350 instead of 650 UNet sample-forwards per image.  Not available with
+        add_target / add_source (they read the target offsets)."""
+        if minimal and (add_target or add_source):
+            raise ValueError("minimal=True drops the target-row offsets that add_target / add_source need")
         L = latents.shape[0]
         blends = list(blend_word) if per_image_params else [blend_word] * L
         eqs = list(eq_params) if per_image_params else [eq_params] * L
@@ -188,12 +207,16 @@ class BatchedDirectInversionP2P:
             raise ValueError("one source prompt, target prompt, blend_word and eq_params per image")
         fwd_g = guidance_scale if forward_guidance_scale is None else forward_guidance_scale
         x_stars, noise_loss = self.invert(latents, prompts_src, prompts_tar, guidance_scale=fwd_g,
-                                          inverse_guidance_scale=inverse_guidance_scale, loss_scales=loss_scales)
+                                          inverse_guidance_scale=inverse_guidance_scale, loss_scales=loss_scales,
+                                          source_rows_only=minimal)
         x_T = x_stars[self.num_ddim_steps]
         fwd_loss = noise_loss
         if add_source:  # p2p_editor.py:930-932: the source branch's offset on both branches
             fwd_loss = torch.cat([noise_loss[:, :L]] * 2, dim=1).contiguous()
-        recon = self.forward(x_T, fwd_loss, fwd_g, controllers=None, add_target=add_target or add_source)
+        if minimal:
+            recon = torch.cat([x_stars[0], x_stars[0]]).contiguous()  # source rows = z0 by the invariant; targets not produced
+        else:
+            recon = self.forward(x_T, fwd_loss, fwd_g, controllers=None, add_target=add_target or add_source)
         controllers = [make_controller(pipeline=self.model, prompts=[prompts_src[i], prompts_tar[i]],
                                        is_replace_controller=is_replace_controller,
                                        cross_replace_steps={"default_": cross_replace_steps},

@@ -198,7 +198,7 @@ class P2PEditor:
 
     def edit_batch(self, images, prompts_src, prompts_tar, guidance_scale=7.5, cross_replace_steps=0.4,
                    self_replace_steps=0.6, blend_word=None, eq_params=None, is_replace_controller=False,
-                   per_image_params=False):
+                   per_image_params=False, minimal=False):
         """`directinversion+p2p` for L images in ONE pass (UNet batch L for the inversion, 4 L afterwards): `images` is
         an (L,4,64,64) latent tensor or a list of L image paths / HWC uint8 arrays.  Returns batched.BatchEditResult
         for latents, a list of L reference-format PIL strips for images."""
@@ -215,7 +215,8 @@ class P2PEditor:
             lat.to(self.ldm_stable.device, torch.float32), list(prompts_src), list(prompts_tar),
             guidance_scale=guidance_scale, cross_replace_steps=cross_replace_steps,
             self_replace_steps=self_replace_steps, blend_word=blend_word, eq_params=eq_params,
-            is_replace_controller=is_replace_controller, per_image_params=per_image_params, device=self.device)
+            is_replace_controller=is_replace_controller, per_image_params=per_image_params, device=self.device,
+            minimal=minimal)
         if is_latent or self.ldm_stable.vae is None:
             return res
         out = []

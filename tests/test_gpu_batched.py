@@ -280,3 +280,27 @@ def test_config1_20_step_inversion_matches_the_reference(cuda):
         assert torch.equal(traj[0, 0].cpu(), ref[0])
         assert max(errs) < 1e-2
         m.unet.close()
+
+
+def test_minimal_350_gives_the_same_edit(model):
+    """SURVEY.md section 8d "minimal-350": skipping the reconstruction pass and the target rows of the offset pass does not
+    change what the default method returns - the reconstruction's source row IS x_stars[0] (2e-5), the source offsets
+    are the same quantity computed in a smaller batch (another rounding-noise realisation, hence not bit-identical)."""
+    ed = P2PEditor(["directinversion+p2p"], "cuda:0", num_ddim_steps=4, model=model)
+    src, tgt = synth.CAT_PROMPTS
+    zs = torch.cat([synth.synth_latent(i) for i in range(2)]).cuda()
+    calls0 = model.unet.kernel_launches()
+    full = ed.edit_batch(zs, [src] * 2, [tgt] * 2, blend_word=BLEND, eq_params=EQ)
+    calls1 = model.unet.kernel_launches()
+    mini = ed.edit_batch(zs, [src] * 2, [tgt] * 2, blend_word=BLEND, eq_params=EQ, minimal=True)
+    calls2 = model.unet.kernel_launches()
+    torch.cuda.synchronize()
+    assert torch.equal(full.x_stars, mini.x_stars)
+    assert (mini.reconstruct_latents[:2] - zs).abs().max() == 0 and (full.reconstruct_latents[:2] - zs).abs().max() < 2e-5
+    assert (mini.latents[:2] - zs).abs().max() < 2e-5
+    e_nl = float((full.noise_loss[:, :2] - mini.noise_loss[:, :2]).norm() / full.x_stars[1:].norm())
+    e_edit = G.rel_l2(mini.latents[2:], full.latents[2:])
+    print(f"minimal-350 vs faithful-650: source offsets |diff|/|latent| {e_nl:.2e}, edited latents rel-L2 {e_edit:.2e}; "
+          f"kernel launches {calls1 - calls0} vs {calls2 - calls1}")
+    assert e_nl < 2e-2 and e_edit < 8e-2
+    assert (calls2 - calls1) < 0.8 * (calls1 - calls0)  # three 4-step loops instead of four (the batch is smaller too)
