@@ -82,6 +82,9 @@ typedef struct pnp_attn_ctrl {
    *   map_weight[w] * sum_{k < map_count[w]} P_src[:, mapper[w] + k]          (identity: count 1, weight 1). */
   int32_t map_count[PNP_MAX_SLOTS][PNP_TOKENS];
   float map_weight[PNP_MAX_SLOTS][PNP_TOKENS];
+  /* Plug-and-Play feature injection (run_editing_pnp.py:244-294): the conv2 output of up_blocks.1.resnets.1 of row r is
+   * computed from the hidden state of row conv_src_row[r] (the residual / shortcut term stays row r's own); identity = r */
+  int32_t conv_src_row[PNP_MAX_BATCH];
   /* AttentionStore for LocalBlend: rows with store_slot[r] >= 0 accumulate their (post-injection) 16x16 cross maps of
    * the five layers down_cross[2:4] + up_cross[:3] into slot store_slot[r]. */
   int32_t store_slot[PNP_MAX_BATCH];

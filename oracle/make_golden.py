@@ -330,6 +330,64 @@ def gen_masactrl_pipeline(n_steps: int = 3):
     print("masactrl pipeline fixture written")
 
 
+def gen_pnp(n_steps: int = 3):
+    """Plug-and-Play features with the PnP-Inversion source branch, by the reference's own functions
+    (run_editing_pnp.py): `Preprocess.ddim_inversion` / `ddim_sample` (:88-134), `register_time` (:150-174),
+    `register_attention_control_efficient` (:176-242), `register_conv_control_efficient` (:244-294) and
+    `PNP.denoise_step` (:344-361), compiled from the reference's source text (the module itself loads diffusers models at
+    import) and run on the vendored fp64 UNet.  Harness adaptations, none of them in reference code: the vendored
+    CrossAttention's head reshapes get the diffusers >= 0.10 names the patched forward calls, the scheduler's timesteps
+    are a tensor with steps_offset 1 (the runwayml/stable-diffusion-v1-5 scheduler config)."""
+    import ast
+
+    model = build_model()
+    md = ref_shim.load_my_diffusers()
+    path = os.path.join(ref_shim.REF, "run_editing_pnp.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    want_fn = {"register_time", "register_attention_control_efficient", "register_conv_control_efficient"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want_fn]
+    for cls_name, methods in (("Preprocess", {"ddim_inversion", "ddim_sample"}), ("PNP", {"denoise_step"})):
+        cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls_name)
+        body += [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in methods]
+    ns = dict(torch=torch, np=np)
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    for m in model.unet.modules():
+        if type(m).__name__ == "CrossAttention":
+            m.head_to_batch_dim = m.reshape_heads_to_batch_dim
+            m.batch_to_head_dim = m.reshape_batch_dim_to_heads
+    sched = model.scheduler
+    sched.set_timesteps(n_steps, offset=1)
+    sched.timesteps = torch.from_numpy(np.ascontiguousarray(sched.timesteps)).long()
+    src, tgt = synth.CAT_PROMPTS
+    tok, te = model.tokenizer, model.text_encoder
+    emb = lambda p: te(tok([p]).input_ids)[0]
+    pre = types.SimpleNamespace(unet=model.unet, scheduler=sched)
+    z0 = synth.synth_latent(8).double()
+    t0 = time.time()
+    with torch.no_grad():
+        inverted_x = ns["ddim_inversion"](pre, emb(src), z0)
+        rec = ns["ddim_sample"](pre, inverted_x[-1], emb(src))
+        print("inversion + reconstruction done", time.time() - t0, flush=True)
+        pnp = types.SimpleNamespace(unet=model.unet, scheduler=sched, pnp_guidance_embeds=emb(""),
+                                    text_embeds=torch.cat([emb("ugly, blurry, black, low res, unrealistic"), emb(tgt)]))
+        qk_t = sched.timesteps[: int(n_steps * 0.5)]
+        conv_t = sched.timesteps[: int(n_steps * 0.8)]
+        ns["register_attention_control_efficient"](pnp, qk_t)
+        ns["register_conv_control_efficient"](pnp, conv_t)
+        x = inverted_x[-1]
+        xs = []
+        for i, t in enumerate(sched.timesteps):
+            x = ns["denoise_step"](pnp, x, t, 7.5, inverted_x[-1 - i])
+            xs.append(x)
+        print("pnp sampling done", time.time() - t0, flush=True)
+    np.savez_compressed(os.path.join(GOLD, f"pnp_features_{n_steps}steps.npz"),
+                        timesteps=sched.timesteps.numpy(), inverted_x=torch.cat(inverted_x).float().numpy(),
+                        rec=torch.cat(rec).float().numpy(), xs=torch.cat(xs).float().numpy(),
+                        qk_t=qk_t.numpy(), conv_t=conv_t.numpy())
+    print("pnp fixture written", [int(t) for t in sched.timesteps], "qk", qk_t.tolist(), "conv", conv_t.tolist())
+
+
 def gen_edict():
     """The reference's own `coupled_stablediffusion` (models/edict/edict_functions.py:707-956): deterministic noising of a
     latent pair over the last two of 50 timesteps (init_image_strength 0.04 -> t = 0, 20), then generation from that pair
@@ -434,6 +492,8 @@ if __name__ == "__main__":
         gen_pipeline_full(int(sys.argv[2]) if len(sys.argv) > 2 else 50)
     elif what == "masactrl_pipeline":
         gen_masactrl_pipeline(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
+    elif what == "pnp":
+        gen_pnp(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
     elif what == "masactrl":
         gen_masactrl()
     elif what == "edict":

@@ -39,6 +39,7 @@ class AttnCtrl(C.Structure):
         ("cross_alpha", (C.c_float * PNP_TOKENS) * PNP_MAX_SLOTS),
         ("map_count", (C.c_int32 * PNP_TOKENS) * PNP_MAX_SLOTS),
         ("map_weight", (C.c_float * PNP_TOKENS) * PNP_MAX_SLOTS),
+        ("conv_src_row", C.c_int32 * PNP_MAX_BATCH),
         ("store_slot", C.c_int32 * PNP_MAX_BATCH),
     ]
 

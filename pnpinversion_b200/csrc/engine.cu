@@ -251,6 +251,7 @@ struct DevCtrl {  // device-resident controller state for one forward
   int cross_base[PNP_MAX_BATCH];
   int cross_slot[PNP_MAX_BATCH];
   int store_slot[PNP_MAX_BATCH];
+  int conv_row[PNP_MAX_BATCH];
   int mapper[PNP_MAX_SLOTS][PNP_TOKENS];
   float alphas[PNP_MAX_SLOTS][PNP_TOKENS];
   float equalizer[PNP_MAX_SLOTS][PNP_TOKENS];
@@ -389,6 +390,8 @@ static std::vector<__half> pack_conv3(const std::vector<__half>& w, int cout, in
 // per-handle mutable state (a clone has its own): controller tables, AttentionStore maps, GroupNorm workspace
 static int alloc_state(pnp_engine* e) {
   e->d_ctrl = e->dalloc<DevCtrl>(1);
+  PNP_CHECK(e->d_ctrl != nullptr, "alloc failed");
+  PNP_CUDA(cudaMemset(e->d_ctrl, 0, sizeof(DevCtrl)));  // plan-build trial launches read it before the first push_ctrl
   PNP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ctrl_ring), sizeof(DevCtrl) * kRing, cudaHostAllocDefault));
   e->store = e->dalloc<float>(kStoreFloats);
   PNP_CHECK(e->d_ctrl && e->store, "alloc failed");
@@ -786,6 +789,9 @@ static int build_plan(pnp_engine* e, int B, Plan* pl) {
       ep.bias = w.bias2;
       ep.out = out;
       ep.ldc = w.cout;
+      // Plug-and-Play feature injection point (run_editing_pnp.py:293: up_blocks[1].resnets[1], resnet #14 in execution
+      // order): conv2's taps read the normalised hidden state of row conv_row[b]
+      if (res_idx - 1 == 14) ep.a0_row_map = e->d_ctrl->conv_row;
       ASource s[3];
       int ns = 1;
       s[0] = ASource{NRM, w.cout, w.cout};
@@ -1216,6 +1222,7 @@ void pnp_attn_ctrl_init(pnp_attn_ctrl* c) {
     c->cross_base_row[r] = -1;
     c->cross_slot[r] = -1;
     c->store_slot[r] = -1;
+    c->conv_src_row[r] = r;
   }
   for (int s = 0; s < PNP_MAX_SLOTS; ++s)
     for (int i = 0; i < PNP_TOKENS; ++i) {
@@ -1257,6 +1264,10 @@ static int push_ctrl(pnp_engine* h, int batch, int t_index, const pnp_attn_ctrl*
   memcpy(hc->cross_base, c->cross_base_row, sizeof hc->cross_base);
   memcpy(hc->cross_slot, c->cross_slot, sizeof hc->cross_slot);
   memcpy(hc->store_slot, c->store_slot, sizeof hc->store_slot);
+  for (int r = 0; r < PNP_MAX_BATCH; ++r) {
+    PNP_CHECK(r >= batch || (c->conv_src_row[r] >= 0 && c->conv_src_row[r] < batch), "controller: conv_src_row out of range");
+    hc->conv_row[r] = r < batch ? c->conv_src_row[r] : r;
+  }
   memcpy(hc->mapper, c->mapper, sizeof hc->mapper);
   memcpy(hc->alphas, c->alphas, sizeof hc->alphas);
   memcpy(hc->equalizer, c->equalizer, sizeof hc->equalizer);

@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           y0 = rem / p.W;
           x0 = rem - y0 * p.W;  // 0 unless the image is wider than one tile (W = 256 / 512: the VAE levels)
         }
+        // feature injection: the taps of source 0 come from another batch row (the shortcut sources do not)
+        const int b0_src0 = (p.a0_row_map != nullptr && !p.linear) ? p.a0_row_map[b0] : b0;
         // K-block cursor kept incrementally (segment, tap offsets, channel chunk): an integer division per K block put
         // a ~150-cycle dependent chain into this loop, which has nothing else to overlap it with
         int seg, cc, dx = 0, dy = 0, tap = 0;
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
           // operands of this K block, computed before the wait
           const CUtensorMap* am = &p.map_a[seg];
           const int c0 = cc * BK, cx = x0 + (seg == 0 ? dx : 0), cy = y0 + (seg == 0 ? dy : 0);
+          const int cb = seg == 0 ? b0_src0 : b0;
           ++cc;
           if (seg == 0) {
             if (cc == p.chunks0) {
@@ -241,10 +244,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             if (!PAIR) mbar_arrive_expect_tx(&full[stage], C::STAGE);
             else if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE);
             if (PAIR) {
-              tma_load_4d_cg2(sa, am, &full[stage], c0, cx, cy, b0);
+              tma_load_4d_cg2(sa, am, &full[stage], c0, cx, cy, cb);
               tma_load_2d_cg2(sb, &p.map_b_half, &full[stage], kb * BK, n_blk * BNT + crank * (BNT / 2));
             } else {
-              tma_load_4d(sa, am, &full[stage], c0, cx, cy, b0);
+              tma_load_4d(sa, am, &full[stage], c0, cx, cy, cb);
 #pragma unroll
               for (int sub = 0; sub < NSUB; ++sub)  // one box (<= 256 rows) per accumulator
                 tma_load_2d(sb + sub * BN * BK * 2, &p.map_b, &full[stage], kb * BK, n_blk * BNT + sub * BN);
@@ -816,6 +819,9 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   p.residual = ep.residual;
   p.ldr = ep.ldr;
   p.out = ep.out;
+  p.a0_row_map = ep.a0_row_map;
+  PNP_CHECK(ep.a0_row_map == nullptr || (!linear && 128 / W >= 1 && 128 / W <= H),
+            "gemm: a source row map needs conv tiles that stay inside one image");
   p.out32 = ep.out_f32_nchw4;
   p.out32_ch = ep.out32_channels;
   p.out_scale = ep.out_scale;

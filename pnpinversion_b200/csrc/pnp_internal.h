@@ -119,6 +119,7 @@ struct alignas(64) GemmParams {
   float* out32;  // GemmEpilogue::out_f32_nchw4
   int out32_ch;  // planes written there (first out32_ch columns of the tile)
   float out_scale;  // accumulators are multiplied by this before bias / residual (1 = off)
+  const int* a0_row_map;  // conv mode: batch row the taps of A source 0 are read from, per output batch row (null = same)
   int exp;  // experiments (PNP_GEMM_EXP, test entry points only): 1 = no TMA copies, 2 = no MMAs
 };
 
@@ -146,6 +147,9 @@ struct GemmEpilogue {
   float* out_f32_nchw4 = nullptr;
   int out32_channels = 4;  // ... or the first 1..8 columns (VAE: 3 image planes, 8 posterior moments)
   float out_scale = 1.0f;  // D = out_scale * (A . W^T) + bias ... (single-head VAE attention: 1/sqrt(C) on Q.K^T)
+  // Plug-and-Play feature injection: source 0 (the 3x3 taps) of output batch row b is read from batch row a0_row_map[b]
+  // (device array), the extra 1x1 shortcut sources stay row b's own.  Needs tiles that do not span images.
+  const int* a0_row_map = nullptr;
 };
 
 // fp16 tiled tensor map with 128-byte swizzle and zero out-of-bounds fill (rank 2..4); strides in bytes for dims 1..

@@ -46,8 +46,9 @@ def _numel(s):
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.AttnCtrl) == 4 * (3 + 5 * 32 + 6 * 8 * 77 + 32)
+    assert C.sizeof(_lib.AttnCtrl) == 4 * (3 + 5 * 32 + 6 * 8 * 77 + 32 + 32)
     assert C.sizeof(_lib.BlendDesc) == 4 * (4 + 2 + 16 + 16 + 2 + 16 + 16 + 2)
+    assert list(_lib.new_ctrl().conv_src_row) == list(range(32))
     assert _lib.StepArgs().loss_scale == 1.0 and _lib.new_ctrl().map_count[3][5] == 1 and _lib.new_ctrl().map_weight[7][76] == 1.0
     c = _lib.new_ctrl()
     assert list(c.self_q_row) == list(range(32)) and all(v == -1 for v in c.cross_base_row)
