@@ -265,7 +265,7 @@ def gen_masactrl():
     print("masactrl_forward.npz written")
 
 
-def gen_masactrl_pipeline(n_steps: int = 3):
+def gen_masactrl_pipeline(n_steps: int = 4):
     """`directinversion+masactrl` end to end with the reference's own loops (run_editing_masactrl.py:89-129):
     DirectInversion.invert with prompts ["", target] (models/p2p/inversion.py), then MasaCtrlPipeline.__call__
     (models/masactrl/diffuser_utils.py:90-193) twice - direct synthesis with the target prompt, and the mutual
@@ -301,6 +301,7 @@ def gen_masactrl_pipeline(n_steps: int = 3):
         def latent2image(self, latents, return_type="pt"):
             return latents
 
+    assert 1000 % n_steps == 0, "the vendored 0.3.0 scheduler yields n + 1 timesteps unless n divides 1000"
     pipe = Harness()
     pipe.unet, pipe.scheduler, pipe.tokenizer, pipe.text_encoder = model.unet, model.scheduler, model.tokenizer, model.text_encoder
     tgt = synth.CAT_PROMPTS[1]
@@ -330,7 +331,7 @@ def gen_masactrl_pipeline(n_steps: int = 3):
     print("masactrl pipeline fixture written")
 
 
-def gen_pnp(n_steps: int = 3):
+def gen_pnp(n_steps: int = 4):
     """Plug-and-Play features with the PnP-Inversion source branch, by the reference's own functions
     (run_editing_pnp.py): `Preprocess.ddim_inversion` / `ddim_sample` (:88-134), `register_time` (:150-174),
     `register_attention_control_efficient` (:176-242), `register_conv_control_efficient` (:244-294) and
@@ -356,6 +357,7 @@ def gen_pnp(n_steps: int = 3):
         if type(m).__name__ == "CrossAttention":
             m.head_to_batch_dim = m.reshape_heads_to_batch_dim
             m.batch_to_head_dim = m.reshape_batch_dim_to_heads
+    assert 1000 % n_steps == 0, "the vendored 0.3.0 scheduler yields n + 1 timesteps unless n divides 1000"
     sched = model.scheduler
     sched.set_timesteps(n_steps, offset=1)
     sched.timesteps = torch.from_numpy(np.ascontiguousarray(sched.timesteps)).long()
@@ -491,9 +493,9 @@ if __name__ == "__main__":
     elif what == "pipeline_full":
         gen_pipeline_full(int(sys.argv[2]) if len(sys.argv) > 2 else 50)
     elif what == "masactrl_pipeline":
-        gen_masactrl_pipeline(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
+        gen_masactrl_pipeline(int(sys.argv[2]) if len(sys.argv) > 2 else 4)
     elif what == "pnp":
-        gen_pnp(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
+        gen_pnp(int(sys.argv[2]) if len(sys.argv) > 2 else 4)
     elif what == "masactrl":
         gen_masactrl()
     elif what == "edict":

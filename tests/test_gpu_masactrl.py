@@ -96,23 +96,23 @@ def test_masactrl_image_batch_through_the_c_loops_matches_single_images(model):
 
 
 def test_directinversion_masactrl_pipeline_matches_reference(cuda):
-    """`directinversion+masactrl` end to end against the REFERENCE's own loops (tests/golden/masactrl_pipeline_3steps.npz:
+    """`directinversion+masactrl` end to end against the REFERENCE's own loops (tests/golden/masactrl_pipeline_4steps.npz:
     DirectInversion.invert + MasaCtrlPipeline.__call__ twice, run_editing_masactrl.py:89-129, vendored fp64 UNet; produced
     by oracle/make_golden.py masactrl_pipeline).  Tolerances as in tests/test_gpu_pipeline.py: inversion latents 5e-3,
     anything after classifier-free guidance 7.5 within 8e-2, the rectified source branch on z0 to fp32 rounding."""
     import os
 
-    gold = os.path.join(os.path.dirname(__file__), "golden", "masactrl_pipeline_3steps.npz")
+    gold = os.path.join(os.path.dirname(__file__), "golden", "masactrl_pipeline_4steps.npz")
     if not os.path.exists(gold):
-        pytest.fail("tests/golden/masactrl_pipeline_3steps.npz missing (python -m oracle.make_golden masactrl_pipeline 3)")
+        pytest.fail("tests/golden/masactrl_pipeline_4steps.npz missing (python -m oracle.make_golden masactrl_pipeline 4)")
     g = np.load(gold)
     m = FusedModel.synthetic(device="cuda:0", max_batch=4, table_dtype="float64")
-    editor = MasaCtrlEditor(["directinversion+masactrl"], "cuda:0", num_ddim_steps=3, model=m)
+    editor = MasaCtrlEditor(["directinversion+masactrl"], "cuda:0", num_ddim_steps=4, model=m)
     z0 = synth.synth_latent(3)
     res = editor("directinversion+masactrl", z0, "", synth.CAT_PROMPTS[1], guidance_scale=7.5, step=1, layper=10)
     torch.cuda.synchronize()
     xs = torch.cat(res.x_stars).cpu()
-    e_xs = [G.rel_l2(xs[k], torch.from_numpy(g["x_stars"][k])) for k in range(1, 4)]
+    e_xs = [G.rel_l2(xs[k], torch.from_numpy(g["x_stars"][k])) for k in range(1, 5)]
     e_fixed = G.rel_l2(res.latents_fixed.cpu(), torch.from_numpy(g["fixed"]))
     e_edit = G.rel_l2(res.latents[1].cpu(), torch.from_numpy(g["out"][1]))
     print(f"masactrl pipeline vs reference: x_stars {e_xs}, direct synthesis {e_fixed:.2e}, masactrl edit {e_edit:.2e}")

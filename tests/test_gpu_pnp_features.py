@@ -1,7 +1,7 @@
 """Plug-and-Play features (`pnpinversion_b200/pnp_features.py`, descriptor fields self_q/k_row + conv_src_row) against the
-REFERENCE's own functions run on the vendored fp64 UNet (tests/golden/pnp_features_3steps.npz, produced by
+REFERENCE's own functions run on the vendored fp64 UNet (tests/golden/pnp_features_4steps.npz, produced by
 oracle/make_golden.py pnp from run_editing_pnp.py's ddim_inversion / ddim_sample / register_*_control_efficient /
-denoise_step).  Step 0 injects Q/K and conv features, step 1 conv features only, step 2 nothing."""
+denoise_step).  Steps 0-1 inject Q/K and conv features, step 2 conv features only, step 3 nothing."""
 import os
 
 import numpy as np
@@ -14,24 +14,24 @@ from pnpinversion_b200.pnp_features import PnPController, PnPFeaturesEditor, pnp
 from tests import gpu_util as G
 
 pytestmark = pytest.mark.gpu
-GOLD = os.path.join(os.path.dirname(__file__), "golden", "pnp_features_3steps.npz")
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "pnp_features_4steps.npz")
 
 
 def test_pnp_features_match_the_reference_run(cuda):
     if not os.path.exists(GOLD):
-        pytest.fail("tests/golden/pnp_features_3steps.npz missing (python -m oracle.make_golden pnp 3)")
+        pytest.fail("tests/golden/pnp_features_4steps.npz missing (python -m oracle.make_golden pnp 4)")
     g = np.load(GOLD)
     m = FusedModel.synthetic(device="cuda:0", max_batch=3, table_dtype="float64")
-    ed = PnPFeaturesEditor(m, 3)
-    assert ed.timesteps == [int(t) for t in g["timesteps"]] == pnp_timesteps(3)  # integer schedule, bit-exact
+    ed = PnPFeaturesEditor(m, 4)
+    assert ed.timesteps == [int(t) for t in g["timesteps"]] == pnp_timesteps(4)  # integer schedule, bit-exact
     src, tgt = synth.CAT_PROMPTS
     z0 = synth.synth_latent(8).cuda()
     inv, rec = ed.extract_latents(z0, [src])
     x = ed.run_pnp(inv, [tgt], guidance_scale=7.5, pnp_f_t=0.8, pnp_attn_t=0.5)
     torch.cuda.synchronize()
-    e_inv = [G.rel_l2(inv[k].cpu(), torch.from_numpy(g["inverted_x"][k:k + 1])) for k in range(1, 4)]
-    e_rec = [G.rel_l2(rec[k].cpu(), torch.from_numpy(g["rec"][2 - k:3 - k])) for k in range(3)]  # ours is reversed like extract_latents
-    e_x = G.rel_l2(x.cpu(), torch.from_numpy(g["xs"][2:3]))
+    e_inv = [G.rel_l2(inv[k].cpu(), torch.from_numpy(g["inverted_x"][k:k + 1])) for k in range(1, 5)]
+    e_rec = [G.rel_l2(rec[k].cpu(), torch.from_numpy(g["rec"][3 - k:4 - k])) for k in range(4)]  # ours is reversed like extract_latents
+    e_x = G.rel_l2(x.cpu(), torch.from_numpy(g["xs"][3:4]))
     print(f"pnp features vs reference: inversion {e_inv}, reconstruction {e_rec}, edited latent {e_x:.2e}")
     assert max(e_inv) < 5e-3 and max(e_rec) < 1e-2 and e_x < 8e-2
     m.unet.close()
