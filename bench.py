@@ -180,8 +180,9 @@ def main():
                          "(config 4, default batch 4 -> UNet batch 16); edict: edict+p2p (config 5, default batch 8)")
     ap.add_argument("--batch", type=int, default=0, help="images that share every UNet call (0 = the workload's default)")
     ap.add_argument("--minimal", action="store_true",
-                    help="p2p only: the 350-forward variant (no reconstruction pass, source-row offsets only; SURVEY.md "
-                         "section 8d) as the timed workload; the default run reports it beside the faithful number")
+                    help="p2p only: the 450-forward variant (no reconstruction pass: its decoded row is the inverted latent "
+                         "by the rectification invariant) as the timed workload; the default run reports it beside the "
+                         "faithful number")
     ap.add_argument("--lanes", type=int, default=1,
                     help="passes in flight per GPU (own CUDA stream / engine handle / host thread, shared weights)")
     args = ap.parse_args()
@@ -214,7 +215,7 @@ def main():
                            what="UNet batch L inversion, 4L offsets, 2L direct synthesis, 4L mutual self-attention pass"),
           "edict": dict(batch=8, fwd=800, rows=3, name="edict+p2p",
                         what="coupled pair: 2 x (50 + 50 + 40) steps at UNet batch 2L, 2 x 40 P2P steps at 3L")}[args.workload]
-    FWD = 350 if (args.minimal and args.workload == "p2p") else WL["fwd"]
+    FWD = 450 if (args.minimal and args.workload == "p2p") else WL["fwd"]
     sd = synth.synth_unet_state_dict(0)
     NB = max(1, args.batch or WL["batch"])  # images per pass
     NL = max(1, args.lanes)          # concurrent passes
@@ -331,7 +332,7 @@ def main():
     minimal_line = None
     if args.workload == "p2p" and not args.minimal:
         minimal_now[0] = True
-        edit_step([z_pass[first + ln] for ln in range(NL)])  # its UNet batch 2*NB plan is built outside the timing
+        edit_step([z_pass[first + ln] for ln in range(NL)])
         torch.cuda.synchronize()
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ksteps = min(2, args.steps)
@@ -345,9 +346,10 @@ def main():
         if dist is not None:
             dist.all_reduce(msm, op=dist.ReduceOp.MAX)
         minimal_line = {"value": world * ksteps * L / (float(msm.item()) / 1000.0), "unit": "images/s", "steps": ksteps,
-                        "unet_forwards_per_image": 350,
-                        "what": "same outputs for directinversion+p2p: no reconstruction pass (its decoded row is the "
-                                "inverted latent by the rectification invariant), offsets of the source rows only"}
+                        "unet_forwards_per_image": 450,
+                        "what": "same outputs for directinversion+p2p without the reconstruction pass (its decoded row is "
+                                "the inverted latent by the rectification invariant; bit-identical edit, "
+                                "tests/test_gpu_batched.py)"}
     ctx_rows = {"p2p": 4, "masactrl": 4, "edict": 9}[args.workload] * NB  # edict: 4 coupled passes encode 2+2+2+3 rows per image
     h2d = NL * (NB * 4 * 64 * 64 * 4 + ctx_rows * 77 * 768 * 4)
     d2h = NL * 2 * NB * 4 * 64 * 64 * 4
@@ -429,7 +431,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": f"{WL['name']} 50 steps, {L} image(s) per step and GPU = {NL} concurrent pass(es) x "
                                f"{NB} image(s) per pass ({WL['what']}), "
-                               + ("faithful " if FWD == WL["fwd"] else "MINIMAL (see minimal_350) ") +
+                               + ("faithful " if FWD == WL["fwd"] else "MINIMAL (no reconstruction pass) ") +
                                f"{FWD} UNet sample-forwards per image, "
                                "SD-1.x random-init UNet, cat prompts"
                                + (", step loops inside libpnpinv.so (pnp_run_loop)" if args.workload != "edict" else ""),
@@ -445,7 +447,7 @@ def main():
         "roofline": roofline,
     }
     if minimal_line is not None:
-        line["minimal_350"] = minimal_line
+        line["minimal_450"] = minimal_line
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

@@ -105,7 +105,7 @@ class BatchedDirectInversionP2P:
 
     # -- the four loops ------------------------------------------------------------------------------------------
     def invert(self, latents: torch.Tensor, prompts_src: Sequence[str], prompts_tar: Sequence[str], guidance_scale=7.5,
-               inverse_guidance_scale=None, loss_scales=None, source_rows_only=False):
+               inverse_guidance_scale=None, loss_scales=None):
         """DirectInversion.invert for L images: (x_stars (n+1,L,..), noise_loss (n,2L,..)); `inverse_guidance_scale`
         not None is invert_with_guidance_scale_vary_guidance (inversion.py:412-419), `loss_scales` the not_full /
         skip_step ablations (:478-526)."""
@@ -129,17 +129,6 @@ class BatchedDirectInversionP2P:
             ctx_inv, g_inv = torch.cat([uncond[:L], cond[:L]]).contiguous(), float(inverse_guidance_scale)
         run_loop(m, _lib.PNP_LOOP_INVERT, n, L, L, inv_t, inv_co, g_inv, ctx_inv, z, traj=x_stars)
         self._sched = (ts, fwd_co)
-        if source_rows_only:
-            # the default method rectifies the SOURCE rows only (p2p_guidance_forward.py:113-114 reads noise_loss[:1]):
-            # their offsets do not depend on the target rows of the batch, so the offset pass can run on the L source
-            # prompts alone (UNet batch 2L instead of 4L); the target rows of noise_loss are returned as zeros
-            noise_src = torch.empty((n, L, 4, 64, 64), device=m.device, dtype=torch.float32)
-            ctx_src = torch.cat([uncond[:L], cond[:L]]).contiguous()
-            cur = x_stars[n].clone().contiguous()
-            run_loop(m, _lib.PNP_LOOP_OFFSET, n, L, L, ts, fwd_co, guidance_scale, ctx_src, cur, traj=x_stars,
-                     loss=noise_src, loss_scales=loss_scales)
-            noise_loss = torch.cat([noise_src, torch.zeros_like(noise_src)], dim=1).contiguous()
-            return x_stars, noise_loss
         noise_loss = torch.empty((n, 2 * L, 4, 64, 64), device=m.device, dtype=torch.float32)
         cur = torch.cat([x_stars[n]] * 2).contiguous()
         run_loop(m, _lib.PNP_LOOP_OFFSET, n, 2 * L, L, ts, fwd_co, guidance_scale, self._ctx, cur, traj=x_stars,
@@ -193,13 +182,14 @@ class BatchedDirectInversionP2P:
         """`blend_word` / `eq_params` apply to every image, or are lists with one entry per image when
         `per_image_params` is set.
 
-        `minimal=True` ("minimal-350"): the work the default method's OUTPUT does not depend on is
-        skipped - the reconstruction pass (the editor decodes only its source row, which the rectification pins to
-        x_stars[0] = the inverted latent, tests assert 2e-5) and the target rows of the offset pass (never read by
-        `latents[:1] + noise_loss[:1]`): 350 instead of 650 UNet sample-forwards per image.  Not available with
-        add_target / add_source (they read the target offsets)."""
-        if minimal and (add_target or add_source):
-            raise ValueError("minimal=True drops the target-row offsets that add_target / add_source need")
+        `minimal=True` skips the reconstruction pass: the editor decodes only its SOURCE row, and the rectification pins
+        that row to x_stars[0] = the inverted latent (tests assert 2e-5), so the 200 sample-forwards of that pass change
+        nothing the method returns: 450 instead of 650 per image.  SURVEY.md section 8d also proposes dropping the target
+        rows of the offset pass ("minimal-350"); that is exact only in exact arithmetic.  The invariant holds on this
+        engine because the offset pass and the edit pass evaluate the source rows in the SAME batch composition - rows of
+        one call are bit-reproducible - while another batch size is another realisation of the fp16 rounding noise
+        (DESIGN.md section 2): offsets computed at batch 2L no longer cancel the edit pass's batch-4L predictions and
+        the source branch drifts away (measured: O(1) after 4 steps).  So the offsets keep their full batch."""
         L = latents.shape[0]
         blends = list(blend_word) if per_image_params else [blend_word] * L
         eqs = list(eq_params) if per_image_params else [eq_params] * L
@@ -207,8 +197,7 @@ class BatchedDirectInversionP2P:
             raise ValueError("one source prompt, target prompt, blend_word and eq_params per image")
         fwd_g = guidance_scale if forward_guidance_scale is None else forward_guidance_scale
         x_stars, noise_loss = self.invert(latents, prompts_src, prompts_tar, guidance_scale=fwd_g,
-                                          inverse_guidance_scale=inverse_guidance_scale, loss_scales=loss_scales,
-                                          source_rows_only=minimal)
+                                          inverse_guidance_scale=inverse_guidance_scale, loss_scales=loss_scales)
         x_T = x_stars[self.num_ddim_steps]
         fwd_loss = noise_loss
         if add_source:  # p2p_editor.py:930-932: the source branch's offset on both branches
