@@ -423,9 +423,11 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const __half* _
 }
 
 int gn_ppc(int B, int HW) {
-  // pixels per CTA: aim for >= ~256 CTAs, at least 8 pixels each
+  // pixels per CTA: aim for >= ~256 CTAs (tuned at B <= 4), ~1024 for image batches (B >= 16: 84 MB tensors, the
+  // statistics pass wants every SM several CTAs deep), at least 8 pixels each
+  const long want = B >= 16 ? 1024 : 256;
   int ppc = HW;
-  while (ppc > 8 && HW / ppc < 128 && static_cast<long>(B) * (HW / ppc) < 256) ppc >>= 1;  // <= 128 slices
+  while (ppc > 8 && HW / ppc < 128 && static_cast<long>(B) * (HW / ppc) < want) ppc >>= 1;  // <= 128 slices
   return ppc;
 }
 
@@ -718,8 +720,13 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   const size_t sm2 = (2 * static_cast<size_t>(C) + 2 * GN_GROUPS) * sizeof(float);
   // the apply pass is pure streaming: fewer, fatter CTAs than the statistics pass
   // one pass of 4 vectors per thread per CTA where possible (1024 vectors per CTA)
+  // ... up to ~8 CTAs per SM; beyond that (image batches: B >= 16) the CTAs get fatter instead of more numerous, so that
+  // the per-CTA prologue (statistics + gamma / beta into shared memory, two barriers) is amortised over several
+  // iterations of loads in flight (ncu, B = 32: 1.9 TB/s with 1024-vector CTAs)
+  const long total_vec = static_cast<long>(B) * HW * (C / 8);
+  const long per_cta = std::max<long>(1024, total_vec / (148 * 8));
   int ppa = ppc;
-  while (ppa > 1 && ppa * (C / 8) > 1024 && HW % (ppa / 2) == 0) ppa >>= 1;
+  while (ppa > 1 && static_cast<long>(ppa) * (C / 8) > per_cta && HW % (ppa / 2) == 0) ppa >>= 1;
   PNP_CUDA(launch_k(gn_apply_kernel, dim3(HW / ppa, B), dim3(256), sm2, s, x0, C0, x1, C1, HW, mean_rstd, gamma, beta,
                     do_silu ? 1 : 0, out, ppa));
   return 0;
