@@ -48,10 +48,14 @@ def test_feature_injection_really_copies_the_source_rows(cuda):
     ctrl.t = 981
     x = torch.cat([synth.synth_latent(i) for i in range(3)]).cuda()
     m.unet.set_controller(None)
-    plain = m.unet(x, 981, encoder_hidden_states=ctx)["sample"]
+    first = m.unet(x, 981, encoder_hidden_states=ctx)["sample"].clone()
+    plain = m.unet(x, 981, encoder_hidden_states=ctx)["sample"].clone()
     m.unet.set_controller(ctrl)
-    inj = m.unet(x, 981, encoder_hidden_states=ctx)["sample"]
+    inj = m.unet(x, 981, encoder_hidden_states=ctx)["sample"].clone()
     torch.cuda.synchronize()
+    print(f"pnp rows: first-vs-replay {G.rel_l2(first, plain):.2e}; source row plain-vs-injected {G.rel_l2(inj[0], plain[0]):.2e}; "
+          f"injected rows {G.rel_l2(inj[1], plain[1]):.2e} {G.rel_l2(inj[2], plain[2]):.2e}")
+    assert torch.equal(first, plain)
     assert torch.equal(plain[0], inj[0])  # the source row is never touched
     assert G.rel_l2(inj[1], plain[1]) > 1e-2 and G.rel_l2(inj[2], plain[2]) > 1e-2
     ctrl.t = 1  # outside both schedules: identity descriptor
