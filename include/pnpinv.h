@@ -229,6 +229,11 @@ int pnp_vae_kernel_launches(pnp_vae* h, int64_t* out);
 int pnp_test_gemm(const uint16_t* a_dev, int M, int K, int lda, const uint16_t* w_dev, int N, const float* bias_dev,
                   const uint16_t* residual_dev, uint16_t* out_dev, int ldc, int geglu, int bn, int split,
                   void* stream); /* split: 0 auto, 1 off, n>1 force n K-splits */
+/* D[M,N] = [A0 | A1][M, K0+K1] . W[N, K0+K1]^T: two A sources along K (how a hi/lo split of the activation operand runs on
+ * the unchanged kernel: A0 = fp16(A), A1 = fp16(A - A0), W = [W | W]); reps > 1 launches it that many times and returns
+ * the mean device time per launch in *ms_out (CUDA events) */
+int pnp_test_gemm2(const uint16_t* a0_dev, int K0, const uint16_t* a1_dev, int K1, int M, const uint16_t* w_dev, int N,
+                   uint16_t* out_dev, int reps, float* ms_out, void* stream);
 int pnp_test_conv3x3(const uint16_t* x_dev, int B, int H, int W, int C, const uint16_t* w_dev, int N,
                      const uint16_t* sc0_dev, int sc0_C, const uint16_t* sc1_dev, int sc1_C, const float* bias_dev,
                      const uint16_t* residual_dev, uint16_t* out_dev, int bn, int split, void* stream);

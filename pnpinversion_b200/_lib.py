@@ -148,6 +148,7 @@ SIGNATURES = {
     "pnp_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "pnp_vae_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
     "pnp_test_gemm": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pnp_test_gemm2": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, C.POINTER(_f), _vp]),
     "pnp_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "pnp_test_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp]),
     "pnp_test_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _vp]),

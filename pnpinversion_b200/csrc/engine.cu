@@ -1684,6 +1684,42 @@ int pnp_test_gemm(const uint16_t* a_dev, int M, int K, int lda, const uint16_t* 
   return test_launch_with_ws(&gp, as_stream(stream));
 }
 
+int pnp_test_gemm2(const uint16_t* a0_dev, int K0, const uint16_t* a1_dev, int K1, int M, const uint16_t* w_dev, int N,
+                   uint16_t* out_dev, int reps, float* ms_out, void* stream) {
+  GemmEpilogue ep;
+  ep.out = reinterpret_cast<__half*>(out_dev);
+  ep.ldc = N;
+  ASource s[2];
+  int ns = 1;
+  s[0] = ASource{reinterpret_cast<const __half*>(a0_dev), K0, K0};
+  if (a1_dev != nullptr && K1 > 0) s[ns++] = ASource{reinterpret_cast<const __half*>(a1_dev), K1, K1};
+  GemmPlan gp;
+  // conv mode with one tap per source and a [1, 128-pixel] image: the multi-source form of the linear GEMM
+  PNP_CHECK(M % 128 == 0, "pnp_test_gemm2: M must be a multiple of 128");
+  int rc = gemm_plan_create(&gp, s, ns, 1, false, M / 128, 1, 128, reinterpret_cast<const __half*>(w_dev), N, K0 + (ns > 1 ? K1 : 0),
+                            ep, 0, test_sms(), 1);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  rc = gemm_launch(gp, st);
+  if (rc) return rc;
+  if (reps > 1 && ms_out != nullptr) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (int r = 0; r < reps && rc == 0; ++r) rc = gemm_launch(gp, st);
+    cudaEventRecord(e1, st);
+    PNP_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  PNP_CUDA(cudaStreamSynchronize(st));
+  return rc;
+}
+
 int pnp_test_conv3x3(const uint16_t* x_dev, int B, int H, int W, int C, const uint16_t* w_dev, int N,
                      const uint16_t* sc0_dev, int sc0_C, const uint16_t* sc1_dev, int sc1_C, const float* bias_dev,
                      const uint16_t* residual_dev, uint16_t* out_dev, int bn, int split, void* stream) {

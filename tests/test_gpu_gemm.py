@@ -143,3 +143,39 @@ def test_split_k_linear(cuda):
     w = _mk((N, K), cuda, 24, K ** -0.5)
     out = G.gemm(a, w, split=3)
     assert G.rel_l2(out, a.float() @ w.float().t()) < 1e-3
+
+
+def test_split_operand_gemm_accuracy_and_cost(cuda):
+    """What the north-star's 1e-3 would take: the activation operand as a hi/lo pair of fp16 values
+    (~22 bits) runs on the UNCHANGED tcgen05 kernel as two A sources along K against [W | W].  Measured here on a
+    projection-sized GEMM: the operand-rounding error disappears (weights are exact fp16 on both sides, as in the parity
+    setup) and the launch costs about twice the plain one."""
+    import ctypes as C
+
+    from pnpinversion_b200 import _lib
+
+    lib = _lib.load()
+    M, K, N = 16384, 1280, 1280
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(M, K, generator=g, dtype=torch.float64)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).half()
+    ref = (a @ w.double().t()).cuda()
+    hi = a.half()
+    lo = (a - hi.double()).half()
+    hi_d, lo_d, w_d = hi.cuda().contiguous(), lo.cuda().contiguous(), w.cuda().contiguous()
+    w2_d = torch.cat([w_d, w_d], dim=1).contiguous()
+    out1 = torch.empty(M, N, dtype=torch.float16, device=cuda)
+    out2 = torch.empty_like(out1)
+    ms1, ms2 = C.c_float(), C.c_float()
+    _lib.check(lib.pnp_test_gemm2(G.ptr(hi_d), K, None, 0, M, G.ptr(w_d), N, G.ptr(out1), 20, C.byref(ms1), G.stream()))
+    _lib.check(lib.pnp_test_gemm2(G.ptr(hi_d), K, G.ptr(lo_d), K, M, G.ptr(w2_d), N, G.ptr(out2), 20, C.byref(ms2), G.stream()))
+    torch.cuda.synchronize()
+    # fp16 OUTPUT rounding is common to both; compare against the fp64 product rounded to fp16 as well
+    ref16 = ref.half().double()
+    e_plain = G.rel_l2(out1.double(), ref)
+    e_split = G.rel_l2(out2.double(), ref)
+    e_floor = G.rel_l2(ref16, ref)
+    print(f"split-operand GEMM {M}x{N}x{K}: rel-L2 vs fp64 plain {e_plain:.2e}, hi/lo split {e_split:.2e} (fp16 output rounding "
+          f"alone {e_floor:.2e}); time {ms1.value * 1e3:.1f} us -> {ms2.value * 1e3:.1f} us (x{ms2.value / ms1.value:.2f})")
+    assert e_split < 1.15 * e_floor and e_plain > 1.2 * e_floor
+    assert 1.3 < ms2.value / ms1.value < 2.6

@@ -8,3 +8,4 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.
 grep -n '"rank"' gpurun_out/r2s7_cli2.log; find /tmp/pie_out -name "*.jpg" | wc -l
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 --no-config1 > gpurun_out/r2s7_ref2.log 2>&1
 tail -1 gpurun_out/r2s7_ref2.log | cut -c1-200
+python -m pytest tests/test_gpu_pnp_features.py tests/test_gpu_batched.py -q --timeout 900 -s > gpurun_out/r2s7_pytest.log 2>&1; grep -n "pnp rows|passed|failed|FAILED" gpurun_out/r2s7_pytest.log | cut -c1-300
