@@ -175,7 +175,14 @@ class MasaCtrlBatchResult:
 class MasaCtrlEditor:
     def __init__(self, method_list, device, num_ddim_steps=50, model=None) -> None:
         if model is None:
-            raise RuntimeError("no SD-1.x checkpoint is available offline: pass model=FusedModel...(max_batch>=4)")
+            # the reference downloads CompVis/stable-diffusion-v1-4 here (run_editing_masactrl.py:69-70); offline the
+            # checkpoint directory comes from PNP_SD_CHECKPOINT, else the seeded random-init stand-in is used
+            import os
+
+            from .model import FusedModel
+            ckpt = os.environ.get("PNP_SD_CHECKPOINT")
+            model = (FusedModel.from_pretrained(ckpt, device=str(device)) if ckpt
+                     else FusedModel.synthetic(device=str(device), with_vae=True))
         self.device = device
         self.method_list = method_list
         self.num_ddim_steps = num_ddim_steps

@@ -61,7 +61,7 @@ class P2PEditor:
             from .model import FusedModel
             ckpt = os.environ.get("PNP_SD_CHECKPOINT")
             model = (FusedModel.from_pretrained(ckpt, device=str(device)) if ckpt
-                     else FusedModel.synthetic(device=str(device)))
+                     else FusedModel.synthetic(device=str(device), with_vae=True))
         self.ldm_stable = model
         self.ldm_stable.scheduler.set_timesteps(self.num_ddim_steps)
         # the C-side step loops need the fused engine; a test double of the engine keeps the Python loops
