@@ -10,56 +10,63 @@ import torch
 from .seq_aligner import get_word_inds  # noqa: F401  (re-exported, the reference has it in both modules)
 
 
+def _read_rgb(image):
+    """A file path -> HWC uint8 array (first three channels); arrays pass through."""
+    if isinstance(image, str):
+        from PIL import Image
+
+        return np.asarray(Image.open(image))[..., :3]
+    return image
+
+
 def load_512(image_path, left=0, right=0, top=0, bottom=0):
-    """Path or HWC uint8 array -> centre-cropped 512x512x3 uint8 (utils/utils.py:27-46)."""
+    """Path or HWC uint8 array -> 512x512x3 uint8: optional margins, centre crop to a square, resize.
+
+    Same results as `utils/utils.py:27-46`, including its margin clamping - each margin is limited so that at least one
+    pixel survives, and the TOP margin is limited by the LEFT one (`h - left - 1`, the reference's arithmetic, kept so
+    that callers who pass margins get identical crops)."""
     from PIL import Image
 
-    if isinstance(image_path, str):
-        image = np.array(Image.open(image_path))[:, :, :3]
-    else:
-        image = image_path
-    h, w, _ = image.shape
-    left = min(left, w - 1)
-    right = min(right, w - left - 1)
-    top = min(top, h - left - 1)
-    bottom = min(bottom, h - top - 1)
-    image = image[top:h - bottom, left:w - right]
-    h, w, _ = image.shape
-    if h < w:
-        off = (w - h) // 2
-        image = image[:, off:off + h]
-    elif w < h:
-        off = (h - w) // 2
-        image = image[off:off + w]
-    return np.array(Image.fromarray(image).resize((512, 512)))
+    img = _read_rgb(image_path)
+    rows, cols = img.shape[:2]
+    left = min(left, cols - 1)
+    right = min(right, cols - left - 1)
+    top = min(top, rows - left - 1)  # sic: limited by `left`, as in the reference
+    bottom = min(bottom, rows - top - 1)
+    img = img[top:rows - bottom, left:cols - right]
+    rows, cols = img.shape[:2]
+    side = min(rows, cols)
+    r0, c0 = (rows - side) // 2, (cols - side) // 2  # the longer axis loses (longer - shorter) // 2 at its start
+    return np.array(Image.fromarray(img[r0:r0 + side, c0:c0 + side]).resize((512, 512)))
 
 
 def init_latent(latent, model, height, width, generator, batch_size):
+    """utils/utils.py:48-55: the start latent (drawn when absent) and its batch-expanded view on the model's device."""
+    shape = (model.unet.in_channels, height // 8, width // 8)
     if latent is None:
-        latent = torch.randn((1, model.unet.in_channels, height // 8, width // 8), generator=generator)
-    latents = latent.expand(batch_size, model.unet.in_channels, height // 8, width // 8).to(model.device)
-    return latent, latents
+        latent = torch.randn((1, *shape), generator=generator)
+    return latent, latent.expand(batch_size, *shape).to(model.device)
 
 
 @torch.no_grad()
 def latent2image(model, latents, return_type="np", rounding=False):
-    latents = 1 / 0.18215 * latents.detach()
-    image = model.decode(latents)["sample"]
-    if return_type == "np":
-        image = (image / 2 + 0.5).clamp(0, 1)
-        image = image.cpu().permute(0, 2, 3, 1).numpy()
-        # utils/utils.py:79 truncates; EDICT's prep_image_for_return rounds (edict_functions.py:698)
-        image = (image * 255).round().astype(np.uint8) if rounding else (image * 255).astype(np.uint8)
-    return image
+    """`model` is the VAE handle.  utils/utils.py:58-66: decode(z / 0.18215), to [0,1], HWC uint8 by TRUNCATION;
+    EDICT's prep_image_for_return rounds instead (edict_functions.py:698) -> `rounding=True`."""
+    image = model.decode(latents.detach() * (1 / 0.18215))["sample"]
+    if return_type != "np":
+        return image
+    hwc = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy() * 255
+    return (hwc.round() if rounding else hwc).astype(np.uint8)
 
 
 @torch.no_grad()
 def image2latent(model, image):
+    """`model` is the VAE handle.  utils/utils.py:68-80: 4-D tensors are latents already; an HWC uint8 image becomes
+    encode(x / 127.5 - 1).latent_dist.mean * 0.18215."""
     if isinstance(image, torch.Tensor) and image.dim() == 4:
-        return image  # already a latent (synthetic-latent path)
-    image = torch.from_numpy(np.asarray(image)).float() / 127.5 - 1
-    image = image.permute(2, 0, 1).unsqueeze(0).to(model.device)
-    return model.encode(image)["latent_dist"].mean * 0.18215
+        return image
+    x = torch.from_numpy(np.asarray(image)).float().div(127.5).sub(1).permute(2, 0, 1)[None].to(model.device)
+    return model.encode(x)["latent_dist"].mean * 0.18215
 
 
 def _set_window(alpha, bounds, prompt_ind, word_inds=None):

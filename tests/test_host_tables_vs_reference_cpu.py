@@ -322,3 +322,41 @@ def test_local_blend_host_parameters_match_the_reference(ref):
         m = prod.LocalBlend(prompts, words, tokenizer=tok, num_ddim_steps=steps)
         assert torch.equal(m.alpha_layers, r.alpha_layers.reshape(2, -1).to(m.alpha_layers.dtype)), prompts
         assert m.start_blend == r.start_blend and tuple(m.th) == tuple(r.th) and m.counter == r.counter == 0
+
+
+def test_load_512_and_latent_glue_match_the_reference(ref):
+    """utils/utils.py:27-80: load_512 on odd shapes and margins (incl. the top-margin-limited-by-left quirk),
+    latent2image / image2latent on a stand-in VAE, init_latent."""
+    import types
+
+    import numpy as np
+
+    rng = np.random.RandomState(5)
+    for shape, margins in (((480, 640), (0, 0, 0, 0)), ((700, 512), (10, 20, 30, 40)), ((512, 512), (0, 0, 0, 0)),
+                           ((300, 900), (850, 5, 200, 7)), ((333, 222), (3, 500, 400, 2))):
+        img = rng.randint(0, 256, shape + (3,)).astype(np.uint8)
+        a = ptp_utils.load_512(img, *margins)
+        b = ref.utils.load_512(img, *margins)
+        assert a.shape == (512, 512, 3) and np.array_equal(a, b), (shape, margins)
+
+    class Vae:
+        def decode(self, z):
+            return {"sample": torch.tanh(z[:, :3].repeat_interleave(2, -1).repeat_interleave(2, -2) * 3)}
+
+        def encode(self, x):
+            m = torch.nn.functional.avg_pool2d(x, 8)
+            return {"latent_dist": types.SimpleNamespace(mean=torch.cat([m, m[:, :1]], 1))}
+
+        device = torch.device("cpu")
+
+    vae = Vae()
+    z = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(1))
+    assert np.array_equal(ptp_utils.latent2image(vae, z), ref.utils.latent2image(vae, z))
+    img = rng.randint(0, 256, (64, 64, 3)).astype(np.uint8)
+    assert torch.equal(ptp_utils.image2latent(vae, img), ref.utils.image2latent(vae, img))
+    assert ptp_utils.image2latent(vae, z) is z
+    model = types.SimpleNamespace(unet=types.SimpleNamespace(in_channels=4), device=torch.device("cpu"))
+    g1, g2 = torch.Generator().manual_seed(9), torch.Generator().manual_seed(9)
+    l1, b1 = ptp_utils.init_latent(None, model, 512, 512, g1, 3)
+    l2, b2 = ref.utils.init_latent(None, model, 512, 512, g2, 3)
+    assert torch.equal(l1, l2) and torch.equal(b1, b2) and b1.shape == (3, 4, 64, 64)
