@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-image-path", action="store_true", help="skip the image-path (VAE) end-to-end measurement")
     ap.add_argument("--no-config1", action="store_true", help="reference arm: skip the full 20-step config-1 timing")
     ap.add_argument("--workload", default="p2p", choices=["p2p", "masactrl", "edict"],
                     help="p2p: directinversion+p2p (BASELINE configs 2/3, the headline); masactrl: directinversion+masactrl "
@@ -350,6 +351,31 @@ def main():
                         "what": "same outputs for directinversion+p2p without the reconstruction pass (its decoded row is "
                                 "the inverted latent by the rectification invariant; bit-identical edit, "
                                 "tests/test_gpu_batched.py)"}
+    # the image-path API end to end (P2PEditor.edit_batch on HWC uint8 host arrays -> 2048x512 PIL strips): VAE encode,
+    # the four loops, VAE decodes of the reconstruction and edit latents, panel assembly on the host; one step, rank 0
+    image_line = None
+    if args.workload == "p2p" and not args.minimal and rank == 0 and not args.no_image_path:
+        import numpy as np
+
+        from pnpinversion_b200.vae import FusedVAE
+
+        parent.vae = FusedVAE(synth.synth_vae_state_dict(0), device=str(dev))
+        rng = np.random.RandomState(7)
+        imgs = [rng.randint(0, 256, (512, 512, 3)).astype(np.uint8) for _ in range(NB)]
+        ed0 = lanes.editors[0]
+        ed0.edit_batch(imgs[:1], [src], [tgt], blend_word=BLEND, eq_params=EQ)  # VAE plans (B = 1, 2) built outside the timing
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        strips = ed0.edit_batch(imgs, [src] * NB, [tgt] * NB, guidance_scale=7.5, cross_replace_steps=0.4,
+                                self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        assert len(strips) == NB and strips[0].size == (2048, 512)
+        image_line = {"value": NB / wall, "unit": "images/s", "images": NB, "seconds": wall,
+                      "h2d_bytes": NB * 512 * 512 * 3, "d2h_bytes": NB * 4 * 3 * 512 * 512 * 4,
+                      "what": "host wall clock around P2PEditor.edit_batch(list of HWC uint8 arrays) -> PIL strips: VAE encode + "
+                              "650 UNet forwards + 4 VAE decodes per image + panel assembly (synthetic VAE weights)"}
+        parent.vae = None
     ctx_rows = {"p2p": 4, "masactrl": 4, "edict": 9}[args.workload] * NB  # edict: 4 coupled passes encode 2+2+2+3 rows per image
     h2d = NL * (NB * 4 * 64 * 64 * 4 + ctx_rows * 77 * 768 * 4)
     d2h = NL * 2 * NB * 4 * 64 * 64 * 4
@@ -448,6 +474,8 @@ def main():
     }
     if minimal_line is not None:
         line["minimal_450"] = minimal_line
+    if image_line is not None:
+        line["image_path_e2e"] = image_line
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
