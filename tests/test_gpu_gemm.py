@@ -107,11 +107,13 @@ def test_conv3x3_fused_shortcut_over_concat(cuda):
     assert G.rel_l2(out, ref.permute(0, 2, 3, 1)) < 1e-3
 
 
+@pytest.mark.parametrize("B", [2, 8])
 @pytest.mark.parametrize("split", [1, 3])
-def test_conv3x3_two_accumulators_320(cuda, split):
-    """128 x 320 tiles = two interleaved accumulators of 160 columns (one accumulator set in TMEM: a CTA that gets a second
-    tile must wait for its own epilogue), with bias, residual and split-K."""
-    B, H, C, N = 2, 64, 64, 1280  # 64 x 4 = 256 tiles (x splits) on 148 CTAs
+def test_conv3x3_two_accumulators_320(cuda, split, B):
+    """128 x 320 tiles = two accumulators of 160 columns, rotating over THREE 160-column TMEM buffers (tile i uses buffers
+    2i % 3 and (2i+1) % 3, the epilogue hands the first one back early), with bias, residual and split-K.  B = 8 gives
+    every CTA 7 (x splits) tiles, i.e. more than two full rotation periods with both barrier parities on every buffer."""
+    H, C, N = 64, 64, 1280  # B*32 x 4 = 256 / 1024 tiles (x splits) on 148 CTAs
     x = _mk((B, H, H, C), cuda, 40)
     w = _mk((N, C, 3, 3), cuda, 41, (9 * C) ** -0.5)
     bias = torch.randn(N, device=cuda) * 0.1
