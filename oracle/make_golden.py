@@ -318,7 +318,8 @@ def gen_masactrl_pipeline(n_steps: int = 4):
         mutils.regiter_attention_editor_diffusers(model, mutils.AttentionBase())
         fixed = pipe([tgt], latents=x_t, num_inference_steps=n_steps, guidance_scale=7.5, noise_loss_list=None)
         print("direct synthesis done", time.time() - t0, flush=True)
-        editor = masactrl.MutualSelfAttentionControl(1, 10, total_steps=n_steps)
+        # run_editing_masactrl.py:89 defaults (step 4, layer 10) for a full schedule; step 1 for the short fixtures
+        editor = masactrl.MutualSelfAttentionControl(4 if n_steps >= 10 else 1, 10, total_steps=n_steps)
         mutils.regiter_attention_editor_diffusers(model, editor)
         out = pipe(prompts, latents=x_t.expand(2, -1, -1, -1), num_inference_steps=n_steps, guidance_scale=7.5,
                    noise_loss_list=noise_loss)

@@ -156,8 +156,13 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     } else {
       tile = work % total_tiles;
       split = work / total_tiles;
-      m_blk = tile % p.m_tiles;
-      n_blk = tile / p.m_tiles;
+      if (p.raster) {
+        n_blk = tile % p.n_tiles;
+        m_blk = tile / p.n_tiles;
+      } else {
+        m_blk = tile % p.m_tiles;
+        n_blk = tile / p.m_tiles;
+      }
     }
   };
 
@@ -833,6 +838,18 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   p.splits = splits;
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   const int tiles = p.m_tiles * p.n_tiles;
+  {
+    // Tile order.  With M tiles fastest the 148 CTAs in flight share one weight tile and walk down the activations, once
+    // per N tile: fine while the activations stay in L2 between passes, but an 84 MB activation (B = 32 at 64x64x320)
+    // was streamed from HBM n_tiles times (ncu, GEGLU projection: 754 MB read for 84 MB of A, 54 % DRAM, 49 % tensor).
+    // N tiles fastest makes the CTAs in flight share activation tiles instead; the weights (<= 30 MB) live in L2.
+    static const int force = [] { const char* e = getenv("PNP_GEMM_RASTER"); return e ? atoi(e) : -1; }();
+    size_t a_cols = 0;
+    for (int i = 0; i < nsrc; ++i) a_cols += static_cast<size_t>(srcs[i].C);
+    const size_t a_bytes = static_cast<size_t>(M) * a_cols * 2;
+    static const size_t min_mb = [] { const char* e = getenv("PNP_GEMM_RASTER_MB"); return e ? atoi(e) : 40; }();
+    p.raster = force >= 0 ? force : ((p.n_tiles > 1 && a_bytes > (min_mb << 20)) ? 1 : 0);
+  }
   plan->bn = bn;
   plan->nsub = nsub;
   plan->grid = std::min(tiles * p.splits, num_sms);

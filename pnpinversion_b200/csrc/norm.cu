@@ -29,7 +29,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
   return u;
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with ex2.approx + rcp.approx (2 MUFU, ~2 ulp of fp32: far below the fp16 rounding of the result); an IEEE
+// division here made the streaming normalisation passes issue-bound (ncu: 2.0 TB/s at 55 % issue utilisation).
+// x -> -inf: exp = inf, 1 + inf = inf, __fdividef(x, inf) = -0.
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------ GroupNorm
 constexpr int GN_GROUPS = 32;
@@ -229,6 +232,62 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
           f[e] = do_silu ? silu(y) : y;
         }
         *reinterpret_cast<uint4*>(out + (row0 + pixs[j]) * C + v * 8) = pack8(f);
+      }
+    }
+  }
+}
+
+// Streaming normalise (+SiLU), the HBM-bound half of GroupNorm for image batches (84 MB in + 84 MB out per launch at
+// B = 32, 64x64x320).  The block size is a multiple of the 16-byte vectors per pixel, so the flat vector index
+// tid + k * blockDim keeps its channel vector: every thread owns ONE channel vector, its eight scale / shift pairs live in
+// registers, and the loop is U independent 16-byte loads, 8 FMAs + SiLUs each, U stores - no integer division, no shared
+// memory.  `reverse`: CTAs walk the tensor back to front.  The statistics pass (and the GEMM before it) touched the
+// tensor front to back, so with an LRU-like L2 smaller than the tensor a front-to-back reader misses everything while a
+// back-to-front reader still finds the tail; and the consumer (an implicit-GEMM conv reading front to back) then finds
+// the head of the output this kernel wrote last.
+template <int U>
+__global__ void __launch_bounds__(512) gn_apply_vec_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1,
+                                                           int C1, int HW, const float* __restrict__ mean_rstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int do_silu, __half* __restrict__ out, int ppc, int reverse) {
+  pdl_sync();
+  const int C = C0 + C1, nvec = C >> 3, nvec0 = C0 >> 3;
+  const int b = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int slice = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int v = threadIdx.x % nvec, py = threadIdx.x / nvec, rows_y = blockDim.x / nvec;
+  const int cpg = C / GN_GROUPS;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = v * 8 + e, g = c / cpg;
+    const float2 mr = __ldg(reinterpret_cast<const float2*>(mean_rstd + (b * GN_GROUPS + g) * 2));
+    sc[e] = mr.y * __ldg(gamma + c);
+    sh[e] = __ldg(beta + c) - mr.x * sc[e];
+  }
+  const size_t row0 = static_cast<size_t>(b) * HW + static_cast<size_t>(slice) * ppc;
+  const bool first = v < nvec0;
+  const __half* src = first ? x0 + row0 * C0 + v * 8 : x1 + row0 * C1 + (v - nvec0) * 8;
+  const size_t sstride = first ? C0 : C1;
+  __half* dst = out + row0 * C + v * 8;
+  for (int p0 = py; p0 < ppc; p0 += U * rows_y) {
+    uint4 u[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int p = p0 + j * rows_y;
+      if (p < ppc) u[j] = __ldg(reinterpret_cast<const uint4*>(src + p * sstride));
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int p = p0 + j * rows_y;
+      if (p < ppc) {
+        float f[8];
+        unpack8(u[j], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float y = fmaf(f[e], sc[e], sh[e]);
+          f[e] = do_silu ? silu(y) : y;
+        }
+        *reinterpret_cast<uint4*>(dst + static_cast<size_t>(p) * C) = pack8(f);
       }
     }
   }
@@ -727,6 +786,16 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   const long per_cta = std::max<long>(1024, total_vec / (148 * 8));
   int ppa = ppc;
   while (ppa > 1 && static_cast<long>(ppa) * (C / 8) > per_cta && HW % (ppa / 2) == 0) ppa >>= 1;
+  // block = a multiple of both the warp and the vectors per pixel (every thread keeps its channel vector)
+  static const int apply_mode = [] { const char* e = getenv("PNP_GN_APPLY"); return e ? atoi(e) : 3; }();  // 0 old, 1 vec, 3 vec + reverse
+  int lcm = nvec;
+  while (lcm % 32) lcm += nvec;
+  if (apply_mode != 0 && lcm <= 512) {
+    const int threads_a = lcm * ((256 + lcm - 1) / lcm);
+    PNP_CUDA(launch_k(gn_apply_vec_kernel<4>, dim3(HW / ppa, B), dim3(threads_a), 0, s, x0, C0, x1, C1, HW, mean_rstd, gamma,
+                      beta, do_silu ? 1 : 0, out, ppa, (apply_mode & 2) ? 1 : 0));
+    return 0;
+  }
   PNP_CUDA(launch_k(gn_apply_kernel, dim3(HW / ppa, B), dim3(256), sm2, s, x0, C0, x1, C1, HW, mean_rstd, gamma, beta,
                     do_silu ? 1 : 0, out, ppa));
   return 0;

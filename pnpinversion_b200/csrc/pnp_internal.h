@@ -110,6 +110,8 @@ struct alignas(64) GemmParams {
   // split-K (small-M, weight-streaming layers): `splits` CTAs share one output tile, each reduces a K range into
   // ws[split][M][N] (fp32); the last CTA to arrive (counters[tile]) sums the slices in index order and runs the epilogue
   int splits, kb_per_split;
+  int raster;  // tile order of the persistent loop: 0 = M tiles fastest (CTAs in flight share a weight tile), 1 = N tiles fastest
+               // (they share an activation tile: for activations larger than L2, which would be streamed once per N tile)
   float* ws;
   int* counters;
   volatile unsigned int* dbg;
