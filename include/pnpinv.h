@@ -240,6 +240,9 @@ int pnp_test_conv3x3(const uint16_t* x_dev, int B, int H, int W, int C, const ui
 int pnp_test_groupnorm(const uint16_t* x0_dev, int C0, const uint16_t* x1_dev, int C1, int B, int HW,
                        const float* gamma_dev, const float* beta_dev, float eps, int silu, uint16_t* out_dev,
                        void* stream);
+/* which GroupNorm path groupnorm_launch takes for this shape on the current device: 0 = statistics + apply (two kernels),
+ * 1 = single-launch cluster kernel, 2 = register-resident kernel (one CTA per image x group chunk) */
+int pnp_test_groupnorm_path(int C, int B, int HW);
 int pnp_test_layernorm(const uint16_t* x_dev, int rows, int C, const float* gamma_dev, const float* beta_dev,
                        float eps, uint16_t* out_dev, void* stream);
 int pnp_test_self_attention(const uint16_t* qkv_dev, int B, int H, int N, int d, const int32_t* q_row_dev,

@@ -151,6 +151,7 @@ SIGNATURES = {
     "pnp_test_gemm2": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, C.POINTER(_f), _vp]),
     "pnp_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "pnp_test_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp]),
+    "pnp_test_groupnorm_path": (_i, [_i, _i, _i]),
     "pnp_test_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "pnp_test_self_attention": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pnp_test_self_attention_tc": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),

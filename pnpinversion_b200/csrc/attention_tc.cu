@@ -434,21 +434,33 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
 }
 
 // V part of the fused QKV activation [B*N, ld] -> V^T [B][H][41][N] (row 40 is pre-filled with ones by the owner of the
-// buffer).  One CTA: 64 tokens of one (b, h); shared-memory tile transpose, 128-byte coalesced on both sides.
-__global__ void __launch_bounds__(256) vt_transpose_kernel(const __half* __restrict__ v, int ld, int N,
+// buffer).  One CTA: 128 tokens of one (b, h), 16-byte accesses on both sides (a token's 40 halves are five vectors, a
+// V^T row of 128 tokens sixteen), transposed through shared memory.  The first version moved single halves: 88 us per
+// layer at B = 32 (2.1 TB/s) for 84 MB in, 86 MB out.
+constexpr int VT_TOK = 128;
+__global__ void __launch_bounds__(320) vt_transpose_kernel(const __half* __restrict__ v, int ld, int N,
                                                            __half* __restrict__ vt) {
-  __shared__ __half tile[D][64 + 2];
+  __shared__ __align__(16) __half tile[D][VT_TOK + 8];
   pdl_sync();
-  const int t0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
-  for (int i = threadIdx.x; i < 64 * D; i += blockDim.x) {
-    const int tok = i / D, j = i - tok * D;
-    tile[j][tok] = v[(static_cast<size_t>(b) * N + t0 + tok) * ld + h * D + j];
+  const int t0 = blockIdx.x * VT_TOK, h = blockIdx.y, b = blockIdx.z;
+  const int vec = threadIdx.x % 5, tk = threadIdx.x / 5;  // 64 tokens x 5 vectors per pass
+  uint4 u[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+    u[r] = __ldg(reinterpret_cast<const uint4*>(v + (static_cast<size_t>(b) * N + t0 + tk + 64 * r) * ld + h * D + vec * 8));
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const __half* hh = reinterpret_cast<const __half*>(&u[r]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) tile[vec * 8 + e][tk + 64 * r] = hh[e];
   }
   __syncthreads();
   __half* dst = vt + (static_cast<size_t>(b) * 8 + h) * 41 * N + t0;
-  for (int i = threadIdx.x; i < D * 64; i += blockDim.x) {
-    const int j = i / 64, tok = i - j * 64;
-    dst[static_cast<size_t>(j) * N + tok] = tile[j][tok];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int idx = threadIdx.x + 320 * r;  // 40 rows x 16 vectors
+    const int j = idx >> 4, seg = idx & 15;
+    *reinterpret_cast<uint4*>(dst + static_cast<size_t>(j) * N + seg * 8) = *reinterpret_cast<const uint4*>(&tile[j][seg * 8]);
   }
 }
 
@@ -522,7 +534,7 @@ int self_attention_tc_launch(const SelfAttnTcParams& p, cudaStream_t s) {
     PNP_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
-  PNP_CUDA(launch_k(vt_transpose_kernel, dim3(p.N / 64, 8, p.B), dim3(256), 0, s, p.v_src, p.ld, p.N, p.vt));
+  PNP_CUDA(launch_k(vt_transpose_kernel, dim3(p.N / VT_TOK, 8, p.B), dim3(320), 0, s, p.v_src, p.ld, p.N, p.vt));
   if (p.cluster == 2)
     PNP_CUDA(launch_kc(self_attn_tc_kernel<true>, dim3(p.N / QT, 8, p.B), dim3(640), SMEM_BYTES, s, 2, p));
   else

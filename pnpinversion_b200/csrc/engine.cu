@@ -703,7 +703,7 @@ struct PlanBuilder {
                  bool silu, __half* out) {
     pnp_engine* en = e;
     const int Bn = B;
-    op(1, 0.0, groupnorm_kernel_count(c0 + c1, hw),
+    op(1, 0.0, groupnorm_kernel_count(c0 + c1, Bn, hw),
        [=](cudaStream_t s) { return groupnorm_launch(x0, c0, x1, c1, Bn, hw, g, b, eps, silu, out, en->gn_partials, s); });
   }
   void layernorm(const __half* x, int rows, int c, const float* g, const float* b, __half* out) {
@@ -1755,6 +1755,8 @@ int pnp_test_groupnorm(const uint16_t* x0_dev, int C0, const uint16_t* x1_dev, i
   cudaFree(partials);
   return rc;
 }
+
+int pnp_test_groupnorm_path(int C, int B, int HW) { return groupnorm_path(C, B, HW); }
 
 int pnp_test_layernorm(const uint16_t* x_dev, int rows, int C, const float* gamma_dev, const float* beta_dev,
                        float eps, uint16_t* out_dev, void* stream) {

@@ -351,12 +351,20 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
       const int m = m_blk * BM + row;
       const bool valid = m < p.M;
       // the residual does not depend on the accumulator: fetch the first chunk before waiting for the MMAs
-      uint4 rcur[4], rnext[4];
+      // ... three chunks deep: a K = 320 projection with a residual is HBM-bound and its epilogue thread has one 64-byte
+      // row segment per chunk to fetch; with one chunk of look-ahead an SM kept 16 KB of residual in flight (3.4 TB/s over
+      // the chip for such a launch), with three it is 48 KB
+      constexpr int RD = 3;
+      uint4 rb[RD][4];
       const bool has_res = p.residual != nullptr && valid && !p.geglu;
       const __half* res_row = has_res ? p.residual + static_cast<size_t>(m) * p.ldr + n_blk * BNT : nullptr;
-      if (has_res && half < BNT / 32) {
-        ldg256_nc(res_row + half * 32, rcur[0], rcur[1]);
-        ldg256_nc(res_row + half * 32 + 16, rcur[2], rcur[3]);
+#pragma unroll
+      for (int d = 0; d < RD; ++d) {
+        const int c = half + 2 * d;
+        if (has_res && c < BNT / 32) {
+          ldg256_nc(res_row + c * 32, rb[d][0], rb[d][1]);
+          ldg256_nc(res_row + c * 32 + 16, rb[d][2], rb[d][3]);
+        }
       }
       if (prof) {
         const long long t = clock64();
@@ -415,18 +423,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             if (!from_ws) {
               uint32_t r[32];
               tmem_ld_32x32b_x32(taddr + c * 32, r);
-              if (has_res && c + 2 < BNT / 32) {  // prefetch the next chunk's residual under the TMEM load
-                ldg256_nc(res_row + (c + 2) * 32, rnext[0], rnext[1]);
-                ldg256_nc(res_row + (c + 2) * 32 + 16, rnext[2], rnext[3]);
-              }
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             } else {
-              if (has_res && c + 2 < BNT / 32) {
-                ldg256_nc(res_row + (c + 2) * 32, rnext[0], rnext[1]);
-                ldg256_nc(res_row + (c + 2) * 32 + 16, rnext[2], rnext[3]);
-              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
               if (valid) {
@@ -489,9 +489,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
               }
             } else if (valid) {
               if (has_res) {
+                const int slot = (c0 / 2) % RD;  // static after unrolling: the ring stays in registers
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const __half2* h = reinterpret_cast<const __half2*>(&rcur[j]);
+                  const __half2* h = reinterpret_cast<const __half2*>(&rb[slot][j]);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const float2 f = __half22float2(h[e]);
@@ -499,8 +500,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                     v[j * 8 + e * 2 + 1] += f.y;
                   }
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+                if (c + 2 * RD < BNT / 32) {  // refill the slot with the chunk three iterations ahead
+                  ldg256_nc(res_row + (c + 2 * RD) * 32, rb[slot][0], rb[slot][1]);
+                  ldg256_nc(res_row + (c + 2 * RD) * 32 + 16, rb[slot][2], rb[slot][3]);
+                }
               }
               __half* op = p.out + static_cast<size_t>(m) * p.ldc + n0;
               uint4 u[4];

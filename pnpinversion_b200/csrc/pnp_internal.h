@@ -178,7 +178,8 @@ long gemm_model_cost(int M, int N, int num_kb, bool geglu, int bnt, int splits, 
 int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, int HW, const float* gamma,
                      const float* beta, float eps, bool silu, __half* out, float* partials, cudaStream_t s);
 size_t groupnorm_partials_floats(int B, int HW);
-int groupnorm_kernel_count(int C, int HW);      // 1 = cluster kernel, 2 = statistics + apply (what groupnorm_launch will launch)
+int groupnorm_path(int C, int B, int HW);  // 0 = statistics + apply, 1 = cluster kernel, 2 = register-resident kernel
+int groupnorm_kernel_count(int C, int B, int HW);  // kernels groupnorm_launch will launch: 1 = register-resident or cluster kernel, 2 = statistics + apply
 size_t groupnorm_workspace_floats(int B, int HW);  // partials + mean/rstd + per-batch counters (zero-initialised)
 int layernorm_launch(const __half* x, int rows, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t s);

@@ -536,7 +536,7 @@ struct VBuilder {
   void groupnorm(const __half* x, int c, int hw, const float* g, const float* b, bool silu, __half* out) {
     pnp_vae* en = e;
     const int Bn = B;
-    op(groupnorm_kernel_count(c, hw),
+    op(groupnorm_kernel_count(c, Bn, hw),
        [=](cudaStream_t s) { return groupnorm_launch(x, c, nullptr, 0, Bn, hw, g, b, 1e-6f, silu, out, en->gn_ws, s); });
   }
   // resnet.py:331-365 without time embedding, GroupNorm eps 1e-6

@@ -39,6 +39,18 @@ def test_groupnorm(cuda, B, HW, C0, C1, silu):
     assert G.rel_l2(out, ref) < 6e-4
 
 
+@pytest.mark.parametrize("B,HW,C0,C1,silu", [(8, 256, 1280, 0, True), (32, 256, 1280, 1280, True), (16, 256, 1280, 640, True),
+                                             (8, 64, 1280, 0, False), (32, 64, 1280, 1280, True), (16, 1024, 640, 0, True),
+                                             (8, 1024, 640, 640, True), (32, 1024, 640, 0, False), (6, 256, 1280, 0, True)])
+def test_gn_register_resident_path(cuda, B, HW, C0, C1, silu):
+    """Image batches: the low-resolution levels take the register-resident kernel (one CTA per image x chunk of whole groups,
+    one read, centred variance from registers); it must actually be the path taken and match torch's fp32 GroupNorm."""
+    lib = _lib.load()
+    assert lib.pnp_test_groupnorm_path(C0 + C1, B, HW) == 2
+    assert lib.pnp_test_groupnorm_path(C0 + C1, 2, HW) != 2  # too few CTAs at small batch: cluster / two-kernel paths
+    test_groupnorm(cuda, B, HW, C0, C1, silu)
+
+
 def test_groupnorm_cluster_kernel_path(cuda):
     """By default the single-launch cluster kernel (statistics exchanged through distributed shared memory) takes the small
     tensors (HW <= 256) and the statistics + apply pair the large ones; PNP_GN_CLUSTER=16 forces the cluster kernel for
