@@ -322,43 +322,50 @@ __device__ __forceinline__ void softmax77(float (&s)[XNT][4], float sl2, int nk,
   }
 }
 
+// One CTA = `tiles_per_cta` consecutive 64-query tiles of one (batch row, head).  K, V (and for an edited row the source
+// row's K and the 77-entry tables) are staged ONCE; the query tiles stream through a double buffer, the next tile's
+// cp.async running under the current tile's MMAs.  The first version staged 12 KB of K/V for every 5 KB query tile and
+// ran one load -> wait -> compute -> store chain per CTA at 12 warps per SM: 177 us per 64x64 layer at B = 32 for 168 MB
+// of compulsory traffic.
 template <int D>
 __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnParams p) {
   using G = Geo<D>;
   constexpr int QT = 64 * G::PITCH;
   constexpr int KT = XK * G::PITCH;
   extern __shared__ __align__(16) uint8_t sm[];
-  uint8_t* sQ = sm;
-  uint8_t* sK = sQ + QT;
+  uint8_t* sQ = sm;             // two query tiles
+  uint8_t* sK = sQ + 2 * QT;
   uint8_t* sV = sK + KT;
-  uint8_t* sQs = sV + KT;   // source-row Q (edited rows only)
-  uint8_t* sKs = sQs + QT;  // source-row K
+  uint8_t* sQs = sV + KT;       // source-row Q (edited rows only), single buffer: refilled once its fragments are in registers
+  uint8_t* sKs = sQs + QT;      // source-row K
   float* sP = reinterpret_cast<float*>(sKs + KT);  // [4 warps][16][XK]
   float* sTab = sP + 4 * 16 * XK;                  // alphas[80], eq[80], ca[80], int mapper[80], int count[80], weight[80]
   pdl_sync();
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int C = p.H * D;
   const int base = p.base_row ? p.base_row[b] : -1;
   const int slot = p.edit_slot ? p.edit_slot[b] : -1;
   const bool edit = base >= 0 && slot >= 0;
-  const int rows_valid = min(64, p.N - qt * 64);
+  const int ntiles = (p.N + 63) / 64;
+  const int qt0 = blockIdx.x * p.tiles_per_cta;
+  const int qt1 = min(qt0 + p.tiles_per_cta, ntiles);
 
-  const __half* qg = p.q + (static_cast<size_t>(b) * p.N + qt * 64) * p.ldq + h * D;
+  const __half* qrow = p.q + static_cast<size_t>(b) * p.N * p.ldq + h * D;
+  const __half* qsrow = p.q + static_cast<size_t>(edit ? base : 0) * p.N * p.ldq + h * D;
   const __half* kg = p.kv + static_cast<size_t>(b) * p.nk * p.ldkv + h * D;
   const __half* vg = kg + C;
-  zero_pad_cols<D>(sQ, 64);
+  zero_pad_cols<D>(sQ, 128);
   zero_pad_cols<D>(sK, XK);
-  load_tile_async<D>(sQ, qg, p.ldq, 64, rows_valid);
+  load_tile_async<D>(sQ, qrow + static_cast<size_t>(qt0) * 64 * p.ldq, p.ldq, 64, min(64, p.N - qt0 * 64));
   load_tile_async<D>(sK, kg, p.ldkv, XK, p.nk);
   load_tile_async<D>(sV, vg, p.ldkv, XK, p.nk);
   if (edit) {
-    const __half* qsg = p.q + (static_cast<size_t>(base) * p.N + qt * 64) * p.ldq + h * D;
     const __half* ksg = p.kv + static_cast<size_t>(base) * p.nk * p.ldkv + h * D;
     zero_pad_cols<D>(sQs, 64);
     zero_pad_cols<D>(sKs, XK);
-    load_tile_async<D>(sQs, qsg, p.ldq, 64, rows_valid);
+    load_tile_async<D>(sQs, qsrow + static_cast<size_t>(qt0) * 64 * p.ldq, p.ldq, 64, min(64, p.N - qt0 * 64));
     load_tile_async<D>(sKs, ksg, p.ldkv, XK, p.nk);
     for (int i = threadIdx.x; i < XK; i += blockDim.x) {
       const bool ok = i < p.nk;
@@ -371,65 +378,79 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnParams p
     }
   }
   cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
 
   const float sl2 = p.scale * 1.4426950408889634f;
-  uint32_t qf[G::KS][4];
-  float s[XNT][4];
-  if (edit) {
-    // source probabilities for the same queries -> smem
-    load_q_frags<D>(qf, sQs, warp, lane);
-    qk_tile<D, XNT>(s, qf, sKs, lane);
-    softmax77(s, sl2, p.nk, lane);
-    float* myP = sP + warp * 16 * XK;
-#pragma unroll
-    for (int nt = 0; nt < XNT; ++nt) {
-      const int c = nt * 8 + 2 * t;
-      myP[g * XK + c] = s[nt][0];
-      myP[g * XK + c + 1] = s[nt][1];
-      myP[(g + 8) * XK + c] = s[nt][2];
-      myP[(g + 8) * XK + c + 1] = s[nt][3];
+  const int ss = (p.store != nullptr && p.store_slot) ? p.store_slot[b] : -1;
+  __half* og = p.o + static_cast<size_t>(b) * p.N * p.ldo + h * D;
+  for (int qt = qt0; qt < qt1; ++qt) {
+    const uint8_t* sQc = sQ + ((qt - qt0) & 1) * QT;
+    const int rows_valid = min(64, p.N - qt * 64);
+    cp_async_wait<0>();
+    __syncthreads();  // tile qt has landed; every warp is done with tile qt-1 (the other query buffer is free)
+    const bool more = qt + 1 < qt1;
+    if (more)
+      load_tile_async<D>(sQ + ((qt + 1 - qt0) & 1) * QT, qrow + static_cast<size_t>(qt + 1) * 64 * p.ldq, p.ldq, 64,
+                         min(64, p.N - (qt + 1) * 64));
+    uint32_t qf[G::KS][4];
+    float s[XNT][4];
+    if (edit) {
+      // source probabilities for the same queries -> smem
+      load_q_frags<D>(qf, sQs, warp, lane);
+      __syncthreads();  // (CTA-uniform branch) the source-Q buffer is in registers everywhere: refill it for the next tile
+      if (more)
+        load_tile_async<D>(sQs, qsrow + static_cast<size_t>(qt + 1) * 64 * p.ldq, p.ldq, 64, min(64, p.N - (qt + 1) * 64));
     }
-    __syncwarp();
-  }
-  load_q_frags<D>(qf, sQ, warp, lane);
-  qk_tile<D, XNT>(s, qf, sK, lane);
-  softmax77(s, sl2, p.nk, lane);
-  if (edit) {
-    // attention_control.py:319-323 (Refine gather+blend), :340-345 (Reweight), :276-277 (time gate)
-    const float* myP = sP + warp * 16 * XK;
-    const float* al = sTab;
-    const float* eq = sTab + XK;
-    const float* ca = sTab + 2 * XK;
-    const int* mp = reinterpret_cast<const int*>(sTab + 3 * XK);
-    const int* mcnt = reinterpret_cast<const int*>(sTab + 4 * XK);
-    const float* mw = sTab + 5 * XK;
+    cp_async_commit();
+    if (edit) {
+      qk_tile<D, XNT>(s, qf, sKs, lane);
+      softmax77(s, sl2, p.nk, lane);
+      float* myP = sP + warp * 16 * XK;
 #pragma unroll
-    for (int nt = 0; nt < XNT; ++nt) {
+      for (int nt = 0; nt < XNT; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        myP[g * XK + c] = s[nt][0];
+        myP[g * XK + c + 1] = s[nt][1];
+        myP[(g + 8) * XK + c] = s[nt][2];
+        myP[(g + 8) * XK + c + 1] = s[nt][3];
+      }
+      __syncwarp();
+    }
+    load_q_frags<D>(qf, sQc, warp, lane);
+    qk_tile<D, XNT>(s, qf, sK, lane);
+    softmax77(s, sl2, p.nk, lane);
+    if (edit) {
+      // attention_control.py:319-323 (Refine gather+blend), :340-345 (Reweight), :276-277 (time gate)
+      const float* myP = sP + warp * 16 * XK;
+      const float* al = sTab;
+      const float* eq = sTab + XK;
+      const float* ca = sTab + 2 * XK;
+      const int* mp = reinterpret_cast<const int*>(sTab + 3 * XK);
+      const int* mcnt = reinterpret_cast<const int*>(sTab + 4 * XK);
+      const float* mw = sTab + 5 * XK;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = nt * 8 + 2 * t + (e & 1);
-        const int r = g + (e >> 1) * 8;
-        if (c < p.nk) {
-          const float pt = s[nt][e];
-          int mc = mp[c];
-          if (mc < 0) mc += p.nk;  // torch negative index: -1 -> last column (seq_aligner.py:96,116)
-          // AttentionReplace with unequal spans: weight * sum of `count` consecutive source tokens
-          // (seq_aligner.py:168-174); count 1 / weight 1 is the plain gather of Refine and of equal-length Replace
-          float ps = myP[r * XK + mc];
-          const int cnt = mcnt[c];
-          for (int k2 = 1; k2 < cnt; ++k2) ps += myP[r * XK + min(mc + k2, XK - 1)];
-          ps *= mw[c];
-          float nw = ps * al[c] + pt * (1.f - al[c]);
-          nw = nw * eq[c];
-          s[nt][e] = nw * ca[c] + (1.f - ca[c]) * pt;
+      for (int nt = 0; nt < XNT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = nt * 8 + 2 * t + (e & 1);
+          const int r = g + (e >> 1) * 8;
+          if (c < p.nk) {
+            const float pt = s[nt][e];
+            int mc = mp[c];
+            if (mc < 0) mc += p.nk;  // torch negative index: -1 -> last column (seq_aligner.py:96,116)
+            // AttentionReplace with unequal spans: weight * sum of `count` consecutive source tokens
+            // (seq_aligner.py:168-174); count 1 / weight 1 is the plain gather of Refine and of equal-length Replace
+            float ps = myP[r * XK + mc];
+            const int cnt = mcnt[c];
+            for (int k2 = 1; k2 < cnt; ++k2) ps += myP[r * XK + min(mc + k2, XK - 1)];
+            ps *= mw[c];
+            float nw = ps * al[c] + pt * (1.f - al[c]);
+            nw = nw * eq[c];
+            s[nt][e] = nw * ca[c] + (1.f - ca[c]) * pt;
+          }
         }
       }
+      __syncwarp();  // the next tile's source probabilities overwrite myP
     }
-  }
-  if (p.store != nullptr) {
-    const int ss = p.store_slot ? p.store_slot[b] : -1;
     if (ss >= 0) {
       float* st = p.store + ((static_cast<size_t>(ss) * p.H + h) * p.N + qt * 64 + warp * 16) * 77;
 #pragma unroll
@@ -442,33 +463,33 @@ __global__ void __launch_bounds__(128) cross_attn_kernel(const CrossAttnParams p
         }
       }
     }
-  }
-  float o[G::NT][4];
+    float o[G::NT][4];
 #pragma unroll
-  for (int i = 0; i < G::NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  pv_tile<D, XNT>(o, s, sV, lane);
-  __half* og = p.o + static_cast<size_t>(b) * p.N * p.ldo + h * D;
-  if (rows_valid == 64) {
-    store_o<D>(o, 1.f, 1.f, og, p.ldo, qt * 64 + warp * 16, lane);
-  } else {
-    const int r0 = warp * 16 + g;
+    for (int i = 0; i < G::NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    pv_tile<D, XNT>(o, s, sV, lane);
+    if (rows_valid == 64) {
+      store_o<D>(o, 1.f, 1.f, og, p.ldo, qt * 64 + warp * 16, lane);
+    } else {
+      const int r0 = warp * 16 + g;
 #pragma unroll
-    for (int nt = 0; nt < G::NT; ++nt) {
-      if (r0 < rows_valid)
-        *reinterpret_cast<__half2*>(og + static_cast<size_t>(qt * 64 + r0) * p.ldo + nt * 8 + 2 * t) =
-            __floats2half2_rn(o[nt][0], o[nt][1]);
-      if (r0 + 8 < rows_valid)
-        *reinterpret_cast<__half2*>(og + static_cast<size_t>(qt * 64 + r0 + 8) * p.ldo + nt * 8 + 2 * t) =
-            __floats2half2_rn(o[nt][2], o[nt][3]);
+      for (int nt = 0; nt < G::NT; ++nt) {
+        if (r0 < rows_valid)
+          *reinterpret_cast<__half2*>(og + static_cast<size_t>(qt * 64 + r0) * p.ldo + nt * 8 + 2 * t) =
+              __floats2half2_rn(o[nt][0], o[nt][1]);
+        if (r0 + 8 < rows_valid)
+          *reinterpret_cast<__half2*>(og + static_cast<size_t>(qt * 64 + r0 + 8) * p.ldo + nt * 8 + 2 * t) =
+              __floats2half2_rn(o[nt][2], o[nt][3]);
+      }
     }
   }
+  cp_async_wait<0>();
 }
 
 template <int D>
 size_t self_smem() { return 5 * 64 * Geo<D>::PITCH; }
 template <int D>
 size_t cross_smem() {
-  return 2 * 64 * Geo<D>::PITCH + 3 * XK * Geo<D>::PITCH + 4 * 16 * XK * sizeof(float) + 6 * XK * sizeof(float);
+  return 3 * 64 * Geo<D>::PITCH + 3 * XK * Geo<D>::PITCH + 4 * 16 * XK * sizeof(float) + 6 * XK * sizeof(float);
 }
 
 template <int D>
@@ -490,7 +511,14 @@ int launch_cross(const CrossAttnParams& p, cudaStream_t s) {
                                   static_cast<int>(cross_smem<D>())));
     attr = true;
   }
-  PNP_CUDA(launch_k(cross_attn_kernel<D>, dim3((p.N + 63) / 64, p.H, p.B), dim3(128), cross_smem<D>(), s, p));
+  // tiles per CTA: as many as keep two waves of CTAs (3 per SM at d = 40) on the chip, at most 8
+  CrossAttnParams q = p;
+  const int ntiles = (p.N + 63) / 64;
+  static const int tpc_max = [] { const char* e = getenv("PNP_CROSS_TPC"); return e ? std::max(1, atoi(e)) : 8; }();
+  int tpc = tpc_max;
+  while (tpc > 1 && static_cast<long>((ntiles + tpc - 1) / tpc) * p.H * p.B < 888) tpc >>= 1;
+  q.tiles_per_cta = tpc;
+  PNP_CUDA(launch_k(cross_attn_kernel<D>, dim3((ntiles + tpc - 1) / tpc, p.H, p.B), dim3(128), cross_smem<D>(), s, q));
   return 0;
 }
 

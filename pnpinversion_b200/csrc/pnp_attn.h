@@ -47,6 +47,7 @@ struct CrossAttnParams {
   const float* map_weight;   // [slots][77] weight of that sum (null = 1)
   float* store;
   const int* store_slot;
+  int tiles_per_cta = 1;  // consecutive 64-query tiles one CTA walks (set by the launcher)
 };
 
 int self_attention_launch(const SelfAttnParams& p, cudaStream_t s);
