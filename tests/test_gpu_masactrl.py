@@ -125,3 +125,38 @@ def test_directinversion_masactrl_pipeline_matches_reference(cuda):
     assert G.rel_l2(b.latents[1].cpu(), torch.from_numpy(g["out"][1])) < 8e-2
     assert G.rel_l2(b.latents_fixed.cpu(), torch.from_numpy(g["fixed"])) < 8e-2
     m.unet.close()
+
+
+def test_directinversion_masactrl_50_steps_vs_reference(cuda):
+    """BASELINE config 4 at its real length: `directinversion+masactrl`, 50 DDIM steps, mutual self-attention from step 4 /
+    layer 10 (run_editing_masactrl.py:89 defaults) against the REFERENCE's own loops on the vendored fp64 UNet
+    (tests/golden/masactrl_pipeline_50steps.npz, oracle/make_golden.py masactrl_pipeline 50: 350 fp64 UNet sample-forwards).
+    Asserted: the inversion trajectory (no guidance: 5e-3 like the 4-step fixture), the rectified source branch (exact in
+    both implementations), the MasaCtrl edit, whose keys / values come from the rectified source branch.  The direct
+    synthesis (`fixed`) is 50 free-running steps at guidance 7.5 from x_T: rounding noise is amplified without anything
+    pulling the trajectory back (the same effect as the reconstruction pass of tests/test_gpu_pipeline.py), so it is
+    reported and only bounded."""
+    import os
+
+    gold = os.path.join(os.path.dirname(__file__), "golden", "masactrl_pipeline_50steps.npz")
+    if not os.path.exists(gold):
+        pytest.fail("tests/golden/masactrl_pipeline_50steps.npz missing (python -m oracle.make_golden masactrl_pipeline 50)")
+    g = np.load(gold)
+    m = FusedModel.synthetic(device="cuda:0", max_batch=4)  # float32 tables: the configuration bench.py runs
+    editor = MasaCtrlEditor(["directinversion+masactrl"], "cuda:0", num_ddim_steps=50, model=m)
+    z0 = synth.synth_latent(3)
+    b = editor.edit_batch(z0.cuda(), [synth.CAT_PROMPTS[1]], guidance_scale=7.5, step=4, layper=10)
+    torch.cuda.synchronize()
+    xs = torch.cat(b.x_stars).cpu() if isinstance(b.x_stars, (list, tuple)) else b.x_stars.cpu()
+    gx = torch.from_numpy(g["x_stars"])
+    e_xs = [G.rel_l2(xs[k].reshape(gx[k].shape), gx[k]) for k in range(1, gx.shape[0])]
+    e_fixed = G.rel_l2(b.latents_fixed.cpu(), torch.from_numpy(g["fixed"]))
+    e_edit = G.rel_l2(b.latents[1].cpu(), torch.from_numpy(g["out"][1]))
+    e_src = float((b.latents[0].cpu() - z0[0]).abs().max())
+    print(f"masactrl 50-step parity: x_stars max {max(e_xs):.2e} (x_T {e_xs[-1]:.2e}), source branch max-abs {e_src:.1e}, "
+          f"masactrl edit {e_edit:.2e}, direct synthesis {e_fixed:.2e}")
+    assert max(e_xs) < 5e-3
+    assert e_src < 2e-5 and (torch.from_numpy(g["out"][0]) - z0[0]).abs().max() < 2e-5
+    assert e_edit < 0.2
+    assert e_fixed < 2.0
+    m.unet.close()
