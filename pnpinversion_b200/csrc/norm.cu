@@ -38,7 +38,9 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 constexpr int GN_GROUPS = 32;
 constexpr int GN_MAX_VPT = 2;
 
-// partials[b][slice][g] = (mean, M2) over ppc*cpg elements
+// partials[b][slice][g] = (mean, M2) over ppc*cpg elements.  VPT = 16-byte vectors per thread (2 only for C > 2048): as a
+// run-time value it cost 90 registers = 2 CTAs per SM = 30 KB of loads in flight per SM (ncu: 42 us for 84 MB).
+template <int VPT>
 __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
                                 int ppc, int tx_n, int rows_y, int vpt, float* __restrict__ partials, float eps,
                                 float* __restrict__ mean_rstd, int* __restrict__ counters) {
@@ -48,21 +50,21 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
   const int nvec0 = C0 >> 3;
   const int b = blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;  // blockDim is always 256; rows ty >= rows_y idle
-  float s[GN_MAX_VPT][8], ss[GN_MAX_VPT][8];
+  float s[VPT][8], ss[VPT][8];
 #pragma unroll
-  for (int i = 0; i < GN_MAX_VPT; ++i)
+  for (int i = 0; i < VPT; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[i][e] = ss[i][e] = 0.f;
   if (ty < rows_y) {
     constexpr int U = 4;  // pixels in flight per thread (memory-level parallelism: these kernels are latency-bound)
     for (int pix0 = ty; pix0 < ppc; pix0 += U * rows_y) {
-      uint4 u[U][GN_MAX_VPT];
+      uint4 u[U][VPT];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const int pix = pix0 + j * rows_y;
         const size_t row = static_cast<size_t>(b) * HW + static_cast<size_t>(slice) * ppc + pix;
 #pragma unroll
-        for (int i = 0; i < GN_MAX_VPT; ++i) {
+        for (int i = 0; i < VPT; ++i) {
           u[j][i] = make_uint4(0, 0, 0, 0);
           if (i < vpt && pix < ppc) {
             const int v = tx + i * tx_n;
@@ -74,7 +76,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
 #pragma unroll
       for (int j = 0; j < U; ++j) {
 #pragma unroll
-        for (int i = 0; i < GN_MAX_VPT; ++i) {
+        for (int i = 0; i < VPT; ++i) {
           if (i < vpt) {
             float f[8];
             unpack8(u[j][i], f);  // out-of-range pixels were loaded as zeros: they add nothing
@@ -89,7 +91,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
     }
     float* mine = sm + static_cast<size_t>(ty) * 2 * C;
 #pragma unroll
-    for (int i = 0; i < GN_MAX_VPT; ++i) {
+    for (int i = 0; i < VPT; ++i) {
       if (i < vpt) {
         const int v = tx + i * tx_n;
 #pragma unroll
@@ -651,27 +653,20 @@ int gn_ppc(int B, int HW) {
 
 // ------------------------------------------------------------------ LayerNorm: one warp per token
 template <int VPL, int R>  // VPL 16-byte vectors per lane (C <= 8*32*VPL), R rows in flight per warp
-__global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, float eps, __half* __restrict__ out) {
-  pdl_sync();
+__global__ void __launch_bounds__(256, VPL <= 2 ? 3 : 1)
+ln_kernel(const __half* __restrict__ x, int rows, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+          float eps, __half* __restrict__ out) {
+  // gamma / beta live in shared memory: as 16 * VPL registers per thread they held the kernel at 2 CTAs per SM (ncu: 3 TB/s)
+  __shared__ __align__(16) float sgam[8 * 32 * VPL], sbet[8 * 32 * VPL];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sgam[c] = gamma[c];
+    sbet[c] = beta[c];
+  }
+  __syncthreads();
+  pdl_sync();  // the parameters are constants: staged before waiting for the predecessor
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = C >> 3;
-  float gam[VPL][8], bet[VPL][8];  // issued before the activations are needed: one latency, not two in series
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-      gam[i][0] = g0.x; gam[i][1] = g0.y; gam[i][2] = g0.z; gam[i][3] = g0.w;
-      gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
-      bet[i][0] = b0.x; bet[i][1] = b0.y; bet[i][2] = b0.z; bet[i][3] = b0.w;
-      bet[i][4] = b1.x; bet[i][5] = b1.y; bet[i][6] = b1.z; bet[i][7] = b1.w;
-    }
-  }
   for (int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; row0 < rows; row0 += nwarps * R) {
     uint4 u[R][VPL];
 #pragma unroll
@@ -717,8 +712,10 @@ __global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const f
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
-          const float* gg = gam[i];
-          const float* bb = bet[i];
+          const float4 g0 = *reinterpret_cast<const float4*>(sgam + v * 8), g1 = *reinterpret_cast<const float4*>(sgam + v * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sbet + v * 8), b1 = *reinterpret_cast<const float4*>(sbet + v * 8 + 4);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           float y[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * gg[e] + bb[e];
@@ -913,7 +910,8 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
   const size_t sm1 = static_cast<size_t>(rows_y) * 2 * C * sizeof(float);
   static bool attr1 = false;
   if (!attr1) {
-    PNP_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    PNP_CUDA(cudaFuncSetAttribute(gn_stats_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    PNP_CUDA(cudaFuncSetAttribute(gn_stats_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr1 = true;
   }
   PNP_CHECK(sm1 <= 160 * 1024, "groupnorm: smem");
@@ -962,8 +960,12 @@ int groupnorm_launch(const __half* x0, int C0, const __half* x1, int C1, int B, 
                          eps, gamma, beta, do_silu ? 1 : 0, out));
     return 0;
   }
-  PNP_CUDA(launch_k(gn_stats_kernel, dim3(nslices, B), dim3(256), sm1, s, x0, C0, x1, C1, HW, ppc, tx_n, rows_y, vpt, parts,
-                    eps, mean_rstd, counters));
+  if (vpt == 1)
+    PNP_CUDA(launch_k(gn_stats_kernel<1>, dim3(nslices, B), dim3(256), sm1, s, x0, C0, x1, C1, HW, ppc, tx_n, rows_y, vpt,
+                      parts, eps, mean_rstd, counters));
+  else
+    PNP_CUDA(launch_k(gn_stats_kernel<2>, dim3(nslices, B), dim3(256), sm1, s, x0, C0, x1, C1, HW, ppc, tx_n, rows_y, vpt,
+                      parts, eps, mean_rstd, counters));
   const size_t sm2 = (2 * static_cast<size_t>(C) + 2 * GN_GROUPS) * sizeof(float);
   // the apply pass is pure streaming: fewer, fatter CTAs than the statistics pass
   // one pass of 4 vectors per thread per CTA where possible (1024 vectors per CTA)
