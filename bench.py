@@ -439,8 +439,21 @@ def main():
         "whole_job_tflops": value * FWD * UNET_GFLOP / 1e3,
         "whole_job_frac_of_sustained_peak": value * FWD * UNET_GFLOP / 1e3 / (sustained * world),
     }
-    # `traffic` stays null: DRAM bytes per launch come from an ncu capture, which cannot run inside a timed bench; the
-    # warm-cache captures of this build are under profiles/ (r2_*)
+    # `traffic`: DRAM bytes per GEMM launch cannot be measured inside a timed bench; it comes from the committed ncu
+    # capture of this build at the same UNet batch (profiles/r2_traffic.json, made by tools/traffic_from_ncu.py from a
+    # WARM-cache launch list, `--cache-control none`, one whole forward in its real order) - null for any other batch
+    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")
+    if os.path.exists(tj):
+        with open(tj) as f:
+            tr = json.load(f).get(str(PB))
+        if tr:
+            roofline["traffic"] = tr["gemm_dram_bytes_per_launch"]
+            roofline["traffic_unit"] = "DRAM bytes (read + write) per GEMM launch, ncu warm-cache capture of one forward"
+            roofline["traffic_source"] = tr["source"]
+    ab, nl = C.c_double(0.0), C.c_int(0)
+    _lib.check(lib.pnp_unet_gemm_bytes(model.unet.handle, PB, C.byref(ab), C.byref(nl)))
+    # compulsory bytes of the same launches (activations, weights, residual read once; output written once)
+    roofline["algorithmic_bytes_per_launch"] = ab.value / max(nl.value, 1)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -202,6 +202,9 @@ int pnp_struct_size(int which);
  * flops: algorithmic 2*MAC of the op.  Used by bench.py for the roofline of the dominant kernel. */
 int pnp_unet_profile(pnp_engine* h, int batch, int t_index, int reps, float* ms_out, int32_t* kind_out,
                      double* flops_out, int max_ops, int* n_out); /* each op launched `reps` times back to back */
+/* compulsory HBM bytes of all GEMM / implicit-conv launches of one UNet call at this batch (activations, weights and
+ * residual read once, output written once) and their number: the algorithmic figure ncu's DRAM traffic is held against */
+int pnp_unet_gemm_bytes(pnp_engine* h, int batch, double* bytes_out, int* launches_out);
 int pnp_kernel_launches(pnp_engine* h, int64_t* out); /* kernels launched by this handle so far (graph nodes count) */
 int pnp_set_use_graph(pnp_engine* h, int enable);     /* capture each UNet forward into a CUDA graph (default on) */
 

@@ -135,6 +135,7 @@ SIGNATURES = {
     "pnp_edict_mix": (_i, [_vp, _vp, _vp, _i, _f, _i, _vp]),
     "pnp_store_reset": (_i, [_vp, _vp]),
     "pnp_store_read": (_i, [_vp, _vp, _i64, _vp]),
+    "pnp_unet_gemm_bytes": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(_i)]),
     "pnp_unet_profile": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(C.c_int32), C.POINTER(C.c_double), _i, C.POINTER(_i)]),
     "pnp_debug_read": (_i, [_vp, _i, _i, _vp, _i64, C.POINTER(_i64), _vp]),
     "pnp_struct_size": (_i, [_i]),

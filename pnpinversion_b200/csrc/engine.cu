@@ -1469,6 +1469,18 @@ int pnp_run_loop(pnp_engine* h, const pnp_loop_args* a, void* stream) {
   return 0;
 }
 
+int pnp_unet_gemm_bytes(pnp_engine* h, int batch, double* bytes_out, int* launches_out) {
+  PNP_CHECK(h && h->finalized && bytes_out && launches_out, "pnp_unet_gemm_bytes: bad argument");
+  Plan* pl = nullptr;
+  int rc = get_plan(h, batch, &pl);
+  if (rc) return rc;
+  double b = 0.0;
+  for (const auto& g : pl->gemms) b += static_cast<double>(g->algo_bytes);
+  *bytes_out = b;
+  *launches_out = static_cast<int>(pl->gemms.size());
+  return 0;
+}
+
 int pnp_unet_profile(pnp_engine* h, int batch, int t_index, int reps, float* ms_out, int32_t* kind_out,
                      double* flops_out, int max_ops, int* n_out) {
   PNP_CHECK(h && h->finalized && ms_out && kind_out && flops_out && n_out, "pnp_unet_profile: bad argument");

@@ -855,6 +855,14 @@ int gemm_plan_create(GemmPlan* plan, const ASource* srcs, int nsrc, int taps0, b
   }
   plan->bn = bn;
   plan->nsub = nsub;
+  {
+    size_t a_cols = 0;
+    for (int i = 0; i < nsrc; ++i) a_cols += static_cast<size_t>(srcs[i].C);
+    const size_t out_bytes = ep.out_f32_nchw4 ? static_cast<size_t>(M) * ep.out32_channels * 4
+                                              : static_cast<size_t>(M) * (geglu ? N / 2 : N) * 2;
+    plan->algo_bytes = static_cast<size_t>(M) * a_cols * 2 + static_cast<size_t>(N) * Ktot * 2 + out_bytes +
+                       (ep.residual ? static_cast<size_t>(M) * N * 2 : 0);
+  }
   plan->grid = std::min(tiles * p.splits, num_sms);
   // pair mode (cta_group::2: two vertically adjacent M tiles, each SM stages half of the weight tile) whenever it applies
   plan->cluster = 1;

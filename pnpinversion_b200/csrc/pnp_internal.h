@@ -132,6 +132,7 @@ struct GemmPlan {
   int cluster = 1;
   int grid = 0;
   size_t smem = 0;
+  size_t algo_bytes = 0;  // compulsory HBM traffic of one launch: activations + weights + residual read once, output written once
 };
 
 struct GemmEpilogue {
