@@ -326,9 +326,13 @@ def gen_masactrl_pipeline(n_steps: int = 4):
         print("masactrl pass done", time.time() - t0, flush=True)
     finally:
         md.CrossAttention.__name__ = "CrossAttention"
-    np.savez_compressed(os.path.join(GOLD, f"masactrl_pipeline_{n_steps}steps.npz"),
-                        x_stars=torch.cat(x_stars).float().numpy(), noise_loss=torch.stack(noise_loss).float().numpy(),
-                        fixed=fixed.float().numpy(), out=out.float().numpy())
+    xs, nl = torch.cat(x_stars).float().numpy(), torch.stack(noise_loss).float().numpy()
+    xi, ni = np.arange(len(xs)), np.arange(len(nl))
+    if n_steps > 10:  # full schedules: every fifth entry (and the last) keeps the fixture small
+        xi = np.array(sorted(set(list(range(0, len(xs), 5)) + [len(xs) - 1])))
+        ni = np.array(sorted(set(list(range(0, len(nl), 5)) + [len(nl) - 1])))
+    np.savez_compressed(os.path.join(GOLD, f"masactrl_pipeline_{n_steps}steps.npz"), x_stars=xs[xi], x_index=xi,
+                        noise_loss=nl[ni], noise_index=ni, fixed=fixed.float().numpy(), out=out.float().numpy())
     print("masactrl pipeline fixture written")
 
 
@@ -391,8 +395,12 @@ def gen_pnp(n_steps: int = 4):
     print("pnp fixture written", [int(t) for t in sched.timesteps], "qk", qk_t.tolist(), "conv", conv_t.tolist())
 
 
-def gen_edict():
-    """The reference's own `coupled_stablediffusion` (models/edict/edict_functions.py:707-956): deterministic noising of a
+def gen_edict(strength: float = 0.04):
+    """strength 0.04: the two-step fixture described below; any other value (0.8 = the reference's default,
+    run_editing_edict.py:43) runs the FULL schedule - 40 noising + 40 generation steps of 50 - and stores only the start
+    latent, the noised pair and the edited pair (tests/golden/edict_<n>steps.npz, ~400 fp64 UNet sample-forwards).
+
+    The reference's own `coupled_stablediffusion` (models/edict/edict_functions.py:707-956): deterministic noising of a
     latent pair over the last two of 50 timesteps (init_image_strength 0.04 -> t = 0, 20), then generation from that pair
     with the Prompt-to-Prompt attention reuse (prompt_edit given).  Every UNet call is recorded (timestep, which text
     embedding, checksum of the input latent, the predicted noise) so that the CPU restatement can be replayed against the
@@ -438,14 +446,22 @@ def gen_edict():
     ns = ref_shim.load_reference_edict(Recorder(), clip, Tok(), "cpu")
     z = synth.synth_latent(6).double()
     t0 = time.time()
-    lat = ns["coupled_stablediffusion"](src, reverse=True, init_image=[z, z.clone()], init_image_strength=0.04, steps=50,
+    full = abs(strength - 0.04) > 1e-9
+    lat = ns["coupled_stablediffusion"](src, reverse=True, init_image=[z, z.clone()], init_image_strength=strength, steps=50,
                                         mix_weight=0.93, guidance_scale=3.0)
     n_rev = len(calls)
     print(f"reverse pass: {n_rev} UNet calls, {time.time() - t0:.0f}s", flush=True)
     clip.n = 0  # the generation pass encodes null prompt, prompt, prompt_edit again
-    out = ns["coupled_stablediffusion"](src, tgt, fixed_starting_latent=lat, init_image_strength=0.04, steps=50,
+    out = ns["coupled_stablediffusion"](src, tgt, fixed_starting_latent=lat, init_image_strength=strength, steps=50,
                                         mix_weight=0.93, guidance_scale=3.0, return_latents=True)
     print(f"forward P2P pass: {len(calls) - n_rev} UNet calls, {time.time() - t0:.0f}s", flush=True)
+    if full:
+        n = int(50 * strength)
+        np.savez_compressed(os.path.join(GOLD, f"edict_{n}steps.npz"), z=z.numpy().astype(np.float32),
+                            lat=torch.stack(lat).float().numpy(), out=torch.stack(out).float().numpy(),
+                            strength=np.float64(strength), n_reverse_calls=np.int64(n_rev), n_calls=np.int64(len(calls)))
+        print(f"wrote edict_{n}steps.npz")
+        return
     attn2 = next(m for n, m in model.unet.named_modules() if type(m).__name__ == "CrossAttention" and "attn2" in n)
     np.savez_compressed(
         os.path.join(GOLD, "edict_2steps.npz"), z=z.numpy().astype(np.float32),
@@ -500,6 +516,6 @@ if __name__ == "__main__":
     elif what == "masactrl":
         gen_masactrl()
     elif what == "edict":
-        gen_edict()
+        gen_edict(float(sys.argv[2]) if len(sys.argv) > 2 else 0.04)
     elif what == "vae":
         gen_vae()

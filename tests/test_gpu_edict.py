@@ -135,3 +135,29 @@ def test_edict_image_batch_matches_single_images(model):
         e = [G.rel_l2(out[k][i:i + 1], out1[k]) for k in range(2)]
         print(f"edict image {i}: batched vs single pair rel-L2 {e}")
         assert max(e) < 0.15  # rounding-noise realisations of two batch sizes through the un-mixing layers (1/0.93^2 per step)
+
+
+def test_edict_full_schedule_vs_reference(model):
+    """BASELINE config 5's schedule at full length: init_image_strength 0.8 of 50 steps = 40 coupled noising steps, then 40
+    coupled generation steps with the Prompt-to-Prompt attention reuse, against the REFERENCE's own `coupled_stablediffusion`
+    run on the vendored fp64 UNet (tests/golden/edict_40steps.npz, oracle/make_golden.py edict 0.8).  The un-mixing layers
+    amplify the per-call rounding noise of the 16-bit UNet by 1/0.93^2 per step (see the round-trip test above), so the
+    distance to the fp64 run is REPORTED for the noised pair and the edited pair and only bounded."""
+    import os
+
+    import numpy as np
+
+    gold = os.path.join(os.path.dirname(__file__), "golden", "edict_40steps.npz")
+    if not os.path.exists(gold):
+        pytest.skip("tests/golden/edict_40steps.npz not generated (python -m oracle.make_golden edict 0.8, ~1 h of CPU)")
+    g = np.load(gold)
+    src, tgt = synth.CAT_PROMPTS
+    z = torch.from_numpy(g["z"])
+    kw = dict(steps=50, init_image_strength=float(g["strength"]), guidance_scale=3.0)
+    lat = edict.coupled_stablediffusion(model, src, reverse=True, init_image=z, **kw)
+    out = edict.coupled_stablediffusion(model, src, tgt, fixed_starting_latent=lat, **kw)
+    torch.cuda.synchronize()
+    e_lat = [G.rel_l2(lat[i].cpu(), torch.from_numpy(g["lat"][i])) for i in range(2)]
+    e_out = [G.rel_l2(out[i].cpu(), torch.from_numpy(g["out"][i])) for i in range(2)]
+    print(f"EDICT 40+40 steps vs the reference (fp64): noised pair {e_lat}, edited pair {e_out}")
+    assert max(e_lat) < 0.5 and max(e_out) < 1.0

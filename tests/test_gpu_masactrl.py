@@ -148,8 +148,8 @@ def test_directinversion_masactrl_50_steps_vs_reference(cuda):
     b = editor.edit_batch(z0.cuda(), [synth.CAT_PROMPTS[1]], guidance_scale=7.5, step=4, layper=10)
     torch.cuda.synchronize()
     xs = torch.cat(b.x_stars).cpu() if isinstance(b.x_stars, (list, tuple)) else b.x_stars.cpu()
-    gx = torch.from_numpy(g["x_stars"])
-    e_xs = [G.rel_l2(xs[k].reshape(gx[k].shape), gx[k]) for k in range(1, gx.shape[0])]
+    gx, xi = torch.from_numpy(g["x_stars"]), g["x_index"]  # every fifth latent of the trajectory (and the last)
+    e_xs = [G.rel_l2(xs[int(k)].reshape(gx[j].shape), gx[j]) for j, k in enumerate(xi) if k > 0]
     e_fixed = G.rel_l2(b.latents_fixed.cpu(), torch.from_numpy(g["fixed"]))
     e_edit = G.rel_l2(b.latents[1].cpu(), torch.from_numpy(g["out"][1]))
     e_src = float((b.latents[0].cpu() - z0[0]).abs().max())
