@@ -184,6 +184,10 @@ def main():
                     help="p2p only: the 450-forward variant (no reconstruction pass: its decoded row is the inverted latent "
                          "by the rectification invariant) as the timed workload; the default run reports it beside the "
                          "faithful number")
+    ap.add_argument("--text-encoder", default="synth", choices=["synth", "clip"],
+                    help="synth: seeded embedding-table stand-in evaluated on the host; clip: the fused CLIP text encoder of "
+                         "libpnpinv.so (csrc/clip.cu, random-init SD-1.x text tower) - the prompts are then encoded on the GPU "
+                         "inside every pass")
     ap.add_argument("--lanes", type=int, default=1,
                     help="passes in flight per GPU (own CUDA stream / engine handle / host thread, shared weights)")
     args = ap.parse_args()
@@ -221,8 +225,13 @@ def main():
     NB = max(1, args.batch or WL["batch"])  # images per pass
     NL = max(1, args.lanes)          # concurrent passes
     L = NB * NL                      # images per step and GPU
+    text_encoder = synth.SynthTextEncoder()
+    if args.text_encoder == "clip":
+        from pnpinversion_b200.clip import FusedCLIPTextEncoder
+
+        text_encoder = FusedCLIPTextEncoder(synth.synth_clip_state_dict(0), device=str(dev))
     parent = FusedModel(sd, device=str(dev), max_batch=WL["rows"] * NB, tokenizer=synth.FakeTokenizer(),
-                        text_encoder=synth.SynthTextEncoder())
+                        text_encoder=text_encoder)
     made = []
 
     def make_editor():
@@ -479,6 +488,8 @@ def main():
                    "parallelism": f"image-parallel x{world} GPUs x {NL} concurrent passes (CUDA streams) x {NB} images "
                                   "per UNet call",
                    "l2": "each step streams 1.72 GB of fp16 weights per UNet call (> 126 MB L2), no flush needed",
+                   "text_encoder": ("fused CLIP text encoder on the GPU (csrc/clip.cu, random-init)" if args.text_encoder == "clip"
+                                    else "seeded embedding-table stand-in on the host"),
                    "accumulate": "fp32"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

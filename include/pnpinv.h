@@ -226,6 +226,23 @@ int pnp_vae_encode(pnp_vae* h, const float* image_dev, int batch, int img_h, int
 int pnp_vae_decode(pnp_vae* h, const float* z_dev, int batch, int lat_h, int lat_w, float* image_out_dev, void* stream);
 int pnp_vae_kernel_launches(pnp_vae* h, int64_t* out);
 
+/* ---- CLIP text encoder (`model.text_encoder(input_ids)[0]`: models/p2p/inversion.py:42,50,296,304,
+ * models/p2p/p2p_guidance_forward.py:43,49,86,92, models/edict/edict_functions.py:818-838) ------------------------
+ * The reference takes it from `transformers` (CLIPTextModel of the SD-1.x checkpoint: 768 hidden, 12 pre-LayerNorm
+ * blocks of 12 heads, quick_gelu MLP of 3072, 77 positions, causal mask, final LayerNorm).  Parameters are loaded under
+ * the names of that model's state_dict (`text_model.embeddings.token_embedding.weight`, `text_model.encoder.layers.<i>.
+ * self_attn.q_proj.weight`, ...) as fp16 bits; the layer count and the vocabulary size are taken from what was loaded. */
+typedef struct pnp_clip pnp_clip;
+int pnp_clip_create(int device_ordinal, pnp_clip** out);
+void pnp_clip_destroy(pnp_clip* h);
+int pnp_clip_load_param(pnp_clip* h, const char* name, const uint16_t* data_host, int64_t numel);
+int pnp_clip_finalize(pnp_clip* h);
+int pnp_clip_vocab_size(pnp_clip* h, int* vocab_out, int* layers_out);
+/* input_ids_host: [batch,77] int32 token ids in HOST memory (validated against the vocabulary: an id outside it is an
+ * error, as the embedding lookup of the reference raises); out_dev: [batch,77,768] fp32 last_hidden_state */
+int pnp_clip_encode(pnp_clip* h, const int32_t* input_ids_host, int batch, float* out_dev, void* stream);
+int pnp_clip_kernel_launches(pnp_clip* h, int64_t* out);
+
 /* ---- stand-alone kernel entry points (used by tests/ and bench.py to measure single kernels) ------------------ */
 /* D[M,N] = A[M,K].W[N,K]^T (+bias)(+residual) ; mode 0 plain, 1 GEGLU (N = 2*out columns, weights pre-interleaved by
  * pnp_test_pack_geglu) ; conv3x3: A is NHWC [B,H,W,C], W packed (N, 9*C) tap-major */

@@ -9,6 +9,7 @@ Run in the build container only (the GPU box has no /root/reference):
     python -m oracle.make_golden masactrl      # one B=4 forward through the reference's MutualSelfAttentionControl
     python -m oracle.make_golden edict         # EDICT: 2 coupled steps of inversion + 2 of P2P generation (~5 min)
     python -m oracle.make_golden vae           # vendored AutoencoderKL: encode a 64x64 image, decode an 8x8 latent
+    python -m oracle.make_golden clip          # transformers CLIPTextModel (the reference's text encoder) on four prompts
 
 What runs is the reference's own `DirectInversion.invert`, `direct_inversion_p2p_guidance_forward`,
 `AttentionStore / AttentionRefine / AttentionReweight / LocalBlend`, `register_attention_control`,
@@ -497,6 +498,28 @@ def gen_vae():
           "mean rms %.3f dec rms %.3f" % (float(dist.mean.pow(2).mean().sqrt()), float(dec.pow(2).mean().sqrt())))
 
 
+def gen_clip():
+    """The text encoder the reference calls (`model.text_encoder(ids)[0]`, models/p2p/inversion.py:42,50): the installed
+    `transformers.CLIPTextModel` itself (SD-1.x text tower configuration, fp64) on the synthetic weights of
+    synth.synth_clip_state_dict and the token ids of the null prompt, the cat prompt pair and a 77-token prompt that is
+    truncated (no padding at all)."""
+    import transformers
+    from transformers import CLIPTextConfig, CLIPTextModel
+
+    cfg = CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                         num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu", layer_norm_eps=1e-5)
+    m = CLIPTextModel(cfg).double().eval()
+    sd = synth.synth_clip_state_dict(0)
+    missing, unexpected = m.load_state_dict({k: v.double() for k, v in sd.items()}, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    tok = synth.FakeTokenizer()
+    ids = tok(["", synth.CAT_PROMPTS[0], synth.CAT_PROMPTS[1], " ".join(f"w{i}" for i in range(90))]).input_ids
+    out = m(ids)[0]
+    np.savez_compressed(os.path.join(GOLD, "clip_text.npz"), ids=ids.numpy().astype(np.int32),
+                        out=out.numpy().astype(np.float32), transformers_version=np.array(transformers.__version__))
+    print("wrote clip_text.npz:", tuple(out.shape), "rms %.3f" % float(out.pow(2).mean().sqrt()), "transformers", transformers.__version__)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
@@ -519,3 +542,5 @@ if __name__ == "__main__":
         gen_edict(float(sys.argv[2]) if len(sys.argv) > 2 else 0.04)
     elif what == "vae":
         gen_vae()
+    elif what == "clip":
+        gen_clip()

@@ -148,6 +148,13 @@ SIGNATURES = {
     "pnp_vae_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "pnp_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "pnp_vae_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
+    "pnp_clip_create": (_i, [_i, C.POINTER(_vp)]),
+    "pnp_clip_destroy": (None, [_vp]),
+    "pnp_clip_load_param": (_i, [_vp, C.c_char_p, _vp, _i64]),
+    "pnp_clip_finalize": (_i, [_vp]),
+    "pnp_clip_vocab_size": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "pnp_clip_encode": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "pnp_clip_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
     "pnp_test_gemm": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "pnp_test_gemm2": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, C.POINTER(_f), _vp]),
     "pnp_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),

@@ -139,16 +139,53 @@ def load_unet_state_dict(path: str, strict: bool = True) -> Dict[str, torch.Tens
 
 
 def load_text_components(path: str, device="cpu", dtype=torch.float32):
-    """(tokenizer, text_encoder) from <path>/tokenizer and <path>/text_encoder via transformers, local files only;
-    (None, None) when the directories are absent (the caller then supplies its own, e.g. synth.FakeTokenizer)."""
+    """(tokenizer, text_encoder) from <path>/tokenizer and <path>/text_encoder, local files only; (None, None) when the
+    directories are absent (the caller then supplies its own, e.g. synth.FakeTokenizer).  The tokenizer is
+    `transformers.CLIPTokenizer`.  On a CUDA device the text encoder is the fused one (clip.py -> csrc/clip.cu), fed
+    with the weights of `text_encoder/` read straight from its safetensors / bin file; device="cpu" returns the
+    `transformers.CLIPTextModel` itself (used by the CPU tests as the comparison model, never by the editors)."""
     tok_dir, enc_dir = os.path.join(path, "tokenizer"), os.path.join(path, "text_encoder")
     if not (os.path.isdir(tok_dir) and os.path.isdir(enc_dir)):
         return None, None
-    from transformers import CLIPTextModel, CLIPTokenizer
+    from transformers import CLIPTokenizer
 
     tok = CLIPTokenizer.from_pretrained(tok_dir, local_files_only=True)
+    if torch.device(device).type == "cuda":
+        from .clip import FusedCLIPTextEncoder
+
+        return tok, FusedCLIPTextEncoder(load_clip_state_dict(enc_dir), device=device)
+    from transformers import CLIPTextModel
+
     enc = CLIPTextModel.from_pretrained(enc_dir, local_files_only=True).to(device=device, dtype=dtype).eval()
     return tok, enc
+
+
+def load_clip_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """The CLIPTextModel tensors of `<path>` (= `<checkpoint>/text_encoder`, or a weight file): `model.safetensors` /
+    `pytorch_model.bin`, validated against clip.clip_text_param_specs for the layer count / vocabulary found in the file."""
+    from .clip import clip_text_param_specs, count_layers
+
+    if os.path.isdir(path):
+        cands = [os.path.join(path, n) for n in ("model.safetensors", "model.fp16.safetensors", "pytorch_model.bin",
+                                                 "pytorch_model.fp16.bin")]
+        f = next((c for c in cands if os.path.isfile(c)), None)
+        if f is None:
+            raise FileNotFoundError(f"no text-encoder weight file under {path}")
+    else:
+        f = path
+    sd = read_state_dict(f)
+    layers = count_layers(sd)
+    tok = sd.get("text_model.embeddings.token_embedding.weight")
+    if layers == 0 or tok is None:
+        raise ValueError(f"{f} is not a CLIPTextModel state dict (text_model.* tensors missing)")
+    res = {}
+    for name, shape in clip_text_param_specs(layers, tok.shape[0]):
+        if name not in sd:
+            raise ValueError(f"{f}: {name} missing")
+        if tuple(sd[name].shape) != tuple(shape):
+            raise ValueError(f"{f}: {name} has shape {tuple(sd[name].shape)}, expected {shape}")
+        res[name] = sd[name]
+    return res
 
 
 # diffusers >= 0.15 renamed the VAE attention projections; the engine takes the 0.3.0 .. 0.14 names of the reference's pins

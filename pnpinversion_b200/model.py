@@ -5,7 +5,8 @@
     model.scheduler.{timesteps, alphas_cumprod, final_alpha_cumprod, config, set_timesteps, step}
     model.vae / model.tokenizer / model.text_encoder / model.device
 
-The VAE, tokenizer and CLIP text encoder are "next" rows; they are pluggable attributes here.
+The VAE (vae.py -> csrc/vae.cu) and the CLIP text encoder (clip.py -> csrc/clip.cu) are fused handles of the same
+library; the tokenizer is a pluggable attribute (`transformers.CLIPTokenizer` for a checkpoint directory).
 """
 from __future__ import annotations
 
@@ -159,9 +160,10 @@ class FusedModel:
 
     @classmethod
     def synthetic(cls, device="cuda:0", max_batch: int = 4, seed: int = 0, table_dtype: str = "float32",
-                  with_vae: bool = False):
+                  with_vae: bool = False, with_clip: bool = False):
         """Random-init SD-1.x UNet (+ VAE) + fake tokenizer / text encoder (pnpinversion_b200/synth.py) -- the offline
-        stand-in for StableDiffusionPipeline.from_pretrained("CompVis/stable-diffusion-v1-4")."""
+        stand-in for StableDiffusionPipeline.from_pretrained("CompVis/stable-diffusion-v1-4").  `with_clip`: the fused CLIP
+        text encoder (csrc/clip.cu) with random-init weights instead of the embedding-table stand-in."""
         from . import synth
 
         vae = None
@@ -169,9 +171,13 @@ class FusedModel:
             from .vae import FusedVAE
 
             vae = FusedVAE(synth.synth_vae_state_dict(seed), device=device)
+        text_encoder = synth.SynthTextEncoder()
+        if with_clip:
+            from .clip import FusedCLIPTextEncoder
+
+            text_encoder = FusedCLIPTextEncoder(synth.synth_clip_state_dict(seed), device=device)
         return cls(synth.synth_unet_state_dict(seed), device=device, max_batch=max_batch,
-                   tokenizer=synth.FakeTokenizer(), text_encoder=synth.SynthTextEncoder(), vae=vae,
-                   table_dtype=table_dtype)
+                   tokenizer=synth.FakeTokenizer(), text_encoder=text_encoder, vae=vae, table_dtype=table_dtype)
 
     @classmethod
     def from_state_dict_file(cls, path: str, **kw):

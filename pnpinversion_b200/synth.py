@@ -75,6 +75,32 @@ def synth_vae_state_dict(seed: int = 0, dtype=torch.float16) -> Dict[str, torch.
     return out
 
 
+def synth_clip_state_dict(seed: int = 0, layers: int = 12, vocab: int = 49408, dtype=torch.float16) -> Dict[str, torch.Tensor]:
+    """Seeded stand-in for the SD-1.x CLIP text encoder weights (names of `transformers.CLIPTextModel.state_dict()`):
+    embeddings N(0,1) (token) / 0.3 N(0,1) (position), projections U(-b,b) with b = gain/sqrt(fan_in) (gain 3 on q / k so the
+    causal attention rows are peaked, 2 elsewhere), LayerNorms near identity, small biases."""
+    from .clip import clip_text_param_specs
+
+    out: Dict[str, torch.Tensor] = {}
+    for idx, (name, shape) in enumerate(clip_text_param_specs(layers, vocab)):
+        g = torch.Generator().manual_seed(700_001 + seed * 1_000_003 + idx)
+        if "token_embedding" in name:
+            t = torch.randn(shape, generator=g)
+        elif "position_embedding" in name:
+            t = torch.randn(shape, generator=g) * 0.3
+        elif "layer_norm" in name:
+            t = torch.randn(shape, generator=g) * 0.1
+            if name.endswith("weight"):
+                t = t + 1.0
+        elif name.endswith("bias"):
+            t = torch.randn(shape, generator=g) * 0.05
+        else:
+            gain = 3.0 if ("q_proj" in name or "k_proj" in name) else 2.0
+            t = (torch.rand(shape, generator=g) * 2.0 - 1.0) * (gain / math.sqrt(shape[1]))
+        out[name] = t.to(dtype)
+    return out
+
+
 class FakeTokenizer:
     """Whitespace tokenizer with the CLIP tokenizer's call surface (what the reference touches:
     `__call__(..., padding="max_length", max_length=77, truncation=True, return_tensors="pt").input_ids`,

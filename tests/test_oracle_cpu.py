@@ -192,3 +192,45 @@ def test_vae_parameter_table_has_the_reference_layout():
     assert len(specs) == 248 and sum(int(np.prod(s)) for _, s in specs) == 83_653_863  # 83.65 M parameters
     sd = synth.synth_vae_state_dict(0)
     assert list(sd) == [k for k, _ in specs] and all(tuple(sd[k].shape) == s for k, s in specs)
+
+
+def test_oracle_clip_matches_transformers():
+    """oracle/clip_ref.py against the transformers CLIPTextModel the reference calls (tests/golden/clip_text.npz, made by
+    oracle/make_golden.py clip from the installed transformers) and, where transformers is importable, against a live model
+    on other token ids."""
+    from oracle import clip_ref
+
+    g = np.load(os.path.join(GOLD, "clip_text.npz"))
+    sd = synth.synth_clip_state_dict(0)
+    ref = clip_ref.ClipTextRef(sd)
+    out = ref(torch.from_numpy(g["ids"]).long())
+    assert _rel(out, torch.from_numpy(g["out"])) < 1e-6  # fixture stored as float32
+    try:
+        from transformers import CLIPTextConfig, CLIPTextModel
+    except Exception:
+        return
+    cfg = CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                         num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu", layer_norm_eps=1e-5)
+    m = CLIPTextModel(cfg).double().eval()
+    m.load_state_dict({k: v.double() for k, v in sd.items()}, strict=False)
+    ids = synth.PieceTokenizer()(["a photo of a dog", "watercolor painting of mountains at dusk"]).input_ids
+    with torch.no_grad():
+        live = m(ids)[0]
+    assert _rel(ref(ids), live) < 1e-12
+
+
+def test_clip_parameter_table_matches_transformers():
+    from pnpinversion_b200.clip import clip_text_param_specs, count_layers
+
+    specs = clip_text_param_specs()
+    assert len(specs) == 2 + 12 * 16 + 2 and sum(int(np.prod(s)) for _, s in specs) == 123060480
+    sd = synth.synth_clip_state_dict(0, layers=2, vocab=100)
+    assert count_layers(sd) == 2 and sd["text_model.embeddings.token_embedding.weight"].shape == (100, 768)
+    try:
+        from transformers import CLIPTextConfig, CLIPTextModel
+    except Exception:
+        return
+    cfg = CLIPTextConfig(vocab_size=100, hidden_size=768, intermediate_size=3072, num_hidden_layers=2,
+                         num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu")
+    names = {k: tuple(v.shape) for k, v in CLIPTextModel(cfg).state_dict().items() if "position_ids" not in k}
+    assert names == dict(clip_text_param_specs(2, 100))
