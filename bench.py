@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-image-path", action="store_true", help="skip the image-path (VAE) end-to-end measurement")
+    ap.add_argument("--no-single-image", action="store_true", help="skip the one-image-per-pass (batch=1) measurement")
     ap.add_argument("--no-config1", action="store_true", help="reference arm: skip the full 20-step config-1 timing")
     ap.add_argument("--workload", default="p2p", choices=["p2p", "masactrl", "edict"],
                     help="p2p: directinversion+p2p (BASELINE configs 2/3, the headline); masactrl: directinversion+masactrl "
@@ -385,6 +386,28 @@ def main():
                       "what": "host wall clock around P2PEditor.edit_batch(list of HWC uint8 arrays) -> PIL strips: VAE encode + "
                               "650 UNet forwards + 4 VAE decodes per image + panel assembly (synthetic VAE weights)"}
         parent.vae = None
+    # BASELINE config 2 as worded ("batch=1"): one image at a time through the same editor (UNet batch 1 / 4), two images
+    # after one warm-up image that builds the plans of those batch sizes; device-resident input, rank 0
+    single_line = None
+    if args.workload == "p2p" and not args.minimal and rank == 0 and not args.no_single_image and NB > 1:
+        ed0 = lanes.editors[0]
+
+        def one(i):
+            return ed0.edit_batch(z_pass[first][i:i + 1].reshape(1, 4, 64, 64).to(dev), [src], [tgt], guidance_scale=7.5,
+                                  cross_replace_steps=0.4, self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
+
+        one(0)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(2):
+            one(i % NB)
+        s1.record()
+        torch.cuda.synchronize()
+        sec = s0.elapsed_time(s1) / 1000.0 / 2
+        single_line = {"value": 1.0 / sec, "unit": "images/s", "seconds_per_image": sec, "images": 2,
+                       "what": "one image per pass (UNet batch 1 for the inversion, 4 for the guided loops), faithful 650 "
+                               "forwards, same handle and weights; CUDA events"}
     ctx_rows = {"p2p": 4, "masactrl": 4, "edict": 9}[args.workload] * NB  # edict: 4 coupled passes encode 2+2+2+3 rows per image
     h2d = NL * (NB * 4 * 64 * 64 * 4 + ctx_rows * 77 * 768 * 4)
     d2h = NL * 2 * NB * 4 * 64 * 64 * 4
@@ -500,6 +523,8 @@ def main():
         line["minimal_450"] = minimal_line
     if image_line is not None:
         line["image_path_e2e"] = image_line
+    if single_line is not None:
+        line["single_image"] = single_line
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
