@@ -3,7 +3,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr -Iinclude
 SRC := pnpinversion_b200/csrc
-OBJS := $(SRC)/gemm_sm100.o $(SRC)/norm.o $(SRC)/attention.o $(SRC)/attention_tc.o $(SRC)/epilogue.o $(SRC)/engine.o $(SRC)/vae.o $(SRC)/clip.o
+OBJS := $(SRC)/gemm_sm100.o $(SRC)/norm.o $(SRC)/attention.o $(SRC)/attention_tc.o $(SRC)/epilogue.o $(SRC)/engine.o $(SRC)/vae.o $(SRC)/clip.o $(SRC)/probe.o
 LIB := pnpinversion_b200/libpnpinv.so
 
 all: $(LIB)
