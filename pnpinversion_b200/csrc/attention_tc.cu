@@ -24,6 +24,16 @@
 // quarter, 64 keys each), so that one group's conversions overlap the other group's exponentials on the MUFU.
 // All hand-offs are mbarriers; every wait is bounded (mbar_wait).
 //
+// MODE 2 (pair, PNP_ATTN_CLUSTER=3): the two CTAs of a cluster (256 consecutive queries of one (b, h) on two SMs) share
+// ONE instruction stream of tcgen05.mma.cta_group::2 (M = 256) issued by the leader CTA.  Measured with csrc/probe.cu
+// (profiles/r2_mma_probe.txt): a lone M=128 MMA with N = 48 / 128 costs 68 / 96 cycles whatever its math (24 / 64), a
+// cta_group::2 MMA with M = 256 and N = 64 / 128 costs 56 / 75 cycles for BOTH SMs - the instruction floor is paid once per
+// pair.  Each CTA stages half of every key tile (64 keys = N half of S) and half of the V^T rows (32 of 64 = N half of
+// O), its TMA loads complete on the leader's barriers, the leader's commits are multicast to both CTAs, and the softmax
+// warps of the peer arrive on the leader's barriers through the cluster address space.
+// POLY: that many of every 8 packed exponentials are evaluated on the FMA pipe (Cody-Waite + cubic in half2) instead
+// of the MUFU, which becomes the bound once the MMA floor is halved.
+//
 // Controllers (same semantics as attention.cu): per-batch-row source indirection for Q / K / V.
 // Reference algebra: models/p2p/attention_control.py:34-45 (sim = q k^T * scale; softmax; attn @ v).
 #include <algorithm>
@@ -44,6 +54,8 @@ constexpr int K_BYTES = KT * 128;
 constexpr int VT_ROWS = 48;              // 40 d + ones row + zero rows
 constexpr int VT_ATOM = VT_ROWS * 128;   // 64 keys x 48 rows
 constexpr int VT_BYTES = 2 * VT_ATOM;    // 128 keys
+constexpr int VT_ROWS_P = 64;            // pair mode: O has 64 columns, each CTA stages 32 rows of V^T
+constexpr int VT_ATOM_P = 32 * 128;      // 64 keys x 32 rows
 constexpr int NS = 3;  // K and V^T ring depth: with 2 the MMA warp waited 14 % of the kernel for the tiles (PNP_ATTN_PROF)
 constexpr int OFF_K = 0;
 constexpr int OFF_VT = OFF_K + NS * K_BYTES;
@@ -55,6 +67,9 @@ constexpr int COL_S = 0;    // two S accumulators of 128 fp32 columns
 constexpr int COL_O = 256;  // O accumulator: 48 fp32 columns
 constexpr int COL_P = 320;  // two probability tiles, 128 keys as 64 columns of packed fp16 pairs each
 constexpr int COL_Q = 448;  // the query tile: 48 (40 + zero padding) head-dim values as 24 columns of packed fp16 pairs
+// defaults of the launch variant (PNP_ATTN_CLUSTER / PNP_ATTN_POLY override them when a plan is made)
+constexpr int kDefaultMode = 1;
+constexpr int kDefaultPoly = 0;
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -64,6 +79,33 @@ __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
   uint32_t y;
   asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
   return y;
+}
+
+// 2^x for a packed pair on the FMA / ALU pipes: n = round(x) through the 1551 = 1536 + 15 trick (the sum has an ulp of 1, so
+// its low mantissa bits are n + 15 = the biased exponent of 2^n), f = x - n in [-0.5, 0.5], cubic minimax of 2^f, scale by
+// the exponent bits.  x is clamped to >= -15 (result 0 below 2^-14.5, where the MUFU path would return subnormals) and
+// must be <= 15.49 (larger values only occur in an optimistic attempt that is repeated anyway).  Max relative error
+// 9.4e-4 (2 ulp of fp16), mean 1.7e-4 against 1.2e-4 for correct rounding (numpy emulation, all fp16 inputs).
+__device__ __forceinline__ uint32_t ex2_poly_h2(uint32_t xu) {
+  const __half2 x = __hmax2(*reinterpret_cast<const __half2*>(&xu), __float2half2_rn(-15.0f));
+  const __half2 magic = __float2half2_rn(1551.0f);
+  const __half2 t = __hadd2(x, magic);
+  const __half2 f = __hsub2(x, __hsub2(t, magic));
+  __half2 pl = __hfma2(__float2half2_rn(0.05508868f), f, __float2half2_rn(0.24260405f));
+  pl = __hfma2(pl, f, __float2half2_rn(0.69327624f));
+  pl = __hfma2(pl, f, __float2half2_rn(0.99992894f));
+  const uint32_t sc = (*reinterpret_cast<const uint32_t*>(&t) << 10) & 0x7C007C00u;
+  const __half2 r = __hmul2(pl, *reinterpret_cast<const __half2*>(&sc));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+// which of the 32 packed exponentials of a thread and tile go to the FMA pipe: POLY of every 8, spread out
+template <int POLY>
+__device__ __forceinline__ constexpr bool use_poly(int i) {
+  return POLY == 0 ? false
+         : POLY == 2 ? (i % 4 == 1)
+         : POLY == 3 ? (i % 8 == 1 || i % 8 == 4 || i % 8 == 6)
+         : POLY == 4 ? (i % 2 == 1)
+                     : (i % 8 < POLY);
 }
 
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -76,8 +118,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-template <bool CL2>
+template <int MODE, int POLY>  // MODE 0: one CTA per query tile; 1: cluster of two sharing K / V through TMA multicast; 2: pair (cta_group::2)
 __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_constant__ SelfAttnTcParams p) {
+  constexpr bool CL2 = MODE == 1;
+  constexpr bool PAIR = MODE == 2;
+  constexpr bool CLUSTER = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -103,11 +148,12 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_qk);
     tma_prefetch_desc(&p.map_vt);
-    if (CL2) tma_prefetch_desc(&p.map_k64);
+    if (CLUSTER) tma_prefetch_desc(&p.map_k64);
+    if (PAIR) tma_prefetch_desc(&p.map_vt32);
   }
-  const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
+  const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 4);  // the four warps that copy the query rows into TMEM
+    mbar_init(q_full, PAIR ? 8 : 4);  // the four warps that copy the query rows into TMEM (pair: of both CTAs, on the leader)
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], CL2 ? 2 : 1);  // with a cluster both CTAs' MMAs must release a stage: the peer writes into it
@@ -116,18 +162,20 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);  // one arrival per warp of the softmax group that owns this buffer
-      mbar_init(&p_full[i], 8);
+      mbar_init(&s_empty[i], PAIR ? 16 : 8);  // one arrival per warp of the softmax group that owns this buffer (pair: both CTAs' groups)
+      mbar_init(&p_full[i], PAIR ? 16 : 8);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
     *ovf_flag = 0;
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_cg2(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();  // the peer's barriers exist before anything is multicast into this CTA
+  if (CLUSTER) cluster_sync_all();  // the peer's barriers (and tensor memory) exist before anything reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();
@@ -150,6 +198,10 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
       mbar_wait(bar, parity, p.dbg, tag);
     }
   };
+  // arrival on a barrier the MMA issuer waits on: in pair mode that is the LEADER's copy, whichever CTA the warp is in
+  auto arrive_mma = [&](uint64_t* bar) {
+    if (PAIR) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar);
+  };
   int kc = 0, vc = 0;       // K / V^T ring counters (producer and MMA issuer each advance their own copy)
   int su[2] = {0, 0};       // uses so far of S accumulator b (MMA issuer: both; a softmax warp: su[0] = its group's buffer)
   int pu[2] = {0, 0};       // uses so far of probability buffer b (same convention)
@@ -165,7 +217,14 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         auto load_k = [&](int j) {
           const int ks = kc % NS;
           twait(&k_empty[ks], ((kc / NS) & 1) ^ 1u, 11, 0);
-          if (elect_one()) {
+          if (PAIR) {
+            // each CTA stages its 64 keys (= its half of the N dimension of S) at the start of its own stage; both loads
+            // complete on the leader's barrier
+            if (elect_one()) {
+              if (crank == 0) mbar_arrive_expect_tx(&k_full[ks], K_BYTES);
+              tma_load_4d_cg2(smem + OFF_K + ks * K_BYTES, &p.map_k64, &k_full[ks], 0, h, 1, bk * p.N + j * KT + crank * 64);
+            }
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(&k_full[ks], K_BYTES);
             if (CL2) {  // this CTA fetches half of the key tile and multicasts it to both CTAs of the cluster
               tma_load_4d_mc(smem + OFF_K + ks * K_BYTES + crank * (K_BYTES / 2), &p.map_k64, &k_full[ks], 0x3, 0, h, 1,
@@ -180,7 +239,14 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         auto load_v = [&](int j) {
           const int vs = vc % NS;
           twait(&v_empty[vs], ((vc / NS) & 1) ^ 1u, 12, 1);
-          if (elect_one()) {
+          if (PAIR) {
+            // rows [32 crank, 32 crank + 32) of V^T (= this CTA's half of the 64 columns of O): 0..39 head dim, 40 ones, rest zero fill
+            if (elect_one()) {
+              if (crank == 0) mbar_arrive_expect_tx(&v_full[vs], 4 * VT_ATOM_P);
+              tma_load_4d_cg2(smem + OFF_VT + vs * VT_BYTES, &p.map_vt32, &v_full[vs], j * KT, crank * 32, h, bv);
+              tma_load_4d_cg2(smem + OFF_VT + vs * VT_BYTES + VT_ATOM_P, &p.map_vt32, &v_full[vs], j * KT + 64, crank * 32, h, bv);
+            }
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(&v_full[vs], VT_BYTES);
             if (CL2) {
               tma_load_4d_mc(smem + OFF_VT + vs * VT_BYTES + crank * VT_ATOM, &p.map_vt, &v_full[vs], 0x3,
@@ -202,10 +268,11 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         }
       }
     } else if (warp == 1) {
-      {
-        // -------------------------------------------------------------- MMA issuer (whole warp, elected lane issues)
-        constexpr uint32_t idesc_qk = umma_idesc_f16(QT, KT);
-        constexpr uint32_t idesc_pv = umma_idesc_f16(QT, VT_ROWS);
+      if (!PAIR || crank == 0) {
+        // -------------------------------------------------------------- MMA issuer (whole warp, elected lane issues; pair: the
+        // leader drives both SMs)
+        constexpr uint32_t idesc_qk = umma_idesc_f16(PAIR ? 2 * QT : QT, KT);
+        constexpr uint32_t idesc_pv = umma_idesc_f16(PAIR ? 2 * QT : QT, PAIR ? VT_ROWS_P : VT_ROWS);
         auto issue_qk = [&](int buf) {  // S tile into accumulator `buf` (pass-B tile j lives in buffer j & 1)
           const int ks = kc % NS;
           twait(&k_full[ks], (kc / NS) & 1, 21, 0);
@@ -214,10 +281,17 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + OFF_K + ks * K_BYTES));
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k)  // head dim 40 -> 48 = three K=16 steps (key columns 40..63 are TMA zero fill)
-              umma_f16_ts(tmem_base + COL_S + buf * KT, tmem_base + COL_Q + 8 * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
-            if (CL2) umma_commit_mc(&k_empty[ks], 0x3); else umma_commit(&k_empty[ks]);
-            umma_commit(&s_full[buf]);
+            for (int k = 0; k < 3; ++k) {  // head dim 40 -> 48 = three K=16 steps (key columns 40..63 are TMA zero fill)
+              if (PAIR) umma_f16_ts_cg2(tmem_base + COL_S + buf * KT, tmem_base + COL_Q + 8 * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
+              else umma_f16_ts(tmem_base + COL_S + buf * KT, tmem_base + COL_Q + 8 * k, bdesc + 2u * k, idesc_qk, k > 0 ? 1u : 0u);
+            }
+            if (PAIR) {
+              umma_commit_mc_cg2(&k_empty[ks], 0x3);
+              umma_commit_mc_cg2(&s_full[buf], 0x3);
+            } else {
+              if (CL2) umma_commit_mc(&k_empty[ks], 0x3); else umma_commit(&k_empty[ks]);
+              umma_commit(&s_full[buf]);
+            }
           }
           __syncwarp();
           ++kc;
@@ -242,17 +316,25 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {  // 128 keys = 8 K=16 steps: 8 TMEM columns of P, two 64-key swizzle atoms of V^T
-              const uint64_t bdesc = umma_desc_sw128_kmajor(v_addr + (k >> 2) * VT_ATOM) + 2u * (k & 3);
-              umma_f16_ts(tmem_base + COL_O, tmem_base + COL_P + pb * 64 + 8 * k, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+              const uint64_t bdesc = umma_desc_sw128_kmajor(v_addr + (k >> 2) * (PAIR ? VT_ATOM_P : VT_ATOM)) + 2u * (k & 3);
+              if (PAIR) umma_f16_ts_cg2(tmem_base + COL_O, tmem_base + COL_P + pb * 64 + 8 * k, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+              else umma_f16_ts(tmem_base + COL_O, tmem_base + COL_P + pb * 64 + 8 * k, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&p_empty[pb]);
-            if (CL2) umma_commit_mc(&v_empty[vs], 0x3); else umma_commit(&v_empty[vs]);
+            if (PAIR) {
+              umma_commit_mc_cg2(&p_empty[pb], 0x3);
+              umma_commit_mc_cg2(&v_empty[vs], 0x3);
+            } else {
+              umma_commit(&p_empty[pb]);
+              if (CL2) umma_commit_mc(&v_empty[vs], 0x3); else umma_commit(&v_empty[vs]);
+            }
           }
           __syncwarp();
           ++pu[pb];
           ++vc;
         }
-        if (elect_one()) umma_commit(o_full);
+        if (elect_one()) {
+          if (PAIR) umma_commit_mc_cg2(o_full, 0x3); else umma_commit(o_full);
+        }
         __syncwarp();
       }
     } else if (warp >= 4) {
@@ -296,7 +378,7 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(q_full);
+        if (lane == 0) arrive_mma(q_full);
       }
       // pass A: row maxima of the raw scores (first tile only in the optimistic attempt)
       float mx = -INFINITY;
@@ -312,7 +394,7 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[g]);
+        if (lane == 0) arrive_mma(&s_empty[g]);
       }
       rowmax_x[(g * 2 + cg) * 128 + row] = mx;
       asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -336,7 +418,7 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           if (hf == 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[g]);
+            if (lane == 0) arrive_mma(&s_empty[g]);
           }
           if (attempt == 0) smax = fmaxf(smax, max32(r));
 #pragma unroll
@@ -347,14 +429,14 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         for (int hf = 0; hf < 2; ++hf) {
           uint32_t ph[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) ph[i] = ex2_h2(xh[hf * 16 + i]);
+          for (int i = 0; i < 16; ++i) ph[i] = use_poly<POLY>(hf * 16 + i) ? ex2_poly_h2(xh[hf * 16 + i]) : ex2_h2(xh[hf * 16 + i]);
           if (hf == 0) twait(&p_empty[g], (pu[0] & 1) ^ 1u, 33, 1);
           tmem_st_32x32b_x16(p_addr + hf * 16, ph);  // A operand of the P V MMA, straight from registers
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g]);
+        if (lane == 0) arrive_mma(&p_full[g]);
       }
       if (attempt == 0 && fmaf(smax, p.sl2, -off) > 15.0f) *ovf_flag = 1;
       // epilogue: O / l  (column 40 of O is the row sum of the probabilities)
@@ -404,7 +486,7 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
     // all roles have finished this attempt: decide (cluster-wide) whether the exact two-pass schedule is needed
     __syncthreads();
     int again = *ovf_flag;
-    if (CL2) {
+    if (CLUSTER) {
       cluster_sync_all();
       uint32_t peer_addr, peer_val;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_addr) : "r"(smem_u32(const_cast<int*>(ovf_flag))), "r"(crank ^ 1u));
@@ -426,10 +508,10 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on this CTA
+  if (CLUSTER) cluster_sync_all();  // nobody leaves while the peer may still multicast into / arrive on / read from this CTA
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -506,6 +588,9 @@ int self_attention_tc_plan(SelfAttnTcParams* p, const __half* qkv, int ld, __hal
     const uint32_t box[4] = {64, VT_ROWS, 1, 1};
     int rc = encode_tensor_map_f16(&p->map_vt, vt, 4, dims, strides, box);
     if (rc) return rc;
+    const uint32_t box32[4] = {64, 32, 1, 1};
+    rc = encode_tensor_map_f16(&p->map_vt32, vt, 4, dims, strides, box32);
+    if (rc) return rc;
   }
   p->q_src = qkv;
   p->v_src = qkv + 2 * 8 * D;
@@ -522,24 +607,42 @@ int self_attention_tc_plan(SelfAttnTcParams* p, const __half* qkv, int ld, __hal
   p->dbg = debug_words_device();
   // cluster of 2 (K / V^T tiles multicast to two query tiles) is opt-in: measured 9.25 ms vs 9.16 ms per B=4 UNet call
   // without it once the issue loops were fixed (TMA multicast does not pay below cluster size 8 on this part)
-  p->cluster = 1;
-  if (const char* ev = getenv("PNP_ATTN_CLUSTER")) p->cluster = (atoi(ev) == 2 && (N / QT) % 2 == 0) ? 2 : 1;
+  // 3 = pair: the two CTAs share one stream of tcgen05.mma.cta_group::2 instructions (the M=128 instruction floor is paid
+  // once per two SMs, profiles/r2_mma_probe.txt)
+  p->cluster = kDefaultMode;
+  p->poly = kDefaultPoly;
+  if (const char* ev = getenv("PNP_ATTN_CLUSTER")) p->cluster = atoi(ev);
+  if (const char* ev = getenv("PNP_ATTN_POLY")) p->poly = atoi(ev);
+  if (p->cluster < 1 || p->cluster > 3 || (N / QT) % 2 != 0) p->cluster = 1;
+  if (p->poly != 0 && p->poly != 2 && p->poly != 3 && p->poly != 4) p->poly = 0;
+  if (p->cluster == 2) p->poly = 0;
+  if (p->cluster == 1 && p->poly != 0) p->poly = 3;
+  return 0;
+}
+
+template <int MODE, int POLY>
+static int launch_variant(const SelfAttnTcParams& p, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    PNP_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<MODE, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  PNP_CUDA(launch_kc(self_attn_tc_kernel<MODE, POLY>, dim3(p.N / QT, 8, p.B), dim3(640), SMEM_BYTES, s, MODE == 0 ? 1 : 2, p));
   return 0;
 }
 
 int self_attention_tc_launch(const SelfAttnTcParams& p, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    PNP_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    PNP_CUDA(cudaFuncSetAttribute(self_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
-  }
   PNP_CUDA(launch_k(vt_transpose_kernel, dim3(p.N / VT_TOK, 8, p.B), dim3(320), 0, s, p.v_src, p.ld, p.N, p.vt));
-  if (p.cluster == 2)
-    PNP_CUDA(launch_kc(self_attn_tc_kernel<true>, dim3(p.N / QT, 8, p.B), dim3(640), SMEM_BYTES, s, 2, p));
-  else
-    PNP_CUDA(launch_k(self_attn_tc_kernel<false>, dim3(p.N / QT, 8, p.B), dim3(640), SMEM_BYTES, s, p));
-  return 0;
+  if (p.cluster == 2) return launch_variant<1, 0>(p, s);
+  if (p.cluster == 3) {
+    switch (p.poly) {
+      case 2: return launch_variant<2, 2>(p, s);
+      case 3: return launch_variant<2, 3>(p, s);
+      case 4: return launch_variant<2, 4>(p, s);
+      default: return launch_variant<2, 0>(p, s);
+    }
+  }
+  return p.poly ? launch_variant<0, 3>(p, s) : launch_variant<0, 0>(p, s);
 }
 
 }  // namespace pnp

@@ -57,7 +57,9 @@ struct alignas(64) SelfAttnTcParams {
   CUtensorMap map_qk;  // fused QKV activation viewed as [B*N][3][8][40]
   CUtensorMap map_vt;  // V^T scratch [B][8][41][N] (row 40 = ones)
   CUtensorMap map_k64;  // same view as map_qk with a 64-row box (cluster-of-2 multicast: each CTA loads half a K tile)
-  int cluster;          // 1 or 2
+  CUtensorMap map_vt32;  // V^T with a 32-row box (pair mode: each CTA stages half of the 64 columns of O)
+  int cluster;          // 1 = one CTA per query tile, 2 = cluster of two with TMA multicast, 3 = pair (tcgen05.mma.cta_group::2)
+  int poly;             // packed exponentials per 8 evaluated on the FMA pipe instead of the MUFU (0, 2, 3, 4)
   const __half* q_src;  // Q part of the fused activation (rows are copied into TMEM by the kernel)
   const __half* v_src;  // V part of the fused activation (transpose source)
   int ld;

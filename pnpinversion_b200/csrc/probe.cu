@@ -22,16 +22,6 @@ struct ProbeParams {
   volatile unsigned int* dbg;
 };
 
-__device__ __forceinline__ void umma_f16_ts_cg2(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 constexpr int PROBE_OPERAND_BYTES = 64 * 1024;
 constexpr int PROBE_SMEM = PROBE_OPERAND_BYTES + 256 + 1024;
 constexpr int PROBE_COL_A = 448;

@@ -204,3 +204,76 @@ def test_self_attention_tcgen05_optimistic_pass_falls_back_when_fp16_would_overf
     err = G.rel_l2(out, ref)
     print("tc attention with forced fallback: rel-L2", err)
     assert err < 3e-3
+
+
+# ---- pair mode (PNP_ATTN_CLUSTER=3: two CTAs share one stream of tcgen05.mma.cta_group::2 instructions) and the FMA-pipe
+# exponentials (PNP_ATTN_POLY): same tolerances as the default variant; with the polynomial off the arithmetic is the same
+@pytest.mark.parametrize("poly", [0, 3])
+@pytest.mark.parametrize("N,B", [(256, 1), (1024, 2), (4096, 2)])
+def test_self_attention_tcgen05_pair(cuda, monkeypatch, N, B, poly):
+    lib = _lib.load()
+    d = 40
+    qkv = _mk((B, N, 3 * H * d), cuda, 31 + N, 1.0)
+    qkv[..., :2 * H * d] *= 1.5
+    ident = list(range(B))
+    ref = _self_ref(qkv, d, ident, ident, ident)
+    monkeypatch.setenv("PNP_ATTN_CLUSTER", "1")
+    monkeypatch.setenv("PNP_ATTN_POLY", "0")
+    base = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(base), G.stream()))
+    monkeypatch.setenv("PNP_ATTN_CLUSTER", "3")
+    monkeypatch.setenv("PNP_ATTN_POLY", str(poly))
+    out = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    err, err0 = G.rel_l2(out, ref), G.rel_l2(base, ref)
+    print(f"pair tc attention N={N} B={B} poly={poly}: rel-L2 {err:.3e} (single-CTA kernel {err0:.3e}), "
+          f"identical to it: {torch.equal(out, base)}")
+    assert err < 2e-3
+    if poly == 0:
+        assert G.rel_l2(out, base.float()) < 2e-4  # same products and sums; only the V^T padding (48 -> 64 columns) differs
+
+
+def test_self_attention_tcgen05_pair_row_indirection_and_fallback(cuda, monkeypatch):
+    monkeypatch.setenv("PNP_ATTN_CLUSTER", "3")
+    monkeypatch.setenv("PNP_ATTN_POLY", "3")
+    lib = _lib.load()
+    B, N, d = 4, 1024, 40
+    qkv = _mk((B, N, 3 * H * d), cuda, 77, 1.2)
+    q_row, k_row, v_row = [0, 1, 2, 2], [0, 0, 2, 2], [0, 0, 2, 3]
+    dq, dk, dv = (torch.tensor(r, dtype=torch.int32, device=cuda) for r in (q_row, k_row, v_row))
+    out = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, G.ptr(dq), G.ptr(dk), G.ptr(dv), G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    assert G.rel_l2(out, _self_ref(qkv, d, q_row, k_row, v_row)) < 2e-3
+    # later keys with far larger scores: the optimistic pass overflows fp16 and the two-pass schedule takes over, cluster-wide
+    B = 2
+    qkv = _mk((B, N, 3 * H * d), cuda, 91, 1.0)
+    c = H * d
+    qkv[:, 256:, c:2 * c] *= 12.0
+    out = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    ident = list(range(B))
+    assert torch.isfinite(out.float()).all()
+    err = G.rel_l2(out, _self_ref(qkv, d, ident, ident, ident))
+    print("pair tc attention with forced fallback: rel-L2", err)
+    assert err < 3e-3
+
+
+@pytest.mark.parametrize("mode,poly", [(1, 0), (1, 3), (3, 3)])
+def test_self_attention_tcgen05_wide_logits(cuda, monkeypatch, mode, poly):
+    """Logits with a standard deviation of 4 nats: most probabilities of a row are below 2^-15 of its maximum - where the
+    polynomial path flushes to zero and the MUFU path returns fp16 subnormals.  Both must stay within the tolerance."""
+    monkeypatch.setenv("PNP_ATTN_CLUSTER", str(mode))
+    monkeypatch.setenv("PNP_ATTN_POLY", str(poly))
+    lib = _lib.load()
+    B, N, d = 1, 4096, 40
+    qkv = _mk((B, N, 3 * H * d), cuda, 123, 1.0)
+    qkv[..., :2 * H * d] *= 2.0
+    out = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    err = G.rel_l2(out, _self_ref(qkv, d, [0], [0], [0]))
+    print(f"tc attention, wide logits, mode {mode} poly {poly}: rel-L2 {err:.3e}")
+    assert err < 3e-3

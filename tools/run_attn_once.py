@@ -1,22 +1,60 @@
-"""One launch of the tcgen05 self-attention at the UNet's largest shape (B=4, 4096 tokens) -- target for ncu."""
-import sys, os
+"""The tcgen05 self-attention at the UNet's largest shape (4096 tokens, 8 heads of 40) - target for ncu, and with `sweep`
+the launch variants side by side (PNP_ATTN_CLUSTER: 1 one CTA per query tile, 2 multicast cluster, 3 cta_group::2 pair;
+PNP_ATTN_POLY: packed exponentials per 8 on the FMA pipe).
+
+    python tools/run_attn_once.py            # one variant (the environment's), B = 4
+    python tools/run_attn_once.py sweep      # all variants at B = 4 and B = 32
+"""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
-from pnpinversion_b200 import _lib
-from tests import gpu_util as G
+import torch  # noqa: E402
+
+from pnpinversion_b200 import _lib  # noqa: E402
+from tests import gpu_util as G  # noqa: E402
 
 lib = _lib.load()
-B, N, H, d = 4, 4096, 8, 40
-g = torch.Generator(device="cpu").manual_seed(5)
-qkv = (torch.randn(B, N, 3 * H * d, generator=g)).to(torch.float16).cuda()
-out = torch.zeros(B, N, H * d, dtype=torch.float16, device="cuda")
-for _ in range(3):
-    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(10):
-    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
-e1.record()
-torch.cuda.synchronize()
-print("tc attention B=4 N=4096: %.1f us per call (incl. V transpose + plan)" % (e0.elapsed_time(e1) * 100))
+N, H, d = 4096, 8, 40
+
+
+def time_variant(qkv, out, B, reps=10):
+    for _ in range(3):
+        _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1000.0 / reps
+
+
+def main():
+    sweep = len(sys.argv) > 1 and sys.argv[1] == "sweep"
+    for B in ((4, 32) if sweep else (4,)):
+        g = torch.Generator(device="cpu").manual_seed(5)
+        qkv = torch.randn(B, N, 3 * H * d, generator=g).to(torch.float16).cuda()
+        out = torch.zeros(B, N, H * d, dtype=torch.float16, device="cuda")
+        variants = [(1, 0), (1, 3), (2, 0), (3, 0), (3, 2), (3, 3), (3, 4)] if sweep else [None]
+        base = None
+        for v in variants:
+            if v is not None:
+                os.environ["PNP_ATTN_CLUSTER"], os.environ["PNP_ATTN_POLY"] = str(v[0]), str(v[1])
+            us = time_variant(qkv, out, B)
+            if sweep:  # kernel-only time (V transpose + attention, CUDA events inside the entry point) and the role counters -> stderr
+                os.environ["PNP_ATTN_PROF"] = "1"
+                for _ in range(2):
+                    _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+                del os.environ["PNP_ATTN_PROF"]
+            if base is None:
+                base = out.clone()
+            diff = float((out.float() - base.float()).norm() / base.float().norm())
+            gf = 4.0 * B * H * N * N * d / 1e9
+            print(f"tc attention B={B} N=4096 variant (cluster, poly)={v}: {us:8.1f} us per call (incl. V transpose + plan + "
+                  f"vt alloc) = {gf / us * 1e-3:6.1f} TFLOP/s; rel diff to the first variant {diff:.2e}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
