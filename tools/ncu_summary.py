@@ -16,11 +16,12 @@ WANT = [  # (column title, substrings the metric name must contain)
     ("regs", ("launch__registers_per_thread",)),
     ("xu%", ("sm__inst_executed_pipe_xu", "pct_of_peak_sustained_active")),
     ("issue%", ("smsp__issue_active.avg.pct_of_peak_sustained_active",)),
-    ("dram%", ("dram__throughput.avg.pct_of_peak_sustained_elapsed",)),
+    ("dram%", ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",)),
     ("sm%", ("sm__throughput.avg.pct_of_peak_sustained_elapsed",)),
     ("grid", ("launch__grid_size",)),
 ]
-SCALE = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+SCALE = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+         "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
 
 
 def main():
@@ -38,16 +39,20 @@ def main():
             f.write(f"# {note}\n")
         f.write("id,kernel," + ",".join(t for t, _ in cols) + "\n")
         for n, r in enumerate(data):
-            name = re.sub(r"^void |pnp::|\(anonymous namespace\)::|<unnamed>::|\(.*$", "", r[kcol])
+            name = re.sub(r"^void |pnp::|\(anonymous namespace\)::|<unnamed>::|\(.*$", "", r[kcol]).replace("unnamed>::", "")
             vals = []
             for title, idx in cols:
                 if idx is None or idx >= len(r) or r[idx] == "":
                     vals.append("")
                     continue
-                v = float(r[idx].replace(",", ""))
+                try:
+                    v = float(r[idx].replace(",", ""))
+                except ValueError:  # "no data" / "n/a"
+                    vals.append("")
+                    continue
                 v *= SCALE.get(units[idx], 1.0) if ("[us]" in title or "[MB]" in title) else 1.0
                 vals.append(f"{v:.3f}" if v != int(v) or "%" in title else str(int(v)))
-            f.write(f"{n},{name}," + ",".join(vals) + "\n")
+            f.write(f'{n},"{name}",' + ",".join(vals) + "\n")
     print("wrote", dst, len(data), "launches; missing columns:", [t for t, i in cols if i is None])
 
 
