@@ -233,6 +233,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
+// same without the release fence (ptxas turns a cluster-scope release into a full fence + L1 invalidate): for hand-offs whose
+// payload lives in tensor memory and is ordered by tcgen05.wait / tcgen05.fence, not by the generic memory model
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
 // A operand from TMEM (128 lanes = rows, packed fp16 pairs along the columns: 8 columns per K=16 step), B from shared memory.
 // In SS mode every M=128 MMA first streams its 128 A rows out of shared memory, which costs ~128 cycles whatever N is
 // (measured: ~130 cycles per MMA for N = 48 ... 160); with A in TMEM the MMA takes N/2 cycles.
