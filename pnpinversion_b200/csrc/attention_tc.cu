@@ -71,6 +71,7 @@ constexpr int COL_Q = 448;  // the query tile: 48 (40 + zero padding) head-dim v
 constexpr int kDefaultMode = 1;
 constexpr int kDefaultPoly = 0;
 constexpr int kDefaultRolesHi = 0;
+constexpr int kDefaultSched = 0;  // 1 = event-driven MMA issue order (see the MMA issuer)
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -281,10 +282,12 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
         // leader drives both SMs)
         constexpr uint32_t idesc_qk = umma_idesc_f16(PAIR ? 2 * QT : QT, KT);
         constexpr uint32_t idesc_pv = umma_idesc_f16(PAIR ? 2 * QT : QT, PAIR ? VT_ROWS_P : VT_ROWS);
-        auto issue_qk = [&](int buf) {  // S tile into accumulator `buf` (pass-B tile j lives in buffer j & 1)
+        auto issue_qk = [&](int buf, bool wait) {  // S tile into accumulator `buf` (pass-B tile j lives in buffer j & 1)
           const int ks = kc % NS;
-          twait(&k_full[ks], (kc / NS) & 1, 21, 0);
-          twait(&s_empty[buf], (su[buf] & 1) ^ 1u, 22, 1);
+          if (wait) {
+            twait(&k_full[ks], (kc / NS) & 1, 21, 0);
+            twait(&s_empty[buf], (su[buf] & 1) ^ 1u, 22, 1);
+          }
           tc_fence_after();
           const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + OFF_K + ks * K_BYTES));
           if (elect_one()) {
@@ -309,16 +312,12 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           mbar_wait(q_full, 0, p.dbg, 20);
           tc_fence_after();
         }
-        for (int j = 0; j < TA; ++j) issue_qk(j & 1);  // pass A
-        issue_qk(0);                                    // pass B, tiles 0 and 1
-        if (T > 1) issue_qk(1);
-        for (int j = 0; j < T; ++j) {
-          // S(j+2) goes into the buffer S(j) came from as soon as its softmax group has pulled S(j) into registers:
-          // each group always has its next tile waiting, and the two groups run half a tile apart
-          if (j + 2 < T) issue_qk(j & 1);
+        auto issue_pv = [&](int j, bool wait) {  // O += P(j) V(j)
           const int pb = j & 1, vs = vc % NS;
-          twait(&p_full[pb], pu[pb] & 1, 23, 2);
-          twait(&v_full[vs], (vc / NS) & 1, 24, 3);
+          if (wait) {
+            twait(&p_full[pb], pu[pb] & 1, 23, 2);
+            twait(&v_full[vs], (vc / NS) & 1, 24, 3);
+          }
           tc_fence_after();
           const uint32_t v_addr = smem_u32(smem + OFF_VT + vs * VT_BYTES);
           if (elect_one()) {
@@ -339,6 +338,63 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
           __syncwarp();
           ++pu[pb];
           ++vc;
+        };
+        for (int j = 0; j < TA; ++j) issue_qk(j & 1, true);  // pass A
+        if (p.sched == 0) {
+          issue_qk(0, true);                                  // pass B, tiles 0 and 1
+          if (T > 1) issue_qk(1, true);
+          for (int j = 0; j < T; ++j) {
+            // S(j+2) goes into the buffer S(j) came from as soon as its softmax group has pulled S(j) into registers:
+            // each group always has its next tile waiting, and the two groups run half a tile apart
+            if (j + 2 < T) issue_qk(j & 1, true);
+            issue_pv(j, true);
+          }
+        } else {
+          // Event-driven order: whichever of "next S tile" / "next P V product" has its inputs ready is issued, S first.
+          // In the fixed order above S(j+2) sits behind the wait for P(j-1) of the OTHER softmax group, which couples the
+          // two groups: the tile period settles near the softmax LATENCY of one tile (~1800 cycles) minus the stagger
+          // instead of at the throughput of the slower pipe (role counters: every group waits ~1200 cycles per tile for
+          // its scores while the MMA warp waits for probabilities).
+          int nq = 0, np = 0;
+          bool idle = false;
+          long long idle0 = 0;
+          while (np < T) {
+            bool did = false;
+            if (nq < T) {
+              const int buf = nq & 1, ks = kc % NS;
+              const bool ok = mbar_try_wait(&k_full[ks], (kc / NS) & 1) && mbar_try_wait(&s_empty[buf], (su[buf] & 1) ^ 1u);
+              if (__all_sync(0xffffffffu, ok)) {
+                issue_qk(buf, false);
+                ++nq;
+                did = true;
+              }
+            }
+            if (!did && np < nq) {
+              const int pb = np & 1, vs = vc % NS;
+              const bool ok = mbar_try_wait(&p_full[pb], pu[pb] & 1) && mbar_try_wait(&v_full[vs], (vc / NS) & 1);
+              if (__all_sync(0xffffffffu, ok)) {
+                issue_pv(np, false);
+                ++np;
+                did = true;
+              }
+            }
+            if (did) {
+              if (idle && prof) pw[2] += clock64() - idle0;
+              idle = false;
+            } else if (!idle) {
+              idle = true;
+              idle0 = clock64();
+            } else if (clock64() - idle0 > (1ll << 31)) {  // bounded like mbar_wait
+              if (p.dbg != nullptr) {
+                p.dbg[0] = 0xDEAD0000u | 25u;
+                p.dbg[1] = blockIdx.x;
+                p.dbg[2] = static_cast<unsigned>(nq);
+                p.dbg[3] = static_cast<unsigned>(np);
+                __threadfence_system();
+              }
+              __trap();
+            }
+          }
         }
         if (elect_one()) {
           if (PAIR) umma_commit_mc_cg2(o_full, 0x3); else umma_commit(o_full);
@@ -620,6 +676,8 @@ int self_attention_tc_plan(SelfAttnTcParams* p, const __half* qkv, int ld, __hal
   p->cluster = kDefaultMode;
   p->poly = kDefaultPoly;
   p->roles_hi = kDefaultRolesHi;
+  p->sched = kDefaultSched;
+  if (const char* ev = getenv("PNP_ATTN_SCHED")) p->sched = atoi(ev) != 0;
   if (const char* ev = getenv("PNP_ATTN_ROLES")) p->roles_hi = atoi(ev) != 0;
   if (const char* ev = getenv("PNP_ATTN_CLUSTER")) p->cluster = atoi(ev);
   if (const char* ev = getenv("PNP_ATTN_POLY")) p->poly = atoi(ev);

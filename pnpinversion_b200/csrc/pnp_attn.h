@@ -60,6 +60,7 @@ struct alignas(64) SelfAttnTcParams {
   CUtensorMap map_vt32;  // V^T with a 32-row box (pair mode: each CTA stages half of the 64 columns of O)
   int cluster;          // 1 = one CTA per query tile, 2 = cluster of two with TMA multicast, 3 = pair (tcgen05.mma.cta_group::2)
   int poly;             // packed exponentials per 8 evaluated on the FMA pipe instead of the MUFU (0, 2, 3, 4)
+  int sched;            // MMA issue order: 0 = fixed (S(j+2), then P(j) V(j)), 1 = event-driven (whichever has its inputs, S first)
   int roles_hi;         // 1 = TMA / MMA / allocator roles on the highest warp ids (issue priority), softmax warps on 0..15
   const __half* q_src;  // Q part of the fused activation (rows are copied into TMEM by the kernel)
   const __half* v_src;  // V part of the fused activation (transpose source)

@@ -1,6 +1,7 @@
 """The tcgen05 self-attention at the UNet's largest shape (4096 tokens, 8 heads of 40) - target for ncu, and with `sweep`
 the launch variants side by side (PNP_ATTN_CLUSTER: 1 one CTA per query tile, 2 multicast cluster, 3 cta_group::2 pair;
-PNP_ATTN_POLY: packed exponentials per 8 on the FMA pipe).
+PNP_ATTN_POLY: packed exponentials per 8 on the FMA pipe; PNP_ATTN_ROLES: roles on the highest warp ids; PNP_ATTN_SCHED:
+event-driven MMA issue order).
 
     python tools/run_attn_once.py            # one variant (the environment's), B = 4
     python tools/run_attn_once.py sweep [B ...]   # all variants (x warp-role layouts, PNP_ATTN_ROLES) at B = 4 and 32
@@ -38,11 +39,13 @@ def main():
         g = torch.Generator(device="cpu").manual_seed(5)
         qkv = torch.randn(B, N, 3 * H * d, generator=g).to(torch.float16).cuda()
         out = torch.zeros(B, N, H * d, dtype=torch.float16, device="cuda")
-        variants = [(1, 0, 0), (1, 0, 1), (1, 3, 1), (3, 0, 0), (3, 0, 1), (3, 2, 1), (3, 3, 1), (3, 4, 1)] if sweep else [None]
+        # (cluster mode, poly, roles_hi, sched)
+        variants = [(1, 0, 0, 0), (1, 0, 0, 1), (1, 3, 0, 1), (1, 0, 1, 1), (3, 0, 0, 0), (3, 0, 0, 1), (3, 3, 0, 1), (3, 4, 0, 1)] if sweep else [None]
         base = None
         for v in variants:
             if v is not None:
-                os.environ["PNP_ATTN_CLUSTER"], os.environ["PNP_ATTN_POLY"], os.environ["PNP_ATTN_ROLES"] = str(v[0]), str(v[1]), str(v[2])
+                for k, val in zip(("PNP_ATTN_CLUSTER", "PNP_ATTN_POLY", "PNP_ATTN_ROLES", "PNP_ATTN_SCHED"), v):
+                    os.environ[k] = str(val)
             us = time_variant(qkv, out, B)
             if sweep:  # kernel-only time (V transpose + attention, CUDA events inside the entry point) and the role counters -> stderr
                 os.environ["PNP_ATTN_PROF"] = "1"
@@ -53,7 +56,7 @@ def main():
                 base = out.clone()
             diff = float((out.float() - base.float()).norm() / base.float().norm())
             gf = 4.0 * B * H * N * N * d / 1e9
-            print(f"tc attention B={B} N=4096 variant (cluster, poly, roles_hi)={v}: {us:8.1f} us per call (incl. V transpose + plan + "
+            print(f"tc attention B={B} N=4096 variant (cluster, poly, roles_hi, sched)={v}: {us:8.1f} us per call (incl. V transpose + plan + "
                   f"vt alloc) = {gf / us * 1e-3:6.1f} TFLOP/s; rel diff to the first variant {diff:.2e}", flush=True)
 
 
