@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
             bool did = false;
             if (nq < T) {
               const int buf = nq & 1, ks = kc % NS;
-              const bool ok = mbar_try_wait(&k_full[ks], (kc / NS) & 1) && mbar_try_wait(&s_empty[buf], (su[buf] & 1) ^ 1u);
+              const bool ok = mbar_test_wait(&k_full[ks], (kc / NS) & 1) && mbar_test_wait(&s_empty[buf], (su[buf] & 1) ^ 1u);
               if (__all_sync(0xffffffffu, ok)) {
                 issue_qk(buf, false);
                 ++nq;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(640, 1) self_attn_tc_kernel(const __grid_const
             }
             if (!did && np < nq) {
               const int pb = np & 1, vs = vc % NS;
-              const bool ok = mbar_try_wait(&p_full[pb], pu[pb] & 1) && mbar_try_wait(&v_full[vs], (vc / NS) & 1);
+              const bool ok = mbar_test_wait(&p_full[pb], pu[pb] & 1) && mbar_test_wait(&v_full[vs], (vc / NS) & 1);
               if (__all_sync(0xffffffffu, ok)) {
                 issue_pv(np, false);
                 ++np;

@@ -40,7 +40,7 @@ def main():
         qkv = torch.randn(B, N, 3 * H * d, generator=g).to(torch.float16).cuda()
         out = torch.zeros(B, N, H * d, dtype=torch.float16, device="cuda")
         # (cluster mode, poly, roles_hi, sched)
-        variants = [(1, 0, 0, 0), (1, 0, 0, 1), (1, 3, 0, 1), (1, 0, 1, 1), (3, 0, 0, 0), (3, 0, 0, 1), (3, 3, 0, 1), (3, 4, 0, 1)] if sweep else [None]
+        variants = [(1, 0, 0, 0), (1, 0, 0, 1), (1, 3, 0, 1), (1, 0, 1, 1), (3, 0, 0, 1), (3, 3, 0, 1)] if sweep else [None]
         base = None
         for v in variants:
             if v is not None:
