@@ -29,6 +29,13 @@ def r16(x):
     return x.to(torch.float16).to(x.dtype)
 
 
+def tf32(x):
+    """round to nearest even on a 10-bit mantissa, fp32 exponent (cuDNN / cuBLAS TF32 operand conversion)"""
+    b = x.to(torch.float32).contiguous().view(torch.int32)
+    b = (b + 0x0FFF + ((b >> 13) & 1)) & ~0x1FFF
+    return b.view(torch.float32).to(x.dtype)
+
+
 def split16(x):
     """hi + lo fp16 pair (what a 2-MMA split-operand GEMM would consume): ~22 bits."""
     hi = x.to(torch.float16).to(x.dtype)
@@ -106,6 +113,11 @@ class UNetEmu(unet_ref.UNetRef):
         return self.q(self._conv(x, name + ".proj_out", padding=0) + x_in, "stream")
 
     def _conv(self, x, name, stride=1, padding=1):
+        if self.rnd.get("tf32_conv"):
+            # what the reference's own GPU path does by default: torch.backends.cudnn.allow_tf32 is True, so every cuDNN
+            # convolution rounds its operands to TF32 (10 mantissa bits, the width of fp16; fp32 exponent range).  The
+            # synthetic weights are fp16 values and therefore exact in TF32: only the activation operand is rounded.
+            x = tf32(x)
         out = super()._conv(x, name, stride, padding)
         if name == "conv_in" or "samplers" in name:
             out = self.q(out, "stream")
@@ -142,6 +154,8 @@ def main():
         for c in CLASSES if c not in ("stream", "inner_stream", "h1", "probs")}
     configs["everything split: fp32 streams, hi/lo GEMM and attention operands (gn_out, ln_out, attn_out, geglu_out, qkv), fp32 probs"] = {
         c: "split" for c in ("gn_out", "ln_out", "attn_out", "geglu_out", "qkv")}
+    configs["REFERENCE on a GPU with its defaults: exact fp32 except cuDNN TF32 convolutions (torch.backends.cudnn.allow_tf32 = True)"] = {
+        "tf32_conv": True}
     if args.configs:
         want = args.configs.split(",")
         configs = {k: v for k, v in configs.items() if k == "exact" or any(w in k for w in want)}
