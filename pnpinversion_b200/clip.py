@@ -9,6 +9,7 @@ No CPU fallback: the output is a CUDA tensor on the device the handle was create
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Dict, List, Tuple
 
 import torch
@@ -60,6 +61,7 @@ class FusedCLIPTextEncoder:
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
+        self._lock = threading.Lock()  # one handle may serve several lanes (parallel.EditLanes): its plan buffers are shared
         layers = count_layers(state_dict)
         if layers == 0:
             raise _lib.PnpError("not a CLIPTextModel state dict: text_model.encoder.layers.0.layer_norm1.weight is missing")
@@ -101,11 +103,13 @@ class FusedCLIPTextEncoder:
         ids32 = ids.detach().to("cpu", torch.int32).contiguous()
         B = ids32.shape[0]
         out = torch.empty((B, POSITIONS, HIDDEN), device=self.device, dtype=torch.float32)
-        with torch.cuda.device(self.device):
+        with self._lock, torch.cuda.device(self.device):
             for b0 in range(0, B, 64):
                 nb = min(64, B - b0)
                 _lib.check(self._lib.pnp_clip_encode(self._h, C.c_void_p(ids32[b0:b0 + nb].data_ptr()), nb,
                                                      C.c_void_p(out[b0:b0 + nb].data_ptr()), _lib.current_stream_ptr()))
+            # the next caller (possibly another lane on another stream) reuses the plan's buffers: finish before unlocking
+            torch.cuda.current_stream().synchronize()
         return _Out((out,))
 
     def to(self, *a, **k):  # the reference moves its pipeline with .to(device); the handle already lives there
