@@ -109,3 +109,44 @@ def test_original_ldm_single_file_layout_is_converted(tmp_path):
     assert checkpoint.check_unet_state_dict(back) == ([], [], [])
     with pytest.raises(ValueError):
         checkpoint.ldm_to_diffusers_unet({"model.diffusion_model.label_emb.0.0.weight": torch.empty((1,), device="meta")})
+
+
+def test_clip_text_encoder_weights_are_read_and_validated(tmp_path):
+    """`<checkpoint>/text_encoder/model.safetensors` -> the tensors the fused CLIP text encoder loads (clip.py), whatever
+    the layer count / vocabulary of the file; `position_ids` buffers of older transformers versions are ignored, a missing
+    or mis-shaped tensor is reported by name.  Also written by a live `transformers.CLIPTextModel` when importable."""
+    from safetensors.torch import save_file
+
+    from pnpinversion_b200 import synth
+    from pnpinversion_b200.clip import clip_text_param_specs
+
+    enc = tmp_path / "text_encoder"
+    enc.mkdir()
+    sd = synth.synth_clip_state_dict(0, layers=2, vocab=64)
+    full = dict(sd)
+    full["text_model.embeddings.position_ids"] = torch.arange(77).unsqueeze(0)
+    save_file({k: v.contiguous() for k, v in full.items()}, str(enc / "model.safetensors"))
+    got = checkpoint.load_clip_state_dict(str(enc))
+    assert list(got) == [n for n, _ in clip_text_param_specs(2, 64)]
+    assert all(torch.equal(got[k], sd[k]) for k in got)
+    bad = dict(sd)
+    del bad["text_model.encoder.layers.1.mlp.fc2.bias"]
+    save_file({k: v.contiguous() for k, v in bad.items()}, str(enc / "model.safetensors"))
+    with pytest.raises(ValueError, match="layers.1.mlp.fc2.bias missing"):
+        checkpoint.load_clip_state_dict(str(enc))
+    bad = dict(sd)
+    bad["text_model.final_layer_norm.weight"] = torch.zeros(10)
+    save_file({k: v.contiguous() for k, v in bad.items()}, str(enc / "model.safetensors"))
+    with pytest.raises(ValueError, match="final_layer_norm.weight has shape"):
+        checkpoint.load_clip_state_dict(str(enc))
+    with pytest.raises(FileNotFoundError):
+        checkpoint.load_clip_state_dict(str(tmp_path / "text_encoder_absent"))
+    try:
+        from transformers import CLIPTextConfig, CLIPTextModel
+    except Exception:
+        return
+    cfg = CLIPTextConfig(vocab_size=64, hidden_size=768, intermediate_size=3072, num_hidden_layers=2,
+                         num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu")
+    CLIPTextModel(cfg).save_pretrained(str(enc))
+    live = checkpoint.load_clip_state_dict(str(enc))
+    assert {k: tuple(v.shape) for k, v in live.items()} == dict(clip_text_param_specs(2, 64))
