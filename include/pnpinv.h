@@ -274,8 +274,10 @@ int pnp_test_cross_attention(const uint16_t* q_dev, const uint16_t* kv_dev, int 
                              const pnp_attn_ctrl* ctrl_host, float* store_dev, uint16_t* out_dev, void* stream);
 /* tcgen05.mma instruction-cost probe (csrc/probe.cu, tools/mma_probe.py): `n` back-to-back MMAs of shape M x N x 16
  * (cta_group 1: M = 64 / 128; cta_group 2: M = 256 on a cluster of two SMs), A operand from tensor memory or shared
- * memory, round-robin over `nacc` accumulators; cycles_out_host[0] = cycles to issue them, [1] = cycles until the commit */
-int pnp_test_mma_probe(int cta_group, int M, int N, int a_from_tmem, int n, int nacc, int64_t* cycles_out_host);
+ * memory, round-robin over `nacc` accumulators, issued in elected blocks of `group` (1..8) instructions, `commit` = a
+ * tcgen05.commit after every block; cycles_out_host[0] = cycles to issue them, [1] = cycles until the final commit arrives */
+int pnp_test_mma_probe(int cta_group, int M, int N, int a_from_tmem, int n, int nacc, int group, int commit,
+                       int64_t* cycles_out_host);
 int pnp_test_upsample2x(const uint16_t* x_dev, int B, int H, int W, int C, uint16_t* out_dev, void* stream);
 int pnp_test_im2col_s2(const uint16_t* x_dev, int B, int H, int W, int C, uint16_t* out_dev, void* stream);
 

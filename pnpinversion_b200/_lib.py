@@ -148,7 +148,7 @@ SIGNATURES = {
     "pnp_vae_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "pnp_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "pnp_vae_kernel_launches": (_i, [_vp, C.POINTER(_i64)]),
-    "pnp_test_mma_probe": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(_i64)]),
+    "pnp_test_mma_probe": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i64)]),
     "pnp_clip_create": (_i, [_i, C.POINTER(_vp)]),
     "pnp_clip_destroy": (None, [_vp]),
     "pnp_clip_load_param": (_i, [_vp, C.c_char_p, _vp, _i64]),

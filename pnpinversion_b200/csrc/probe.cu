@@ -5,7 +5,8 @@
 // operand (then it does not), and what do M = 64 instructions (the transposed product O^T = V^T P^T) cost?
 //
 // One CTA (or one cluster of two for cta_group::2) issues `n` back-to-back MMAs of one shape on whatever bits are in its
-// shared / tensor memory, round-robin over `nacc` accumulators, commits, and reports the cycles until the commit arrives.
+// shared / tensor memory, round-robin over `nacc` accumulators, in elected issue blocks of `group` instructions with or
+// without a tcgen05.commit after each block, and reports the cycles until the final commit arrives.
 #include <cstring>
 #include <string>
 
@@ -18,6 +19,7 @@ namespace {
 
 struct ProbeParams {
   int cg2, M, N, ts, n, nacc;
+  int group, commit;  // MMAs per elected issue block (1..8); 1 = a tcgen05.commit after every block (onto a barrier nobody waits on)
   long long* out;  // [4]: issue cycles, total cycles, n, clock rate placeholder
   volatile unsigned int* dbg;
 };
@@ -31,7 +33,8 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const ProbeParams p) 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* done = reinterpret_cast<uint64_t*>(smem + PROBE_OPERAND_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* sink = done + 1;  // target of the intermediate commits: more pending arrivals than commits, never waited on
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
   // operands: fp16 1.0 everywhere (any finite pattern would do)
@@ -39,6 +42,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const ProbeParams p) 
   fence_proxy_async_smem();
   if (warp == 0 && lane == 0) {
     mbar_init(done, 1);
+    mbar_init(sink, 0xFFFFFu);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -68,10 +72,10 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const ProbeParams p) 
       const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem + 32 * 1024));
       const uint32_t stride = static_cast<uint32_t>((p.N + 31) & ~31);
       const long long t0 = clock64();
-      for (int it = 0; it < p.n; it += 8) {
+      for (int it = 0; it < p.n; it += p.group) {
         if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
+#pragma unroll 1
+          for (int k = 0; k < p.group; ++k) {
             const int i = it + k;
             const uint32_t d = tmem_base + static_cast<uint32_t>(i % p.nacc) * stride;
             const uint32_t acc = i >= p.nacc ? 1u : 0u;
@@ -84,6 +88,9 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const ProbeParams p) 
               if (p.ts) umma_f16_ts(d, tmem_base + PROBE_COL_A, bd, idesc, acc);
               else umma_f16_ss(d, adesc + 2u * (k & 3), bd, idesc, acc);
             }
+          }
+          if (p.commit) {  // what the product kernels do after every K block / S tile / P V product
+            if (CG2) umma_commit_mc_cg2(sink, 0x3); else umma_commit(sink);
           }
         }
         __syncwarp();
@@ -118,10 +125,12 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const ProbeParams p) 
 
 using namespace pnp;
 
-extern "C" int pnp_test_mma_probe(int cta_group, int M, int N, int a_from_tmem, int n, int nacc, int64_t* cycles_out_host) {
+extern "C" int pnp_test_mma_probe(int cta_group, int M, int N, int a_from_tmem, int n, int nacc, int group, int commit,
+                                  int64_t* cycles_out_host) {
   PNP_CHECK(cycles_out_host != nullptr, "pnp_test_mma_probe: null output");
   PNP_CHECK(cta_group == 1 || cta_group == 2, "pnp_test_mma_probe: cta_group 1 or 2");
-  PNP_CHECK(n >= 8 && n % 8 == 0 && n <= (1 << 20), "pnp_test_mma_probe: n must be a multiple of 8");
+  PNP_CHECK(group >= 1 && group <= 8, "pnp_test_mma_probe: 1..8 MMAs per issue block");
+  PNP_CHECK(n >= 8 && n % group == 0 && n <= (1 << 18), "pnp_test_mma_probe: n must be a multiple of the block size, <= 2^18");
   PNP_CHECK(M == 64 || M == 128 || M == 256, "pnp_test_mma_probe: M");
   PNP_CHECK((cta_group == 2) == (M == 256), "pnp_test_mma_probe: M = 256 needs cta_group 2 (and only that is probed)");
   PNP_CHECK(N >= 16 && N <= 256 && N % 16 == 0, "pnp_test_mma_probe: N");
@@ -143,6 +152,8 @@ extern "C" int pnp_test_mma_probe(int cta_group, int M, int N, int a_from_tmem, 
   p.ts = a_from_tmem;
   p.n = n;
   p.nacc = nacc;
+  p.group = group;
+  p.commit = commit ? 1 : 0;
   p.out = out;
   p.dbg = debug_words_device();
   cudaError_t e;

@@ -15,7 +15,7 @@ def test_mma_probe_reports_cycles(cuda, cg, M, N, ts):
     lib = _lib.load()
     out = (C.c_int64 * 2)()
     n = 256
-    _lib.check(lib.pnp_test_mma_probe(cg, M, N, ts, n, 1, out))
+    _lib.check(lib.pnp_test_mma_probe(cg, M, N, ts, n, 1, 8, 0, out))
     issue, total = out[0] / n, out[1] / n
     print(f"tcgen05.mma cta_group::{cg} M={M} N={N} A from {'tmem' if ts else 'smem'}: {total:.1f} cycles per instruction")
     math_cycles = (M // cg) * N * 16 / 4096
@@ -25,5 +25,6 @@ def test_mma_probe_reports_cycles(cuda, cg, M, N, ts):
 def test_mma_probe_rejects_shapes_the_instruction_does_not_have():
     lib = _lib.load()
     out = (C.c_int64 * 2)()
-    for args in ((1, 256, 64, 1, 64, 1), (2, 256, 48, 1, 64, 1), (1, 128, 40, 1, 64, 1), (1, 128, 256, 1, 64, 4)):
+    for args in ((1, 256, 64, 1, 64, 1, 8, 0), (2, 256, 48, 1, 64, 1, 8, 0), (1, 128, 40, 1, 64, 1, 8, 0),
+                 (1, 128, 256, 1, 64, 4, 8, 0), (1, 128, 64, 1, 64, 1, 9, 0), (1, 128, 64, 1, 60, 1, 8, 1)):
         assert lib.pnp_test_mma_probe(*args, out) != 0

@@ -44,7 +44,7 @@ def group(which, n):
                 continue
             try:
                 for _ in range(2):  # second run: instruction cache and clocks warm
-                    _lib.check(lib.pnp_test_mma_probe(cg, M, N, ts, n, nacc, out))
+                    _lib.check(lib.pnp_test_mma_probe(cg, M, N, ts, n, nacc, 8, 0, out))
             except Exception as e:  # noqa: BLE001
                 print(f"{cg:>9} {M:>4} {N:>4} {'tmem' if ts else 'smem':>5} {nacc:>3}   FAILED: {str(e)[:120]}", flush=True)
                 return
