@@ -97,6 +97,9 @@ class FusedCLIPTextEncoder:
     def __call__(self, input_ids, attention_mask=None, **kwargs):
         if attention_mask is not None:
             raise _lib.PnpError("FusedCLIPTextEncoder: attention_mask is not supported (the reference never passes one)")
+        extra = [k for k, v in kwargs.items() if v not in (None, False) and k != "return_dict"]
+        if extra:  # output_hidden_states / output_attentions / position_ids ...: not computed here, so not silently dropped
+            raise _lib.PnpError(f"FusedCLIPTextEncoder: unsupported arguments {extra} (only last_hidden_state is produced)")
         ids = torch.as_tensor(input_ids)
         if ids.dim() != 2 or ids.shape[1] != POSITIONS:
             raise _lib.PnpError(f"FusedCLIPTextEncoder: expected input_ids (B,{POSITIONS}), got {tuple(ids.shape)}")
