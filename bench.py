@@ -365,33 +365,45 @@ def main():
                                 "tests/test_gpu_batched.py)"}
     # the image-path API end to end (P2PEditor.edit_batch on HWC uint8 host arrays -> 2048x512 PIL strips): VAE encode,
     # the four loops, VAE decodes of the reconstruction and edit latents, panel assembly on the host; one step, rank 0
-    image_line = None
-    if args.workload == "p2p" and not args.minimal and rank == 0 and not args.no_image_path:
+    def side_measurement(fn):
+        """The figures beside the headline (rank 0, no collective inside) must not take the headline down with them: an
+        exception is recorded in the line instead."""
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    def measure_image_path():
         import numpy as np
 
         from pnpinversion_b200.vae import FusedVAE
 
         parent.vae = FusedVAE(synth.synth_vae_state_dict(0), device=str(dev))
-        rng = np.random.RandomState(7)
-        imgs = [rng.randint(0, 256, (512, 512, 3)).astype(np.uint8) for _ in range(NB)]
-        ed0 = lanes.editors[0]
-        ed0.edit_batch(imgs[:1], [src], [tgt], blend_word=BLEND, eq_params=EQ)  # VAE plans (B = 1, 2) built outside the timing
-        torch.cuda.synchronize()
-        w0 = time.perf_counter()
-        strips = ed0.edit_batch(imgs, [src] * NB, [tgt] * NB, guidance_scale=7.5, cross_replace_steps=0.4,
-                                self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - w0
-        assert len(strips) == NB and strips[0].size == (2048, 512)
-        image_line = {"value": NB / wall, "unit": "images/s", "images": NB, "seconds": wall,
-                      "h2d_bytes": NB * 512 * 512 * 3, "d2h_bytes": NB * 4 * 3 * 512 * 512 * 4,
-                      "what": "host wall clock around P2PEditor.edit_batch(list of HWC uint8 arrays) -> PIL strips: VAE encode + "
-                              "650 UNet forwards + 4 VAE decodes per image + panel assembly (synthetic VAE weights)"}
-        parent.vae = None
+        try:
+            rng = np.random.RandomState(7)
+            imgs = [rng.randint(0, 256, (512, 512, 3)).astype(np.uint8) for _ in range(NB)]
+            ed0 = lanes.editors[0]
+            ed0.edit_batch(imgs[:1], [src], [tgt], blend_word=BLEND, eq_params=EQ)  # VAE plans (B = 1, 2) built outside the timing
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            strips = ed0.edit_batch(imgs, [src] * NB, [tgt] * NB, guidance_scale=7.5, cross_replace_steps=0.4,
+                                    self_replace_steps=0.6, blend_word=BLEND, eq_params=EQ)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - w0
+            assert len(strips) == NB and strips[0].size == (2048, 512)
+            return {"value": NB / wall, "unit": "images/s", "images": NB, "seconds": wall,
+                    "h2d_bytes": NB * 512 * 512 * 3, "d2h_bytes": NB * 4 * 3 * 512 * 512 * 4,
+                    "what": "host wall clock around P2PEditor.edit_batch(list of HWC uint8 arrays) -> PIL strips: VAE encode + "
+                            "650 UNet forwards + 4 VAE decodes per image + panel assembly (synthetic VAE weights)"}
+        finally:
+            parent.vae = None
+
+    image_line = None
+    if args.workload == "p2p" and not args.minimal and rank == 0 and not args.no_image_path:
+        image_line = side_measurement(measure_image_path)
     # BASELINE config 2 as worded ("batch=1"): one image at a time through the same editor (UNet batch 1 / 4), two images
     # after one warm-up image that builds the plans of those batch sizes; device-resident input, rank 0
-    single_line = None
-    if args.workload == "p2p" and not args.minimal and rank == 0 and not args.no_single_image and NB > 1:
+    def measure_single_image():
         ed0 = lanes.editors[0]
 
         def one(i):
@@ -407,9 +419,13 @@ def main():
         s1.record()
         torch.cuda.synchronize()
         sec = s0.elapsed_time(s1) / 1000.0 / 2
-        single_line = {"value": 1.0 / sec, "unit": "images/s", "seconds_per_image": sec, "images": 2,
-                       "what": "one image per pass (UNet batch 1 for the inversion, 4 for the guided loops), faithful 650 "
-                               "forwards, same handle and weights; CUDA events"}
+        return {"value": 1.0 / sec, "unit": "images/s", "seconds_per_image": sec, "images": 2,
+                "what": "one image per pass (UNet batch 1 for the inversion, 4 for the guided loops), faithful 650 "
+                        "forwards, same handle and weights; CUDA events"}
+
+    single_line = None
+    if args.workload == "p2p" and not args.minimal and rank == 0 and not args.no_single_image and NB > 1:
+        single_line = side_measurement(measure_single_image)
     ctx_rows = {"p2p": 4, "masactrl": 4, "edict": 9}[args.workload] * NB  # edict: 4 coupled passes encode 2+2+2+3 rows per image
     # per pass: NB latents from pinned memory + the prompts: token ids ([rows,77] int32) when the fused CLIP text encoder runs
     # on the GPU, the [rows,77,768] fp32 context rows when the host stand-in computes them
