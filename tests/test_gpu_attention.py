@@ -277,3 +277,25 @@ def test_self_attention_tcgen05_wide_logits(cuda, monkeypatch, mode, poly):
     err = G.rel_l2(out, _self_ref(qkv, d, [0], [0], [0]))
     print(f"tc attention, wide logits, mode {mode} poly {poly}: rel-L2 {err:.3e}")
     assert err < 3e-3
+
+
+@pytest.mark.parametrize("cluster,roles,sched", [(1, 1, 0), (1, 0, 1), (3, 0, 1), (3, 1, 1)])
+def test_self_attention_tcgen05_role_layout_and_issue_order_are_bit_identical(cuda, monkeypatch, cluster, roles, sched):
+    """PNP_ATTN_ROLES (TMA / MMA roles on the highest warp ids) and PNP_ATTN_SCHED (event-driven MMA issue order, barriers
+    probed with mbarrier.test_wait) change when instructions are issued, not what they compute."""
+    lib = _lib.load()
+    B, N, d = 2, 4096, 40
+    qkv = _mk((B, N, 3 * H * d), cuda, 211, 1.0)
+    qkv[..., :2 * H * d] *= 1.5
+    outs = []
+    for env in ((1, 0, 0), (cluster, roles, sched)):
+        for k, v in zip(("PNP_ATTN_CLUSTER", "PNP_ATTN_ROLES", "PNP_ATTN_SCHED"), env):
+            monkeypatch.setenv(k, str(v))
+        monkeypatch.setenv("PNP_ATTN_POLY", "0")
+        out = torch.zeros(B, N, H * d, dtype=torch.float16, device=cuda)
+        _lib.check(lib.pnp_test_self_attention_tc(G.ptr(qkv), B, N, None, None, None, G.ptr(out), G.stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    ident = list(range(B))
+    assert G.rel_l2(outs[0], _self_ref(qkv, d, ident, ident, ident)) < 2e-3
+    assert torch.equal(outs[0], outs[1])
