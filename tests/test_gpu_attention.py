@@ -279,7 +279,7 @@ def test_self_attention_tcgen05_wide_logits(cuda, monkeypatch, mode, poly):
     assert err < 3e-3
 
 
-@pytest.mark.parametrize("cluster,roles,sched", [(1, 1, 0), (1, 0, 1), (3, 0, 1), (3, 1, 1)])
+@pytest.mark.parametrize("cluster,roles,sched", [(1, 1, 0), (1, 0, 1), (1, 1, 1), (3, 0, 1), (3, 1, 0)])
 def test_self_attention_tcgen05_role_layout_and_issue_order_are_bit_identical(cuda, monkeypatch, cluster, roles, sched):
     """PNP_ATTN_ROLES (TMA / MMA roles on the highest warp ids) and PNP_ATTN_SCHED (event-driven MMA issue order, barriers
     probed with mbarrier.test_wait) change when instructions are issued, not what they compute."""
